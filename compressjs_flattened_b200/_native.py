@@ -1,0 +1,77 @@
+"""ctypes loader for libbz2b200.so (the CUDA library behind include/bz2b200.h).
+
+There is no CPU fallback: if the shared library is missing, or no CUDA device can be
+opened, every entry point raises.  (tests/sim/ builds a CPU *simulation* of the kernels for
+logic tests; it is loaded only by tests through `Library(path=...)`, never from here.)
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+DEFAULT_SO = os.path.join(_HERE, "libbz2b200.so")
+
+E_LEVEL, E_CUDA, E_ARG = -100, -101, -102
+
+
+class Stats(C.Structure):
+    _fields_ = [("in_bytes", C.c_uint64), ("out_bytes", C.c_uint64), ("n_blocks", C.c_uint32),
+                ("sort_rounds", C.c_uint32), ("rle1_bytes", C.c_uint64), ("mtf_syms", C.c_uint64),
+                ("sort_slots", C.c_uint64), ("kernel_launches", C.c_uint32), ("d1_triggered", C.c_uint32),
+                ("ms_total", C.c_float), ("ms_stage", C.c_float * 8)]
+
+
+class BlockRec(C.Structure):
+    _fields_ = [("s", C.c_int64), ("p", C.c_int64), ("e_true", C.c_int64), ("Ge", C.c_uint64),
+                ("outR", C.c_uint32), ("n", C.c_uint32), ("crc", C.c_uint32), ("orig_ptr", C.c_uint32)]
+
+
+class BlockMeta(C.Structure):
+    _fields_ = [("alpha", C.c_uint32), ("m", C.c_uint32), ("used", C.c_uint32 * 8), ("n_groups", C.c_uint32),
+                ("n_sel", C.c_uint32), ("bits", C.c_uint64), ("d1", C.c_uint32), ("pad", C.c_uint32)]
+
+
+class Library:
+    """Thin typed view of the C ABI."""
+
+    def __init__(self, path=None):
+        path = path or DEFAULT_SO
+        if not os.path.exists(path):
+            raise RuntimeError(
+                f"{path} not found: build the CUDA extension first (python -c 'import __graft_entry__ as g; g.build()'). "
+                "There is no CPU fallback.")
+        L = C.CDLL(path)
+        vp, u8pp, szp = C.c_void_p, C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(C.c_size_t)
+        L.bz2b200_create.argtypes = [C.c_int, C.POINTER(vp)]
+        L.bz2b200_destroy.argtypes = [vp]
+        L.bz2b200_destroy.restype = None
+        L.bz2b200_compress.argtypes = [vp, vp, C.c_size_t, C.c_int, u8pp, szp]
+        L.bz2b200_decompress.argtypes = [vp, vp, C.c_size_t, C.c_int, u8pp, szp]
+        L.bz2b200_decompress_block.argtypes = [vp, vp, C.c_size_t, C.c_uint64, u8pp, szp]
+        L.bz2b200_table.argtypes = [vp, vp, C.c_size_t, C.c_int, C.POINTER(C.POINTER(C.c_uint64)),
+                                    C.POINTER(C.POINTER(C.c_uint32)), szp]
+        L.bz2b200_free.argtypes = [vp]
+        L.bz2b200_free.restype = None
+        L.bz2b200_compress_device.argtypes = [vp, vp, C.c_size_t, C.c_int, vp, C.c_size_t, szp]
+        L.bz2b200_decompress_device.argtypes = [vp, vp, C.c_size_t, C.c_int, vp, C.c_size_t, szp]
+        L.bz2b200_compress_bound.argtypes = [C.c_size_t, C.c_int]
+        L.bz2b200_compress_bound.restype = C.c_size_t
+        L.bz2b200_strerror.argtypes = [C.c_int]
+        L.bz2b200_strerror.restype = C.c_char_p
+        L.bz2b200_last_error.argtypes = [vp]
+        L.bz2b200_last_error.restype = C.c_char_p
+        L.bz2b200_last_stats.argtypes = [vp, C.POINTER(Stats)]
+        L.bz2b200_debug_fetch.argtypes = [vp, C.c_int, C.c_int, vp, C.c_size_t]
+        L.bz2b200_debug_fetch.restype = C.c_longlong
+        L.bz2b200_debug_set_block_cap.argtypes = [vp, C.c_uint32]
+        self.L = L
+        self.path = path
+
+
+_default = None
+
+
+def default_library():
+    global _default
+    if _default is None:
+        _default = Library()
+    return _default

@@ -1,0 +1,224 @@
+"""Host-side mirror of the reference's `Bzip2` object (BJ = /root/reference/Bzip2_joined_.js).
+
+    Bzip2.compressFile(input, output=None, props=None)        BJ:2199-2249
+    Bzip2.decompressFile(input, output=None, multistream=False)  BJ:1769-1796
+    Bzip2.decompressBlock(input, bitpos, output=None)         BJ:1797-1818
+    Bzip2.table(input, callback, multistream=False)           BJ:1823-1863
+
+Same names, argument meaning and error behaviour as the JavaScript API; the work is done by
+the CUDA library behind include/bz2b200.h.  Coercions follow Util.coerceInputStream /
+coerceOutputStream (BJ:178-272):
+  input : bytes-like / list of ints / object with readByte() (-1 at EOF)
+  output: None -> returns a new bytes object (the JS returns a fresh Uint8Array);
+          int  -> expected size, TypeError('outputsize does not match decoded input') if wrong;
+          bytearray/memoryview -> filled in place, same size check;
+          object with writeByte(b) -> bytes pushed one at a time, flush() called if present,
+          the object itself is returned.
+Errors: `Bzip2Error` (a TypeError, like the JS `_throw`, BJ:1384-1391) carrying `.errorCode`;
+a bad level raises ValueError('Invalid block size multiplier') (JS: Error, BJ:2208).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _native
+
+EOF = -1
+
+
+class Bzip2Error(TypeError):
+    def __init__(self, code, message):
+        super().__init__(message)
+        self.errorCode = code
+
+
+class Err:  # BJ:1365-1375
+    OK = 0
+    LAST_BLOCK = -1
+    NOT_BZIP_DATA = -2
+    UNEXPECTED_INPUT_EOF = -3
+    UNEXPECTED_OUTPUT_EOF = -4
+    DATA_ERROR = -5
+    OUT_OF_MEMORY = -6
+    OBSOLETE_INPUT = -7
+    END_OF_BLOCK = -8
+
+
+def _coerce_input(inp):
+    """Util.coerceInputStream (BJ:178-220): drain any source into a contiguous uint8 array."""
+    if hasattr(inp, "readByte"):
+        out = bytearray()
+        while True:
+            ch = inp.readByte()
+            if ch == EOF:
+                break
+            out.append(ch)
+        return np.frombuffer(bytes(out), dtype=np.uint8)
+    if isinstance(inp, np.ndarray):
+        return np.ascontiguousarray(inp, dtype=np.uint8).reshape(-1)
+    if isinstance(inp, (bytes, bytearray, memoryview)):
+        return np.frombuffer(inp, dtype=np.uint8)
+    return np.asarray(list(inp), dtype=np.uint8)
+
+
+def _deliver(data, output):
+    """Util.coerceOutputStream + BufferStream.getBuffer (BJ:222-272)."""
+    if output is None or output is False:
+        return bytes(data)
+    if hasattr(output, "writeByte"):
+        for b in data:
+            output.writeByte(b)
+        if hasattr(output, "flush"):
+            output.flush()
+        return output
+    if isinstance(output, int):
+        if output != len(data):
+            raise TypeError("outputsize does not match decoded input")
+        return bytes(data)
+    mv = memoryview(output)
+    if len(mv) != len(data):
+        raise TypeError("outputsize does not match decoded input")
+    mv[:] = data
+    return output
+
+
+class Bzip2Engine:
+    """One CUDA context (one GPU).  `Bzip2` below is the process-wide default instance."""
+
+    def __init__(self, device=0, library=None):
+        self._lib = library or _native.default_library()
+        self._L = self._lib.L
+        self._ctx = C.c_void_p()
+        rc = self._L.bz2b200_create(device, C.byref(self._ctx))
+        if rc:
+            raise RuntimeError(f"bz2b200_create(device={device}) failed ({rc}): no usable CUDA device; "
+                               "this package has no CPU fallback")
+        self.Err = Err
+
+    def close(self):
+        if self._ctx:
+            self._L.bz2b200_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- error mapping (BJ:1376-1391) --
+    def _raise(self, rc):
+        if rc == _native.E_LEVEL:
+            raise ValueError("Invalid block size multiplier")
+        msg = self._L.bz2b200_strerror(rc).decode()
+        if rc in (_native.E_CUDA, _native.E_ARG):
+            raise RuntimeError(msg + ": " + self._L.bz2b200_last_error(self._ctx).decode())
+        raise Bzip2Error(rc, msg)
+
+    def _take(self, ptr, n):
+        data = C.string_at(ptr, n) if n else b""
+        self._L.bz2b200_free(ptr)
+        return data
+
+    # -- the four methods of the reference object --
+    def compressFile(self, input, output=None, props=None):
+        level = props if isinstance(props, (int, float)) and not isinstance(props, bool) else 9  # BJ:2204-2206
+        if level < 1 or level > 9 or int(level) != level:
+            raise ValueError("Invalid block size multiplier")
+        a = _coerce_input(input)
+        out, n = C.POINTER(C.c_uint8)(), C.c_size_t()
+        rc = self._L.bz2b200_compress(self._ctx, a.ctypes.data, a.size, int(level), C.byref(out), C.byref(n))
+        if rc:
+            self._raise(rc)
+        return _deliver(self._take(out, n.value), output)
+
+    def decompressFile(self, input, output=None, multistream=False):
+        a = _coerce_input(input)
+        out, n = C.POINTER(C.c_uint8)(), C.c_size_t()
+        rc = self._L.bz2b200_decompress(self._ctx, a.ctypes.data, a.size, int(bool(multistream)), C.byref(out), C.byref(n))
+        if rc:
+            self._raise(rc)
+        return _deliver(self._take(out, n.value), output)
+
+    def decompressBlock(self, input, pos, output=None):
+        a = _coerce_input(input)
+        out, n = C.POINTER(C.c_uint8)(), C.c_size_t()
+        rc = self._L.bz2b200_decompress_block(self._ctx, a.ctypes.data, a.size, int(pos), C.byref(out), C.byref(n))
+        if rc:
+            self._raise(rc)
+        return _deliver(self._take(out, n.value), output)
+
+    def table(self, input, callback, multistream=False):
+        a = _coerce_input(input)
+        pos, sz, n = C.POINTER(C.c_uint64)(), C.POINTER(C.c_uint32)(), C.c_size_t()
+        rc = self._L.bz2b200_table(self._ctx, a.ctypes.data, a.size, int(bool(multistream)), C.byref(pos), C.byref(sz), C.byref(n))
+        if rc:
+            self._raise(rc)
+        try:
+            for i in range(n.value):
+                callback(int(pos[i]), int(sz[i]))
+        finally:
+            self._L.bz2b200_free(pos)
+            self._L.bz2b200_free(sz)
+
+    # -- extras used by bench.py / tests --
+    def stats(self):
+        st = _native.Stats()
+        self._L.bz2b200_last_stats(self._ctx, C.byref(st))
+        return st
+
+    def compress_device(self, d_in_ptr, n, level, d_out_ptr, out_cap):
+        olen = C.c_size_t()
+        rc = self._L.bz2b200_compress_device(self._ctx, d_in_ptr, n, level, d_out_ptr, out_cap, C.byref(olen))
+        if rc:
+            self._raise(rc)
+        return olen.value
+
+    def decompress_device(self, d_in_ptr, n, multistream, d_out_ptr, out_cap):
+        olen = C.c_size_t()
+        rc = self._L.bz2b200_decompress_device(self._ctx, d_in_ptr, n, int(bool(multistream)), d_out_ptr, out_cap, C.byref(olen))
+        if rc:
+            self._raise(rc)
+        return olen.value
+
+    def compress_bound(self, n, level=9):
+        return int(self._L.bz2b200_compress_bound(n, level))
+
+    def debug_fetch(self, what, blk, nbytes):
+        buf = np.zeros(nbytes, dtype=np.uint8)
+        got = self._L.bz2b200_debug_fetch(self._ctx, what, blk, buf.ctypes.data, nbytes)
+        if got < 0:
+            self._raise(int(got))
+        return buf[:got]
+
+    def debug_set_block_cap(self, cap):
+        """tests only: 0 restores level*100000-19"""
+        rc = self._L.bz2b200_debug_set_block_cap(self._ctx, cap)
+        if rc:
+            self._raise(rc)
+
+    def block_table(self):
+        nb = self.stats().n_blocks
+        raw = self.debug_fetch(0, 0, C.sizeof(_native.BlockRec) * nb)
+        return (_native.BlockRec * nb).from_buffer_copy(raw.tobytes()) if nb else []
+
+    def block_meta(self):
+        nb = self.stats().n_blocks
+        raw = self.debug_fetch(4, 0, C.sizeof(_native.BlockMeta) * nb)
+        return (_native.BlockMeta * nb).from_buffer_copy(raw.tobytes()) if nb else []
+
+
+class _Lazy:
+    """`Bzip2` global of the reference (BJ:2198-2255): created on first use."""
+    _eng = None
+
+    def _get(self):
+        if _Lazy._eng is None:
+            _Lazy._eng = Bzip2Engine(0)
+        return _Lazy._eng
+
+    def __getattr__(self, name):
+        return getattr(self._get(), name)
+
+
+Bzip2 = _Lazy()

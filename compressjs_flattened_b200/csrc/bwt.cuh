@@ -1,0 +1,333 @@
+// bwt.cuh -- K-S2: cyclic-rotation BWT of every block by GPU prefix doubling.
+//
+// Replaces BWT.bwtransform2 (BJ:928-971) / SA_IS (BJ:730-857).  Semantics kept:
+// rotations sorted lexicographically (unsigned bytes); equal rotations (periodic
+// block) in DESCENDING start index; U[j] = byte before
+// the j-th rotation; origPtr = rank of rotation 0.
+//
+// Algorithm (Larsson-Sadakane doubling, all blocks of the batch at once):
+//   ISA[i]  = current rank of rotation i = SA index of the first slot of its group
+//   active  = compacted list of the slots whose group still has > 1 member, in SA
+//             order: (a_idx = rotation, a_rank = its group rank, a_pos = SA index of the slot)
+//   round h : key = (a_rank << 20) | ISA[(i+h) mod n]  -> batched LSD radix sort of
+//             the 40-bit keys (5 passes of 8 bits) -> new group heads where keys
+//             change -> ISA update -> singletons leave the active list.
+//   start   : key = first 5 bytes of the rotation (same 40-bit machinery), h = 5.
+//   h >= n  : remaining ties are identical rotations: key2 = n-1-i (descending index).
+// Every block's active slots are padded to a multiple of SORT_TILE so a tile never
+// straddles two blocks; tile_blk[] maps a tile to its block.
+#pragma once
+#include "common.cuh"
+#include "rle1.cuh"
+
+#define SORT_TILE 4096
+#define SORT_THREADS 512  // x 8 keys, warp-striped
+#define SORT_E 8
+#define SEG_THREADS 256   // x 16 slots, blocked
+#define SEG_E 16
+#define KEEP_BIT 0x80000000u
+
+// ---- per-round bookkeeping: tiles of each block ------------------------------------------
+// seg_tile0[p] = first tile of block p, seg_tile0[nb] = number of tiles; totals[0] = tiles,
+// totals[1] = active slots (read back by the host each round).
+__global__ void __launch_bounds__(1024) k_tilemap(const u32 *__restrict__ seg_cnt, int nb, u32 *__restrict__ seg_tile0,
+                                                  u32 *__restrict__ tile_blk, u64 *__restrict__ totals) {
+  __shared__ u32 ws[33];
+  __shared__ u64 ws64[33];
+  u32 carry = 0;
+  u64 act = 0;
+  for (int base = 0; base < nb; base += blockDim.x) {
+    int p = base + threadIdx.x;
+    u32 c = p < nb ? seg_cnt[p] : 0;
+    u32 tiles = (c + SORT_TILE - 1) / SORT_TILE, tot;
+    u32 t0 = carry + block_excl_sum<u32>(tiles, tot, ws);
+    if (p < nb) {
+      seg_tile0[p] = t0;
+      for (u32 t = 0; t < tiles; t++) tile_blk[t0 + t] = (u32)p;
+    }
+    carry += tot;
+    act += block_sum<u64>((u64)c, ws64);
+  }
+  if (threadIdx.x == 0) { seg_tile0[nb] = carry; totals[0] = carry; totals[1] = act; }
+}
+
+__global__ void k_seg_init(const BlockRec *__restrict__ recs, int nb, u32 *__restrict__ seg_cnt) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < nb) seg_cnt[p] = recs[p].n;
+}
+
+// ---- key construction ------------------------------------------------------------------------
+// mode 0: first five bytes of each rotation; also initialises a_pos/a_rank/vals for the full block.
+__global__ void __launch_bounds__(SEG_THREADS) k_keys_init(const u8 *__restrict__ blk, i64 blk_stride, const BlockRec *__restrict__ recs,
+                                                           const u32 *__restrict__ seg_tile0, const u32 *__restrict__ tile_blk,
+                                                           u64 *__restrict__ keys, u32 *__restrict__ vals, u32 *__restrict__ a_rank,
+                                                           u32 *__restrict__ a_pos) {
+  u32 tile = blockIdx.x, p = tile_blk[tile];
+  u32 n = recs[p].n;
+  const u8 *T = blk + (i64)p * blk_stride;
+  u32 l0 = (tile - seg_tile0[p]) * SORT_TILE;
+  u64 g0 = (u64)tile * SORT_TILE;
+  for (int e = 0; e < SEG_E; e++) {
+    u32 lj = l0 + e * SEG_THREADS + threadIdx.x;
+    if (lj >= n) continue;
+    u64 key = 0;
+    u32 x = lj;
+    for (int k = 0; k < 5; k++) {
+      key = (key << 8) | T[x];
+      x = x + 1 == n ? 0 : x + 1;
+    }
+    u64 g = g0 + (lj - l0);
+    keys[g] = key;
+    vals[g] = lj;
+    a_rank[g] = 0;
+    a_pos[g] = lj;
+  }
+}
+// doubling round: key = (group rank << 20) | rank of the rotation h further on (or n-1-i once h >= n)
+__global__ void __launch_bounds__(SEG_THREADS) k_keys_round(const BlockRec *__restrict__ recs, const u32 *__restrict__ seg_cnt,
+                                                            const u32 *__restrict__ seg_tile0, const u32 *__restrict__ tile_blk,
+                                                            const u32 *__restrict__ isa, i64 isa_stride, u32 h,
+                                                            const u32 *__restrict__ a_idx, const u32 *__restrict__ a_rank,
+                                                            u64 *__restrict__ keys) {
+  u32 tile = blockIdx.x, p = tile_blk[tile];
+  u32 n = recs[p].n, cnt = seg_cnt[p];
+  const u32 *I = isa + (i64)p * isa_stride;
+  u32 l0 = (tile - seg_tile0[p]) * SORT_TILE;
+  u64 g0 = (u64)tile * SORT_TILE;
+  for (int e = 0; e < SEG_E; e++) {
+    u32 lj = l0 + e * SEG_THREADS + threadIdx.x;
+    if (lj >= cnt) continue;
+    u64 g = g0 + (lj - l0);
+    u32 i = a_idx[g], k2;
+    if (h >= n) k2 = n - 1 - i;
+    else { u32 x = i + h; if (x >= n) x -= n; k2 = I[x]; }
+    keys[g] = ((u64)a_rank[g] << 20) | k2;
+  }
+}
+
+// ---- one LSD radix pass (8-bit digit), batched over blocks ---------------------------------
+__global__ void __launch_bounds__(SORT_THREADS) k_rs_hist(const u64 *__restrict__ keys, const u32 *__restrict__ seg_cnt,
+                                                          const u32 *__restrict__ seg_tile0, const u32 *__restrict__ tile_blk, int shift,
+                                                          u32 *__restrict__ hist) {
+  __shared__ u32 h[256];
+  u32 tile = blockIdx.x, p = tile_blk[tile];
+  u32 cnt = seg_cnt[p], l0 = (tile - seg_tile0[p]) * SORT_TILE;
+  u64 g0 = (u64)tile * SORT_TILE;
+  if (threadIdx.x < 256) h[threadIdx.x] = 0;
+  __syncthreads();
+  for (int e = 0; e < SORT_E; e++) {
+    u32 o = e * SORT_THREADS + threadIdx.x;
+    if (l0 + o < cnt) atomicAdd(&h[(u32)(keys[g0 + o] >> shift) & 255u], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x < 256) hist[(u64)tile * 256 + threadIdx.x] = h[threadIdx.x];
+}
+// per block: column-wise exclusive prefix over its tiles (in place) + exclusive digit bases
+__global__ void __launch_bounds__(256) k_rs_scan(u32 *__restrict__ hist, const u32 *__restrict__ seg_tile0, u32 *__restrict__ digit_base) {
+  __shared__ u32 ws[33];
+  u32 p = blockIdx.x, d = threadIdx.x;
+  u32 t0 = seg_tile0[p], t1 = seg_tile0[p + 1];
+  u32 acc = 0;
+  u32 t = t0;
+  for (; t + 4 <= t1; t += 4) {  // 4 independent loads in flight
+    u32 a = hist[(u64)t * 256 + d], b = hist[(u64)(t + 1) * 256 + d], c = hist[(u64)(t + 2) * 256 + d], e = hist[(u64)(t + 3) * 256 + d];
+    hist[(u64)t * 256 + d] = acc; acc += a;
+    hist[(u64)(t + 1) * 256 + d] = acc; acc += b;
+    hist[(u64)(t + 2) * 256 + d] = acc; acc += c;
+    hist[(u64)(t + 3) * 256 + d] = acc; acc += e;
+  }
+  for (; t < t1; t++) { u32 a = hist[(u64)t * 256 + d]; hist[(u64)t * 256 + d] = acc; acc += a; }
+  u32 tot;
+  u32 base = block_excl_sum<u32>(acc, tot, ws);
+  digit_base[(u64)p * 256 + d] = base;
+}
+__global__ void __launch_bounds__(SORT_THREADS) k_rs_scatter(const u64 *__restrict__ keys_in, const u32 *__restrict__ vals_in,
+                                                             u64 *__restrict__ keys_out, u32 *__restrict__ vals_out,
+                                                             const u32 *__restrict__ seg_cnt, const u32 *__restrict__ seg_tile0,
+                                                             const u32 *__restrict__ tile_blk, int shift, const u32 *__restrict__ hist,
+                                                             const u32 *__restrict__ digit_base) {
+  __shared__ u32 wcnt[SORT_THREADS / 32][256];
+  __shared__ u32 base[256];
+  u32 tile = blockIdx.x, p = tile_blk[tile];
+  u32 cnt = seg_cnt[p], l0 = (tile - seg_tile0[p]) * SORT_TILE;
+  u64 g0 = (u64)tile * SORT_TILE, gp = (u64)seg_tile0[p] * SORT_TILE;
+  int lane = lane_id(), w = warp_id();
+  for (int i = threadIdx.x; i < (SORT_THREADS / 32) * 256; i += SORT_THREADS) (&wcnt[0][0])[i] = 0;
+  if (threadIdx.x < 256) base[threadIdx.x] = digit_base[(u64)p * 256 + threadIdx.x] + hist[(u64)tile * 256 + threadIdx.x];
+  __syncthreads();
+  u64 key[SORT_E];
+  u32 val[SORT_E], rk[SORT_E];
+  u32 lt = (1u << lane) - 1;
+#pragma unroll
+  for (int e = 0; e < SORT_E; e++) {
+    u32 o = (u32)w * (32 * SORT_E) + e * 32 + lane;
+    bool ok = l0 + o < cnt;
+    key[e] = ok ? keys_in[g0 + o] : 0;
+    val[e] = ok ? vals_in[g0 + o] : 0;
+    u32 d = ok ? ((u32)(key[e] >> shift) & 255u) : 256u;
+    u32 peers = __match_any_sync(FULL_MASK, d);
+    int leader = __ffs((int)peers) - 1;
+    u32 old = 0;
+    if (lane == leader && ok) { old = wcnt[w][d]; wcnt[w][d] = old + __popc(peers); }
+    old = __shfl_sync(FULL_MASK, old, leader);
+    rk[e] = old + __popc(peers & lt);
+    __syncwarp();
+  }
+  __syncthreads();
+  if (threadIdx.x < 256) {  // exclusive prefix of each digit over the warps
+    u32 acc = 0;
+    for (int ww = 0; ww < SORT_THREADS / 32; ww++) { u32 t = wcnt[ww][threadIdx.x]; wcnt[ww][threadIdx.x] = acc; acc += t; }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int e = 0; e < SORT_E; e++) {
+    u32 o = (u32)w * (32 * SORT_E) + e * 32 + lane;
+    if (l0 + o < cnt) {
+      u32 d = (u32)(key[e] >> shift) & 255u;
+      u64 dst = gp + base[d] + wcnt[w][d] + rk[e];
+      keys_out[dst] = key[e];
+      vals_out[dst] = val[e];
+    }
+  }
+}
+
+// ---- regrouping after a sort ---------------------------------------------------------------
+__device__ __forceinline__ void seg_load_flags(const u64 *__restrict__ keys, u64 g0, u32 l0, u32 cnt, u64 k[SEG_E], u32 &flags, u32 &lbase) {
+  lbase = l0 + threadIdx.x * SEG_E;
+  u64 g = g0 + (u64)threadIdx.x * SEG_E;
+  flags = 0;
+  u64 prev = (lbase > 0 && lbase < cnt) ? keys[g - 1] : 0;
+#pragma unroll
+  for (int e = 0; e < SEG_E; e++) {
+    if (lbase + e < cnt) {
+      k[e] = keys[g + e];
+      if (lbase + e == 0 || k[e] != prev) flags |= 1u << e;
+      prev = k[e];
+    }
+  }
+}
+// last sub-group head (slot index within the block) of every tile, or -1
+__global__ void __launch_bounds__(SEG_THREADS) k_sub_heads(const u64 *__restrict__ keys, const u32 *__restrict__ seg_cnt,
+                                                           const u32 *__restrict__ seg_tile0, const u32 *__restrict__ tile_blk,
+                                                           int *__restrict__ tile_last) {
+  __shared__ int ws[33];
+  u32 tile = blockIdx.x, p = tile_blk[tile];
+  u32 cnt = seg_cnt[p], l0 = (tile - seg_tile0[p]) * SORT_TILE;
+  u64 k[SEG_E];
+  u32 flags, lbase;
+  seg_load_flags(keys, (u64)tile * SORT_TILE, l0, cnt, k, flags, lbase);
+  int last = flags ? (int)(lbase + (31 - __clz((int)flags))) : -1;
+  last = block_max<int>(last, ws);
+  if (threadIdx.x == 0) tile_last[tile] = last;
+}
+// per block: exclusive max-scan (mode 0, int, identity -1) or exclusive sum-scan (mode 1, u32;
+// also writes the block's new count) of a per-tile array over the block's tiles
+__global__ void __launch_bounds__(256) k_seg_scan(const u32 *__restrict__ seg_tile0, int mode, const int *__restrict__ in, int *__restrict__ out,
+                                                  u32 *__restrict__ seg_cnt_new) {
+  __shared__ int ws[33];
+  u32 p = blockIdx.x, t0 = seg_tile0[p], t1 = seg_tile0[p + 1];
+  int carry = mode == 0 ? -1 : 0;
+  for (u32 base = t0; base < t1; base += blockDim.x) {
+    u32 t = base + threadIdx.x;
+    int tot;
+    if (mode == 0) {
+      int v = t < t1 ? in[t] : -1;
+      int e = block_excl_max<int>(v, -1, tot, ws);
+      if (t < t1) out[t] = e > carry ? e : carry;
+      if (tot > carry) carry = tot;
+    } else {
+      int v = t < t1 ? in[t] : 0;
+      int e = block_excl_sum<int>(v, tot, ws);
+      if (t < t1) out[t] = carry + e;
+      carry += tot;
+    }
+  }
+  if (mode == 1 && threadIdx.x == 0) seg_cnt_new[p] = (u32)carry;
+}
+// new rank of every active slot, ISA update, keep flag, per-tile kept count
+__global__ void __launch_bounds__(SEG_THREADS) k_rank_apply(const u64 *__restrict__ keys, const u32 *__restrict__ idx,
+                                                            const u32 *__restrict__ a_pos, const u32 *__restrict__ seg_cnt,
+                                                            const u32 *__restrict__ seg_tile0, const u32 *__restrict__ tile_blk,
+                                                            const int *__restrict__ tile_carry, u32 *__restrict__ isa, i64 isa_stride,
+                                                            u32 *__restrict__ r_new, int *__restrict__ tile_keep) {
+  __shared__ int ws[33];
+  u32 tile = blockIdx.x, p = tile_blk[tile];
+  u32 cnt = seg_cnt[p], l0 = (tile - seg_tile0[p]) * SORT_TILE;
+  u64 g0 = (u64)tile * SORT_TILE, gp = (u64)seg_tile0[p] * SORT_TILE;
+  u64 k[SEG_E];
+  u32 flags, lbase;
+  seg_load_flags(keys, g0, l0, cnt, k, flags, lbase);
+  int my_last = flags ? (int)(lbase + (31 - __clz((int)flags))) : -1, tot;
+  int hb = block_excl_max<int>(my_last, -1, tot, ws);
+  int carry = tile_carry[tile];
+  int cur = hb > carry ? hb : carry;
+  u64 g = g0 + (u64)threadIdx.x * SEG_E;
+  // is the slot after my last one a head?  (needed for the singleton test)
+  u32 nxt = lbase + SEG_E;
+  bool next_head = true;
+  if (nxt < cnt && lbase < cnt) next_head = keys[g + SEG_E] != k[SEG_E - 1];
+  int kept = 0;
+  u32 *I = isa + (i64)p * isa_stride;
+#pragma unroll
+  for (int e = 0; e < SEG_E; e++) {
+    u32 lj = lbase + e;
+    if (lj < cnt) {
+      bool head = (flags >> e) & 1u;
+      if (head) cur = (int)lj;
+      bool nh = e + 1 < SEG_E ? (lj + 1 >= cnt || ((flags >> (e + 1)) & 1u)) : (lj + 1 >= cnt || next_head);
+      u32 rank = a_pos[gp + (u32)cur];
+      bool single = head && nh;
+      I[idx[g + e]] = rank;
+      r_new[g + e] = rank | (single ? 0u : KEEP_BIT);
+      kept += single ? 0 : 1;
+    }
+  }
+  kept = block_sum<int>(kept, ws);
+  if (threadIdx.x == 0) tile_keep[tile] = kept;
+}
+// move the surviving slots to the next round's (re-padded) layout
+__global__ void __launch_bounds__(SEG_THREADS) k_compact(const u32 *__restrict__ idx, const u32 *__restrict__ a_pos, const u32 *__restrict__ r_new,
+                                                         const u32 *__restrict__ seg_cnt, const u32 *__restrict__ seg_tile0,
+                                                         const u32 *__restrict__ tile_blk, const int *__restrict__ keep_prefix,
+                                                         const u32 *__restrict__ seg_tile0_new, u32 *__restrict__ idx_out,
+                                                         u32 *__restrict__ rank_out, u32 *__restrict__ pos_out) {
+  __shared__ int ws[33];
+  u32 tile = blockIdx.x, p = tile_blk[tile];
+  u32 cnt = seg_cnt[p], l0 = (tile - seg_tile0[p]) * SORT_TILE;
+  u64 g = (u64)tile * SORT_TILE + (u64)threadIdx.x * SEG_E;
+  u32 lbase = l0 + threadIdx.x * SEG_E;
+  u32 r[SEG_E];
+  int mine = 0;
+#pragma unroll
+  for (int e = 0; e < SEG_E; e++) {
+    r[e] = lbase + e < cnt ? r_new[g + e] : 0;
+    mine += (r[e] & KEEP_BIT) ? 1 : 0;
+  }
+  int tot;
+  int pre = block_excl_sum<int>(mine, tot, ws);
+  u64 dst = (u64)seg_tile0_new[p] * SORT_TILE + (u32)keep_prefix[tile] + (u32)pre;
+#pragma unroll
+  for (int e = 0; e < SEG_E; e++) {
+    if (r[e] & KEEP_BIT) {
+      idx_out[dst] = idx[g + e];
+      rank_out[dst] = r[e] & ~KEEP_BIT;
+      pos_out[dst] = a_pos[g + e];
+      dst++;
+    }
+  }
+}
+
+// ---- final: L column and origPtr from the inverse suffix array -----------------------------
+__global__ void __launch_bounds__(256) k_bwt_gather(const u8 *__restrict__ blk, i64 blk_stride, BlockRec *__restrict__ recs,
+                                                    const u32 *__restrict__ isa, i64 isa_stride, u8 *__restrict__ L, i64 l_stride) {
+  u32 p = blockIdx.y;
+  u32 n = recs[p].n;
+  const u8 *T = blk + (i64)p * blk_stride;
+  const u32 *I = isa + (i64)p * isa_stride;
+  u8 *out = L + (i64)p * l_stride;
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    u32 r = I[i];
+    out[r] = T[i == 0 ? n - 1 : i - 1];
+    if (i == 0) recs[p].orig_ptr = r;
+  }
+}

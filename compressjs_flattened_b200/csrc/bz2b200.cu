@@ -1,0 +1,416 @@
+// bz2b200.cu -- host orchestration and the C ABI (include/bz2b200.h).
+//
+// Product build: nvcc -gencode arch=compute_100a,code=sm_100a -> libbz2b200.so (CUDA only; every
+// entry point fails with BZ2B200_E_CUDA when no device is present -- there is no CPU path).
+// Test build:    g++ -DBZ_SIM (cusim.h) -> tests/sim/libbz2b200_sim.so, kernel-logic tests only.
+#include "../../include/bz2b200.h"
+#include "common.cuh"
+#include "rle1.cuh"
+#include "bwt.cuh"
+#include "mtf.cuh"
+#include "huff.cuh"
+#include "decode.cuh"
+
+#include <string>
+#include <vector>
+
+namespace {
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+};
+
+struct Ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  bz2b200_stats st{};
+  std::vector<DevBuf *> pool;
+  // compress-side buffers
+  DevBuf in, tile_last, tile_first, head_carry, tile_emit, g_tile, recs, nblk, blk, crcpart, pow256;
+  DevBuf isa, keysA, keysB, valsA, valsB, rankA, rankB, posA, posB, rnew, hist, digit_base;
+  DevBuf seg_cnt, seg_cnt2, seg_tile0, seg_tile0b, tile_blk, tile_blkb, tile_i0, tile_i1, tile_i2, tile_i3, totals;
+  DevBuf Lcol, ranks, lastocc, A, freq, meta, W, bit_off, scrc, out, out_len;
+  // decode-side buffers
+  DevBuf d_in, cand, ncand, dmeta, dsyms, dL, dtt, dwalk, dblk, dout, dmisc;
+  // host staging (pinned)
+  void *h_pin = nullptr;
+  size_t h_pin_cap = 0;
+  // last compress, for debug_fetch
+  u32 cap_override = 0;  // tests only
+  int last_nb = 0;
+  i64 last_bs = 0, last_as = 0;
+  cudaEvent_t ev[10]{};
+  bool ev_ok = false;
+  Ctx() {
+    DevBuf *all[] = {&in, &tile_last, &tile_first, &head_carry, &tile_emit, &g_tile, &recs, &nblk, &blk, &crcpart, &pow256,
+                     &isa, &keysA, &keysB, &valsA, &valsB, &rankA, &rankB, &posA, &posB, &rnew, &hist, &digit_base,
+                     &seg_cnt, &seg_cnt2, &seg_tile0, &seg_tile0b, &tile_blk, &tile_blkb, &tile_i0, &tile_i1, &tile_i2, &tile_i3, &totals,
+                     &Lcol, &ranks, &lastocc, &A, &freq, &meta, &W, &bit_off, &scrc, &out, &out_len,
+                     &d_in, &cand, &ncand, &dmeta, &dsyms, &dL, &dtt, &dwalk, &dblk, &dout, &dmisc};
+    for (DevBuf *b : all) pool.push_back(b);
+  }
+};
+
+#define CK(call)                                                                         \
+  do {                                                                                   \
+    cudaError_t _e = (call);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      c->err = std::string(#call) + ": " + cudaGetErrorString(_e);                       \
+      return BZ2B200_E_CUDA;                                                             \
+    }                                                                                    \
+  } while (0)
+
+int ensure(Ctx *c, DevBuf &b, size_t bytes) {
+  if (bytes <= b.cap) return 0;
+  if (b.p) CK(cudaFree(b.p));
+  b.p = nullptr;
+  b.cap = 0;
+  size_t want = bytes + bytes / 8 + 4096;
+  CK(cudaMalloc(&b.p, want));
+  b.cap = want;
+  return 0;
+}
+int ensure_pinned(Ctx *c, size_t bytes) {
+  if (bytes <= c->h_pin_cap) return 0;
+  if (c->h_pin) CK(cudaFreeHost(c->h_pin));
+  c->h_pin = nullptr;
+  c->h_pin_cap = 0;
+  CK(cudaMallocHost(&c->h_pin, bytes + 4096));
+  c->h_pin_cap = bytes + 4096;
+  return 0;
+}
+#define ENS(buf, bytes)                         \
+  do {                                          \
+    int _r = ensure(c, (buf), (size_t)(bytes)); \
+    if (_r) return _r;                          \
+  } while (0)
+template <typename T> T *P(DevBuf &b) { return reinterpret_cast<T *>(b.p); }
+
+#define LAUNCH(kern, grid, block, smem, ...)                        \
+  do {                                                              \
+    KLAUNCH(kern, grid, block, smem, c->stream, __VA_ARGS__);       \
+    c->st.kernel_launches++;                                        \
+  } while (0)
+
+inline i64 round_up(i64 v, i64 a) { return (v + a - 1) / a * a; }
+
+int mark(Ctx *c, int i) {
+  if (c->ev_ok) CK(cudaEventRecord(c->ev[i], c->stream));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------ compress
+int compress_device(Ctx *c, const u8 *d_in, size_t n_, int level, u32 *d_out, size_t out_cap, size_t *out_len, bool own_out) {
+  if (level < 1 || level > 9) return BZ2B200_E_LEVEL;
+  c->st = bz2b200_stats{};
+  c->st.in_bytes = n_;
+  const i64 N = (i64)n_;
+  const u32 B = c->cap_override ? c->cap_override : (u32)level * 100000u - 19u;  // BJ:2212-2220
+  const i64 T = (N + RLE_TILE - 1) / RLE_TILE;
+  const int max_blocks = (int)(N / ((i64)B * 4 / 5) + 2);
+  int rc;
+  if ((rc = mark(c, 0))) return rc;
+  ENS(c->recs, sizeof(BlockRec) * (size_t)max_blocks);
+  ENS(c->nblk, 64);
+  int nb = 0;
+  std::vector<BlockRec> hrecs;
+  if (N > 0) {
+    ENS(c->tile_last, 8 * T); ENS(c->tile_first, 8 * T); ENS(c->head_carry, 8 * T);
+    ENS(c->tile_emit, 4 * T); ENS(c->g_tile, 8 * (T + 1));
+    LAUNCH(k_rle_heads, (unsigned)T, RLE_THREADS, 0, d_in, N, P<i64>(c->tile_last), P<i64>(c->tile_first));
+    LAUNCH(k_scan_excl_max_i64, 1, 1024, 0, P<i64>(c->tile_last), P<i64>(c->head_carry), T);
+    LAUNCH(k_rle_count, (unsigned)T, RLE_THREADS, 0, d_in, N, P<i64>(c->head_carry), P<u32>(c->tile_emit));
+    LAUNCH(k_scan_excl_sum_u32_u64, 1, 1024, 0, P<u32>(c->tile_emit), P<u64>(c->g_tile), T);
+    LAUNCH(k_rle_cut, 1, RLE_THREADS, 0, d_in, N, B, P<i64>(c->head_carry), P<i64>(c->tile_first), P<u64>(c->g_tile), T,
+           P<BlockRec>(c->recs), max_blocks, P<int>(c->nblk));
+    CK(cudaMemcpyAsync(&nb, c->nblk.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (nb < 0) { c->err = "internal: block table overflow"; return BZ2B200_E_CUDA; }
+    hrecs.resize((size_t)nb);
+    if (nb) CK(cudaMemcpy(hrecs.data(), c->recs.p, sizeof(BlockRec) * (size_t)nb, cudaMemcpyDeviceToHost));
+  }
+  c->st.n_blocks = (u32)nb;
+  const i64 BS = round_up((i64)B + 1, 256);  // per-block stride of byte arrays (block, L, ranks)
+  const i64 AS = round_up((i64)B + 2, 128);  // per-block stride of the u16 symbol array
+  c->last_nb = nb; c->last_bs = BS; c->last_as = AS;
+  ENS(c->meta, sizeof(BlockMeta) * (size_t)(nb + 1));
+  ENS(c->bit_off, 8 * (size_t)(nb + 2));
+  ENS(c->scrc, 64);
+  ENS(c->out_len, 64);
+  i64 WS = 0;
+  if (nb) {
+    // ---- S1 emit + CRC ----
+    ENS(c->blk, (size_t)nb * BS);
+    LAUNCH(k_rle_emit, (unsigned)T, RLE_THREADS, 0, d_in, N, B, P<i64>(c->head_carry), P<u64>(c->g_tile), P<BlockRec>(c->recs), nb,
+           P<u8>(c->blk), BS);
+    i64 max_len = 0;
+    for (auto &r : hrecs) { if (r.p - r.s > max_len) max_len = r.p - r.s; c->st.rle1_bytes += r.n; }
+    int max_chunks = (int)((max_len + CRC_CHUNK - 1) / CRC_CHUNK);
+    ENS(c->crcpart, 4 * (size_t)nb * max_chunks);
+    if (!c->pow256.p) {
+      ENS(c->pow256, 1024);
+      u32 h[256];
+      for (int j = 0; j < 256; j++) h[j] = crc_xpow(8ull * 256 * (u64)j);
+      CK(cudaMemcpy(c->pow256.p, h, sizeof h, cudaMemcpyHostToDevice));
+    }
+    LAUNCH(k_crc_chunks, dim3((unsigned)max_chunks, (unsigned)nb), 256, 0, d_in, P<BlockRec>(c->recs), P<u32>(c->pow256), P<u32>(c->crcpart),
+           max_chunks);
+    LAUNCH(k_crc_fold, (unsigned)((nb + 127) / 128), 128, 0, P<BlockRec>(c->recs), nb, P<u32>(c->crcpart), max_chunks,
+           crc_xpow(8ull * CRC_CHUNK));
+    if ((rc = mark(c, 1))) return rc;
+
+    // ---- S2 BWT ----
+    size_t slots = 0;
+    for (auto &r : hrecs) slots += (size_t)round_up(r.n, SORT_TILE);
+    size_t tiles0 = slots / SORT_TILE;
+    ENS(c->isa, 4 * (size_t)nb * BS);
+    ENS(c->keysA, 8 * slots); ENS(c->keysB, 8 * slots);
+    ENS(c->valsA, 4 * slots); ENS(c->valsB, 4 * slots);
+    ENS(c->rankA, 4 * slots); ENS(c->rankB, 4 * slots);
+    ENS(c->posA, 4 * slots); ENS(c->posB, 4 * slots);
+    ENS(c->rnew, 4 * slots);
+    ENS(c->hist, 4 * 256 * tiles0); ENS(c->digit_base, 4 * 256 * (size_t)nb);
+    ENS(c->seg_cnt, 4 * (size_t)nb); ENS(c->seg_cnt2, 4 * (size_t)nb);
+    ENS(c->seg_tile0, 4 * (size_t)(nb + 1)); ENS(c->seg_tile0b, 4 * (size_t)(nb + 1));
+    ENS(c->tile_blk, 4 * tiles0); ENS(c->tile_blkb, 4 * tiles0);
+    ENS(c->tile_i0, 4 * tiles0); ENS(c->tile_i1, 4 * tiles0); ENS(c->tile_i2, 4 * tiles0); ENS(c->tile_i3, 4 * tiles0);
+    ENS(c->totals, 64);
+    u32 *seg_cnt = P<u32>(c->seg_cnt), *seg_cnt_n = P<u32>(c->seg_cnt2);
+    u32 *tile0 = P<u32>(c->seg_tile0), *tile0_n = P<u32>(c->seg_tile0b);
+    u32 *tblk = P<u32>(c->tile_blk), *tblk_n = P<u32>(c->tile_blkb);
+    u32 *rank = P<u32>(c->rankA), *rank_n = P<u32>(c->rankB), *pos = P<u32>(c->posA), *pos_n = P<u32>(c->posB);
+    u64 *kA = P<u64>(c->keysA), *kB = P<u64>(c->keysB);
+    u32 *vA = P<u32>(c->valsA), *vB = P<u32>(c->valsB);
+    u64 totals[2] = {0, 0};
+    LAUNCH(k_seg_init, (unsigned)((nb + 255) / 256), 256, 0, P<BlockRec>(c->recs), nb, seg_cnt);
+    LAUNCH(k_tilemap, 1, 1024, 0, seg_cnt, nb, tile0, tblk, P<u64>(c->totals));
+    unsigned Ta = (unsigned)tiles0;
+    LAUNCH(k_keys_init, Ta, SEG_THREADS, 0, P<u8>(c->blk), BS, P<BlockRec>(c->recs), tile0, tblk, kA, vA, rank, pos);
+    u32 h = 5;
+    for (int round = 0;; round++) {
+      c->st.sort_rounds++;
+      c->st.sort_slots += (u64)Ta * SORT_TILE;
+      u64 *ki = kA, *ko = kB;
+      u32 *vi = vA, *vo = vB;
+      for (int pass = 0; pass < 5; pass++) {
+        LAUNCH(k_rs_hist, Ta, SORT_THREADS, 0, ki, seg_cnt, tile0, tblk, pass * 8, P<u32>(c->hist));
+        LAUNCH(k_rs_scan, (unsigned)nb, 256, 0, P<u32>(c->hist), tile0, P<u32>(c->digit_base));
+        LAUNCH(k_rs_scatter, Ta, SORT_THREADS, 0, ki, vi, ko, vo, seg_cnt, tile0, tblk, pass * 8, P<u32>(c->hist), P<u32>(c->digit_base));
+        u64 *tk = ki; ki = ko; ko = tk;
+        u32 *tv = vi; vi = vo; vo = tv;
+      }
+      // sorted data is now in (ki, vi) == (kB, vB)
+      LAUNCH(k_sub_heads, Ta, SEG_THREADS, 0, ki, seg_cnt, tile0, tblk, P<int>(c->tile_i0));
+      LAUNCH(k_seg_scan, (unsigned)nb, 256, 0, tile0, 0, P<int>(c->tile_i0), P<int>(c->tile_i1), (u32 *)nullptr);
+      LAUNCH(k_rank_apply, Ta, SEG_THREADS, 0, ki, vi, pos, seg_cnt, tile0, tblk, P<int>(c->tile_i1), P<u32>(c->isa), BS, P<u32>(c->rnew),
+             P<int>(c->tile_i2));
+      LAUNCH(k_seg_scan, (unsigned)nb, 256, 0, tile0, 1, P<int>(c->tile_i2), P<int>(c->tile_i3), seg_cnt_n);
+      LAUNCH(k_tilemap, 1, 1024, 0, seg_cnt_n, nb, tile0_n, tblk_n, P<u64>(c->totals));
+      LAUNCH(k_compact, Ta, SEG_THREADS, 0, vi, pos, P<u32>(c->rnew), seg_cnt, tile0, tblk, P<int>(c->tile_i3), tile0_n, vA, rank_n, pos_n);
+      CK(cudaMemcpyAsync(totals, c->totals.p, sizeof totals, cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      { u32 *t; t = seg_cnt; seg_cnt = seg_cnt_n; seg_cnt_n = t; t = tile0; tile0 = tile0_n; tile0_n = t;
+        t = tblk; tblk = tblk_n; tblk_n = t; t = rank; rank = rank_n; rank_n = t; t = pos; pos = pos_n; pos_n = t; }
+      Ta = (unsigned)totals[0];
+      if (totals[1] == 0) break;
+      LAUNCH(k_keys_round, Ta, SEG_THREADS, 0, P<BlockRec>(c->recs), seg_cnt, tile0, tblk, P<u32>(c->isa), BS, h, vA, rank, kA);
+      h = h >= (1u << 24) ? h : h * 2;
+    }
+    ENS(c->Lcol, (size_t)nb * BS);
+    LAUNCH(k_bwt_gather, dim3(64, (unsigned)nb), 256, 0, P<u8>(c->blk), BS, P<BlockRec>(c->recs), P<u32>(c->isa), BS, P<u8>(c->Lcol), BS);
+    if ((rc = mark(c, 2))) return rc;
+
+    // ---- S3 MTF + RLE2 ----
+    const i64 nseg_max = (BS + MTF_SEG - 1) / MTF_SEG;
+    ENS(c->ranks, (size_t)nb * BS);
+    ENS(c->lastocc, 4 * 256 * (size_t)nseg_max * nb);
+    ENS(c->A, 2 * (size_t)nb * AS);
+    ENS(c->freq, 4 * BZ_MAX_SYMS * (size_t)nb);
+    LAUNCH(k_mtf_rle2, (unsigned)nb, MTF_THREADS, 0, P<u8>(c->Lcol), BS, P<BlockRec>(c->recs), P<int>(c->lastocc), nseg_max * 256,
+           P<u8>(c->ranks), P<u16>(c->A), AS, P<u32>(c->freq), P<BlockMeta>(c->meta));
+    if ((rc = mark(c, 3))) return rc;
+
+    // ---- S4/S5 Huffman + emission ----
+    u64 maxbits = 80 + 25 + 16 + 256 + 18 + 7ull * ((B + 1 + 49) / 50) + 6ull * (5 + 258 * 39) + 20ull * (B + 1);
+    WS = round_up((i64)((maxbits + 31) / 32) + 2, 64);
+    ENS(c->W, 4 * (size_t)nb * WS);
+    CK(cudaMemsetAsync(c->W.p, 0, 4 * (size_t)nb * WS, c->stream));
+#ifndef BZ_SIM
+    static bool attr_set = false;
+    if (!attr_set) {
+      CK(cudaFuncSetAttribute(k_huff_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HufSmem)));
+      attr_set = true;
+    }
+#endif
+    LAUNCH(k_huff_encode, (unsigned)nb, HUF_THREADS, sizeof(HufSmem), P<u16>(c->A), AS, P<u32>(c->freq), P<BlockRec>(c->recs),
+           P<BlockMeta>(c->meta), P<u32>(c->W), WS);
+  } else {
+    for (int i = 1; i <= 3; i++) if ((rc = mark(c, i))) return rc;
+  }
+  if ((rc = mark(c, 4))) return rc;
+
+  // ---- S6 stitch ----
+  LAUNCH(k_stitch_offsets, 1, 1024, 0, P<BlockMeta>(c->meta), P<BlockRec>(c->recs), nb, P<u64>(c->bit_off), P<u32>(c->scrc));
+  u64 total_bits = 0;
+  CK(cudaMemcpyAsync(&total_bits, P<u64>(c->bit_off) + nb, 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  size_t need = (size_t)((total_bits + 80 + 7) / 8);
+  size_t need_w = round_up((i64)need, 4) + 8;
+  if (own_out) {
+    ENS(c->out, need_w);
+    d_out = P<u32>(c->out);
+  } else if (out_cap < need_w) {
+    c->err = "output buffer too small";
+    return BZ2B200_E_UNEXPECTED_OUTPUT_EOF;
+  }
+  CK(cudaMemsetAsync(d_out, 0, need_w, c->stream));
+  if (nb) LAUNCH(k_stitch, dim3(32, (unsigned)nb), 256, 0, P<u32>(c->W), WS, P<u64>(c->bit_off), d_out);
+  LAUNCH(k_stream_ends, 1, 32, 0, d_out, P<u64>(c->bit_off), nb, P<u32>(c->scrc), level, P<u64>(c->out_len));
+  u64 olen = 0;
+  CK(cudaMemcpyAsync(&olen, c->out_len.p, 8, cudaMemcpyDeviceToHost, c->stream));
+  if ((rc = mark(c, 5))) return rc;
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaGetLastError());
+  *out_len = (size_t)olen;
+  c->st.out_bytes = olen;
+  if (nb) {
+    std::vector<BlockMeta> hm((size_t)nb);
+    CK(cudaMemcpy(hm.data(), c->meta.p, sizeof(BlockMeta) * (size_t)nb, cudaMemcpyDeviceToHost));
+    for (auto &m : hm) { c->st.mtf_syms += m.m; c->st.d1_triggered |= m.d1; }
+  }
+  if (c->ev_ok) {
+    for (int i = 0; i < 5; i++) CK(cudaEventElapsedTime(&c->st.ms_stage[i], c->ev[i], c->ev[i + 1]));
+    CK(cudaEventElapsedTime(&c->st.ms_total, c->ev[0], c->ev[5]));
+  }
+  return BZ2B200_OK;
+}
+
+#include "decode_host.inl"
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------ C ABI
+extern "C" {
+
+int bz2b200_create(int device, bz2b200_ctx **ctx) {
+  if (!ctx) return BZ2B200_E_ARG;
+  *ctx = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return BZ2B200_E_CUDA;
+  if (cudaSetDevice(device) != cudaSuccess) return BZ2B200_E_CUDA;
+  Ctx *c = new Ctx();
+  c->device = device;
+  if (cudaStreamCreate(&c->stream) != cudaSuccess) { delete c; return BZ2B200_E_CUDA; }
+  c->ev_ok = true;
+  for (auto &e : c->ev) if (cudaEventCreate(&e) != cudaSuccess) c->ev_ok = false;
+  *ctx = reinterpret_cast<bz2b200_ctx *>(c);
+  return BZ2B200_OK;
+}
+
+void bz2b200_destroy(bz2b200_ctx *ctx) {
+  Ctx *c = reinterpret_cast<Ctx *>(ctx);
+  if (!c) return;
+  cudaSetDevice(c->device);
+  for (DevBuf *b : c->pool) if (b->p) cudaFree(b->p);
+  if (c->h_pin) cudaFreeHost(c->h_pin);
+  if (c->ev_ok) for (auto &e : c->ev) cudaEventDestroy(e);
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int bz2b200_compress_device(bz2b200_ctx *ctx, const void *d_in, size_t n, int level, void *d_out, size_t out_cap, size_t *out_len) {
+  Ctx *c = reinterpret_cast<Ctx *>(ctx);
+  if (!c || !out_len || (n && !d_in) || !d_out || ((uintptr_t)d_in & 15) || ((uintptr_t)d_out & 3)) return BZ2B200_E_ARG;
+  CK(cudaSetDevice(c->device));
+  return compress_device(c, (const u8 *)d_in, n, level, (u32 *)d_out, out_cap, out_len, false);
+}
+
+int bz2b200_compress(bz2b200_ctx *ctx, const uint8_t *in, size_t n, int level, uint8_t **out, size_t *out_len) {
+  Ctx *c = reinterpret_cast<Ctx *>(ctx);
+  if (!c || !out || !out_len || (n && !in)) return BZ2B200_E_ARG;
+  if (level < 1 || level > 9) return BZ2B200_E_LEVEL;
+  CK(cudaSetDevice(c->device));
+  ENS(c->in, n + 64);
+  if (n) CK(cudaMemcpyAsync(c->in.p, in, n, cudaMemcpyHostToDevice, c->stream));
+  size_t olen = 0;
+  int rc = compress_device(c, P<u8>(c->in), n, level, nullptr, 0, &olen, true);
+  if (rc) return rc;
+  uint8_t *res = (uint8_t *)malloc(olen ? olen : 1);
+  if (!res) return BZ2B200_E_OUT_OF_MEMORY;
+  CK(cudaMemcpy(res, c->out.p, olen, cudaMemcpyDeviceToHost));
+  *out = res;
+  *out_len = olen;
+  return BZ2B200_OK;
+}
+
+size_t bz2b200_compress_bound(size_t n, int level) {
+  if (level < 1 || level > 9) level = 9;
+  size_t B = (size_t)level * 100000 - 19;
+  size_t nblocks = n / (B * 4 / 5) + 2;
+  // RLE1 expands by at most 5/4, Huffman codes are at most 20 bits per symbol
+  return (n + n / 4 + nblocks) * 20 / 8 + nblocks * (10 + 4 + 32 + 3 + 18001 + 6 * 1300) + 64;
+}
+
+void bz2b200_free(void *p) { free(p); }
+
+const char *bz2b200_strerror(int rc) {
+  switch (rc) {  // messages of BJ:1376-1383
+    case BZ2B200_OK: return "OK";
+    case BZ2B200_E_LAST_BLOCK: return "Bad file checksum";
+    case BZ2B200_E_NOT_BZIP_DATA: return "Not bzip data";
+    case BZ2B200_E_UNEXPECTED_INPUT_EOF: return "Unexpected input EOF";
+    case BZ2B200_E_UNEXPECTED_OUTPUT_EOF: return "Unexpected output EOF";
+    case BZ2B200_E_DATA_ERROR: return "Data error";
+    case BZ2B200_E_OUT_OF_MEMORY: return "Out of memory";
+    case BZ2B200_E_OBSOLETE_INPUT: return "Obsolete (pre 0.9.5) bzip format not supported.";
+    case BZ2B200_E_LEVEL: return "Invalid block size multiplier";
+    case BZ2B200_E_CUDA: return "CUDA failure";
+    case BZ2B200_E_ARG: return "bad argument";
+    default: return "unknown error";
+  }
+}
+
+const char *bz2b200_last_error(bz2b200_ctx *ctx) {
+  Ctx *c = reinterpret_cast<Ctx *>(ctx);
+  return c ? c->err.c_str() : "no context";
+}
+
+int bz2b200_last_stats(bz2b200_ctx *ctx, bz2b200_stats *st) {
+  Ctx *c = reinterpret_cast<Ctx *>(ctx);
+  if (!c || !st) return BZ2B200_E_ARG;
+  *st = c->st;
+  return BZ2B200_OK;
+}
+
+long long bz2b200_debug_fetch(bz2b200_ctx *ctx, int what, int blk, void *dst, size_t cap) {
+  Ctx *c = reinterpret_cast<Ctx *>(ctx);
+  if (!c || !dst) return BZ2B200_E_ARG;
+  const void *src = nullptr;
+  size_t bytes = 0;
+  int nb = c->last_nb;
+  if (what != 0 && what != 4 && (blk < 0 || blk >= nb)) return BZ2B200_E_ARG;
+  switch (what) {
+    case 0: src = c->recs.p; bytes = sizeof(BlockRec) * (size_t)nb; break;
+    case 1: src = P<u8>(c->blk) + (i64)blk * c->last_bs; bytes = (size_t)c->last_bs; break;
+    case 2: src = P<u8>(c->Lcol) + (i64)blk * c->last_bs; bytes = (size_t)c->last_bs; break;
+    case 3: src = P<u16>(c->A) + (i64)blk * c->last_as; bytes = 2 * (size_t)c->last_as; break;
+    case 4: src = c->meta.p; bytes = sizeof(BlockMeta) * (size_t)nb; break;
+    default: return BZ2B200_E_ARG;
+  }
+  if (bytes > cap) bytes = cap;
+  if (bytes && cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) return BZ2B200_E_CUDA;
+  return (long long)bytes;
+}
+
+int bz2b200_debug_set_block_cap(bz2b200_ctx *ctx, uint32_t cap) {
+  Ctx *c = reinterpret_cast<Ctx *>(ctx);
+  if (!c || (cap && cap < 8) || cap > 899981) return BZ2B200_E_ARG;
+  c->cap_override = cap;
+  return BZ2B200_OK;
+}
+
+#include "decode_abi.inl"
+
+}  // extern "C"

@@ -1,0 +1,357 @@
+// rle1.cuh -- K-S1: RLE1 + block cut points + block CRC.
+//
+// Replaces readBlock (BJ:1954-1985), the do/while block loop of compressFile
+// (BJ:2233-2242) and CRC32.updateCRC (BJ:1065-1067).
+//
+// The reference's RLE1 automaton restarts at every block, and a block ends when
+// `pos` reaches B = level*100000-19 OUTPUT bytes, so block k+1's input offset
+// depends on block k.  We make that parallel as follows.  Away from a block
+// start the automaton's state at input position i depends only on the offset d
+// of i inside its maximal run of equal bytes: with q = d % 255, byte i emits a
+// literal iff q < 4 and additionally the (eager) count byte iff q == 3.  So
+//   G(i) = number of bytes emitted before input position i ("global-fresh" coordinates)
+// is a prefix sum.  Only the first run of a block differs: when the previous
+// block was cut inside a run, the remainder of that run is encoded from a fresh
+// state; its encoding has a closed form.
+//   k_rle_heads  : per 4 KiB tile, first/last run head
+//   k_scan_*     : exclusive scans over the tile summaries (one CTA)
+//   k_rle_count  : per tile, number of emitted bytes -> G at tile granularity
+//   k_rle_cut    : one CTA walks the blocks: closed form for the first run, then
+//                  a binary search on G for the cut; O(log tiles) per block
+//   k_rle_emit   : every input position writes its 0-2 output bytes
+//   k_crc_*      : chunked CRC with x^n mod P recombination
+#pragma once
+#include "common.cuh"
+
+#define RLE_TILE 4096
+#define RLE_THREADS 256
+#define CRC_CHUNK 65536
+
+struct BlockRec {
+  i64 s;        // first input byte of the block
+  i64 p;        // one past the last input byte consumed (= next block's s)
+  i64 e_true;   // end of the maximal run that contains s (first run head > s, or N)
+  u64 Ge;       // G(e_true); meaningful when e_true < p
+  u32 outR;     // output bytes produced by input [s, min(e_true, p))
+  u32 n;        // block length after RLE1
+  u32 crc;      // block CRC (BJ:2237-2239)
+  u32 orig_ptr; // filled by the BWT stage
+};
+
+struct RleView {
+  u8 b[16];
+  u32 flags;      // bit j: position p0+j starts a run
+  u32 em;         // 2 bits per position: bytes emitted in global-fresh coordinates
+  int nvalid;
+  i64 p0;
+  i64 head_before;  // last run head <= p0-1 (or -1)
+  u32 gpre;         // emitted bytes in this tile before p0
+};
+
+__device__ __forceinline__ void rle_load(const u8 *__restrict__ in, i64 N, i64 tile, RleView &v) {
+  v.p0 = tile * RLE_TILE + (i64)threadIdx.x * 16;
+  i64 left = N - v.p0;
+  v.nvalid = left >= 16 ? 16 : (left > 0 ? (int)left : 0);
+  if (v.nvalid == 16) {
+    uint4 w = *reinterpret_cast<const uint4 *>(in + v.p0);
+    u32 ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int j = 0; j < 16; j++) v.b[j] = (u8)(ww[j >> 2] >> (8 * (j & 3)));
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; j++) v.b[j] = j < v.nvalid ? in[v.p0 + j] : 0;
+  }
+  u32 f = 0;
+  if (v.nvalid > 0) {
+    u8 prev = v.p0 > 0 ? in[v.p0 - 1] : 0;
+    if (v.p0 == 0 || v.b[0] != prev) f |= 1u;
+#pragma unroll
+    for (int j = 1; j < 16; j++)
+      if (j < v.nvalid && v.b[j] != v.b[j - 1]) f |= 1u << j;
+  }
+  v.flags = f;
+}
+
+// Full per-thread view of a tile: run heads, emitted-byte counts and their prefix.
+// ws64/ws32: >= 33 entries of shared memory each.  All RLE_THREADS threads call it.
+__device__ __forceinline__ void rle_view(const u8 *__restrict__ in, i64 N, i64 tile, const i64 *__restrict__ head_carry,
+                                         RleView &v, u32 &tile_total, i64 *ws64, u32 *ws32) {
+  rle_load(in, N, tile, v);
+  i64 my_last = v.flags ? v.p0 + (31 - __clz((int)v.flags)) : (i64)-1;
+  i64 tot;
+  i64 hb = block_excl_max<i64>(my_last, (i64)-1, tot, ws64);
+  i64 carry = head_carry[tile];
+  v.head_before = hb > carry ? hb : carry;
+  i64 cur = v.head_before;
+  u32 em = 0, cnt = 0;
+#pragma unroll
+  for (int j = 0; j < 16; j++) {
+    if (j < v.nvalid) {
+      if (v.flags & (1u << j)) cur = v.p0 + j;
+      u32 q = (u32)((u64)(v.p0 + j - cur) % 255u);
+      u32 e = (q < 4 ? 1u : 0u) + (q == 3 ? 1u : 0u);
+      em |= e << (2 * j);
+      cnt += e;
+    }
+  }
+  v.em = em;
+  v.gpre = block_excl_sum<u32>(cnt, tile_total, ws32);
+}
+
+__global__ void __launch_bounds__(RLE_THREADS) k_rle_heads(const u8 *__restrict__ in, i64 N, i64 *__restrict__ tile_last,
+                                                           i64 *__restrict__ tile_first) {
+  __shared__ i64 ws[33];
+  RleView v;
+  i64 tile = blockIdx.x;
+  rle_load(in, N, tile, v);
+  i64 last = v.flags ? v.p0 + (31 - __clz((int)v.flags)) : (i64)-1;
+  i64 first = v.flags ? v.p0 + (__ffs((int)v.flags) - 1) : (i64)0x7fffffffffffffffLL;
+  last = block_max<i64>(last, ws);
+  first = block_min<i64>(first, ws);
+  if (threadIdx.x == 0) {
+    tile_last[tile] = last;
+    tile_first[tile] = first == (i64)0x7fffffffffffffffLL ? (i64)-1 : first;
+  }
+}
+
+__global__ void __launch_bounds__(RLE_THREADS) k_rle_count(const u8 *__restrict__ in, i64 N, const i64 *__restrict__ head_carry,
+                                                           u32 *__restrict__ tile_emit) {
+  __shared__ i64 ws64[33];
+  __shared__ u32 ws32[33];
+  RleView v;
+  u32 total;
+  rle_view(in, N, blockIdx.x, head_carry, v, total, ws64, ws32);
+  if (threadIdx.x == 0) tile_emit[blockIdx.x] = total;
+}
+
+// out[i] = max(in[0..i)) (identity -1); single CTA of 1024 threads
+__global__ void __launch_bounds__(1024) k_scan_excl_max_i64(const i64 *__restrict__ in, i64 *__restrict__ out, i64 n) {
+  __shared__ i64 ws[33];
+  i64 carry = -1;
+  for (i64 base = 0; base < n; base += blockDim.x) {
+    i64 i = base + threadIdx.x;
+    i64 v = i < n ? in[i] : (i64)-1, tot;
+    i64 e = block_excl_max<i64>(v, (i64)-1, tot, ws);
+    if (i < n) out[i] = e > carry ? e : carry;
+    if (tot > carry) carry = tot;
+  }
+}
+// out[i] = sum(in[0..i)), out[n] = total; single CTA of 1024 threads
+__global__ void __launch_bounds__(1024) k_scan_excl_sum_u32_u64(const u32 *__restrict__ in, u64 *__restrict__ out, i64 n) {
+  __shared__ u64 ws[33];
+  u64 carry = 0;
+  for (i64 base = 0; base < n; base += blockDim.x) {
+    i64 i = base + threadIdx.x;
+    u64 v = i < n ? (u64)in[i] : 0, tot;
+    u64 e = block_excl_sum<u64>(v, tot, ws);
+    if (i < n) out[i] = carry + e;
+    carry += tot;
+  }
+  if (threadIdx.x == 0) out[n] = carry;
+}
+
+// Sequential walk over the blocks (one CTA).  See the file header.
+__global__ void __launch_bounds__(RLE_THREADS) k_rle_cut(const u8 *__restrict__ in, i64 N, u32 B, const i64 *__restrict__ head_carry,
+                                                         const i64 *__restrict__ tile_first, const u64 *__restrict__ g_tile, i64 T,
+                                                         BlockRec *__restrict__ recs, int max_blocks, int *__restrict__ n_blocks) {
+  __shared__ i64 ws64[33];
+  __shared__ u32 ws32[33];
+  __shared__ u64 sh_u64;
+  __shared__ i64 sh_i64;
+  const i64 INF = (i64)0x7fffffffffffffffLL;
+  i64 s = 0;
+  int k = 0;
+  RleView v;
+  u32 tt;
+  while (s < N && k < max_blocks) {
+    // (1) end of the run that contains s
+    i64 ts = s / RLE_TILE;
+    rle_load(in, N, ts, v);
+    i64 cand = INF;
+    for (int j = 0; j < v.nvalid; j++)
+      if ((v.flags & (1u << j)) && v.p0 + j > s) { cand = v.p0 + j; break; }
+    i64 e = block_min<i64>(cand, ws64);
+    for (i64 t0 = ts + 1; e == INF && t0 < T; t0 += RLE_THREADS) {
+      i64 t = t0 + threadIdx.x;
+      i64 c2 = INF;
+      if (t < T) { i64 f = tile_first[t]; if (f >= 0) c2 = f; }
+      e = block_min<i64>(c2, ws64);
+    }
+    if (e == INF) e = N;
+    // (2) closed form for the fresh run [s, e)
+    u64 R = (u64)(e - s);
+    u64 kfull = R / 255;
+    u32 rem = (u32)(R % 255), c = B, out = 0;
+    u64 consumed = 0;
+    u64 fit = c >= 6 ? (u64)((c - 1) / 5) : 0;
+    u64 ncons = kfull < fit ? kfull : fit;
+    out = (u32)(5 * ncons);
+    c -= (u32)(5 * ncons);
+    consumed = 255 * ncons;
+    u32 l = ncons < kfull ? 255u : rem;
+    if (l == 0) {
+    } else if (l <= 3) {
+      if (c > l) { out += l; c -= l; consumed += l; }
+      else { out += c; consumed += c; c = 0; }
+    } else {
+      if (c >= 6) { out += 5; c -= 5; consumed += l; }
+      else if (c == 5) { out += 5; consumed += 4; c = 0; }
+      else if (c == 4) { out += 4; consumed += 4; c = 0; }
+      else { out += c; consumed += c; c = 0; }
+    }
+    BlockRec r;
+    r.s = s; r.e_true = e; r.Ge = 0; r.outR = out; r.crc = 0; r.orig_ptr = 0;
+    if (c == 0) {
+      r.p = s + (i64)consumed;
+      r.n = out;
+    } else if (e >= N) {
+      r.p = N;
+      r.n = out;
+    } else {
+      // (3) global-fresh coordinates from e with c bytes of room
+      i64 te = e / RLE_TILE;
+      rle_view(in, N, te, head_carry, v, tt, ws64, ws32);
+      if (e >= v.p0 && e < v.p0 + 16) {
+        u32 g = v.gpre;
+        for (int j = 0; j < (int)(e - v.p0); j++) g += (v.em >> (2 * j)) & 3u;
+        sh_u64 = g_tile[te] + g;
+      }
+      __syncthreads();
+      u64 Ge = sh_u64;
+      __syncthreads();
+      r.Ge = Ge;
+      u64 target = Ge + c;
+      if (target > g_tile[T]) {
+        r.p = N;
+        r.n = out + (u32)(g_tile[T] - Ge);
+      } else {
+        if (threadIdx.x == 0) {  // last tile whose base is below the target
+          i64 lo = te, hi = T - 1;
+          while (lo < hi) {
+            i64 mid = (lo + hi + 1) >> 1;
+            if (g_tile[mid] < target) lo = mid; else hi = mid - 1;
+          }
+          sh_i64 = lo;
+        }
+        __syncthreads();
+        i64 tc = sh_i64;
+        __syncthreads();
+        rle_view(in, N, tc, head_carry, v, tt, ws64, ws32);
+        u64 run = g_tile[tc] + v.gpre;
+        i64 c3 = INF;
+        for (int j = 0; j < v.nvalid; j++) {
+          run += (v.em >> (2 * j)) & 3u;
+          if (run >= target) { c3 = v.p0 + j; break; }
+        }
+        i64 icut = block_min<i64>(c3, ws64);
+        r.p = icut + 1;
+        r.n = B;
+      }
+    }
+    if (threadIdx.x == 0) recs[k] = r;
+    s = r.p;
+    k++;
+  }
+  if (threadIdx.x == 0) *n_blocks = (s < N) ? -1 : k;  // -1: max_blocks too small (cannot happen with the host's bound)
+}
+
+__global__ void __launch_bounds__(RLE_THREADS) k_rle_emit(const u8 *__restrict__ in, i64 N, u32 B, const i64 *__restrict__ head_carry,
+                                                          const u64 *__restrict__ g_tile, const BlockRec *__restrict__ recs, int nblocks,
+                                                          u8 *__restrict__ blk, i64 blk_stride) {
+  __shared__ i64 ws64[33];
+  __shared__ u32 ws32[33];
+  RleView v;
+  u32 tt;
+  i64 tile = blockIdx.x;
+  rle_view(in, N, tile, head_carry, v, tt, ws64, ws32);
+  if (v.nvalid == 0) return;
+  // block containing p0: last k with recs[k].s <= p0
+  int lo = 0, hi = nblocks - 1;
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (recs[mid].s <= v.p0) lo = mid; else hi = mid - 1;
+  }
+  int k = lo;
+  BlockRec r = recs[k];
+  u8 *out = blk + (i64)k * blk_stride;
+  i64 cur = v.head_before;
+  u64 g = g_tile[tile] + v.gpre;
+  for (int j = 0; j < v.nvalid; j++) {
+    i64 i = v.p0 + j;
+    if (v.flags & (1u << j)) cur = i;
+    u32 e = (v.em >> (2 * j)) & 3u;
+    while (i >= r.p) { k++; r = recs[k]; out = blk + (i64)k * blk_stride; }
+    if (i < r.e_true) {  // fresh first run of the block
+      u64 d = (u64)(i - r.s);
+      u64 jj = d / 255;
+      u32 q = (u32)(d % 255);
+      if (q < 4) out[5 * jj + q] = v.b[j];
+      if (q == 3) {
+        u64 cp = 5 * jj + 4;
+        if (cp < r.n) {
+          u64 left = (u64)(r.e_true - r.s) - 255 * jj;
+          u32 l = left > 255 ? 255u : (u32)left;
+          out[cp] = (cp == (u64)B - 1) ? (u8)0 : (u8)(l - 4);
+        }
+      }
+    } else if (e) {
+      u64 op = r.outR + (g - r.Ge);
+      out[op] = v.b[j];
+      if (e == 2) {
+        u64 cp = op + 1;
+        if (cp < r.n) {
+          u32 cnt = 0;
+          if (cp != (u64)B - 1) {
+            i64 x = i + 1;
+            while (cnt < 251 && x < N && in[x] == v.b[j]) { cnt++; x++; }
+          }
+          out[cp] = (u8)cnt;
+        }
+      }
+    }
+    g += e;
+  }
+}
+
+// raw CRC (register starts at 0) of every 64 KiB chunk of every block's input range
+__global__ void __launch_bounds__(256) k_crc_chunks(const u8 *__restrict__ in, const BlockRec *__restrict__ recs,
+                                                    const u32 *__restrict__ pow256, u32 *__restrict__ part, int max_chunks) {
+  __shared__ u32 tab[256];
+  __shared__ u32 ws[33];
+  int k = blockIdx.y, c = blockIdx.x;
+  tab[threadIdx.x] = crc_table_entry(threadIdx.x);
+  __syncthreads();
+  i64 s = recs[k].s, p = recs[k].p;
+  i64 c0 = s + (i64)c * CRC_CHUNK;
+  if (c0 >= p) return;
+  i64 c1 = c0 + CRC_CHUNK < p ? c0 + CRC_CHUNK : p;
+  i64 a = c0 + (i64)threadIdx.x * 256;
+  i64 b = a + 256 < c1 ? a + 256 : c1;
+  u32 crc = 0;
+  if (a < b) {
+    for (i64 i = a; i < b; i++) crc = (crc << 8) ^ tab[(crc >> 24) ^ in[i]];
+    u64 after = (u64)(c1 - b);
+    u32 shift = (c1 - c0 == CRC_CHUNK) ? pow256[255 - threadIdx.x] : crc_xpow(8 * after);
+    crc = crc_mulmod(crc, shift);
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) crc ^= __shfl_xor_sync(FULL_MASK, crc, d);
+  if (lane_id() == 0) ws[warp_id()] = crc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    u32 x = 0;
+    for (int i = 0; i < 8; i++) x ^= ws[i];
+    part[(i64)k * max_chunks + c] = x;
+  }
+}
+
+__global__ void k_crc_fold(BlockRec *__restrict__ recs, int nblocks, const u32 *__restrict__ part, int max_chunks, u32 pow_chunk) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nblocks) return;
+  i64 len = recs[k].p - recs[k].s;
+  u32 crc = 0xffffffffu;
+  int c = 0;
+  for (; len >= CRC_CHUNK; len -= CRC_CHUNK, c++) crc = crc_mulmod(crc, pow_chunk) ^ part[(i64)k * max_chunks + c];
+  if (len > 0) crc = crc_mulmod(crc, crc_xpow(8 * (u64)len)) ^ part[(i64)k * max_chunks + c];
+  recs[k].crc = ~crc;
+}

@@ -1,0 +1,91 @@
+/*
+ * bz2b200.h -- C ABI of the B200-native bzip2 block compressor / decompressor.
+ *
+ * This is the drop-in boundary for the bzip2 path of compressjs
+ * (BJ = /root/reference/Bzip2_joined_.js).  Every entry point is what an FFI for that
+ * path binds (N-API addon for the JS shim, ctypes in this repo's tests); plain pointers
+ * and sizes only.  Return value: 0 or the reference's negative Err codes (BJ:1365-1375),
+ * BZ2B200_E_LEVEL for `Invalid block size multiplier` (BJ:2208), BZ2B200_E_CUDA for a
+ * device failure.  No exceptions cross the ABI.  Calls are blocking, like the JS API.
+ *
+ *   replaces                               entry point
+ *   Bzip2.compressFile   (BJ:2199-2249)    bz2b200_compress / bz2b200_compress_device
+ *   Bzip2.decompressFile (BJ:1769-1796)    bz2b200_decompress / bz2b200_decompress_device
+ *   Bzip2.decompressBlock(BJ:1797-1818)    bz2b200_decompress_block
+ *   Bzip2.table          (BJ:1823-1863)    bz2b200_table
+ *   Err / ErrorMessages  (BJ:1365-1383)    bz2b200_strerror
+ */
+#ifndef BZ2B200_H
+#define BZ2B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+  BZ2B200_OK = 0,
+  BZ2B200_E_LAST_BLOCK = -1,
+  BZ2B200_E_NOT_BZIP_DATA = -2,
+  BZ2B200_E_UNEXPECTED_INPUT_EOF = -3,
+  BZ2B200_E_UNEXPECTED_OUTPUT_EOF = -4,
+  BZ2B200_E_DATA_ERROR = -5,
+  BZ2B200_E_OUT_OF_MEMORY = -6,
+  BZ2B200_E_OBSOLETE_INPUT = -7,
+  BZ2B200_E_END_OF_BLOCK = -8,
+  BZ2B200_E_LEVEL = -100,   /* Error('Invalid block size multiplier') */
+  BZ2B200_E_CUDA = -101,    /* CUDA runtime failure; see bz2b200_last_error */
+  BZ2B200_E_ARG = -102
+};
+
+typedef struct bz2b200_ctx bz2b200_ctx;
+
+typedef struct {
+  uint64_t in_bytes, out_bytes;
+  uint32_t n_blocks;
+  uint32_t sort_rounds;      /* prefix-doubling rounds of the last compress */
+  uint64_t rle1_bytes;       /* sum of block lengths after RLE1 */
+  uint64_t mtf_syms;         /* sum of nMTF */
+  uint64_t sort_slots;       /* sum over rounds of slots sorted */
+  uint32_t kernel_launches;  /* kernels launched by the last call */
+  uint32_t d1_triggered;
+  float ms_total;            /* device time of the last call (CUDA events) */
+  float ms_stage[8];         /* compress: rle1, bwt, mtf, huff, stitch; decompress: scan, huff, ibwt, out */
+} bz2b200_stats;
+
+/* One context per calling thread / per GPU.  `device` = CUDA ordinal. */
+int bz2b200_create(int device, bz2b200_ctx **ctx);
+void bz2b200_destroy(bz2b200_ctx *ctx);
+
+/* Host-buffer entry points (what the JS shim / ctypes call).  The input is caller-owned and
+ * only read; *out is allocated by the library and released with bz2b200_free. */
+int bz2b200_compress(bz2b200_ctx *ctx, const uint8_t *in, size_t n, int level, uint8_t **out, size_t *out_len);
+int bz2b200_decompress(bz2b200_ctx *ctx, const uint8_t *in, size_t n, int multistream, uint8_t **out, size_t *out_len);
+int bz2b200_decompress_block(bz2b200_ctx *ctx, const uint8_t *in, size_t n, uint64_t bitpos, uint8_t **out, size_t *out_len);
+int bz2b200_table(bz2b200_ctx *ctx, const uint8_t *in, size_t n, int multistream, uint64_t **bitpos, uint32_t **sizes, size_t *count);
+void bz2b200_free(void *p);
+
+/* Device-resident entry points: input already in HBM (16-byte aligned), output written to a
+ * caller-provided device buffer of out_cap bytes (multiple of 4).  Used for the roofline figure. */
+int bz2b200_compress_device(bz2b200_ctx *ctx, const void *d_in, size_t n, int level, void *d_out, size_t out_cap, size_t *out_len);
+int bz2b200_decompress_device(bz2b200_ctx *ctx, const void *d_in, size_t n, int multistream, void *d_out, size_t out_cap, size_t *out_len);
+/* upper bound of the compressed size of n input bytes at `level` (for sizing d_out) */
+size_t bz2b200_compress_bound(size_t n, int level);
+
+const char *bz2b200_strerror(int rc);
+const char *bz2b200_last_error(bz2b200_ctx *ctx);
+int bz2b200_last_stats(bz2b200_ctx *ctx, bz2b200_stats *st);
+
+/* Stage dumps for the parity tests (tests/ only): after a compress call, copy an intermediate
+ * of block `blk` to host.  what: 0 = BlockRec table (all blocks), 1 = RLE1'd block bytes,
+ * 2 = BWT L column, 3 = MTF/RLE2 symbols (u16), 4 = BlockMeta table (all blocks).
+ * Returns the number of bytes written to dst (<= cap) or a negative error. */
+long long bz2b200_debug_fetch(bz2b200_ctx *ctx, int what, int blk, void *dst, size_t cap);
+/* tests/ only: override the block capacity B (0 = level*100000-19) to stress the cut-point logic. */
+int bz2b200_debug_set_block_cap(bz2b200_ctx *ctx, uint32_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -79,9 +79,17 @@ size_t orc_rle1_block(const uint8_t *in, size_t n_in, size_t cap, uint8_t *block
   return pos;
 }
 
+/* test hook: override the block capacity (0 = the reference's level*100000-19) so that the
+ * cut-point logic can be stressed with thousands of tiny blocks */
+static size_t g_cap_override = 0;
+void orc_debug_set_block_cap(size_t cap) { g_cap_override = cap; }
+static size_t block_cap(int level) {
+  return g_cap_override ? g_cap_override : (size_t)level * 100000 - 19; /* BJ:2212-2220 */
+}
+
 size_t orc_cut_points(const uint8_t *in, size_t n, int level, uint64_t **starts,
                       uint32_t **lens, uint32_t **crcs) {
-  size_t cap = (size_t)level * 100000 - 19; /* BJ:2212-2220 */
+  size_t cap = block_cap(level);
   size_t alloc = n / (cap * 4 / 5) + 4, nb = 0, ip = 0;
   uint64_t *s = malloc((alloc + 1) * sizeof *s);
   uint32_t *l = malloc(alloc * sizeof *l), *c = malloc(alloc * sizeof *c);
@@ -634,7 +642,7 @@ int orc_compress_mt(const uint8_t *in, size_t n, int level, int sort_mode, int t
   uint64_t *starts;
   uint32_t *lens, *crcs;
   size_t nb = orc_cut_points(in, n, level, &starts, &lens, &crcs);
-  mt_job J = {in, (size_t)level * 100000 - 19, sort_mode, nb, starts, crcs, NULL, NULL, 0,
+  mt_job J = {in, block_cap(level), sort_mode, nb, starts, crcs, NULL, NULL, 0,
               PTHREAD_MUTEX_INITIALIZER};
   J.outs = calloc(nb ? nb : 1, sizeof *J.outs);
   J.infos = calloc(nb ? nb : 1, sizeof *J.infos);

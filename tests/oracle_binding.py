@@ -68,6 +68,8 @@ def lib():
         L.orc_huff_lengths.restype = None
         L.orc_block_stages.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.POINTER(BlockInfo),
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_debug_set_block_cap.argtypes = [C.c_size_t]
+        L.orc_debug_set_block_cap.restype = None
         _lib = L
     return _lib
 
@@ -127,6 +129,11 @@ def table(data, multistream=False):
     lib().orc_free(pos)
     lib().orc_free(sz)
     return res
+
+
+def set_block_cap(cap):
+    """test hook: 0 restores the reference's capacity"""
+    lib().orc_debug_set_block_cap(cap)
 
 
 def crc32(data):
