@@ -113,7 +113,8 @@ class Bzip2Engine:
         msg = self._L.bz2b200_strerror(rc).decode()
         if rc in (_native.E_CUDA, _native.E_ARG):
             raise RuntimeError(msg + ": " + self._L.bz2b200_last_error(self._ctx).decode())
-        raise Bzip2Error(rc, msg)
+        detail = self._L.bz2b200_last_error(self._ctx).decode()
+        raise Bzip2Error(rc, msg + (": " + detail if detail else ""))  # _throw(status, optDetail), BJ:1384-1391
 
     def _take(self, ptr, n):
         data = C.string_at(ptr, n) if n else b""

@@ -11,6 +11,7 @@
 #include "huff.cuh"
 #include "decode.cuh"
 
+#include <algorithm>
 #include <string>
 #include <vector>
 

@@ -108,22 +108,29 @@ struct DecSmem {
   u64 bitpos_after_header;
 };
 
-__global__ void __launch_bounds__(32) k_block_decode(const u8 *__restrict__ in, u64 n, const u64 *__restrict__ cand, u32 ncand, u32 dbuf_cap,
+__global__ void __launch_bounds__(32) k_block_decode(const u8 *__restrict__ in, u64 n, const u64 *__restrict__ cand, u32 ncand, u32 dbuf_cap, int verify,
                                                      DecBlk *__restrict__ out, u8 *__restrict__ dL, i64 l_stride, u8 *__restrict__ dsel) {
   __shared__ DecSmem sm;
   const u32 k = blockIdx.x;
   if (k >= ncand) return;
   const int lane = threadIdx.x;
   const u64 bitpos = cand[k] >> 1;
-  const u32 kind = (u32)(cand[k] & 1);
+  u32 kind = (u32)(cand[k] & 1);
+  if (verify) {  // candidate given by the caller (decompressBlock): read the 48-bit signature here (BJ:1434-1439)
+    BitRd r0;
+    br_init(r0, in, n, bitpos);
+    u64 h = ((u64)br_get(r0, 24) << 24) | br_get(r0, 24);
+    kind = h == BZ_MAGIC_END ? 1u : h == BZ_MAGIC_BLOCK ? 0u : 2u;
+  }
   u8 *Lk = dL + (i64)k * l_stride;
   u8 *sel = dsel + (u64)k * DEC_MAX_SEL;
   DecBlk res;
   res.bitpos = bitpos; res.endbit = 0; res.target_crc = 0; res.orig_ptr = 0; res.count = 0; res.err = 0; res.kind = kind; res.pad = 0;
   BitRd r;
+  res.kind = kind;
   // ---- header (lane 0), BJ:1434-1520 ----
   if (lane == 0) {
-    int err = 0, ng = 0, nsel = 0, sym_total = 0;
+    int err = kind == 2 ? BZ2B200_E_NOT_BZIP_DATA : 0, ng = 0, nsel = 0, sym_total = 0;
     br_init(r, in, n, bitpos + 48);
     res.target_crc = br_get(r, 32);
     if (kind == 0) {
@@ -185,7 +192,7 @@ __global__ void __launch_bounds__(32) k_block_decode(const u8 *__restrict__ in, 
   __syncwarp();
   const int err0 = sm.hdr[0], ng = sm.hdr[1], nsel = sm.hdr[2], sym_total = sm.hdr[3];
   const int S = sym_total + 2;
-  if (kind == 1 || err0) {
+  if (kind != 0 || err0) {
     if (lane == 0) {
       res.err = err0;
       res.endbit = sm.bitpos_after_header;
@@ -242,47 +249,54 @@ __global__ void __launch_bounds__(32) k_block_decode(const u8 *__restrict__ in, 
   // ---- symbols (BJ:1597-1670): lane 0 decodes into a staging buffer, the warp flushes it ----
   u32 count = 0, flushed = 0;
   int err = 0, done = 0;
-  u32 run_pos = 0, t_run = 0, pending = 0;  // pending: copies of `pend_byte` still to be staged
-  u8 pend_byte = 0;
+  u32 run_pos = 0, t_run = 0;
+  u32 pending = 0;   // copies of pend_byte not staged yet (a flushed RUNA/RUNB run)
+  u8 pend_byte = 0, lit = 0;
+  bool has_lit = false;  // literal decoded but not staged yet (it follows the pending run)
   int sym_left = 0, selector = 0, gi = 0;
   if (lane == 0) br_init(r, in, n, sm.bitpos_after_header);
   for (;;) {
-    u32 staged = 0;
     if (lane == 0) {
-      while (staged < DEC_STAGE && !(done && !pending) && !err) {
+      u32 staged = 0;
+      for (;;) {
         if (pending) {
           u32 c = pending < DEC_STAGE - staged ? pending : DEC_STAGE - staged;
           for (u32 q = 0; q < c; q++) sm.stage[staged + q] = pend_byte;
-          staged += c; pending -= c;
-          continue;
+          staged += c;
+          pending -= c;
+          if (pending) break;
         }
+        if (has_lit) {
+          if (staged == DEC_STAGE) break;
+          sm.stage[staged++] = lit;
+          has_lit = false;
+        }
+        if (done || err || staged == DEC_STAGE) break;
         if (!(sym_left--)) {
           sym_left = BZ_GROUP - 1;
           if (selector >= nsel) { err = BZ2B200_E_DATA_ERROR; break; }
           gi = sel[selector++];
         }
         int next;
-        {
-          u32 pk = br_peek(r, DEC_LUT_BITS);
-          u16 e = sm.lut[gi][pk];
-          if (e) {
-            next = e >> 5;
-            r.avail -= (e & 31);
-          } else {
-            int L = sm.minl[gi];
-            int j = (int)br_get(r, (u32)L);
-            for (;; L++) {
-              if (L > sm.maxl[gi]) { err = BZ2B200_E_DATA_ERROR; break; }
-              if (j <= sm.limit[gi][L]) break;
-              j = (j << 1) | (int)br_get(r, 1);
-            }
-            if (err) break;
-            j -= sm.base[gi][L];
-            if (j < 0 || j >= BZ_MAX_SYMS) { err = BZ2B200_E_DATA_ERROR; break; }
-            next = sm.permute[gi][j];
+        u32 pk = br_peek(r, DEC_LUT_BITS);
+        u16 e = sm.lut[gi][pk];
+        if (e) {
+          next = e >> 5;
+          r.avail -= (e & 31);
+        } else {
+          int L = sm.minl[gi];
+          int j = (int)br_get(r, (u32)L);
+          for (;; L++) {
+            if (L > sm.maxl[gi]) { err = BZ2B200_E_DATA_ERROR; break; }
+            if (j <= sm.limit[gi][L]) break;
+            j = (j << 1) | (int)br_get(r, 1);
           }
+          if (err) break;
+          j -= sm.base[gi][L];
+          if (j < 0 || j >= BZ_MAX_SYMS) { err = BZ2B200_E_DATA_ERROR; break; }
+          next = sm.permute[gi][j];
         }
-        if (r.overrun && br_tell(r) > n * 8) { err = BZ2B200_E_UNEXPECTED_INPUT_EOF; break; }  // (reference: spins on zero bits, D3)
+        if (br_tell(r) > n * 8) { err = BZ2B200_E_UNEXPECTED_INPUT_EOF; break; }  // reference: spins on zero bits (D3)
         if (next == 0 || next == 1) {
           if (!run_pos) { run_pos = 1; t_run = 0; }
           t_run += next == 0 ? run_pos : 2 * run_pos;
@@ -303,47 +317,25 @@ __global__ void __launch_bounds__(32) k_block_decode(const u8 *__restrict__ in, 
         u8 v = sm.mtf[i];
         for (int q = i; q > 0; q--) sm.mtf[q] = sm.mtf[q - 1];
         sm.mtf[0] = v;
-        if (pending) {  // the run must be staged before this literal: park the literal behind it
-          // stage what fits of the run now, the literal goes out on a later pass
-          u32 c = pending < DEC_STAGE - staged ? pending : DEC_STAGE - staged;
-          for (u32 q = 0; q < c; q++) sm.stage[staged + q] = pend_byte;
-          staged += c; pending -= c;
-          if (pending || staged == DEC_STAGE) {
-            // could not finish the run (or no room left): remember the literal as a 1-byte run after it
-            // by extending the pending queue: handled through lit_pending below
-            sm.hdr[4] = 1; sm.hdr[5] = sm.sym2byte[v];
-            count++;
-            break;
-          }
-        }
-        sm.stage[staged++] = sm.sym2byte[v];
+        lit = sm.sym2byte[v];
+        has_lit = true;
         count++;
       }
       sm.hdr[6] = (int)staged;
-      sm.hdr[7] = (done && !pending) || err ? 1 : 0;
+      sm.hdr[7] = (err || (done && !pending && !has_lit)) ? 1 : 0;
     }
     __syncwarp();
-    staged = (u32)sm.hdr[6];
+    u32 staged = (u32)sm.hdr[6];
+    int fin = sm.hdr[7];
     for (u32 q = lane; q < staged; q += 32) Lk[flushed + q] = sm.stage[q];
     flushed += staged;
-    int fin = sm.hdr[7];
     __syncwarp();
-    if (lane == 0 && sm.hdr[4]) {  // literal parked behind an unfinished run
-      // drain the rest of the run first (whole passes), then the literal
-      sm.hdr[4] = 0;
-      u8 lit = (u8)sm.hdr[5];
-      // emit remaining run bytes directly (rare path: run crossed a staging boundary)
-      while (pending) { Lk[flushed++] = pend_byte; pending--; }
-      Lk[flushed++] = lit;
-    }
-    flushed = __shfl_sync(FULL_MASK, flushed, 0);
     if (fin) break;
   }
   if (lane == 0) {
-    if (!err && r.overrun && br_tell(r) > n * 8) err = BZ2B200_E_UNEXPECTED_INPUT_EOF;
     if (!err && res.orig_ptr >= count) err = BZ2B200_E_DATA_ERROR;  // BJ:1677
     res.err = err;
-    res.count = count;
+    res.count = err ? 0 : count;
     res.endbit = br_tell(r);
     out[k] = res;
   }
@@ -526,7 +518,7 @@ __global__ void __launch_bounds__(1024) k_rle1_inv(const u8 *__restrict__ blk, i
     u32 c_in = (fn_compose(carry_fn, fe)) & 1u;  // carry_fn is constant: value in bit 0
     // counts
     u32 cnt = 0;
-    u32 emit[4];
+    u32 emit[4] = {0u, 0u, 0u, 0u};
     {
       int cur = hb;
       u32 c = c_in;

@@ -1,0 +1,159 @@
+"""GPU parity tests: the CUDA path, called through the C-ABI (compressjs_flattened_b200 -> libbz2b200.so),
+against the CPU oracle on the same seeded inputs, against the committed goldens, and -- at BASELINE.json's
+full sizes -- through SHA-256 goldens of the oracle's output plus size-independent properties
+(round trip, block index == encoder's block table, CRC folding)."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import HERE, fixture_bytes
+
+pytestmark = pytest.mark.gpu
+
+GOLD = json.load(open(os.path.join(HERE, "golden", "corpus_goldens.json")))
+RNG = np.random.default_rng(11)
+EDGE = {
+    "empty": b"", "one": b"Q", "aaaa": b"aaaa", "aaaaa": b"aaaaa", "a256": b"a" * 256, "a255x": b"a" * 255 + b"x",
+    "zeros1000": bytes(1000), "abab": b"abab", "abc3": b"abcabcabc",
+    "rand64k": RNG.integers(0, 256, 65536, dtype=np.uint8).tobytes(),
+    "rand4sym": RNG.integers(0, 4, 20000, dtype=np.uint8).tobytes(),
+    "two_sym_d1": bytes(RNG.integers(0, 2, 6000, dtype=np.uint8)),
+    "period257": bytes(list(range(256)) + [0]) * 3900,
+    "line97": (b"0123456789abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ-the quick brown fox jumps over a do\n") * 20000,
+}
+
+
+@pytest.mark.parametrize("name", sorted(EDGE))
+def test_edge_cases_byte_identical(gpu_engine, oracle, name):
+    data = EDGE[name]
+    for level in (9, 1):
+        exp, st = oracle.compress(data, level, threads=8, return_stats=True)
+        got = gpu_engine.compressFile(data, None, level)
+        assert got == exp, f"{name} L{level}: {len(got)} vs {len(exp)} bytes"
+        if not st.d1_triggered:
+            assert gpu_engine.decompressFile(exp) == data
+
+
+@pytest.mark.parametrize("n", range(6))
+@pytest.mark.parametrize("level", [1, 2, 5, 9])
+def test_reference_samples_byte_identical(gpu_engine, oracle, n, level):
+    data = fixture_bytes(f"sample{n}.ref")
+    exp = oracle.compress(data, level, threads=8)
+    got = gpu_engine.compressFile(data, None, level)
+    assert got == exp
+    assert gpu_engine.decompressFile(got) == data  # NPM/test/file.js round trip
+
+
+def test_default_level_is_9(gpu_engine, oracle):
+    data = fixture_bytes("sample1.ref")
+    assert gpu_engine.compressFile(data) == oracle.compress(data, 9) == gpu_engine.compressFile(data, None, None)
+
+
+def test_adversarial_suffix_sort_inputs(gpu_engine, oracle):
+    """BASELINE config 5: all-zero and periodic inputs; the doubling must stop at h >= n and apply the tie rule."""
+    cases = [bytes(2_000_000), b"ab" * 500_000, b"abc" * 333_333, b"a" * 899_981, bytes(5) * 179_996]
+    for data in cases:
+        exp = oracle.compress(data, 9, threads=8)
+        assert gpu_engine.compressFile(data, None, 9) == exp
+        assert gpu_engine.stats().sort_rounds <= 21
+        assert gpu_engine.decompressFile(exp) == data
+    assert len(gpu_engine.compressFile(bytes(2_000_000), None, 9)) == 49
+
+
+def test_stage_dumps_match_oracle(gpu_engine, oracle):
+    data = fixture_bytes("sample5.ref")
+    gpu_engine.compressFile(data, None, 9)
+    recs, metas = gpu_engine.block_table(), gpu_engine.block_meta()
+    starts, lens, crcs = oracle.cut_points(data, 9)
+    assert [(r.s, r.n, r.crc) for r in recs] == list(zip(starts[:-1], lens, crcs))
+    facts = [(899981, 298344, 196, 293714), (899981, 105439, 202, 235309), (330739, 144412, 193, 104124)]
+    for k, r in enumerate(recs):
+        blk, _, _ = oracle.rle1_block(data[starts[k]:], 899981)
+        assert gpu_engine.debug_fetch(1, k, r.n).tobytes() == blk.tobytes()
+        st = oracle.block_stages(blk)
+        assert gpu_engine.debug_fetch(2, k, r.n).tobytes() == st["U"].tobytes()
+        A = np.frombuffer(gpu_engine.debug_fetch(3, k, 2 * metas[k].m).tobytes(), dtype=np.uint16)
+        assert np.array_equal(A, st["A"])
+        assert (r.n, r.orig_ptr, metas[k].alpha, metas[k].m) == facts[k] == (st["n"], st["orig_ptr"], st["alpha"], st["m"])
+        assert (metas[k].n_groups, metas[k].n_sel, metas[k].bits) == (st["n_groups"], st["n_sel"], st["bits"] + 80)
+
+
+def test_cut_points_with_runs_across_blocks(gpu_engine, oracle):
+    rng = np.random.default_rng(3)
+    parts = []
+    for _ in range(3000):
+        parts.append(bytes([int(rng.integers(0, 256))]) * int(rng.choice([1, 1, 1, 2, 3, 4, 5, 7, 255, 256, 257, 600, 4000])))
+    data = b"".join(parts) * 3
+    for level in (1, 9):
+        exp = oracle.compress(data, level, threads=8)
+        assert gpu_engine.compressFile(data, None, level) == exp
+        starts, lens, crcs = oracle.cut_points(data, level)
+        assert [(r.s, r.n, r.crc) for r in gpu_engine.block_table()] == list(zip(starts[:-1], lens, crcs))
+        assert gpu_engine.decompressFile(exp) == data
+
+
+def test_decode_reference_fixtures(gpu_engine):
+    for n in range(5):  # NPM/test/bzip2-basic.js, streams made by real bzip2
+        assert gpu_engine.decompressFile(fixture_bytes(f"sample{n}.bz2"), len(fixture_bytes(f"sample{n}.ref"))) == fixture_bytes(f"sample{n}.ref")
+        rows = []  # NPM/test/bzip2-table.js
+        gpu_engine.table(fixture_bytes(f"sample{n}.bz2"), lambda p, s: rows.append(f"{p}\t{s}\n"))
+        assert "".join(rows) == fixture_bytes(f"sample{n}.bzt").decode()
+    assert gpu_engine.decompressBlock(fixture_bytes("sample0.bz2"), 32) == b"This is a test\n"  # NPM/test/bzip2-block.js
+    for f, b in [("sample2", 544888), ("sample4", 32), ("sample4", 1596228), ("sample4", 2342106)]:
+        assert gpu_engine.decompressBlock(fixture_bytes(f + ".bz2"), b, len(fixture_bytes(f"{f}.{b}"))) == fixture_bytes(f"{f}.{b}")
+
+
+def test_decode_errors_match_oracle(gpu_engine, oracle):
+    from compressjs_flattened_b200.bzip2 import Bzip2Error
+    good = oracle.compress(fixture_bytes("sample1.ref")[:30000], 9)
+    blobs = [b"", b"BZ", b"BZh0xxxx", b"XXXXXXXX", good[:-3], good[:200]]
+    for pos in (10, 15, 40, 200, len(good) - 2):
+        x = bytearray(good)
+        x[pos] ^= 0x40
+        blobs.append(bytes(x))
+    for blob in blobs:
+        try:
+            exp = ("ok", oracle.decompress(blob))
+        except oracle.OracleError as e:
+            exp = ("err", e.errorCode)
+        try:
+            got = ("ok", gpu_engine.decompressFile(blob))
+        except Bzip2Error as e:
+            got = ("err", e.errorCode)
+        assert got == exp
+    ms = oracle.compress(b"first stream ") + oracle.compress(b"second stream", 1)
+    assert gpu_engine.decompressFile(ms, None, True) == b"first stream second stream"
+    assert gpu_engine.decompressFile(ms) == b"first stream "
+    with pytest.raises(ValueError, match="Invalid block size multiplier"):
+        gpu_engine.compressFile(b"x", None, 0)
+
+
+@pytest.mark.parametrize("key", ["html:2130640:5:L9", "html:2130640:5:L1", "text:10000000:8:L9", "text:100000000:8:L9", "text:100000000:8:L1"])
+def test_full_size_configs(gpu_engine, key):
+    """BASELINE.json configs 1-3 at full size: SHA-256 of the GPU output == SHA-256 of the oracle's output
+    (tests/golden/corpus_goldens.json, generated by tests/golden/make_corpus_goldens.py), then the
+    size-independent properties: round trip, block index from the magic search == encoder's block table."""
+    from compressjs_flattened_b200.corpus import gen_html, gen_text
+    kind, n, seed, level = key.split(":")
+    n, seed, level = int(n), int(seed), int(level[1:])
+    data = (gen_text if kind == "text" else gen_html)(n, seed)
+    g = GOLD[key]
+    assert hashlib.sha256(data.tobytes()).hexdigest() == g["input_sha256"]
+    comp = gpu_engine.compressFile(data, None, level)
+    st = gpu_engine.stats()
+    assert (len(comp), hashlib.sha256(comp).hexdigest()) == (g["out_bytes"], g["out_sha256"])
+    assert (st.n_blocks, st.rle1_bytes, st.mtf_syms) == (g["n_blocks"], g["rle1_bytes"], g["mtf_syms"])
+    recs = gpu_engine.block_table()
+    sizes_enc = [r.p - r.s for r in recs]
+    fold = 0
+    for r in recs:  # combined CRC is the fold of the block CRCs (BJ:2237) and sits in the last 4 bytes (+padding)
+        fold = (((fold << 1) | (fold >> 31)) ^ r.crc) & 0xFFFFFFFF
+    assert fold.to_bytes(4, "big") in comp[-5:]
+    back = gpu_engine.decompressFile(comp)
+    assert hashlib.sha256(back).hexdigest() == g["input_sha256"]
+    rows = []
+    gpu_engine.table(comp, lambda p, s: rows.append((p, s)))
+    assert [s for _, s in rows] == sizes_enc and rows[0][0] == 32

@@ -1,0 +1,165 @@
+"""Kernel LOGIC on the CPU simulator (tests/sim): the same .cu sources compiled with -DBZ_SIM.
+Parity is checked against the oracle; the real-GPU parity tests are in test_gpu_parity.py."""
+import numpy as np
+import pytest
+
+from conftest import fixture_bytes
+
+RNG = np.random.default_rng(11)
+SMALL = {
+    "empty": b"", "one": b"Q", "aaaa": b"aaaa", "aaaaa": b"aaaaa", "a256": b"a" * 256, "a255x": b"a" * 255 + b"x",
+    "zeros1000": bytes(1000), "abab": b"abab", "abc3": b"abcabcabc", "sample0": b"This is a test\n",
+    "text5k": (b"the quick brown fox jumps over the lazy dog. " * 120)[:5000],
+    "rand3k": RNG.integers(0, 256, 3000, dtype=np.uint8).tobytes(),
+    "rand4sym": RNG.integers(0, 4, 20000, dtype=np.uint8).tobytes(),
+    "two_sym_d1": bytes(RNG.integers(0, 2, 6000, dtype=np.uint8)),
+}
+
+
+@pytest.mark.parametrize("name", sorted(SMALL))
+def test_compress_parity_small(sim_engine, oracle, name):
+    data = SMALL[name]
+    exp, st = oracle.compress(data, 9, return_stats=True)
+    assert sim_engine.compressFile(data, None, 9) == exp
+    if not st.d1_triggered:
+        assert sim_engine.decompressFile(exp) == data
+
+
+def test_compress_parity_multiblock_level1(sim_engine, oracle):
+    data = fixture_bytes("sample5.ref")[:230_000]
+    exp = oracle.compress(data, 1)
+    assert sim_engine.compressFile(data, None, 1) == exp
+    assert sim_engine.stats().n_blocks == 3
+
+
+def test_stage_dumps_match_oracle(sim_engine, oracle):
+    data = fixture_bytes("sample1.ref")[:40_000]
+    sim_engine.compressFile(data, None, 9)
+    recs, metas = sim_engine.block_table(), sim_engine.block_meta()
+    blk, used, crc = oracle.rle1_block(data, 899981)
+    assert (recs[0].s, recs[0].p, recs[0].n, recs[0].crc) == (0, used, len(blk), crc)
+    assert sim_engine.debug_fetch(1, 0, recs[0].n).tobytes() == blk.tobytes()
+    st = oracle.block_stages(blk)
+    assert sim_engine.debug_fetch(2, 0, recs[0].n).tobytes() == st["U"].tobytes() and recs[0].orig_ptr == st["orig_ptr"]
+    A = np.frombuffer(sim_engine.debug_fetch(3, 0, 2 * metas[0].m).tobytes(), dtype=np.uint16)
+    assert np.array_equal(A, st["A"]) and metas[0].alpha == st["alpha"]
+    assert (metas[0].n_groups, metas[0].n_sel, metas[0].bits) == (st["n_groups"], st["n_sel"], st["bits"] + 80)
+
+
+def _runny(rng, n, nsym, plong):
+    out = bytearray()
+    while len(out) < n:
+        v = int(rng.integers(0, nsym))
+        r = rng.random()
+        if r < plong:
+            L = int(rng.choice([4, 5, 6, 7, 8, 254, 255, 256, 257, 258, 259, 260, 509, 510, 511, 512, 513, 700, 1500]))
+        elif r < plong + 0.2:
+            L = int(rng.integers(2, 6))
+        else:
+            L = 1
+        out += bytes([v]) * L
+    return bytes(out[:n])
+
+
+def test_cut_points_stress_tiny_blocks(sim_engine, oracle):
+    """Runs straddling a cut, blocks ending on the 4th run byte / on the count byte, 255-byte chunking:
+    thousands of cuts by overriding the block capacity in both the oracle and the kernels."""
+    rng = np.random.default_rng(7)
+    try:
+        for it in range(12):
+            cap = int(rng.choice([8, 9, 10, 11, 12, 13, 17, 50, 64, 100, 255, 256, 1000]))
+            data = _runny(rng, int(rng.integers(1, 5000)), int(rng.choice([1, 2, 3, 200])), float(rng.choice([0.02, 0.2, 0.6])))
+            oracle.set_block_cap(cap)
+            sim_engine.debug_set_block_cap(cap)
+            exp = oracle.compress(data, 9)
+            got = sim_engine.compressFile(data, None, 9)
+            assert got == exp, f"cap={cap} n={len(data)}"
+            starts, lens, crcs = oracle.cut_points(data, 9)
+            recs = sim_engine.block_table()
+            assert [(r.s, r.n, r.crc) for r in recs] == list(zip(starts[:-1], lens, crcs))
+    finally:
+        oracle.set_block_cap(0)
+        sim_engine.debug_set_block_cap(0)
+
+
+def test_decode_fixtures_and_random_access(sim_engine):
+    for n in (0, 3):
+        assert sim_engine.decompressFile(fixture_bytes(f"sample{n}.bz2")) == fixture_bytes(f"sample{n}.ref")
+    s2 = fixture_bytes("sample2.bz2")
+    rows = []
+    sim_engine.table(s2, lambda p, s: rows.append(f"{p}\t{s}\n"))
+    assert "".join(rows) == fixture_bytes("sample2.bzt").decode()
+    assert sim_engine.decompressBlock(s2, 544888) == fixture_bytes("sample2.544888")
+
+
+def test_decode_periodic_and_runs(sim_engine, oracle):
+    rng = np.random.default_rng(2)
+    cases = [b"abab" * 10, b"aaaab" * 50, bytes(5000), b"abc" * 700,
+             bytes(np.repeat(rng.integers(0, 3, 400, dtype=np.uint8), rng.integers(1, 12, 400))),
+             _runny(rng, 4000, 2, 0.5)]
+    for data in cases:
+        assert sim_engine.decompressFile(oracle.compress(data, 9)) == data
+
+
+def test_decode_errors_match_oracle(sim_engine, oracle):
+    from compressjs_flattened_b200.bzip2 import Bzip2Error
+    good = oracle.compress(b"hello world, hello world")
+    flipped = bytearray(good)
+    flipped[20] ^= 0x10
+    bad_crc = bytearray(good)
+    bad_crc[-1] ^= 0x01
+    for blob in (b"", b"BZ", b"BZh0xxxx", b"XXXXXXXX", good[:-3], good[:20], bytes(flipped), bytes(bad_crc)):
+        try:
+            exp = ("ok", oracle.decompress(blob))
+        except oracle.OracleError as e:
+            exp = ("err", e.errorCode)
+        try:
+            got = ("ok", sim_engine.decompressFile(blob))
+        except Bzip2Error as e:
+            got = ("err", e.errorCode)
+        assert got == exp
+
+
+def test_multistream(sim_engine, oracle):
+    ms = oracle.compress(b"first stream ") + oracle.compress(b"second stream", 1)
+    assert sim_engine.decompressFile(ms, None, True) == b"first stream second stream" == oracle.decompress(ms, True)
+    assert sim_engine.decompressFile(ms) == b"first stream "
+
+
+def test_api_mirror_coercions(sim_engine):
+    """Same argument coercions as Util.coerceInputStream/OutputStream (BJ:178-272)."""
+    data = b"This is a test\n"
+
+    class Src:
+        def __init__(self, b):
+            self.b, self.i = b, 0
+
+        def readByte(self):
+            if self.i >= len(self.b):
+                return -1
+            self.i += 1
+            return self.b[self.i - 1]
+
+    class Sink:
+        def __init__(self):
+            self.out, self.flushed = bytearray(), False
+
+        def writeByte(self, b):
+            self.out.append(b)
+
+        def flush(self):
+            self.flushed = True
+
+    ref = sim_engine.compressFile(data)
+    assert sim_engine.compressFile(list(data)) == ref == sim_engine.compressFile(Src(data)) == sim_engine.compressFile(np.frombuffer(data, np.uint8))
+    assert sim_engine.compressFile(data, None, "not a number") == ref  # non-number props -> level 9 (BJ:2204)
+    sink = Sink()
+    assert sim_engine.compressFile(data, sink) is sink and bytes(sink.out) == ref and sink.flushed
+    assert sim_engine.decompressFile(ref, len(data)) == data
+    with pytest.raises(TypeError, match="outputsize does not match decoded input"):
+        sim_engine.decompressFile(ref, len(data) + 1)
+    buf = bytearray(len(data))
+    assert sim_engine.decompressFile(ref, buf) is buf and bytes(buf) == data
+    for bad in (0, 10, -1, 2.5):
+        with pytest.raises(ValueError, match="Invalid block size multiplier"):
+            sim_engine.compressFile(data, None, bad)
