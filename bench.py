@@ -1,0 +1,284 @@
+#!/usr/bin/env python
+"""bench.py -- bzip2 level-9 compress throughput (BASELINE.json metric) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--level 9] [--mb 100]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" = one pass of the hot path (Bzip2.compressFile at level 9) over one 100 MB batch of
+synthetic enwik8-like text per GPU (BASELINE.json configs[1]; at N > 1 every rank takes its own
+100 MB block-range shard of the N x 100 MB corpus: weak scaling, no collective on the data path).
+
+  value     whole-job MB/s (MB = 1e6 uncompressed input bytes) with the input resident in HBM,
+            timed on the device with CUDA events on the launching stream, max over ranks
+  e2e       same metric through the reference-facing host API (Bzip2.compressFile over host
+            buffers -> bz2b200_compress): pinned host input, H2D + kernels + D2H all inside the
+            timed region
+  roofline  the dominant kernel (k_rs_scatter, the radix-sort scatter of the BWT stage): algorithmic
+            bytes / live CUDA-event time vs the measured HBM copy peak (MEASURED_PEAKS.json)
+  cpu_baseline  the CPU oracle (a C port of the reference's algorithm, oracle/) on the host cores,
+            on a bounded sample of the same workload (rank 0, N = 1 only)
+
+--impl reference times that CPU port with all host threads on the same config/metric.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "bzip2-9 compress MB/s, byte-identical output"
+UNIT = "MB/s"
+
+
+def workload_desc(level, mb, n_gpus):
+    return {"workload": f"bzip2 level {level} ({level * 100} KB blocks) on {mb} MB synthetic enwik8-like text per GPU "
+                        f"(compressjs_flattened_b200.corpus.gen_text, seed 8; BASELINE.json configs[1])",
+            "level": level, "bytes_per_gpu": mb * 1_000_000, "parallelism": f"block-range shards x{n_gpus}, no collective",
+            "l2": "two distinct 100 MB input buffers alternate between steps (200 MB > 126 MB L2); sort state is 4.4 GB"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0, set()
+        for t, line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9 or not (t0 - 0.05 <= t <= t1 + 0.15):
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = max(mx, float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+def cpu_baseline(level, sample_mb, threads):
+    import oracle_binding as O
+    from compressjs_flattened_b200.corpus import gen_text
+    data = gen_text(sample_mb * 1_000_000, 8)
+    t0 = time.time()
+    out = O.compress(data, level, O.SORT_STABLE, threads=threads)
+    dt = time.time() - t0
+    return {"value": round(sample_mb / dt, 3), "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"first {sample_mb} MB of the workload, oracle/liboracle.so (C port of Bzip2_joined_.js: SA-IS BWT, same table optimiser), "
+                      f"block-parallel over {threads} pthreads, {dt:.1f} s; the reference itself is single-threaded JavaScript and Node is not installed here",
+            "out_bytes": len(out)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle_binding as O
+    from compressjs_flattened_b200.corpus import gen_text
+    threads = os.cpu_count() or 1
+    sample_mb = args.ref_mb
+    data = gen_text(sample_mb * 1_000_000, 8)
+    for _ in range(min(args.warmup, 1)):
+        O.compress(data[:5_000_000], args.level, threads=threads)
+    times = []
+    for _ in range(args.steps):
+        t0 = time.time()
+        O.compress(data, args.level, threads=threads)
+        times.append(time.time() - t0)
+    ms = 1e3 * sum(times) / len(times)
+    val = sample_mb / (ms / 1e3)
+    line = {"impl": "reference", "metric": METRIC, "value": round(val, 3), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(ms, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": workload_desc(args.level, args.mb, args.gpus),
+            "cpu_baseline": {"value": round(val, 3), "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": f"each step = first {sample_mb} MB of the workload through oracle/liboracle.so on {threads} pthreads "
+                                       "(Node is absent, so the reference's own JS cannot run; the oracle is its C restatement)"},
+            "e2e": {"value": round(val, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--level", type=int, default=9)
+    ap.add_argument("--mb", type=int, default=100)
+    ap.add_argument("--ref-mb", type=int, default=40)
+    ap.add_argument("--cpu-sample-mb", type=int, default=40)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-only", action="store_true", help="device-resident compress steps only (for ncu runs)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from compressjs_flattened_b200 import Bzip2Engine
+    from compressjs_flattened_b200.corpus import gen_text
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    eng = Bzip2Engine(local)
+    nbytes = args.mb * 1_000_000
+    chunks = args.mb
+    # two distinct shards per rank so consecutive steps never re-read a cached input (200 MB > L2)
+    host = [gen_text(nbytes, 8, first_chunk=(2 * rank + j) * chunks) for j in range(2)]
+    pinned = [torch.from_numpy(h).pin_memory() for h in host]
+    d_in = [p.to(dev) for p in pinned]
+    bound = eng.compress_bound(nbytes, args.level)
+    d_out = torch.empty((bound + 3) // 4 * 4, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident: `value` ----------------
+    for i in range(args.warmup):
+        out_len = eng.compress_device(d_in[i % 2].data_ptr(), nbytes, args.level, d_out.data_ptr(), d_out.numel())
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    barrier()
+    t0 = time.time()
+    dev_ms, dom_ms, dom_bytes, dom_launches, launches, stage = 0.0, 0.0, 0, 0, 0, [0.0] * 5
+    for i in range(args.steps):
+        out_len = eng.compress_device(d_in[i % 2].data_ptr(), nbytes, args.level, d_out.data_ptr(), d_out.numel())
+        st = eng.stats()
+        dev_ms += st.ms_total
+        dom_ms += st.dom_ms
+        dom_bytes += st.dom_bytes
+        dom_launches += st.dom_launches
+        launches += st.kernel_launches
+        for k in range(5):
+            stage[k] += st.ms_stage[k]
+    barrier()
+    t1 = time.time()
+    wall_ms = (t1 - t0) * 1e3
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    st_last = eng.stats()
+
+    if args.profile_only:
+        print(json.dumps({"profile_only": True, "ms_per_step": round(dev_ms / args.steps, 3), "launches_per_step": launches // args.steps}), flush=True)
+        return
+    # ---------------- end to end through the host API: `e2e` ----------------
+    L = eng._L
+    out_p, out_n = ctypes.POINTER(ctypes.c_uint8)(), ctypes.c_size_t()
+
+    def host_call(j):
+        rc = L.bz2b200_compress(eng._ctx, pinned[j].data_ptr(), nbytes, args.level, ctypes.byref(out_p), ctypes.byref(out_n))
+        if rc:
+            eng._raise(rc)
+        n = out_n.value
+        L.bz2b200_free(out_p)
+        return n
+
+    host_call(0)
+    barrier()
+    e0 = time.time()
+    e2e_out = 0
+    for i in range(args.steps):
+        e2e_out = host_call(i % 2)
+    barrier()
+    e2e_ms = (time.time() - e0) * 1e3
+
+    # ---------------- decompress (reported alongside) ----------------
+    comp = torch.empty(out_len, dtype=torch.uint8, device=dev)
+    comp.copy_(d_out[:out_len])
+    d_back = torch.empty(nbytes + 64, dtype=torch.uint8, device=dev)
+    dec_steps = max(1, min(args.steps, 3))
+    eng.decompress_device(comp.data_ptr(), out_len, False, d_back.data_ptr(), d_back.numel())
+    dec_ms = 0.0
+    for i in range(dec_steps):
+        got = eng.decompress_device(comp.data_ptr(), out_len, False, d_back.data_ptr(), d_back.numel())
+        dec_ms += eng.stats().ms_total
+    roundtrip_ok = bool(got == nbytes and torch.equal(d_back[:nbytes], d_in[(args.steps - 1) % 2]))
+
+    # ---------------- reduce over ranks ----------------
+    t = torch.tensor([dev_ms, wall_ms, e2e_ms, dec_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms_max, wall_ms_max, e2e_ms_max, dec_ms_max = [float(x) for x in t.tolist()]
+    if rank == 0:
+        peak, peak_src = peaks()
+        total_mb = world * args.mb * args.steps
+        achieved = dom_bytes / 1e9 / (dom_ms / 1e3) if dom_ms > 0 else 0.0
+        line = {
+            "metric": METRIC, "value": round(total_mb / (dev_ms_max / 1e3), 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(dev_ms_max / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic", "config": workload_desc(args.level, args.mb, world),
+            "e2e": {"value": round(total_mb / (e2e_ms_max / 1e3), 2), "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": int(e2e_out),
+                    "ms_per_step": round(e2e_ms_max / args.steps, 3), "api": "bz2b200_compress (host buffers; pinned input, pageable malloc'd output)"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "k_rs_scatter (BWT radix-sort scatter pass)", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                         "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": int(dom_bytes / max(dom_launches, 1)), "launches_per_step": dom_launches // args.steps,
+                         "avg_launch_ms": round(dom_ms / max(dom_launches, 1), 4), "share_of_step": round(dom_ms / dev_ms, 3) if dev_ms else None,
+                         "pipeline_algorithmic_GBps": round((1 + 12 * st_last.rle1_bytes / nbytes + 22 * st_last.mtf_syms / nbytes + 3 * out_len / nbytes)
+                                                            * nbytes / 1e9 / (dev_ms / args.steps / 1e3), 1)},
+            "stage_ms_per_step": {k: round(v / args.steps, 3) for k, v in zip(("rle1_cut_crc", "bwt", "mtf_rle2", "huffman_emit", "stitch"), stage)},
+            "wall_ms_per_step": round(wall_ms_max / args.steps, 3),
+            "clocks": clocks,
+            "decompress": {"value": round(world * args.mb * dec_steps / (dec_ms_max / 1e3), 2), "unit": UNIT, "ms_per_step": round(dec_ms_max / dec_steps, 3),
+                           "roundtrip_bit_exact": roundtrip_ok},
+            "out_bytes_per_step": int(out_len), "blocks_per_step": int(st_last.n_blocks), "sort_rounds": int(st_last.sort_rounds),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args.level, args.cpu_sample_mb, os.cpu_count() or 1)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

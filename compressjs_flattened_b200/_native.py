@@ -17,7 +17,8 @@ class Stats(C.Structure):
     _fields_ = [("in_bytes", C.c_uint64), ("out_bytes", C.c_uint64), ("n_blocks", C.c_uint32),
                 ("sort_rounds", C.c_uint32), ("rle1_bytes", C.c_uint64), ("mtf_syms", C.c_uint64),
                 ("sort_slots", C.c_uint64), ("kernel_launches", C.c_uint32), ("d1_triggered", C.c_uint32),
-                ("ms_total", C.c_float), ("ms_stage", C.c_float * 8)]
+                ("ms_total", C.c_float), ("ms_stage", C.c_float * 8),
+                ("dom_ms", C.c_float), ("dom_launches", C.c_uint32), ("dom_bytes", C.c_uint64)]
 
 
 class BlockRec(C.Structure):

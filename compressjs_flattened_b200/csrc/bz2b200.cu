@@ -44,6 +44,8 @@ struct Ctx {
   i64 last_bs = 0, last_as = 0;
   cudaEvent_t ev[10]{};
   bool ev_ok = false;
+  std::vector<cudaEvent_t> dom_ev;  // start/stop pairs around the dominant kernel's launches
+  size_t dom_used = 0;
   Ctx() {
     DevBuf *all[] = {&in, &tile_last, &tile_first, &head_carry, &tile_emit, &g_tile, &recs, &nblk, &blk, &crcpart, &pow256,
                      &isa, &keysA, &keysB, &valsA, &valsB, &rankA, &rankB, &posA, &posB, &rnew, &hist, &digit_base,
@@ -190,6 +192,9 @@ int compress_device(Ctx *c, const u8 *d_in, size_t n_, int level, u32 *d_out, si
     unsigned Ta = (unsigned)tiles0;
     LAUNCH(k_keys_init, Ta, SEG_THREADS, 0, P<u8>(c->blk), BS, P<BlockRec>(c->recs), tile0, tblk, kA, vA, rank, pos);
     u32 h = 5;
+    u64 totals_active = 0;
+    for (auto &r : hrecs) totals_active += r.n;
+    c->dom_used = 0;
     for (int round = 0;; round++) {
       c->st.sort_rounds++;
       c->st.sort_slots += (u64)Ta * SORT_TILE;
@@ -198,7 +203,18 @@ int compress_device(Ctx *c, const u8 *d_in, size_t n_, int level, u32 *d_out, si
       for (int pass = 0; pass < 5; pass++) {
         LAUNCH(k_rs_hist, Ta, SORT_THREADS, 0, ki, seg_cnt, tile0, tblk, pass * 8, P<u32>(c->hist));
         LAUNCH(k_rs_scan, (unsigned)nb, 256, 0, P<u32>(c->hist), tile0, P<u32>(c->digit_base));
+        if (c->ev_ok) {
+          if (c->dom_used + 2 > c->dom_ev.size()) {
+            cudaEvent_t a, b;
+            CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+            c->dom_ev.push_back(a); c->dom_ev.push_back(b);
+          }
+          CK(cudaEventRecord(c->dom_ev[c->dom_used], c->stream));
+        }
         LAUNCH(k_rs_scatter, Ta, SORT_THREADS, 0, ki, vi, ko, vo, seg_cnt, tile0, tblk, pass * 8, P<u32>(c->hist), P<u32>(c->digit_base));
+        if (c->ev_ok) { CK(cudaEventRecord(c->dom_ev[c->dom_used + 1], c->stream)); c->dom_used += 2; }
+        c->st.dom_launches++;
+        c->st.dom_bytes += 24ull * totals_active;
         u64 *tk = ki; ki = ko; ko = tk;
         u32 *tv = vi; vi = vo; vo = tv;
       }
@@ -215,6 +231,7 @@ int compress_device(Ctx *c, const u8 *d_in, size_t n_, int level, u32 *d_out, si
       { u32 *t; t = seg_cnt; seg_cnt = seg_cnt_n; seg_cnt_n = t; t = tile0; tile0 = tile0_n; tile0_n = t;
         t = tblk; tblk = tblk_n; tblk_n = t; t = rank; rank = rank_n; rank_n = t; t = pos; pos = pos_n; pos_n = t; }
       Ta = (unsigned)totals[0];
+      totals_active = totals[1];
       if (totals[1] == 0) break;
       LAUNCH(k_keys_round, Ta, SEG_THREADS, 0, P<BlockRec>(c->recs), seg_cnt, tile0, tblk, P<u32>(c->isa), BS, h, vA, rank, kA);
       h = h >= (1u << 24) ? h : h * 2;
@@ -284,6 +301,11 @@ int compress_device(Ctx *c, const u8 *d_in, size_t n_, int level, u32 *d_out, si
   if (c->ev_ok) {
     for (int i = 0; i < 5; i++) CK(cudaEventElapsedTime(&c->st.ms_stage[i], c->ev[i], c->ev[i + 1]));
     CK(cudaEventElapsedTime(&c->st.ms_total, c->ev[0], c->ev[5]));
+    for (size_t i = 0; i + 1 < c->dom_used; i += 2) {
+      float ms = 0;
+      CK(cudaEventElapsedTime(&ms, c->dom_ev[i], c->dom_ev[i + 1]));
+      c->st.dom_ms += ms;
+    }
   }
   return BZ2B200_OK;
 }
@@ -317,6 +339,7 @@ void bz2b200_destroy(bz2b200_ctx *ctx) {
   for (DevBuf *b : c->pool) if (b->p) cudaFree(b->p);
   if (c->h_pin) cudaFreeHost(c->h_pin);
   if (c->ev_ok) for (auto &e : c->ev) cudaEventDestroy(e);
+  for (auto &e : c->dom_ev) cudaEventDestroy(e);
   cudaStreamDestroy(c->stream);
   delete c;
 }

@@ -52,6 +52,11 @@ typedef struct {
   uint32_t d1_triggered;
   float ms_total;            /* device time of the last call (CUDA events) */
   float ms_stage[8];         /* compress: rle1, bwt, mtf, huff, stitch; decompress: scan, huff, ibwt, out */
+  /* dominant kernel of the last compress (k_rs_scatter, the radix-sort scatter pass), timed live with
+   * CUDA events on the launching stream; bytes = algorithmic bytes (24 B per sorted slot per pass) */
+  float dom_ms;
+  uint32_t dom_launches;
+  uint64_t dom_bytes;
 } bz2b200_stats;
 
 /* One context per calling thread / per GPU.  `device` = CUDA ordinal. */
