@@ -32,7 +32,7 @@ struct Ctx {
   DevBuf in, tile_last, tile_first, head_carry, tile_emit, g_tile, recs, nblk, blk, crcpart, pow256;
   DevBuf isa, keysA, keysB, valsA, valsB, rankA, rankB, posA, posB, rnew, hist, digit_base;
   DevBuf seg_cnt, seg_cnt2, seg_tile0, seg_tile0b, tile_blk, tile_blkb, tile_i0, tile_i1, tile_i2, tile_i3, totals;
-  DevBuf Lcol, ranks, lastocc, A, freq, meta, W, bit_off, scrc, out, out_len;
+  DevBuf Lcol, ranks, lastocc, A, freq, meta, W, bit_off, scrc, out, out_len, used_bits;
   // decode-side buffers
   DevBuf d_in, cand, ncand, dmeta, dsyms, dL, dtt, dwalk, dblk, dout, dmisc;
   // host staging (pinned)
@@ -50,7 +50,7 @@ struct Ctx {
     DevBuf *all[] = {&in, &tile_last, &tile_first, &head_carry, &tile_emit, &g_tile, &recs, &nblk, &blk, &crcpart, &pow256,
                      &isa, &keysA, &keysB, &valsA, &valsB, &rankA, &rankB, &posA, &posB, &rnew, &hist, &digit_base,
                      &seg_cnt, &seg_cnt2, &seg_tile0, &seg_tile0b, &tile_blk, &tile_blkb, &tile_i0, &tile_i1, &tile_i2, &tile_i3, &totals,
-                     &Lcol, &ranks, &lastocc, &A, &freq, &meta, &W, &bit_off, &scrc, &out, &out_len,
+                     &Lcol, &ranks, &lastocc, &A, &freq, &meta, &W, &bit_off, &scrc, &out, &out_len, &used_bits,
                      &d_in, &cand, &ncand, &dmeta, &dsyms, &dL, &dtt, &dwalk, &dblk, &dout, &dmisc};
     for (DevBuf *b : all) pool.push_back(b);
   }
@@ -246,8 +246,14 @@ int compress_device(Ctx *c, const u8 *d_in, size_t n_, int level, u32 *d_out, si
     ENS(c->lastocc, 4 * 256 * (size_t)nseg_max * nb);
     ENS(c->A, 2 * (size_t)nb * AS);
     ENS(c->freq, 4 * BZ_MAX_SYMS * (size_t)nb);
-    LAUNCH(k_mtf_rle2, (unsigned)nb, MTF_THREADS, 0, P<u8>(c->Lcol), BS, P<BlockRec>(c->recs), P<int>(c->lastocc), nseg_max * 256,
-           P<u8>(c->ranks), P<u16>(c->A), AS, P<u32>(c->freq), P<BlockMeta>(c->meta));
+    ENS(c->used_bits, 32 * (size_t)nb);
+    CK(cudaMemsetAsync(c->used_bits.p, 0, 32 * (size_t)nb, c->stream));
+    LAUNCH(k_mtf_lastocc, dim3((unsigned)((nseg_max + 7) / 8), (unsigned)nb), 256, 0, P<u8>(c->Lcol), BS, P<BlockRec>(c->recs), P<int>(c->lastocc),
+           nseg_max * 256, P<u32>(c->used_bits));
+    LAUNCH(k_mtf_scan, (unsigned)nb, 256, 0, P<BlockRec>(c->recs), P<int>(c->lastocc), nseg_max * 256, P<u32>(c->used_bits), P<BlockMeta>(c->meta));
+    LAUNCH(k_mtf_ranks, dim3((unsigned)((nseg_max + 7) / 8), (unsigned)nb), 256, 0, P<u8>(c->Lcol), BS, P<BlockRec>(c->recs), P<int>(c->lastocc),
+           nseg_max * 256, P<u8>(c->ranks));
+    LAUNCH(k_mtf_rle2, (unsigned)nb, MTF_THREADS, 0, P<BlockRec>(c->recs), P<u8>(c->ranks), BS, P<u16>(c->A), AS, P<u32>(c->freq), P<BlockMeta>(c->meta));
     if ((rc = mark(c, 3))) return rc;
 
     // ---- S4/S5 Huffman + emission ----
