@@ -9,8 +9,9 @@
 //   ISA[i]  = current rank of rotation i = SA index of the first slot of its group
 //   active  = compacted list of the slots whose group still has > 1 member, in SA
 //             order: (a_idx = rotation, a_rank = its group rank, a_pos = SA index of the slot)
-//   round h : key = (a_rank << 20) | ISA[(i+h) mod n]  -> batched LSD radix sort of
-//             the 40-bit keys (5 passes of 8 bits) -> new group heads where keys
+//   round h : key = (a_rank << 40) | ISA[(i+h) mod n] << 20 | i  -> batched LSD radix sort of
+//             bits 20..59 (5 passes of 8 bits); the rotation index rides in the low 20 bits, so a
+//             pass moves keys only -> new group heads where keys
 //             change -> ISA update -> singletons leave the active list.
 //   start   : key = first 5 bytes of the rotation (same 40-bit machinery), h = 5.
 //   h >= n  : remaining ties are identical rotations: key2 = n-1-i (descending index).
@@ -60,8 +61,7 @@ __global__ void k_seg_init(const BlockRec *__restrict__ recs, int nb, u32 *__res
 // mode 0: first five bytes of each rotation; also initialises a_pos/a_rank/vals for the full block.
 __global__ void __launch_bounds__(SEG_THREADS) k_keys_init(const u8 *__restrict__ blk, i64 blk_stride, const BlockRec *__restrict__ recs,
                                                            const u32 *__restrict__ seg_tile0, const u32 *__restrict__ tile_blk,
-                                                           u64 *__restrict__ keys, u32 *__restrict__ vals, u32 *__restrict__ a_rank,
-                                                           u32 *__restrict__ a_pos) {
+                                                           u64 *__restrict__ keys, u32 *__restrict__ a_rank, u32 *__restrict__ a_pos) {
   u32 tile = blockIdx.x, p = tile_blk[tile];
   u32 n = recs[p].n;
   const u8 *T = blk + (i64)p * blk_stride;
@@ -77,8 +77,7 @@ __global__ void __launch_bounds__(SEG_THREADS) k_keys_init(const u8 *__restrict_
       x = x + 1 == n ? 0 : x + 1;
     }
     u64 g = g0 + (lj - l0);
-    keys[g] = key;
-    vals[g] = lj;
+    keys[g] = (key << 20) | lj;
     a_rank[g] = 0;
     a_pos[g] = lj;
   }
@@ -101,7 +100,7 @@ __global__ void __launch_bounds__(SEG_THREADS) k_keys_round(const BlockRec *__re
     u32 i = a_idx[g], k2;
     if (h >= n) k2 = n - 1 - i;
     else { u32 x = i + h; if (x >= n) x -= n; k2 = I[x]; }
-    keys[g] = ((u64)a_rank[g] << 20) | k2;
+    keys[g] = ((u64)a_rank[g] << 40) | ((u64)k2 << 20) | i;
   }
 }
 
@@ -141,8 +140,7 @@ __global__ void __launch_bounds__(256) k_rs_scan(u32 *__restrict__ hist, const u
   u32 base = block_excl_sum<u32>(acc, tot, ws);
   digit_base[(u64)p * 256 + d] = base;
 }
-__global__ void __launch_bounds__(SORT_THREADS) k_rs_scatter(const u64 *__restrict__ keys_in, const u32 *__restrict__ vals_in,
-                                                             u64 *__restrict__ keys_out, u32 *__restrict__ vals_out,
+__global__ void __launch_bounds__(SORT_THREADS) k_rs_scatter(const u64 *__restrict__ keys_in, u64 *__restrict__ keys_out,
                                                              const u32 *__restrict__ seg_cnt, const u32 *__restrict__ seg_tile0,
                                                              const u32 *__restrict__ tile_blk, int shift, const u32 *__restrict__ hist,
                                                              const u32 *__restrict__ digit_base) {
@@ -156,14 +154,13 @@ __global__ void __launch_bounds__(SORT_THREADS) k_rs_scatter(const u64 *__restri
   if (threadIdx.x < 256) base[threadIdx.x] = digit_base[(u64)p * 256 + threadIdx.x] + hist[(u64)tile * 256 + threadIdx.x];
   __syncthreads();
   u64 key[SORT_E];
-  u32 val[SORT_E], rk[SORT_E];
+  u32 rk[SORT_E];
   u32 lt = (1u << lane) - 1;
 #pragma unroll
   for (int e = 0; e < SORT_E; e++) {
     u32 o = (u32)w * (32 * SORT_E) + e * 32 + lane;
     bool ok = l0 + o < cnt;
     key[e] = ok ? keys_in[g0 + o] : 0;
-    val[e] = ok ? vals_in[g0 + o] : 0;
     u32 d = ok ? ((u32)(key[e] >> shift) & 255u) : 256u;
     u32 peers = __match_any_sync(FULL_MASK, d);
     int leader = __ffs((int)peers) - 1;
@@ -186,7 +183,6 @@ __global__ void __launch_bounds__(SORT_THREADS) k_rs_scatter(const u64 *__restri
       u32 d = (u32)(key[e] >> shift) & 255u;
       u64 dst = gp + base[d] + wcnt[w][d] + rk[e];
       keys_out[dst] = key[e];
-      vals_out[dst] = val[e];
     }
   }
 }
@@ -201,7 +197,7 @@ __device__ __forceinline__ void seg_load_flags(const u64 *__restrict__ keys, u64
   for (int e = 0; e < SEG_E; e++) {
     if (lbase + e < cnt) {
       k[e] = keys[g + e];
-      if (lbase + e == 0 || k[e] != prev) flags |= 1u << e;
+      if (lbase + e == 0 || (k[e] >> 20) != (prev >> 20)) flags |= 1u << e;
       prev = k[e];
     }
   }
@@ -245,8 +241,7 @@ __global__ void __launch_bounds__(256) k_seg_scan(const u32 *__restrict__ seg_ti
   if (mode == 1 && threadIdx.x == 0) seg_cnt_new[p] = (u32)carry;
 }
 // new rank of every active slot, ISA update, keep flag, per-tile kept count
-__global__ void __launch_bounds__(SEG_THREADS) k_rank_apply(const u64 *__restrict__ keys, const u32 *__restrict__ idx,
-                                                            const u32 *__restrict__ a_pos, const u32 *__restrict__ seg_cnt,
+__global__ void __launch_bounds__(SEG_THREADS) k_rank_apply(const u64 *__restrict__ keys, const u32 *__restrict__ a_pos, const u32 *__restrict__ seg_cnt,
                                                             const u32 *__restrict__ seg_tile0, const u32 *__restrict__ tile_blk,
                                                             const int *__restrict__ tile_carry, u32 *__restrict__ isa, i64 isa_stride,
                                                             u32 *__restrict__ r_new, int *__restrict__ tile_keep) {
@@ -265,7 +260,7 @@ __global__ void __launch_bounds__(SEG_THREADS) k_rank_apply(const u64 *__restric
   // is the slot after my last one a head?  (needed for the singleton test)
   u32 nxt = lbase + SEG_E;
   bool next_head = true;
-  if (nxt < cnt && lbase < cnt) next_head = keys[g + SEG_E] != k[SEG_E - 1];
+  if (nxt < cnt && lbase < cnt) next_head = (keys[g + SEG_E] >> 20) != (k[SEG_E - 1] >> 20);
   int kept = 0;
   u32 *I = isa + (i64)p * isa_stride;
 #pragma unroll
@@ -277,7 +272,7 @@ __global__ void __launch_bounds__(SEG_THREADS) k_rank_apply(const u64 *__restric
       bool nh = e + 1 < SEG_E ? (lj + 1 >= cnt || ((flags >> (e + 1)) & 1u)) : (lj + 1 >= cnt || next_head);
       u32 rank = a_pos[gp + (u32)cur];
       bool single = head && nh;
-      I[idx[g + e]] = rank;
+      I[(u32)(k[e] & 0xFFFFFu)] = rank;
       r_new[g + e] = rank | (single ? 0u : KEEP_BIT);
       kept += single ? 0 : 1;
     }
@@ -286,7 +281,7 @@ __global__ void __launch_bounds__(SEG_THREADS) k_rank_apply(const u64 *__restric
   if (threadIdx.x == 0) tile_keep[tile] = kept;
 }
 // move the surviving slots to the next round's (re-padded) layout
-__global__ void __launch_bounds__(SEG_THREADS) k_compact(const u32 *__restrict__ idx, const u32 *__restrict__ a_pos, const u32 *__restrict__ r_new,
+__global__ void __launch_bounds__(SEG_THREADS) k_compact(const u64 *__restrict__ keys, const u32 *__restrict__ a_pos, const u32 *__restrict__ r_new,
                                                          const u32 *__restrict__ seg_cnt, const u32 *__restrict__ seg_tile0,
                                                          const u32 *__restrict__ tile_blk, const int *__restrict__ keep_prefix,
                                                          const u32 *__restrict__ seg_tile0_new, u32 *__restrict__ idx_out,
@@ -309,7 +304,7 @@ __global__ void __launch_bounds__(SEG_THREADS) k_compact(const u32 *__restrict__
 #pragma unroll
   for (int e = 0; e < SEG_E; e++) {
     if (r[e] & KEEP_BIT) {
-      idx_out[dst] = idx[g + e];
+      idx_out[dst] = (u32)(keys[g + e] & 0xFFFFFu);
       rank_out[dst] = r[e] & ~KEEP_BIT;
       pos_out[dst] = a_pos[g + e];
       dst++;

@@ -170,7 +170,7 @@ int compress_device(Ctx *c, const u8 *d_in, size_t n_, int level, u32 *d_out, si
     size_t tiles0 = slots / SORT_TILE;
     ENS(c->isa, 4 * (size_t)nb * BS);
     ENS(c->keysA, 8 * slots); ENS(c->keysB, 8 * slots);
-    ENS(c->valsA, 4 * slots); ENS(c->valsB, 4 * slots);
+    ENS(c->valsA, 4 * slots);
     ENS(c->rankA, 4 * slots); ENS(c->rankB, 4 * slots);
     ENS(c->posA, 4 * slots); ENS(c->posB, 4 * slots);
     ENS(c->rnew, 4 * slots);
@@ -185,12 +185,12 @@ int compress_device(Ctx *c, const u8 *d_in, size_t n_, int level, u32 *d_out, si
     u32 *tblk = P<u32>(c->tile_blk), *tblk_n = P<u32>(c->tile_blkb);
     u32 *rank = P<u32>(c->rankA), *rank_n = P<u32>(c->rankB), *pos = P<u32>(c->posA), *pos_n = P<u32>(c->posB);
     u64 *kA = P<u64>(c->keysA), *kB = P<u64>(c->keysB);
-    u32 *vA = P<u32>(c->valsA), *vB = P<u32>(c->valsB);
+    u32 *vA = P<u32>(c->valsA);
     u64 totals[2] = {0, 0};
     LAUNCH(k_seg_init, (unsigned)((nb + 255) / 256), 256, 0, P<BlockRec>(c->recs), nb, seg_cnt);
     LAUNCH(k_tilemap, 1, 1024, 0, seg_cnt, nb, tile0, tblk, P<u64>(c->totals));
     unsigned Ta = (unsigned)tiles0;
-    LAUNCH(k_keys_init, Ta, SEG_THREADS, 0, P<u8>(c->blk), BS, P<BlockRec>(c->recs), tile0, tblk, kA, vA, rank, pos);
+    LAUNCH(k_keys_init, Ta, SEG_THREADS, 0, P<u8>(c->blk), BS, P<BlockRec>(c->recs), tile0, tblk, kA, rank, pos);
     u32 h = 5;
     u64 totals_active = 0;
     for (auto &r : hrecs) totals_active += r.n;
@@ -199,9 +199,8 @@ int compress_device(Ctx *c, const u8 *d_in, size_t n_, int level, u32 *d_out, si
       c->st.sort_rounds++;
       c->st.sort_slots += (u64)Ta * SORT_TILE;
       u64 *ki = kA, *ko = kB;
-      u32 *vi = vA, *vo = vB;
       for (int pass = 0; pass < 5; pass++) {
-        LAUNCH(k_rs_hist, Ta, SORT_THREADS, 0, ki, seg_cnt, tile0, tblk, pass * 8, P<u32>(c->hist));
+        LAUNCH(k_rs_hist, Ta, SORT_THREADS, 0, ki, seg_cnt, tile0, tblk, 20 + pass * 8, P<u32>(c->hist));
         LAUNCH(k_rs_scan, (unsigned)nb, 256, 0, P<u32>(c->hist), tile0, P<u32>(c->digit_base));
         if (c->ev_ok) {
           if (c->dom_used + 2 > c->dom_ev.size()) {
@@ -211,21 +210,20 @@ int compress_device(Ctx *c, const u8 *d_in, size_t n_, int level, u32 *d_out, si
           }
           CK(cudaEventRecord(c->dom_ev[c->dom_used], c->stream));
         }
-        LAUNCH(k_rs_scatter, Ta, SORT_THREADS, 0, ki, vi, ko, vo, seg_cnt, tile0, tblk, pass * 8, P<u32>(c->hist), P<u32>(c->digit_base));
+        LAUNCH(k_rs_scatter, Ta, SORT_THREADS, 0, ki, ko, seg_cnt, tile0, tblk, 20 + pass * 8, P<u32>(c->hist), P<u32>(c->digit_base));
         if (c->ev_ok) { CK(cudaEventRecord(c->dom_ev[c->dom_used + 1], c->stream)); c->dom_used += 2; }
         c->st.dom_launches++;
-        c->st.dom_bytes += 24ull * totals_active;
+        c->st.dom_bytes += 16ull * totals_active;
         u64 *tk = ki; ki = ko; ko = tk;
-        u32 *tv = vi; vi = vo; vo = tv;
       }
-      // sorted data is now in (ki, vi) == (kB, vB)
+      // sorted keys are now in ki == kB
       LAUNCH(k_sub_heads, Ta, SEG_THREADS, 0, ki, seg_cnt, tile0, tblk, P<int>(c->tile_i0));
       LAUNCH(k_seg_scan, (unsigned)nb, 256, 0, tile0, 0, P<int>(c->tile_i0), P<int>(c->tile_i1), (u32 *)nullptr);
-      LAUNCH(k_rank_apply, Ta, SEG_THREADS, 0, ki, vi, pos, seg_cnt, tile0, tblk, P<int>(c->tile_i1), P<u32>(c->isa), BS, P<u32>(c->rnew),
+      LAUNCH(k_rank_apply, Ta, SEG_THREADS, 0, ki, pos, seg_cnt, tile0, tblk, P<int>(c->tile_i1), P<u32>(c->isa), BS, P<u32>(c->rnew),
              P<int>(c->tile_i2));
       LAUNCH(k_seg_scan, (unsigned)nb, 256, 0, tile0, 1, P<int>(c->tile_i2), P<int>(c->tile_i3), seg_cnt_n);
       LAUNCH(k_tilemap, 1, 1024, 0, seg_cnt_n, nb, tile0_n, tblk_n, P<u64>(c->totals));
-      LAUNCH(k_compact, Ta, SEG_THREADS, 0, vi, pos, P<u32>(c->rnew), seg_cnt, tile0, tblk, P<int>(c->tile_i3), tile0_n, vA, rank_n, pos_n);
+      LAUNCH(k_compact, Ta, SEG_THREADS, 0, ki, pos, P<u32>(c->rnew), seg_cnt, tile0, tblk, P<int>(c->tile_i3), tile0_n, vA, rank_n, pos_n);
       CK(cudaMemcpyAsync(totals, c->totals.p, sizeof totals, cudaMemcpyDeviceToHost, c->stream));
       CK(cudaStreamSynchronize(c->stream));
       { u32 *t; t = seg_cnt; seg_cnt = seg_cnt_n; seg_cnt_n = t; t = tile0; tile0 = tile0_n; tile0_n = t;

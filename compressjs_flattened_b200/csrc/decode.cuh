@@ -348,15 +348,21 @@ __global__ void k_dec_seg_init(const DecBlk *__restrict__ blks, const u32 *__res
 }
 __global__ void __launch_bounds__(SEG_THREADS) k_dec_keys(const u8 *__restrict__ dL, i64 l_stride, const u32 *__restrict__ order,
                                                           const u32 *__restrict__ seg_cnt, const u32 *__restrict__ seg_tile0,
-                                                          const u32 *__restrict__ tile_blk, u64 *__restrict__ keys, u32 *__restrict__ vals) {
+                                                          const u32 *__restrict__ tile_blk, u64 *__restrict__ keys) {
   u32 tile = blockIdx.x, p = tile_blk[tile];
   u32 cnt = seg_cnt[p], l0 = (tile - seg_tile0[p]) * SORT_TILE;
   const u8 *Lk = dL + (i64)order[p] * l_stride;
   u64 g0 = (u64)tile * SORT_TILE;
   for (int e = 0; e < SEG_E; e++) {
     u32 lj = l0 + e * SEG_THREADS + threadIdx.x;
-    if (lj < cnt) { keys[g0 + (lj - l0)] = Lk[lj]; vals[g0 + (lj - l0)] = lj; }
+    if (lj < cnt) keys[g0 + (lj - l0)] = ((u64)Lk[lj] << 20) | lj;
   }
+}
+
+// sorted keys -> T vector (position of the slot's byte in the L column)
+__global__ void k_dec_extract(const u64 *__restrict__ keys, u32 *__restrict__ tt, u64 nslots) {
+  u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < nslots) tt[g] = (u32)(keys[g] & 0xFFFFFu);
 }
 
 // ---- K-U4b: list ranking ----------------------------------------------------------------------

@@ -163,17 +163,18 @@ static int decode_device(Ctx *c, const u8 *d_in, size_t n, int multistream, int 
   ENS(c->tile_blk, 4 * (tiles + 1));
   ENS(c->totals, 64);
   ENS(c->keysA, 8 * (slots + 1)); ENS(c->keysB, 8 * (slots + 1));
-  ENS(c->valsA, 4 * (slots + 1)); ENS(c->valsB, 4 * (slots + 1));
+  ENS(c->valsB, 4 * (slots + 1));
   ENS(c->hist, 4 * 256 * (tiles + 1)); ENS(c->digit_base, 4 * 256 * (size_t)nb);
   LAUNCH(k_dec_seg_init, (unsigned)((nb + 255) / 256), 256, 0, P<DecBlk>(c->dmeta), d_order, nb, P<u32>(c->seg_cnt));
   LAUNCH(k_tilemap, 1, 1024, 0, P<u32>(c->seg_cnt), nb, P<u32>(c->seg_tile0), P<u32>(c->tile_blk), P<u64>(c->totals));
   if (tiles) {
     LAUNCH(k_dec_keys, (unsigned)tiles, SEG_THREADS, 0, P<u8>(c->dL), LS, d_order, P<u32>(c->seg_cnt), P<u32>(c->seg_tile0), P<u32>(c->tile_blk),
-           P<u64>(c->keysA), P<u32>(c->valsA));
-    LAUNCH(k_rs_hist, (unsigned)tiles, SORT_THREADS, 0, P<u64>(c->keysA), P<u32>(c->seg_cnt), P<u32>(c->seg_tile0), P<u32>(c->tile_blk), 0, P<u32>(c->hist));
+           P<u64>(c->keysA));
+    LAUNCH(k_rs_hist, (unsigned)tiles, SORT_THREADS, 0, P<u64>(c->keysA), P<u32>(c->seg_cnt), P<u32>(c->seg_tile0), P<u32>(c->tile_blk), 20, P<u32>(c->hist));
     LAUNCH(k_rs_scan, (unsigned)nb, 256, 0, P<u32>(c->hist), P<u32>(c->seg_tile0), P<u32>(c->digit_base));
-    LAUNCH(k_rs_scatter, (unsigned)tiles, SORT_THREADS, 0, P<u64>(c->keysA), P<u32>(c->valsA), P<u64>(c->keysB), P<u32>(c->valsB), P<u32>(c->seg_cnt),
-           P<u32>(c->seg_tile0), P<u32>(c->tile_blk), 0, P<u32>(c->hist), P<u32>(c->digit_base));
+    LAUNCH(k_rs_scatter, (unsigned)tiles, SORT_THREADS, 0, P<u64>(c->keysA), P<u64>(c->keysB), P<u32>(c->seg_cnt),
+           P<u32>(c->seg_tile0), P<u32>(c->tile_blk), 20, P<u32>(c->hist), P<u32>(c->digit_base));
+    LAUNCH(k_dec_extract, (unsigned)((slots + 255) / 256), 256, 0, P<u64>(c->keysB), P<u32>(c->valsB), (u64)slots);
   }
   // ---- K-U4b: list ranking ----
   const i64 BS = round_up((i64)max_cnt + 8, 256);
