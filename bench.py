@@ -41,7 +41,7 @@ UNIT = "MB/s"
 def workload_desc(level, mb, n_gpus):
     return {"workload": f"bzip2 level {level} ({level * 100} KB blocks) on {mb} MB synthetic enwik8-like text per GPU "
                         f"(compressjs_flattened_b200.corpus.gen_text, seed 8; BASELINE.json configs[1])",
-            "level": level, "bytes_per_gpu": mb * 1_000_000, "parallelism": f"block-range shards x{n_gpus}, no collective",
+            "level": level, "bytes_per_gpu": mb * 1_000_000, "parallelism": f"block-range shards x{n_gpus} of one {mb * n_gpus} MB stream; cross-rank: first-block offset chain + bit-length exscan (scalars), no data-path collective",
             "l2": "two distinct 100 MB input buffers alternate between steps (200 MB > 126 MB L2); sort state is 4.4 GB"}
 
 
@@ -166,12 +166,16 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     eng = Bzip2Engine(local)
+    from compressjs_flattened_b200.sharded import compress_shard, gather_and_stitch
     nbytes = args.mb * 1_000_000
     chunks = args.mb
-    # two distinct shards per rank so consecutive steps never re-read a cached input (200 MB > L2)
-    host = [gen_text(nbytes, 8, first_chunk=(2 * rank + j) * chunks) for j in range(2)]
+    halo_mb = 2 if (world > 1 and rank < world - 1) else 0   # bytes after the slice that the last owned block may need
+    # two distinct corpora (j) so consecutive steps never re-read a cached input (200 MB > L2); rank r owns
+    # bytes [r*mb MB, (r+1)*mb MB) of corpus j = one block-range shard of a world*mb MB stream
+    host = [gen_text(nbytes + halo_mb * 1_000_000, 8, first_chunk=j * world * chunks + rank * chunks) for j in range(2)]
     pinned = [torch.from_numpy(h).pin_memory() for h in host]
     d_in = [p.to(dev) for p in pinned]
+    navail = nbytes + halo_mb * 1_000_000
     bound = eng.compress_bound(nbytes, args.level)
     d_out = torch.empty((bound + 3) // 4 * 4, dtype=torch.uint8, device=dev)
     torch.cuda.synchronize()
@@ -182,9 +186,16 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def dev_step(i):
+        if world == 1:
+            return eng.compress_device(d_in[i % 2].data_ptr(), nbytes, args.level, d_out.data_ptr(), d_out.numel())
+        n, _, _ = compress_shard(eng, None, rank * nbytes, nbytes, args.level, rank == world - 1, rank=rank, world=world, device=dev,
+                                 device_ptr=d_in[i % 2].data_ptr(), nbytes=navail, to_host=False)
+        return n
+
     # ---------------- device-resident: `value` ----------------
     for i in range(args.warmup):
-        out_len = eng.compress_device(d_in[i % 2].data_ptr(), nbytes, args.level, d_out.data_ptr(), d_out.numel())
+        out_len = dev_step(i)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -193,7 +204,7 @@ def main():
     t0 = time.time()
     dev_ms, dom_ms, dom_bytes, dom_launches, launches, stage = 0.0, 0.0, 0, 0, 0, [0.0] * 5
     for i in range(args.steps):
-        out_len = eng.compress_device(d_in[i % 2].data_ptr(), nbytes, args.level, d_out.data_ptr(), d_out.numel())
+        out_len = dev_step(i)
         st = eng.stats()
         dev_ms += st.ms_total
         dom_ms += st.dom_ms
@@ -216,6 +227,9 @@ def main():
     out_p, out_n = ctypes.POINTER(ctypes.c_uint8)(), ctypes.c_size_t()
 
     def host_call(j):
+        if world > 1:  # host slice+halo in, host segment out, through the shard API
+            seg, _, _ = compress_shard(eng, host[j], rank * nbytes, nbytes, args.level, rank == world - 1, rank=rank, world=world, device=dev)
+            return len(seg)
         rc = L.bz2b200_compress(eng._ctx, pinned[j].data_ptr(), nbytes, args.level, ctypes.byref(out_p), ctypes.byref(out_n))
         if rc:
             eng._raise(rc)
@@ -232,6 +246,21 @@ def main():
     barrier()
     e2e_ms = (time.time() - e0) * 1e3
 
+    # ---------------- N > 1: stitch the ranks' segments into ONE stream and check it ----------------
+    stitched = None
+    if world > 1:
+        seg, info, _ = compress_shard(eng, host[0], rank * nbytes, nbytes, args.level, rank == world - 1, rank=rank, world=world, device=dev)
+        whole = gather_and_stitch(eng, seg, info, args.level)
+        if rank == 0:
+            back = eng.decompressFile(whole)   # verifies every block CRC and the combined CRC
+            stitched = {"bytes": len(whole), "decoded_bytes": len(back), "blocks": int(eng.stats().n_blocks),
+                        "crc_checked_roundtrip": len(back) == world * nbytes and back[:nbytes] == host[0][:nbytes].tobytes()}
+            del back, whole
+        # per-rank decompress below works on an ordinary single-rank stream of this rank's slice
+        out_len = eng.compress_device(d_in[0].data_ptr(), nbytes, args.level, d_out.data_ptr(), d_out.numel())
+        last_in = 0
+    else:
+        last_in = (args.steps - 1) % 2
     # ---------------- decompress (reported alongside) ----------------
     comp = torch.empty(out_len, dtype=torch.uint8, device=dev)
     comp.copy_(d_out[:out_len])
@@ -242,7 +271,7 @@ def main():
     for i in range(dec_steps):
         got = eng.decompress_device(comp.data_ptr(), out_len, False, d_back.data_ptr(), d_back.numel())
         dec_ms += eng.stats().ms_total
-    roundtrip_ok = bool(got == nbytes and torch.equal(d_back[:nbytes], d_in[(args.steps - 1) % 2]))
+    roundtrip_ok = bool(got == nbytes and torch.equal(d_back[:nbytes], d_in[last_in][:nbytes]))
 
     # ---------------- reduce over ranks ----------------
     t = torch.tensor([dev_ms, wall_ms, e2e_ms, dec_ms], dtype=torch.float64, device=dev)
@@ -271,6 +300,7 @@ def main():
             "clocks": clocks,
             "decompress": {"value": round(world * args.mb * dec_steps / (dec_ms_max / 1e3), 2), "unit": UNIT, "ms_per_step": round(dec_ms_max / dec_steps, 3),
                            "roundtrip_bit_exact": roundtrip_ok},
+            "stitched_stream": stitched,
             "out_bytes_per_step": int(out_len), "blocks_per_step": int(st_last.n_blocks), "sort_rounds": int(st_last.sort_rounds),
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -31,6 +31,11 @@ class BlockMeta(C.Structure):
                 ("n_sel", C.c_uint32), ("bits", C.c_uint64), ("d1", C.c_uint32), ("pad", C.c_uint32)]
 
 
+class ShardInfo(C.Structure):
+    _fields_ = [("next_start", C.c_uint64), ("bits", C.c_uint64), ("n_blocks", C.c_uint32), ("crc_fold", C.c_uint32),
+                ("complete", C.c_uint32), ("bit_phase", C.c_uint32)]
+
+
 class Library:
     """Thin typed view of the C ABI."""
 
@@ -64,6 +69,11 @@ class Library:
         L.bz2b200_debug_fetch.argtypes = [vp, C.c_int, C.c_int, vp, C.c_size_t]
         L.bz2b200_debug_fetch.restype = C.c_longlong
         L.bz2b200_debug_set_block_cap.argtypes = [vp, C.c_uint32]
+        L.bz2b200_shard_begin.argtypes = [vp, vp, C.c_size_t, C.c_int, C.c_int]
+        L.bz2b200_shard_cut.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(ShardInfo)]
+        L.bz2b200_shard_compress.argtypes = [vp, C.POINTER(ShardInfo)]
+        L.bz2b200_shard_emit.argtypes = [vp, C.c_int, C.POINTER(ShardInfo), u8pp, szp]
+        L.bz2b200_stitch_shards.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_char_p), C.POINTER(ShardInfo), u8pp, szp]
         self.L = L
         self.path = path
 

@@ -192,6 +192,47 @@ class Bzip2Engine:
             self._raise(int(got))
         return buf[:got]
 
+    # -- block-range shards (include/bz2b200.h, "multi-GPU") --
+    def shard_begin(self, data, level, device_ptr=None, nbytes=None):
+        if device_ptr is not None:
+            rc = self._L.bz2b200_shard_begin(self._ctx, device_ptr, nbytes, 1, level)
+        else:
+            a = _coerce_input(data)
+            self._shard_keep = a
+            rc = self._L.bz2b200_shard_begin(self._ctx, a.ctypes.data, a.size, 0, level)
+        if rc:
+            self._raise(rc)
+
+    def shard_cut(self, s_start, own_len, is_last):
+        info = _native.ShardInfo()
+        rc = self._L.bz2b200_shard_cut(self._ctx, s_start, own_len, int(is_last), C.byref(info))
+        if rc:
+            self._raise(rc)
+        return info
+
+    def shard_compress(self, info):
+        rc = self._L.bz2b200_shard_compress(self._ctx, C.byref(info))
+        if rc:
+            self._raise(rc)
+        return info
+
+    def shard_emit(self, info, bit_phase, to_host=True):
+        out, n = C.POINTER(C.c_uint8)(), C.c_size_t()
+        rc = self._L.bz2b200_shard_emit(self._ctx, bit_phase, C.byref(info), C.byref(out) if to_host else None, C.byref(n))
+        if rc:
+            self._raise(rc)
+        return self._take(out, n.value) if to_host else n.value
+
+    def stitch_shards(self, level, segs, infos):
+        n = len(segs)
+        arr = (C.c_char_p * n)(*[bytes(s) if len(s) else b"\0" for s in segs])
+        inf = (_native.ShardInfo * n)(*infos)
+        out, ln = C.POINTER(C.c_uint8)(), C.c_size_t()
+        rc = self._L.bz2b200_stitch_shards(level, n, arr, inf, C.byref(out), C.byref(ln))
+        if rc:
+            self._raise(rc)
+        return self._take(out, ln.value)
+
     def debug_set_block_cap(self, cap):
         """tests only: 0 restores level*100000-19"""
         rc = self._L.bz2b200_debug_set_block_cap(self._ctx, cap)

@@ -22,6 +22,7 @@ struct DevBuf {
   size_t cap = 0;
 };
 
+struct Ctx;
 struct Ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -39,6 +40,13 @@ struct Ctx {
   void *h_pin = nullptr;
   size_t h_pin_cap = 0;
   // last compress, for debug_fetch
+  struct Pipe {
+    const u8 *d_in = nullptr;
+    i64 N = 0, T = 0, BS = 0, AS = 0, WS = 0;
+    u32 B = 0;
+    int level = 9, nb = 0;
+    std::vector<BlockRec> hrecs;
+  } pipe;
   u32 cap_override = 0;  // tests only
   int last_nb = 0;
   i64 last_bs = 0, last_as = 0;
@@ -105,20 +113,23 @@ int mark(Ctx *c, int i) {
 }
 
 // ------------------------------------------------------------------------------ compress
-int compress_device(Ctx *c, const u8 *d_in, size_t n_, int level, u32 *d_out, size_t out_cap, size_t *out_len, bool own_out) {
+// The pipeline is split so that a multi-GPU caller can interleave it with the two scalar exchanges of
+// pipe_begin (tile summaries; independent of where the first block starts), pipe_cut
+// (the sequential cut walk from a known first-block offset), pipe_stages (everything per block) and
+// pipe_emit (bit-granular stitch at a given bit offset).
+int pipe_begin(Ctx *c, const u8 *d_in, size_t n_, int level) {
   if (level < 1 || level > 9) return BZ2B200_E_LEVEL;
   c->st = bz2b200_stats{};
   c->st.in_bytes = n_;
-  const i64 N = (i64)n_;
-  const u32 B = c->cap_override ? c->cap_override : (u32)level * 100000u - 19u;  // BJ:2212-2220
-  const i64 T = (N + RLE_TILE - 1) / RLE_TILE;
-  const int max_blocks = (int)(N / ((i64)B * 4 / 5) + 2);
+  c->err.clear();
+  Ctx::Pipe &P_ = c->pipe;
+  P_ = Ctx::Pipe{};
+  P_.d_in = d_in; P_.N = (i64)n_; P_.level = level;
+  P_.B = c->cap_override ? c->cap_override : (u32)level * 100000u - 19u;  // BJ:2212-2220
+  P_.T = (P_.N + RLE_TILE - 1) / RLE_TILE;
+  const i64 N = P_.N, T = P_.T;
   int rc;
   if ((rc = mark(c, 0))) return rc;
-  ENS(c->recs, sizeof(BlockRec) * (size_t)max_blocks);
-  ENS(c->nblk, 64);
-  int nb = 0;
-  std::vector<BlockRec> hrecs;
   if (N > 0) {
     ENS(c->tile_last, 8 * T); ENS(c->tile_first, 8 * T); ENS(c->head_carry, 8 * T);
     ENS(c->tile_emit, 4 * T); ENS(c->g_tile, 8 * (T + 1));
@@ -126,17 +137,44 @@ int compress_device(Ctx *c, const u8 *d_in, size_t n_, int level, u32 *d_out, si
     LAUNCH(k_scan_excl_max_i64, 1, 1024, 0, P<i64>(c->tile_last), P<i64>(c->head_carry), T);
     LAUNCH(k_rle_count, (unsigned)T, RLE_THREADS, 0, d_in, N, P<i64>(c->head_carry), P<u32>(c->tile_emit));
     LAUNCH(k_scan_excl_sum_u32_u64, 1, 1024, 0, P<u32>(c->tile_emit), P<u64>(c->g_tile), T);
-    LAUNCH(k_rle_cut, 1, RLE_THREADS, 0, d_in, N, B, P<i64>(c->head_carry), P<i64>(c->tile_first), P<u64>(c->g_tile), T,
-           P<BlockRec>(c->recs), max_blocks, P<int>(c->nblk));
+  }
+  return BZ2B200_OK;
+}
+
+int pipe_cut(Ctx *c, i64 s_start, i64 own_end) {
+  Ctx::Pipe &P_ = c->pipe;
+  const i64 N = P_.N, T = P_.T;
+  const u32 B = P_.B;
+  const int max_blocks = (int)(N / ((i64)B * 4 / 5) + 2);
+  ENS(c->recs, sizeof(BlockRec) * (size_t)max_blocks);
+  ENS(c->nblk, 64);
+  int nb = 0;
+  P_.hrecs.clear();
+  if (N > 0 && s_start < N && s_start < own_end) {
+    LAUNCH(k_rle_cut, 1, RLE_THREADS, 0, P_.d_in, N, B, P<i64>(c->head_carry), P<i64>(c->tile_first), P<u64>(c->g_tile), T,
+           P<BlockRec>(c->recs), max_blocks, P<int>(c->nblk), s_start, own_end);
     CK(cudaMemcpyAsync(&nb, c->nblk.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     if (nb < 0) { c->err = "internal: block table overflow"; return BZ2B200_E_CUDA; }
-    hrecs.resize((size_t)nb);
-    if (nb) CK(cudaMemcpy(hrecs.data(), c->recs.p, sizeof(BlockRec) * (size_t)nb, cudaMemcpyDeviceToHost));
+    P_.hrecs.resize((size_t)nb);
+    if (nb) CK(cudaMemcpy(P_.hrecs.data(), c->recs.p, sizeof(BlockRec) * (size_t)nb, cudaMemcpyDeviceToHost));
   }
+  P_.nb = nb;
   c->st.n_blocks = (u32)nb;
+  return BZ2B200_OK;
+}
+
+int pipe_stages(Ctx *c) {
+  Ctx::Pipe &P_ = c->pipe;
+  const i64 N = P_.N, T = P_.T;
+  const u32 B = P_.B;
+  const int nb = P_.nb;
+  const u8 *d_in = P_.d_in;
+  std::vector<BlockRec> &hrecs = P_.hrecs;
+  int rc;
   const i64 BS = round_up((i64)B + 1, 256);  // per-block stride of byte arrays (block, L, ranks)
   const i64 AS = round_up((i64)B + 2, 128);  // per-block stride of the u16 symbol array
+  P_.BS = BS; P_.AS = AS;
   c->last_nb = nb; c->last_bs = BS; c->last_as = AS;
   ENS(c->meta, sizeof(BlockMeta) * (size_t)(nb + 1));
   ENS(c->bit_off, 8 * (size_t)(nb + 2));
@@ -146,8 +184,10 @@ int compress_device(Ctx *c, const u8 *d_in, size_t n_, int level, u32 *d_out, si
   if (nb) {
     // ---- S1 emit + CRC ----
     ENS(c->blk, (size_t)nb * BS);
-    LAUNCH(k_rle_emit, (unsigned)T, RLE_THREADS, 0, d_in, N, B, P<i64>(c->head_carry), P<u64>(c->g_tile), P<BlockRec>(c->recs), nb,
-           P<u8>(c->blk), BS);
+    const i64 t_first = hrecs.front().s / RLE_TILE, t_last = (hrecs.back().p + RLE_TILE - 1) / RLE_TILE;
+    (void)T;
+    LAUNCH(k_rle_emit, (unsigned)(t_last - t_first), RLE_THREADS, 0, d_in, N, B, P<i64>(c->head_carry), P<u64>(c->g_tile), P<BlockRec>(c->recs), nb,
+           P<u8>(c->blk), BS, t_first);
     i64 max_len = 0;
     for (auto &r : hrecs) { if (r.p - r.s > max_len) max_len = r.p - r.s; c->st.rle1_bytes += r.n; }
     int max_chunks = (int)((max_len + CRC_CHUNK - 1) / CRC_CHUNK);
@@ -271,14 +311,24 @@ int compress_device(Ctx *c, const u8 *d_in, size_t n_, int level, u32 *d_out, si
   } else {
     for (int i = 1; i <= 3; i++) if ((rc = mark(c, i))) return rc;
   }
+  P_.WS = WS;
   if ((rc = mark(c, 4))) return rc;
+  return BZ2B200_OK;
+}
 
-  // ---- S6 stitch ----
-  LAUNCH(k_stitch_offsets, 1, 1024, 0, P<BlockMeta>(c->meta), P<BlockRec>(c->recs), nb, P<u64>(c->bit_off), P<u32>(c->scrc));
-  u64 total_bits = 0;
-  CK(cudaMemcpyAsync(&total_bits, P<u64>(c->bit_off) + nb, 8, cudaMemcpyDeviceToHost, c->stream));
+// base_bits: 32 for a whole stream (then header and footer are written too), 0..7 for a shard segment
+int pipe_emit(Ctx *c, u64 base_bits, bool whole, u32 *d_out, size_t out_cap, bool own_out, size_t *out_len, u64 *bits_out, u32 *crc_fold) {
+  Ctx::Pipe &P_ = c->pipe;
+  const int nb = P_.nb;
+  LAUNCH(k_stitch_offsets, 1, 1024, 0, P<BlockMeta>(c->meta), P<BlockRec>(c->recs), nb, P<u64>(c->bit_off), P<u32>(c->scrc), base_bits);
+  u64 end_bits = 0;
+  u32 fold = 0;
+  CK(cudaMemcpyAsync(&end_bits, P<u64>(c->bit_off) + nb, 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(&fold, c->scrc.p, 4, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
-  size_t need = (size_t)((total_bits + 80 + 7) / 8);
+  if (bits_out) *bits_out = end_bits - base_bits;
+  if (crc_fold) *crc_fold = fold;
+  size_t need = (size_t)((end_bits + (whole ? 80 : 0) + 7) / 8);
   size_t need_w = round_up((i64)need, 4) + 8;
   if (own_out) {
     ENS(c->out, need_w);
@@ -288,10 +338,13 @@ int compress_device(Ctx *c, const u8 *d_in, size_t n_, int level, u32 *d_out, si
     return BZ2B200_E_UNEXPECTED_OUTPUT_EOF;
   }
   CK(cudaMemsetAsync(d_out, 0, need_w, c->stream));
-  if (nb) LAUNCH(k_stitch, dim3(32, (unsigned)nb), 256, 0, P<u32>(c->W), WS, P<u64>(c->bit_off), d_out);
-  LAUNCH(k_stream_ends, 1, 32, 0, d_out, P<u64>(c->bit_off), nb, P<u32>(c->scrc), level, P<u64>(c->out_len));
-  u64 olen = 0;
-  CK(cudaMemcpyAsync(&olen, c->out_len.p, 8, cudaMemcpyDeviceToHost, c->stream));
+  if (nb) LAUNCH(k_stitch, dim3(32, (unsigned)nb), 256, 0, P<u32>(c->W), P_.WS, P<u64>(c->bit_off), d_out);
+  u64 olen = need;
+  if (whole) {
+    LAUNCH(k_stream_ends, 1, 32, 0, d_out, P<u64>(c->bit_off), nb, P<u32>(c->scrc), P_.level, P<u64>(c->out_len));
+    CK(cudaMemcpyAsync(&olen, c->out_len.p, 8, cudaMemcpyDeviceToHost, c->stream));
+  }
+  int rc;
   if ((rc = mark(c, 5))) return rc;
   CK(cudaStreamSynchronize(c->stream));
   CK(cudaGetLastError());
@@ -300,11 +353,13 @@ int compress_device(Ctx *c, const u8 *d_in, size_t n_, int level, u32 *d_out, si
   if (nb) {
     std::vector<BlockMeta> hm((size_t)nb);
     CK(cudaMemcpy(hm.data(), c->meta.p, sizeof(BlockMeta) * (size_t)nb, cudaMemcpyDeviceToHost));
+    c->st.mtf_syms = 0;
     for (auto &m : hm) { c->st.mtf_syms += m.m; c->st.d1_triggered |= m.d1; }
   }
   if (c->ev_ok) {
     for (int i = 0; i < 5; i++) CK(cudaEventElapsedTime(&c->st.ms_stage[i], c->ev[i], c->ev[i + 1]));
     CK(cudaEventElapsedTime(&c->st.ms_total, c->ev[0], c->ev[5]));
+    c->st.dom_ms = 0;
     for (size_t i = 0; i + 1 < c->dom_used; i += 2) {
       float ms = 0;
       CK(cudaEventElapsedTime(&ms, c->dom_ev[i], c->dom_ev[i + 1]));
@@ -312,6 +367,14 @@ int compress_device(Ctx *c, const u8 *d_in, size_t n_, int level, u32 *d_out, si
     }
   }
   return BZ2B200_OK;
+}
+
+int compress_device(Ctx *c, const u8 *d_in, size_t n_, int level, u32 *d_out, size_t out_cap, size_t *out_len, bool own_out) {
+  int rc;
+  if ((rc = pipe_begin(c, d_in, n_, level))) return rc;
+  if ((rc = pipe_cut(c, 0, (i64)n_))) return rc;
+  if ((rc = pipe_stages(c))) return rc;
+  return pipe_emit(c, 32, true, d_out, out_cap, own_out, out_len, nullptr, nullptr);
 }
 
 #include "decode_host.inl"
@@ -370,6 +433,104 @@ int bz2b200_compress(bz2b200_ctx *ctx, const uint8_t *in, size_t n, int level, u
   CK(cudaMemcpy(res, c->out.p, olen, cudaMemcpyDeviceToHost));
   *out = res;
   *out_len = olen;
+  return BZ2B200_OK;
+}
+
+int bz2b200_shard_begin(bz2b200_ctx *ctx, const void *in, size_t n_avail, int on_device, int level) {
+  Ctx *c = reinterpret_cast<Ctx *>(ctx);
+  if (!c || (n_avail && !in)) return BZ2B200_E_ARG;
+  if (level < 1 || level > 9) return BZ2B200_E_LEVEL;
+  CK(cudaSetDevice(c->device));
+  const u8 *d_in = (const u8 *)in;
+  if (!on_device) {
+    ENS(c->in, n_avail + 64);
+    if (n_avail) CK(cudaMemcpyAsync(c->in.p, in, n_avail, cudaMemcpyHostToDevice, c->stream));
+    d_in = P<u8>(c->in);
+  } else if ((uintptr_t)in & 15) return BZ2B200_E_ARG;
+  return pipe_begin(c, d_in, n_avail, level);
+}
+
+int bz2b200_shard_cut(bz2b200_ctx *ctx, uint64_t s_start, uint64_t own_len, int is_last, bz2b200_shard_info *info) {
+  Ctx *c = reinterpret_cast<Ctx *>(ctx);
+  if (!c || !info) return BZ2B200_E_ARG;
+  CK(cudaSetDevice(c->device));
+  if ((i64)own_len > c->pipe.N) own_len = (uint64_t)c->pipe.N;
+  int rc = pipe_cut(c, (i64)s_start, (i64)own_len);
+  if (rc) return rc;
+  *info = bz2b200_shard_info{};
+  const auto &h = c->pipe.hrecs;
+  info->n_blocks = (uint32_t)h.size();
+  info->next_start = h.empty() ? s_start : (uint64_t)h.back().p;
+  info->complete = 1;
+  if (!is_last && !h.empty() && h.back().p == c->pipe.N && h.back().n < c->pipe.B) info->complete = 0;  // halo too short
+  return BZ2B200_OK;
+}
+
+int bz2b200_shard_compress(bz2b200_ctx *ctx, bz2b200_shard_info *info) {
+  Ctx *c = reinterpret_cast<Ctx *>(ctx);
+  if (!c || !info) return BZ2B200_E_ARG;
+  CK(cudaSetDevice(c->device));
+  int rc = pipe_stages(c);
+  if (rc) return rc;
+  LAUNCH(k_stitch_offsets, 1, 1024, 0, P<BlockMeta>(c->meta), P<BlockRec>(c->recs), c->pipe.nb, P<u64>(c->bit_off), P<u32>(c->scrc), (u64)0);
+  u64 bits = 0;
+  u32 fold = 0;
+  CK(cudaMemcpyAsync(&bits, P<u64>(c->bit_off) + c->pipe.nb, 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(&fold, c->scrc.p, 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  info->bits = bits;
+  info->crc_fold = fold;
+  return BZ2B200_OK;
+}
+
+int bz2b200_shard_emit(bz2b200_ctx *ctx, int bit_phase, bz2b200_shard_info *info, uint8_t **seg, size_t *seg_bytes) {
+  Ctx *c = reinterpret_cast<Ctx *>(ctx);
+  if (!c || !info || !seg_bytes || bit_phase < 0 || bit_phase > 7) return BZ2B200_E_ARG;
+  CK(cudaSetDevice(c->device));
+  size_t olen = 0;
+  int rc = pipe_emit(c, (u64)bit_phase, false, nullptr, 0, true, &olen, nullptr, nullptr);
+  if (rc) return rc;
+  info->bit_phase = (uint32_t)bit_phase;
+  *seg_bytes = olen;
+  if (!seg) return BZ2B200_OK;  // segment stays in HBM (device-resident timing)
+  uint8_t *res = (uint8_t *)malloc(olen ? olen : 1);
+  if (!res) return BZ2B200_E_OUT_OF_MEMORY;
+  if (olen) CK(cudaMemcpy(res, c->out.p, olen, cudaMemcpyDeviceToHost));
+  *seg = res;
+  *seg_bytes = olen;
+  return BZ2B200_OK;
+}
+
+// Host-side assembly of the final stream (pure byte copies; the segments are already bit-aligned by shard_emit).
+int bz2b200_stitch_shards(int level, int n_shards, const uint8_t *const *segs, const bz2b200_shard_info *infos, uint8_t **out, size_t *out_len) {
+  if (level < 1 || level > 9) return BZ2B200_E_LEVEL;
+  if (n_shards < 0 || !out || !out_len || (n_shards && (!segs || !infos))) return BZ2B200_E_ARG;
+  u64 total_bits = 32;
+  for (int r = 0; r < n_shards; r++) total_bits += infos[r].bits;
+  size_t nbytes = (size_t)((total_bits + 80 + 7) / 8);
+  uint8_t *o = (uint8_t *)calloc(nbytes + 8, 1);
+  if (!o) return BZ2B200_E_OUT_OF_MEMORY;
+  o[0] = 'B'; o[1] = 'Z'; o[2] = 'h'; o[3] = (uint8_t)('0' + level);  // BJ:2223-2226
+  u64 bitpos = 32;
+  u32 crc = 0;
+  for (int r = 0; r < n_shards; r++) {
+    if (infos[r].bits) {
+      if (infos[r].bit_phase != (u32)(bitpos & 7)) { free(o); return BZ2B200_E_ARG; }
+      size_t off = (size_t)(bitpos >> 3), len = (size_t)((infos[r].bit_phase + infos[r].bits + 7) / 8);
+      o[off] |= segs[r][0];
+      if (len > 1) memcpy(o + off + 1, segs[r] + 1, len - 1);
+      bitpos += infos[r].bits;
+    }
+    u32 m = infos[r].n_blocks & 31u;
+    crc = (m ? ((crc << m) | (crc >> (32 - m))) : crc) ^ infos[r].crc_fold;  // BJ:2237 over the shard's blocks
+  }
+  u64 vals[2] = {BZ_MAGIC_END, (u64)crc};  // BJ:2245-2247
+  int lens[2] = {48, 32};
+  for (int q = 0; q < 2; q++)
+    for (int i = lens[q] - 1; i >= 0; i--, bitpos++)
+      if ((vals[q] >> i) & 1) o[bitpos >> 3] |= (uint8_t)(0x80u >> (bitpos & 7));
+  *out = o;
+  *out_len = (size_t)((bitpos + 7) / 8);
   return BZ2B200_OK;
 }
 

@@ -341,9 +341,9 @@ __global__ void __launch_bounds__(HUF_THREADS) k_huff_encode(const u16 *__restri
 // Output bytes are produced as big-endian 32-bit words: bit 31 of word 0 is the first bit.
 // offsets: header is 32 bits, block k starts at 32 + sum(bits[0..k)).
 __global__ void __launch_bounds__(1024) k_stitch_offsets(const BlockMeta *__restrict__ meta, const BlockRec *__restrict__ recs, int nb,
-                                                         u64 *__restrict__ bit_off, u32 *__restrict__ stream_crc) {
+                                                         u64 *__restrict__ bit_off, u32 *__restrict__ stream_crc, u64 base_bits) {
   __shared__ u64 ws[33];
-  u64 carry = 32;
+  u64 carry = base_bits;  // 32 for a whole stream (after "BZh9"), the bit phase 0..7 for a shard segment
   for (int base = 0; base < nb; base += blockDim.x) {
     int k = base + threadIdx.x;
     u64 b = k < nb ? meta[k].bits : 0, tot;

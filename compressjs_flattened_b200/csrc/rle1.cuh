@@ -153,17 +153,18 @@ __global__ void __launch_bounds__(1024) k_scan_excl_sum_u32_u64(const u32 *__res
 // Sequential walk over the blocks (one CTA).  See the file header.
 __global__ void __launch_bounds__(RLE_THREADS) k_rle_cut(const u8 *__restrict__ in, i64 N, u32 B, const i64 *__restrict__ head_carry,
                                                          const i64 *__restrict__ tile_first, const u64 *__restrict__ g_tile, i64 T,
-                                                         BlockRec *__restrict__ recs, int max_blocks, int *__restrict__ n_blocks) {
+                                                         BlockRec *__restrict__ recs, int max_blocks, int *__restrict__ n_blocks, i64 s_start,
+                                                         i64 own_end) {
   __shared__ i64 ws64[33];
   __shared__ u32 ws32[33];
   __shared__ u64 sh_u64;
   __shared__ i64 sh_i64;
   const i64 INF = (i64)0x7fffffffffffffffLL;
-  i64 s = 0;
+  i64 s = s_start;  // shards: the walk starts at a known cut point and owns the blocks that start before own_end
   int k = 0;
   RleView v;
   u32 tt;
-  while (s < N && k < max_blocks) {
+  while (s < N && s < own_end && k < max_blocks) {
     // (1) end of the run that contains s
     i64 ts = s / RLE_TILE;
     rle_load(in, N, ts, v);
@@ -252,17 +253,17 @@ __global__ void __launch_bounds__(RLE_THREADS) k_rle_cut(const u8 *__restrict__ 
     s = r.p;
     k++;
   }
-  if (threadIdx.x == 0) *n_blocks = (s < N) ? -1 : k;  // -1: max_blocks too small (cannot happen with the host's bound)
+  if (threadIdx.x == 0) *n_blocks = (s < N && s < own_end) ? -1 : k;  // -1: max_blocks too small (cannot happen with the host's bound)
 }
 
 __global__ void __launch_bounds__(RLE_THREADS) k_rle_emit(const u8 *__restrict__ in, i64 N, u32 B, const i64 *__restrict__ head_carry,
                                                           const u64 *__restrict__ g_tile, const BlockRec *__restrict__ recs, int nblocks,
-                                                          u8 *__restrict__ blk, i64 blk_stride) {
+                                                          u8 *__restrict__ blk, i64 blk_stride, i64 tile_first_owned) {
   __shared__ i64 ws64[33];
   __shared__ u32 ws32[33];
   RleView v;
   u32 tt;
-  i64 tile = blockIdx.x;
+  i64 tile = tile_first_owned + blockIdx.x;
   rle_view(in, N, tile, head_carry, v, tt, ws64, ws32);
   if (v.nvalid == 0) return;
   // block containing p0: last k with recs[k].s <= p0
@@ -276,10 +277,12 @@ __global__ void __launch_bounds__(RLE_THREADS) k_rle_emit(const u8 *__restrict__
   u8 *out = blk + (i64)k * blk_stride;
   i64 cur = v.head_before;
   u64 g = g_tile[tile] + v.gpre;
+  const i64 first = recs[0].s, last = recs[nblocks - 1].p;  // shards own only [first, last)
   for (int j = 0; j < v.nvalid; j++) {
     i64 i = v.p0 + j;
     if (v.flags & (1u << j)) cur = i;
     u32 e = (v.em >> (2 * j)) & 3u;
+    if (i < first || i >= last) { g += e; continue; }
     while (i >= r.p) { k++; r = recs[k]; out = blk + (i64)k * blk_stride; }
     if (i < r.e_true) {  // fresh first run of the block
       u64 d = (u64)(i - r.s);

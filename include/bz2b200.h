@@ -78,6 +78,33 @@ int bz2b200_decompress_device(bz2b200_ctx *ctx, const void *d_in, size_t n, int 
 /* upper bound of the compressed size of n input bytes at `level` (for sizing d_out) */
 size_t bz2b200_compress_bound(size_t n, int level);
 
+/* ---- multi-GPU: block-range shards (one context = one GPU = one shard) ----
+ * A shard is a slice of the input plus a halo after it.  The RLE1 automaton restarts at every block, so a
+ * rank that knows where its first block starts can cut and compress its blocks alone.  Cross-rank data are
+ * three scalars per rank: the first-block offset (a chain r -> r+1), the bit length (exclusive scan) and the
+ * CRC fold.  There is no collective on the data path.
+ *   shard_begin    tile summaries of in[0, n_avail) (does not depend on the first-block offset)
+ *   shard_cut      cut walk from s_start; this shard owns the blocks that start in [s_start, own_len).
+ *                  info->next_start = offset (in this buffer) of the first block of the next shard;
+ *                  info->complete = 0 if the halo ended before the last owned block was full (not the last shard)
+ *   shard_compress all per-block stages; fills info->bits and info->crc_fold
+ *   shard_emit     the segment's bytes, pre-shifted so that its first bit sits at bit `bit_phase` (0..7) of
+ *                  byte 0: the assembler only copies bytes and ORs one boundary byte (seg == NULL: keep it in HBM)
+ *   stitch_shards  host-side assembly: "BZh<level>" + segments + end-of-stream magic + combined CRC */
+typedef struct {
+  uint64_t next_start;
+  uint64_t bits;
+  uint32_t n_blocks;
+  uint32_t crc_fold;   /* fold of this shard's block CRCs starting from 0 (BJ:2237); shard folds compose by rotation */
+  uint32_t complete;
+  uint32_t bit_phase;  /* set by shard_emit */
+} bz2b200_shard_info;
+int bz2b200_shard_begin(bz2b200_ctx *ctx, const void *in, size_t n_avail, int on_device, int level);
+int bz2b200_shard_cut(bz2b200_ctx *ctx, uint64_t s_start, uint64_t own_len, int is_last, bz2b200_shard_info *info);
+int bz2b200_shard_compress(bz2b200_ctx *ctx, bz2b200_shard_info *info);
+int bz2b200_shard_emit(bz2b200_ctx *ctx, int bit_phase, bz2b200_shard_info *info, uint8_t **seg, size_t *seg_bytes);
+int bz2b200_stitch_shards(int level, int n_shards, const uint8_t *const *segs, const bz2b200_shard_info *infos, uint8_t **out, size_t *out_len);
+
 const char *bz2b200_strerror(int rc);
 const char *bz2b200_last_error(bz2b200_ctx *ctx);
 int bz2b200_last_stats(bz2b200_ctx *ctx, bz2b200_stats *st);
