@@ -149,9 +149,12 @@ def test_full_size_configs(gpu_engine, key):
     recs = gpu_engine.block_table()
     sizes_enc = [r.p - r.s for r in recs]
     fold = 0
-    for r in recs:  # combined CRC is the fold of the block CRCs (BJ:2237) and sits in the last 4 bytes (+padding)
+    for r in recs:  # combined CRC = fold of the block CRCs (BJ:2237); it is the last 32 bits before the zero padding
         fold = (((fold << 1) | (fold >> 31)) ^ r.crc) & 0xFFFFFFFF
-    assert fold.to_bytes(4, "big") in comp[-5:]
+    end_bit = 32 + sum(m.bits for m in gpu_engine.block_meta()) + 80
+    assert (end_bit + 7) // 8 == len(comp)
+    tail = int.from_bytes(comp[-16:], "big") >> (len(comp) * 8 - end_bit)
+    assert tail & 0xFFFFFFFF == fold and (tail >> 32) & 0xFFFFFFFFFFFF == 0x177245385090
     back = gpu_engine.decompressFile(comp)
     assert hashlib.sha256(back).hexdigest() == g["input_sha256"]
     rows = []
