@@ -163,8 +163,10 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    ctl = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        ctl = dist.new_group(backend="gloo")   # the per-rank scalars (first-block offset, bit length) travel host-side
     eng = Bzip2Engine(local)
     from compressjs_flattened_b200.sharded import compress_shard, gather_and_stitch
     nbytes = args.mb * 1_000_000
@@ -189,7 +191,7 @@ def main():
     def dev_step(i):
         if world == 1:
             return eng.compress_device(d_in[i % 2].data_ptr(), nbytes, args.level, d_out.data_ptr(), d_out.numel())
-        n, _, _ = compress_shard(eng, None, rank * nbytes, nbytes, args.level, rank == world - 1, rank=rank, world=world, device=dev,
+        n, _, _ = compress_shard(eng, None, rank * nbytes, nbytes, args.level, rank == world - 1, rank=rank, world=world, group=ctl,
                                  device_ptr=d_in[i % 2].data_ptr(), nbytes=navail, to_host=False)
         return n
 
@@ -228,7 +230,7 @@ def main():
 
     def host_call(j):
         if world > 1:  # host slice+halo in, host segment out, through the shard API
-            seg, _, _ = compress_shard(eng, host[j], rank * nbytes, nbytes, args.level, rank == world - 1, rank=rank, world=world, device=dev)
+            seg, _, _ = compress_shard(eng, pinned[j].numpy(), rank * nbytes, nbytes, args.level, rank == world - 1, rank=rank, world=world, group=ctl)
             return len(seg)
         rc = L.bz2b200_compress(eng._ctx, pinned[j].data_ptr(), nbytes, args.level, ctypes.byref(out_p), ctypes.byref(out_n))
         if rc:
@@ -249,8 +251,8 @@ def main():
     # ---------------- N > 1: stitch the ranks' segments into ONE stream and check it ----------------
     stitched = None
     if world > 1:
-        seg, info, _ = compress_shard(eng, host[0], rank * nbytes, nbytes, args.level, rank == world - 1, rank=rank, world=world, device=dev)
-        whole = gather_and_stitch(eng, seg, info, args.level)
+        seg, info, _ = compress_shard(eng, pinned[0].numpy(), rank * nbytes, nbytes, args.level, rank == world - 1, rank=rank, world=world, group=ctl)
+        whole = gather_and_stitch(eng, seg, info, args.level, group=ctl)
         if rank == 0:
             back = eng.decompressFile(whole)   # verifies every block CRC and the combined CRC
             stitched = {"bytes": len(whole), "decoded_bytes": len(back), "blocks": int(eng.stats().n_blocks),
@@ -287,7 +289,7 @@ def main():
             "ms_per_step": round(dev_ms_max / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic", "config": workload_desc(args.level, args.mb, world),
             "e2e": {"value": round(total_mb / (e2e_ms_max / 1e3), 2), "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": int(e2e_out),
-                    "ms_per_step": round(e2e_ms_max / args.steps, 3), "api": "bz2b200_compress (host buffers; pinned input, pageable malloc'd output)"},
+                    "ms_per_step": round(e2e_ms_max / args.steps, 3), "api": "bz2b200_compress (N=1) / bz2b200_shard_begin..emit (N>1): pinned host input, malloc'd host output"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_rs_scatter (BWT radix-sort scatter pass)", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
