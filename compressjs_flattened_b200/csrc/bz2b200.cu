@@ -35,7 +35,7 @@ struct Ctx {
   DevBuf seg_cnt, seg_cnt2, seg_tile0, seg_tile0b, tile_blk, tile_blkb, tile_i0, tile_i1, tile_i2, tile_i3, totals;
   DevBuf Lcol, ranks, lastocc, A, freq, meta, W, bit_off, scrc, out, out_len, used_bits;
   // decode-side buffers
-  DevBuf d_in, cand, ncand, dmeta, dsyms, dL, dtt, dwalk, dblk, dout, dmisc;
+  DevBuf d_in, cand, ncand, dmeta, dsyms, dL, dtt, dwalk, dblk, dout, dmisc, dsel, doff, dperm, dmap;
   // host staging (pinned)
   void *h_pin = nullptr;
   size_t h_pin_cap = 0;
@@ -59,7 +59,7 @@ struct Ctx {
                      &isa, &keysA, &keysB, &valsA, &valsB, &rankA, &rankB, &posA, &posB, &rnew, &hist, &digit_base,
                      &seg_cnt, &seg_cnt2, &seg_tile0, &seg_tile0b, &tile_blk, &tile_blkb, &tile_i0, &tile_i1, &tile_i2, &tile_i3, &totals,
                      &Lcol, &ranks, &lastocc, &A, &freq, &meta, &W, &bit_off, &scrc, &out, &out_len, &used_bits,
-                     &d_in, &cand, &ncand, &dmeta, &dsyms, &dL, &dtt, &dwalk, &dblk, &dout, &dmisc};
+                     &d_in, &cand, &ncand, &dmeta, &dsyms, &dL, &dtt, &dwalk, &dblk, &dout, &dmisc, &dsel, &doff, &dperm, &dmap};
     for (DevBuf *b : all) pool.push_back(b);
   }
 };

@@ -4,11 +4,13 @@
 //   K-U1 k_magic_scan    : every bit offset is tested for the 48-bit block / end-of-stream magic
 //                          (the reference has no search: it walks the stream sequentially; the host
 //                          re-creates that walk over the candidates, so false hits are ignored)
-//   K-U2/3 k_block_decode: one warp per candidate block: header, selectors, code lengths
-//                          (BJ:1434-1581), then Huffman + RLE2^-1 + MTF^-1 (BJ:1597-1670).  Decoding
-//                          is sequential per block (table switch every 50 symbols); parallelism is
-//                          across blocks.  A 10-bit LUT built by simulating the reference's
-//                          limit/base/permute walk serves short codes; long codes take that walk.
+//   K-U2/3a k_huff_parse : one warp per candidate block: header, selectors, code lengths
+//                          (BJ:1434-1581), then bits -> symbols (BJ:1597-1616).  This is the only
+//                          serial part (table switch every 50 symbols); a 10-bit LUT built by replaying
+//                          the reference's limit/base/permute walk serves short codes.
+//   K-U3b k_sym_offsets  : RLE2^-1 as a scan: the k-th RUNA/RUNB of a run = (sym+1)<<k copies of the front
+//   K-U3c k_imtf_*       : MTF^-1 in parallel: per-segment list permutations, composed per block, then every
+//                          segment decodes from its start list (list striped over a warp)
 //   K-U4a                : T-vector = one stable 8-bit radix pass (bwt.cuh kernels) of positions by byte
 //   K-U4b k_ibwt_*       : list ranking: splitters every IBWT_S slots walk to the next splitter,
 //                          one thread per block ranks the splitters, second walk writes bytes
@@ -22,7 +24,6 @@
 #include "bwt.cuh"
 
 #define DEC_LUT_BITS 10
-#define DEC_STAGE 1024
 #define DEC_MAX_SEL 32768
 #define DEC_DBUF_MAX 900000
 #define IBWT_S 256
@@ -35,7 +36,7 @@ struct DecBlk {
   u32 count;       // dbufCount: bytes of the L column
   int err;         // 0 or a negative Err code
   u32 kind;        // 0 = block magic, 1 = end-of-stream magic (then target_crc = stream CRC)
-  u32 pad;
+  u32 nsym;        // symbols parsed, including end-of-block
 };
 
 // ---- K-U1 -----------------------------------------------------------------------------------
@@ -94,6 +95,11 @@ __device__ __forceinline__ u32 br_peek(BitRd &r, u32 nb) {
 }
 __device__ __forceinline__ u64 br_tell(const BitRd &r) { return r.pos * 8 - r.avail; }
 
+#define DEC_RING 1024       // bytes of compressed input staged in shared memory per pass
+#define DEC_SYM_STAGE 1024  // symbols staged per pass
+#define DEC_SYM_STRIDE 900096  // u16 symbols per candidate (dbuf + end-of-block + slack)
+#define IMTF_SEG 4096       // symbols per inverse-MTF segment
+
 struct DecSmem {
   int limit[BZ_MAX_GROUPS][BZ_MAX_CODE + 2];
   int base[BZ_MAX_GROUPS][BZ_MAX_CODE + 2];
@@ -103,13 +109,18 @@ struct DecSmem {
   int minl[BZ_MAX_GROUPS], maxl[BZ_MAX_GROUPS];
   u8 mtf[256];
   u8 sym2byte[256];
-  u8 stage[DEC_STAGE];
-  int hdr[8];  // err, ng, nsel, sym_total
+  __align__(16) u8 ring[DEC_RING + 16];
+  u16 stage[DEC_SYM_STAGE];
+  int hdr[8];  // err, ng, nsel, sym_total, staged, finished
   u64 bitpos_after_header;
 };
 
-__global__ void __launch_bounds__(32) k_block_decode(const u8 *__restrict__ in, u64 n, const u64 *__restrict__ cand, u32 ncand, u32 dbuf_cap, int verify,
-                                                     DecBlk *__restrict__ out, u8 *__restrict__ dL, i64 l_stride, u8 *__restrict__ dsel) {
+// ---- K-U2/3a: header + Huffman parse (bits -> symbols).  One warp per candidate block. -------------
+// Only this part of the decoder is inherently serial (the coding table changes every 50 SYMBOLS, so the
+// position of a group in the bit stream is unknown until everything before it is parsed).  Lane 0 parses;
+// the whole warp prefetches the compressed bytes into a shared-memory ring and flushes the symbols.
+__global__ void __launch_bounds__(32) k_huff_parse(const u8 *__restrict__ in, u64 n, const u64 *__restrict__ cand, u32 ncand, u32 dbuf_cap, int verify,
+                                                   DecBlk *__restrict__ out, u16 *__restrict__ dsym, u8 *__restrict__ dsel, u8 *__restrict__ dmap) {
   __shared__ DecSmem sm;
   const u32 k = blockIdx.x;
   if (k >= ncand) return;
@@ -122,14 +133,13 @@ __global__ void __launch_bounds__(32) k_block_decode(const u8 *__restrict__ in, 
     u64 h = ((u64)br_get(r0, 24) << 24) | br_get(r0, 24);
     kind = h == BZ_MAGIC_END ? 1u : h == BZ_MAGIC_BLOCK ? 0u : 2u;
   }
-  u8 *Lk = dL + (i64)k * l_stride;
+  u16 *Sk = dsym + (u64)k * DEC_SYM_STRIDE;
   u8 *sel = dsel + (u64)k * DEC_MAX_SEL;
   DecBlk res;
-  res.bitpos = bitpos; res.endbit = 0; res.target_crc = 0; res.orig_ptr = 0; res.count = 0; res.err = 0; res.kind = kind; res.pad = 0;
-  BitRd r;
-  res.kind = kind;
+  res.bitpos = bitpos; res.endbit = 0; res.target_crc = 0; res.orig_ptr = 0; res.count = 0; res.err = 0; res.kind = kind; res.nsym = 0;
   // ---- header (lane 0), BJ:1434-1520 ----
   if (lane == 0) {
+    BitRd r;
     int err = kind == 2 ? BZ2B200_E_NOT_BZIP_DATA : 0, ng = 0, nsel = 0, sym_total = 0;
     br_init(r, in, n, bitpos + 48);
     res.target_crc = br_get(r, 32);
@@ -200,6 +210,7 @@ __global__ void __launch_bounds__(32) k_block_decode(const u8 *__restrict__ in, 
     }
     return;
   }
+  for (int i = lane; i < 256; i += 32) dmap[(u64)k * 256 + i] = i < sym_total ? sm.sym2byte[i] : (u8)i;
   // ---- limit / base / permute per table (BJ:1521-1581), one lane per table ----
   if (lane < ng) {
     const int t = lane;
@@ -212,8 +223,8 @@ __global__ void __launch_bounds__(32) k_block_decode(const u8 *__restrict__ in, 
     for (int L = 0; L < BZ_MAX_CODE + 2; L++) { cnt[L] = 0; sm.limit[t][L] = 0; sm.base[t][L] = 0; }
     int pp = 0;
     for (int L = minl; L <= maxl; L++)
-      for (int s = 0; s < S; s++)
-        if (sm.lens[t][s] == L) sm.permute[t][pp++] = (u16)s;
+      for (int s2 = 0; s2 < S; s2++)
+        if (sm.lens[t][s2] == L) sm.permute[t][pp++] = (u16)s2;
     for (int i = 0; i < S; i++) cnt[sm.lens[t][i]]++;
     pp = 0;
     int tt = 0;
@@ -244,100 +255,244 @@ __global__ void __launch_bounds__(32) k_block_decode(const u8 *__restrict__ in, 
     }
     sm.lut[t][prefix] = e;
   }
-  for (int i = lane; i < 256; i += 32) sm.mtf[i] = (u8)i;
   __syncwarp();
-  // ---- symbols (BJ:1597-1670): lane 0 decodes into a staging buffer, the warp flushes it ----
-  u32 count = 0, flushed = 0;
-  int err = 0, done = 0;
-  u32 run_pos = 0, t_run = 0;
-  u32 pending = 0;   // copies of pend_byte not staged yet (a flushed RUNA/RUNB run)
-  u8 pend_byte = 0, lit = 0;
-  bool has_lit = false;  // literal decoded but not staged yet (it follows the pending run)
-  int sym_left = 0, selector = 0, gi = 0;
-  if (lane == 0) br_init(r, in, n, sm.bitpos_after_header);
+  // ---- symbols (BJ:1597-1616): parse passes ----
+  // Lane 0 keeps a 64-bit window (w0 = current word, w1 = next, both big-endian) and `used` bits consumed of w0.
+  // The warp stages DEC_RING bytes (as byte-swapped words) per pass; lane 0 parses whole 50-symbol groups while a
+  // group's worst case (50 x 20 bits, 50 symbols) still fits in the ring and in the symbol stage.
+  const u32 eob = (u32)sym_total + 1;
+  u64 cur_word = sm.bitpos_after_header >> 5;          // index (in 32-bit words of the input) of w0
+  u32 used = (u32)(sm.bitpos_after_header & 31);
+  u32 flushed = 0;
+  int err = 0, done = 0, selector = 0;
+  u32 *ring32 = reinterpret_cast<u32 *>(sm.ring);
+  const u32 RW = DEC_RING / 4;
   for (;;) {
-    if (lane == 0) {
-      u32 staged = 0;
-      for (;;) {
-        if (pending) {
-          u32 c = pending < DEC_STAGE - staged ? pending : DEC_STAGE - staged;
-          for (u32 q = 0; q < c; q++) sm.stage[staged + q] = pend_byte;
-          staged += c;
-          pending -= c;
-          if (pending) break;
-        }
-        if (has_lit) {
-          if (staged == DEC_STAGE) break;
-          sm.stage[staged++] = lit;
-          has_lit = false;
-        }
-        if (done || err || staged == DEC_STAGE) break;
-        if (!(sym_left--)) {
-          sym_left = BZ_GROUP - 1;
-          if (selector >= nsel) { err = BZ2B200_E_DATA_ERROR; break; }
-          gi = sel[selector++];
-        }
-        int next;
-        u32 pk = br_peek(r, DEC_LUT_BITS);
-        u16 e = sm.lut[gi][pk];
-        if (e) {
-          next = e >> 5;
-          r.avail -= (e & 31);
-        } else {
-          int L = sm.minl[gi];
-          int j = (int)br_get(r, (u32)L);
-          for (;; L++) {
-            if (L > sm.maxl[gi]) { err = BZ2B200_E_DATA_ERROR; break; }
-            if (j <= sm.limit[gi][L]) break;
-            j = (j << 1) | (int)br_get(r, 1);
-          }
-          if (err) break;
-          j -= sm.base[gi][L];
-          if (j < 0 || j >= BZ_MAX_SYMS) { err = BZ2B200_E_DATA_ERROR; break; }
-          next = sm.permute[gi][j];
-        }
-        if (br_tell(r) > n * 8) { err = BZ2B200_E_UNEXPECTED_INPUT_EOF; break; }  // reference: spins on zero bits (D3)
-        if (next == 0 || next == 1) {
-          if (!run_pos) { run_pos = 1; t_run = 0; }
-          t_run += next == 0 ? run_pos : 2 * run_pos;
-          run_pos <<= 1;
-          if (t_run > dbuf_cap) { err = BZ2B200_E_DATA_ERROR; break; }
-          continue;
-        }
-        if (run_pos) {
-          run_pos = 0;
-          if (count + t_run > dbuf_cap) { err = BZ2B200_E_DATA_ERROR; break; }
-          pend_byte = sm.sym2byte[sm.mtf[0]];
-          pending = t_run;
-          count += t_run;
-        }
-        if (next > sym_total) { done = 1; continue; }
-        if (count >= dbuf_cap) { err = BZ2B200_E_DATA_ERROR; break; }
-        int i = next - 1;
-        u8 v = sm.mtf[i];
-        for (int q = i; q > 0; q--) sm.mtf[q] = sm.mtf[q - 1];
-        sm.mtf[0] = v;
-        lit = sm.sym2byte[v];
-        has_lit = true;
-        count++;
+    u64 ring_base_w = __shfl_sync(FULL_MASK, cur_word, 0) & ~(u64)3;  // 16-byte aligned
+    for (u32 q = lane; q < RW / 4; q += 32) {
+      u64 src = (ring_base_w + (u64)q * 4) * 4;
+      u32 w[4] = {0, 0, 0, 0};
+      if (src + 16 <= n) {
+        uint4 v = *reinterpret_cast<const uint4 *>(in + src);
+        w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+      } else {
+        for (int z = 0; z < 16; z++) if (src + z < n) w[z >> 2] |= (u32)in[src + z] << (8 * (z & 3));  // bits past EOF read as 0
       }
-      sm.hdr[6] = (int)staged;
-      sm.hdr[7] = (err || (done && !pending && !has_lit)) ? 1 : 0;
+      for (int z = 0; z < 4; z++) ring32[q * 4 + z] = __byte_perm(w[z], 0, 0x0123);
     }
     __syncwarp();
-    u32 staged = (u32)sm.hdr[6];
-    int fin = sm.hdr[7];
-    for (u32 q = lane; q < staged; q += 32) Lk[flushed + q] = sm.stage[q];
+    if (lane == 0) {
+      u32 staged = 0;
+      u32 wpos = (u32)(cur_word - ring_base_w);  // 0..3
+      u32 w0 = ring32[wpos], w1 = ring32[wpos + 1];
+      wpos += 2;                                   // next word to pull
+      while (!done && !err && staged + BZ_GROUP <= DEC_SYM_STAGE && wpos + 34 <= RW) {
+        if (selector >= nsel) { err = BZ2B200_E_DATA_ERROR; break; }  // BJ:1601
+        if (flushed + staged + BZ_GROUP >= DEC_SYM_STRIDE) { err = BZ2B200_E_DATA_ERROR; break; }  // more symbols than any valid block
+        const int gi = sel[selector++];
+        const u16 *lut = sm.lut[gi];
+        for (int i = 0; i < BZ_GROUP; i++) {
+          u32 win = __funnelshift_l(w1, w0, used);  // the next 32 bits of the stream
+          u32 e = lut[win >> (32 - DEC_LUT_BITS)];
+          u32 sym, len;
+          if (e) { sym = e >> 5; len = e & 31u; }
+          else {  // codes longer than the LUT: the reference's limit/base/permute walk (BJ:1605-1616)
+            int L = sm.minl[gi];
+            int j = (int)(win >> (32 - L));
+            for (;; L++) {
+              if (L > sm.maxl[gi]) { err = BZ2B200_E_DATA_ERROR; break; }
+              if (j <= sm.limit[gi][L]) break;
+              j = (j << 1) | (int)((win >> (31 - L)) & 1u);
+            }
+            if (err) break;
+            j -= sm.base[gi][L];
+            if (j < 0 || j >= BZ_MAX_SYMS) { err = BZ2B200_E_DATA_ERROR; break; }
+            sym = sm.permute[gi][j];
+            len = (u32)L;
+          }
+          used += len;
+          if (used >= 32) { w0 = w1; w1 = ring32[wpos++]; used -= 32; }
+          sm.stage[staged++] = (u16)sym;
+          if (sym == eob) { done = 1; break; }
+        }
+      }
+      cur_word = ring_base_w + wpos - 2;
+      if (!err && cur_word * 32 + used > n * 8) err = BZ2B200_E_UNEXPECTED_INPUT_EOF;  // reference: spins on zero bits (D3)
+      sm.hdr[4] = (int)staged;
+      sm.hdr[5] = (err || done) ? 1 : 0;
+    }
+    __syncwarp();
+    u32 staged = (u32)sm.hdr[4];
+    int fin = sm.hdr[5];
+    for (u32 q = lane; q < staged; q += 32) Sk[flushed + q] = sm.stage[q];
     flushed += staged;
     __syncwarp();
     if (fin) break;
   }
   if (lane == 0) {
-    if (!err && res.orig_ptr >= count) err = BZ2B200_E_DATA_ERROR;  // BJ:1677
     res.err = err;
-    res.count = err ? 0 : count;
-    res.endbit = br_tell(r);
+    res.count = 0;  // filled by k_sym_offsets
+    res.nsym = err ? 0 : flushed;
+    res.endbit = cur_word * 32 + used;
     out[k] = res;
+  }
+}
+
+// ---- K-U3b: RLE2^-1 offsets.  One CTA per candidate: the k-th RUNA/RUNB of a run stands for (sym+1) << k copies of
+// the current list front (BJ:1621-1652), a literal for one byte; exclusive scan -> position of every symbol's output.
+__global__ void __launch_bounds__(1024) k_sym_offsets(DecBlk *__restrict__ blks, const u16 *__restrict__ dsym, u32 *__restrict__ doff, u32 dbuf_cap) {
+  __shared__ int wsi[33];
+  __shared__ u32 ws[33];
+  const u32 k = blockIdx.x;
+  const u32 m = blks[k].nsym;
+  if (blks[k].kind != 0 || blks[k].err || m == 0) return;
+  const u16 *Sk = dsym + (u64)k * DEC_SYM_STRIDE;
+  u32 *Ok = doff + (u64)k * DEC_SYM_STRIDE;
+  int carry_lit = -1;  // last non-run symbol so far
+  u32 carry = 0;
+  for (u32 base = 0; base < m; base += 1024 * 4) {
+    u32 i0 = base + threadIdx.x * 4;
+    u32 sy[4];
+    int my_lit = -1;
+    for (int q = 0; q < 4; q++) { sy[q] = i0 + q < m ? Sk[i0 + q] : 2u; if (i0 + q < m && sy[q] >= 2) my_lit = (int)(i0 + q); }
+    int tot_l;
+    int lit = block_excl_max<int>(my_lit, -1, tot_l, wsi);
+    if (carry_lit > lit) lit = carry_lit;
+    u32 cp[4], mine = 0;
+    {
+      int cur = lit;
+      for (int q = 0; q < 4; q++) {
+        u32 i = i0 + q;
+        cp[q] = 0;
+        if (i >= m) continue;
+        if (sy[q] >= 2) { cur = (int)i; cp[q] = i + 1 == m ? 0u : 1u; }  // the last symbol is end-of-block
+        else { u32 kk = i - (u32)(cur + 1); cp[q] = kk < 21 ? (sy[q] + 1) << kk : 0x400000u; }  // > dbuf_cap: caught below
+        mine += cp[q];
+      }
+    }
+    u32 tot;
+    u32 o = carry + block_excl_sum<u32>(mine, tot, ws);
+    for (int q = 0; q < 4; q++) if (i0 + q < m) { Ok[i0 + q] = o; o += cp[q]; }
+    carry += tot;
+    if (carry > 0x40000000u) carry = 0x40000000u;  // saturate: only "too large" matters
+    if (tot_l > carry_lit) carry_lit = tot_l;
+  }
+  if (threadIdx.x == 0) {
+    Ok[m] = carry;
+    // BJ:1647,1663 (dbuf overflow) and BJ:1677 (origPtr past the data) -> DATA_ERROR
+    if (carry > dbuf_cap || blks[k].orig_ptr >= carry) { blks[k].err = BZ2B200_E_DATA_ERROR; blks[k].nsym = 0; carry = 0; }
+    blks[k].count = carry;
+  }
+}
+
+// ---- K-U3c: MTF^-1 in parallel.  The list is striped over the warp like in k_mtf_ranks. ----------------
+__device__ __forceinline__ u32 imtf_step(u32 &hot, u64 &cold, u32 j, int lane) {  // returns list[j], moves it to the front
+  if (j < 32) {
+    u32 byte = __shfl_sync(FULL_MASK, hot, (int)j);
+    u32 up = __shfl_up_sync(FULL_MASK, hot, 1);
+    if (lane <= (int)j) hot = lane == 0 ? byte : up;
+    return byte;
+  }
+  int row = (int)(j >> 5), l = (int)(j & 31);
+  u32 target = __shfl_sync(FULL_MASK, (u32)(cold >> (8 * (row - 1))) & 0xffu, l);
+  u32 carry = target;
+  {
+    u32 last = __shfl_sync(FULL_MASK, hot, 31);
+    u32 up = __shfl_up_sync(FULL_MASK, hot, 1);
+    hot = lane == 0 ? carry : up;
+    carry = last;
+  }
+  for (int r = 1; r <= row; r++) {
+    u32 cur = (u32)(cold >> (8 * (r - 1))) & 0xffu;
+    u32 last = __shfl_sync(FULL_MASK, cur, 31);
+    u32 up = __shfl_up_sync(FULL_MASK, cur, 1);
+    u32 nv = lane == 0 ? carry : up;
+    if (r < row || lane <= l) cold = (cold & ~(0xffULL << (8 * (r - 1)))) | ((u64)nv << (8 * (r - 1)));
+    carry = last;
+  }
+  return target;
+}
+// pass P: permutation of list positions caused by each segment of IMTF_SEG symbols (grid (segs/8, ncand), one warp per segment)
+__global__ void __launch_bounds__(256) k_imtf_perm(const DecBlk *__restrict__ blks, const u16 *__restrict__ dsym, u8 *__restrict__ segperm) {
+  const u32 k = blockIdx.y;
+  const u32 m = blks[k].nsym;
+  const int lane = lane_id();
+  const u32 seg = blockIdx.x * 8 + warp_id();
+  const u32 b0 = seg * IMTF_SEG;
+  if (blks[k].kind != 0 || blks[k].err || b0 >= m) return;
+  const u16 *Sk = dsym + (u64)k * DEC_SYM_STRIDE + b0;
+  u32 hot = (u32)lane;
+  u64 cold = 0;
+  for (int r = 7; r >= 1; r--) cold = (cold << 8) | (u64)(32 * r + lane);
+  u32 lim = m - b0 < IMTF_SEG ? m - b0 : IMTF_SEG;
+  for (u32 c0 = 0; c0 < lim; c0 += 32) {
+    u32 mysym = c0 + lane < lim ? Sk[c0 + lane] : 0u;
+    u32 cnt = lim - c0 < 32 ? lim - c0 : 32;
+    for (u32 t = 0; t < cnt; t++) {
+      u32 sy = __shfl_sync(FULL_MASK, mysym, (int)t);
+      if (sy >= 2 && sy - 1 < 256) imtf_step(hot, cold, sy - 1, lane);  // end-of-block (> sym_total <= 257) is the last symbol: harmless
+    }
+  }
+  u8 *P = segperm + ((u64)k * (DEC_SYM_STRIDE / IMTF_SEG + 1) + seg) * 256;
+  P[lane] = (u8)hot;
+  for (int r = 1; r < 8; r++) P[32 * r + lane] = (u8)(cold >> (8 * (r - 1)));
+}
+// per candidate: the list at the start of every segment (in place over segperm)
+__global__ void __launch_bounds__(32) k_imtf_scan(const DecBlk *__restrict__ blks, const u8 *__restrict__ dmap, u8 *__restrict__ segperm) {
+  __shared__ u8 cur[256];
+  const u32 k = blockIdx.x;
+  const u32 m = blks[k].nsym;
+  if (blks[k].kind != 0 || blks[k].err || m == 0) return;
+  const int lane = threadIdx.x;
+  for (int j = lane; j < 256; j += 32) cur[j] = dmap[(u64)k * 256 + j];
+  __syncwarp();
+  const u32 nseg = (m + IMTF_SEG - 1) / IMTF_SEG;
+  for (u32 s2 = 0; s2 < nseg; s2++) {
+    u8 *P = segperm + ((u64)k * (DEC_SYM_STRIDE / IMTF_SEG + 1) + s2) * 256;
+    u8 nxt[8], old[8];
+    for (int r = 0; r < 8; r++) { old[r] = cur[32 * r + lane]; nxt[r] = cur[P[32 * r + lane]]; }
+    __syncwarp();
+    for (int r = 0; r < 8; r++) { P[32 * r + lane] = old[r]; cur[32 * r + lane] = nxt[r]; }
+    __syncwarp();
+  }
+}
+// pass D: decode every segment from its start list; writes the L column
+__global__ void __launch_bounds__(256) k_imtf_decode(const DecBlk *__restrict__ blks, const u16 *__restrict__ dsym, const u32 *__restrict__ doff,
+                                                     const u8 *__restrict__ segperm, u8 *__restrict__ dL, i64 l_stride) {
+  const u32 k = blockIdx.y;
+  const u32 m = blks[k].nsym;
+  const int lane = lane_id();
+  const u32 seg = blockIdx.x * 8 + warp_id();
+  const u32 b0 = seg * IMTF_SEG;
+  if (blks[k].kind != 0 || blks[k].err || b0 >= m) return;
+  const u16 *Sk = dsym + (u64)k * DEC_SYM_STRIDE + b0;
+  const u32 *Ok = doff + (u64)k * DEC_SYM_STRIDE + b0;
+  u8 *Lk = dL + (i64)k * l_stride;
+  const u8 *P = segperm + ((u64)k * (DEC_SYM_STRIDE / IMTF_SEG + 1) + seg) * 256;
+  u32 hot = P[lane];
+  u64 cold = 0;
+  for (int r = 7; r >= 1; r--) cold = (cold << 8) | P[32 * r + lane];
+  u32 lim = m - b0 < IMTF_SEG ? m - b0 : IMTF_SEG;
+  for (u32 c0 = 0; c0 < lim; c0 += 32) {
+    u32 mysym = c0 + lane < lim ? Sk[c0 + lane] : 0u;
+    u32 myoff = c0 + lane <= lim ? Ok[c0 + lane] : 0u;   // Ok[m] exists: one entry past the last symbol
+    u32 nxoff = c0 + lane + 1 <= lim ? Ok[c0 + lane + 1] : myoff;
+    u32 mylen = c0 + lane < lim ? nxoff - myoff : 0u;
+    u32 cnt = lim - c0 < 32 ? lim - c0 : 32;
+    u32 out_byte = 0;
+    for (u32 t = 0; t < cnt; t++) {
+      u32 sy = __shfl_sync(FULL_MASK, mysym, (int)t);
+      u32 byte;
+      if (sy >= 2 && sy - 1 < 256) byte = imtf_step(hot, cold, sy - 1, lane);
+      else byte = __shfl_sync(FULL_MASK, hot, 0);
+      u32 len = __shfl_sync(FULL_MASK, mylen, (int)t);
+      if (len > 1) {  // a RUNA/RUNB digit: many copies of the front byte, written by the whole warp
+        u32 o = __shfl_sync(FULL_MASK, myoff, (int)t);
+        for (u32 q = lane; q < len; q += 32) Lk[o + q] = (u8)byte;
+      }
+      if (lane == (int)t) out_byte = byte;
+    }
+    if (mylen == 1) Lk[myoff] = (u8)out_byte;
   }
 }
 

@@ -49,7 +49,7 @@ int bz2b200_table(bz2b200_ctx *ctx, const uint8_t *in, size_t n, int multistream
 
 int bz2b200_decompress_device(bz2b200_ctx *ctx, const void *d_in, size_t n, int multistream, void *d_out, size_t out_cap, size_t *out_len) {
   Ctx *c = reinterpret_cast<Ctx *>(ctx);
-  if (!c || !out_len || (n && !d_in) || !d_out) return BZ2B200_E_ARG;
+  if (!c || !out_len || (n && !d_in) || !d_out || ((uintptr_t)d_in & 15)) return BZ2B200_E_ARG;
   CK(cudaSetDevice(c->device));
   if (n < 4) return BZ2B200_E_NOT_BZIP_DATA;
   DecodeResult R;

@@ -59,18 +59,28 @@ static int decode_device(Ctx *c, const u8 *d_in, size_t n, int multistream, int 
   const u32 ncand = (u32)cand.size();
   if ((rc = mark(c, 1))) return rc;
 
-  // ---- K-U2/3: decode every candidate ----
-  const i64 LS = round_up(DEC_DBUF_MAX + DEC_STAGE, 256);
+  // ---- K-U2/3: decode every candidate (serial parse per block, then parallel RLE2^-1 / MTF^-1) ----
+  const i64 LS = round_up(DEC_DBUF_MAX + 1024, 256);
   std::vector<DecBlk> blks(ncand);
   if (ncand) {
+    const size_t nsegs = DEC_SYM_STRIDE / IMTF_SEG + 1;
     ENS(c->cand, 8 * (size_t)ncand);
     CK(cudaMemcpyAsync(c->cand.p, cand.data(), 8 * (size_t)ncand, cudaMemcpyHostToDevice, c->stream));
     ENS(c->dmeta, sizeof(DecBlk) * (size_t)ncand);
     ENS(c->dL, (size_t)ncand * LS);
-    ENS(c->dsyms, (size_t)ncand * DEC_MAX_SEL);
-    LAUNCH(k_block_decode, ncand, 32, 0, d_in, (u64)n, P<u64>(c->cand), ncand, (u32)DEC_DBUF_MAX, mode == DEC_BLOCK ? 1 : 0,
-           P<DecBlk>(c->dmeta), P<u8>(c->dL), LS, P<u8>(c->dsyms));
+    ENS(c->dsel, (size_t)ncand * DEC_MAX_SEL);
+    ENS(c->dsyms, 2 * (size_t)ncand * DEC_SYM_STRIDE);
+    ENS(c->doff, 4 * (size_t)ncand * DEC_SYM_STRIDE);
+    ENS(c->dperm, (size_t)ncand * nsegs * 256);
+    ENS(c->dmap, (size_t)ncand * 256);
+    LAUNCH(k_huff_parse, ncand, 32, 0, d_in, (u64)n, P<u64>(c->cand), ncand, (u32)DEC_DBUF_MAX, mode == DEC_BLOCK ? 1 : 0,
+           P<DecBlk>(c->dmeta), P<u16>(c->dsyms), P<u8>(c->dsel), P<u8>(c->dmap));
+    LAUNCH(k_sym_offsets, ncand, 1024, 0, P<DecBlk>(c->dmeta), P<u16>(c->dsyms), P<u32>(c->doff), (u32)DEC_DBUF_MAX);
     CK(cudaMemcpyAsync(blks.data(), c->dmeta.p, sizeof(DecBlk) * (size_t)ncand, cudaMemcpyDeviceToHost, c->stream));
+    LAUNCH(k_imtf_perm, dim3((unsigned)((nsegs + 7) / 8), ncand), 256, 0, P<DecBlk>(c->dmeta), P<u16>(c->dsyms), P<u8>(c->dperm));
+    LAUNCH(k_imtf_scan, ncand, 32, 0, P<DecBlk>(c->dmeta), P<u8>(c->dmap), P<u8>(c->dperm));
+    LAUNCH(k_imtf_decode, dim3((unsigned)((nsegs + 7) / 8), ncand), 256, 0, P<DecBlk>(c->dmeta), P<u16>(c->dsyms), P<u32>(c->doff), P<u8>(c->dperm),
+           P<u8>(c->dL), LS);
     CK(cudaStreamSynchronize(c->stream));
   }
   if ((rc = mark(c, 2))) return rc;
