@@ -257,19 +257,21 @@ __global__ void __launch_bounds__(32) k_huff_parse(const u8 *__restrict__ in, u6
   }
   __syncwarp();
   // ---- symbols (BJ:1597-1616): parse passes ----
-  // Lane 0 keeps a 64-bit window (w0 = current word, w1 = next, both big-endian) and `used` bits consumed of w0.
-  // The warp stages DEC_RING bytes (as byte-swapped words) per pass; lane 0 parses whole 50-symbol groups while a
-  // group's worst case (50 x 20 bits, 50 symbols) still fits in the ring and in the symbol stage.
+  // The warp stages DEC_RING bytes of the stream (byte-swapped words) per pass.  Inside a pass, all lanes run in
+  // lock step: lane l looks up the code that would start at bit P+l (same table: a group is 50 symbols), then the
+  // warp hops through the 32-bit window -- one shuffle per symbol -- and stores the window's symbols with one
+  // coalesced write.  A window never crosses a 50-symbol group (the table changes there).
   const u32 eob = (u32)sym_total + 1;
-  u64 cur_word = sm.bitpos_after_header >> 5;          // index (in 32-bit words of the input) of w0
-  u32 used = (u32)(sm.bitpos_after_header & 31);
+  u64 cur_bit = sm.bitpos_after_header;  // absolute bit position (uniform across the warp)
   u32 flushed = 0;
   int err = 0, done = 0, selector = 0;
+  u32 left = 0;  // symbols left in the current group
+  int gi = 0;
   u32 *ring32 = reinterpret_cast<u32 *>(sm.ring);
-  const u32 RW = DEC_RING / 4;
+  const u32 RBITS = DEC_RING * 8;
   for (;;) {
-    u64 ring_base_w = __shfl_sync(FULL_MASK, cur_word, 0) & ~(u64)3;  // 16-byte aligned
-    for (u32 q = lane; q < RW / 4; q += 32) {
+    const u64 ring_base_w = (cur_bit >> 5) & ~(u64)3;  // 16-byte aligned word index
+    for (u32 q = lane; q < DEC_RING / 16; q += 32) {
       u64 src = (ring_base_w + (u64)q * 4) * 4;
       u32 w[4] = {0, 0, 0, 0};
       if (src + 16 <= n) {
@@ -281,59 +283,58 @@ __global__ void __launch_bounds__(32) k_huff_parse(const u8 *__restrict__ in, u6
       for (int z = 0; z < 4; z++) ring32[q * 4 + z] = __byte_perm(w[z], 0, 0x0123);
     }
     __syncwarp();
-    if (lane == 0) {
-      u32 staged = 0;
-      u32 wpos = (u32)(cur_word - ring_base_w);  // 0..3
-      u32 w0 = ring32[wpos], w1 = ring32[wpos + 1];
-      wpos += 2;                                   // next word to pull
-      while (!done && !err && staged + BZ_GROUP <= DEC_SYM_STAGE && wpos + 34 <= RW) {
+    u32 P = (u32)(cur_bit - ring_base_w * 32);  // bit offset inside the ring
+    u32 staged = 0;
+    while (!done && !err && staged + 32 <= DEC_SYM_STAGE && P + 96 <= RBITS) {
+      if (left == 0) {
         if (selector >= nsel) { err = BZ2B200_E_DATA_ERROR; break; }  // BJ:1601
         if (flushed + staged + BZ_GROUP >= DEC_SYM_STRIDE) { err = BZ2B200_E_DATA_ERROR; break; }  // more symbols than any valid block
-        const int gi = sel[selector++];
-        const u16 *lut = sm.lut[gi];
-        for (int i = 0; i < BZ_GROUP; i++) {
-          u32 win = __funnelshift_l(w1, w0, used);  // the next 32 bits of the stream
-          u32 e = lut[win >> (32 - DEC_LUT_BITS)];
-          u32 sym, len;
-          if (e) { sym = e >> 5; len = e & 31u; }
-          else {  // codes longer than the LUT: the reference's limit/base/permute walk (BJ:1605-1616)
-            int L = sm.minl[gi];
-            int j = (int)(win >> (32 - L));
-            for (;; L++) {
-              if (L > sm.maxl[gi]) { err = BZ2B200_E_DATA_ERROR; break; }
-              if (j <= sm.limit[gi][L]) break;
-              j = (j << 1) | (int)((win >> (31 - L)) & 1u);
-            }
-            if (err) break;
-            j -= sm.base[gi][L];
-            if (j < 0 || j >= BZ_MAX_SYMS) { err = BZ2B200_E_DATA_ERROR; break; }
-            sym = sm.permute[gi][j];
-            len = (u32)L;
-          }
-          used += len;
-          if (used >= 32) { w0 = w1; w1 = ring32[wpos++]; used -= 32; }
-          sm.stage[staged++] = (u16)sym;
-          if (sym == eob) { done = 1; break; }
-        }
+        gi = sel[selector++];
+        left = BZ_GROUP;
       }
-      cur_word = ring_base_w + wpos - 2;
-      if (!err && cur_word * 32 + used > n * 8) err = BZ2B200_E_UNEXPECTED_INPUT_EOF;  // reference: spins on zero bits (D3)
-      sm.hdr[4] = (int)staged;
-      sm.hdr[5] = (err || done) ? 1 : 0;
+      const u32 bp = P + (u32)lane;
+      const u32 win = __funnelshift_l(ring32[(bp >> 5) + 1], ring32[bp >> 5], bp & 31u);  // 32 bits from bit P+lane
+      const u32 e = sm.lut[gi][win >> (32 - DEC_LUT_BITS)];  // (symbol << 5) | length, 0 = longer than the LUT
+      u32 p = 0, cnt = 0, mysym = 0;
+      while (p < 32 && cnt < left) {
+        u32 ee = __shfl_sync(FULL_MASK, e, (int)p);
+        if (ee == 0) {  // long code: the reference's limit/base/permute walk (BJ:1605-1616) on that lane's window
+          u32 wn = __shfl_sync(FULL_MASK, win, (int)p);
+          int L = sm.minl[gi];
+          int j = (int)(wn >> (32 - L));
+          for (;; L++) {
+            if (L > sm.maxl[gi]) { err = BZ2B200_E_DATA_ERROR; break; }
+            if (j <= sm.limit[gi][L]) break;
+            j = (j << 1) | (int)((wn >> (31 - L)) & 1u);
+          }
+          if (err) break;
+          j -= sm.base[gi][L];
+          if (j < 0 || j >= BZ_MAX_SYMS) { err = BZ2B200_E_DATA_ERROR; break; }
+          ee = ((u32)sm.permute[gi][j] << 5) | (u32)L;
+        }
+        if (lane == (int)cnt) mysym = ee >> 5;
+        cnt++;
+        p += ee & 31u;
+        if ((ee >> 5) == eob) { done = 1; break; }
+      }
+      if (lane < (int)cnt) sm.stage[staged + lane] = (u16)mysym;
+      staged += cnt;
+      left -= cnt;
+      P += p;
     }
+    cur_bit = ring_base_w * 32 + P;
+    if (!err && cur_bit > n * 8) err = BZ2B200_E_UNEXPECTED_INPUT_EOF;  // reference: spins on zero bits (D3)
     __syncwarp();
-    u32 staged = (u32)sm.hdr[4];
-    int fin = sm.hdr[5];
     for (u32 q = lane; q < staged; q += 32) Sk[flushed + q] = sm.stage[q];
     flushed += staged;
     __syncwarp();
-    if (fin) break;
+    if (err || done) break;
   }
   if (lane == 0) {
     res.err = err;
     res.count = 0;  // filled by k_sym_offsets
     res.nsym = err ? 0 : flushed;
-    res.endbit = cur_word * 32 + used;
+    res.endbit = cur_bit;
     out[k] = res;
   }
 }
