@@ -105,13 +105,14 @@ __global__ void __launch_bounds__(SEG_THREADS) k_keys_round(const BlockRec *__re
 }
 
 // ---- one LSD radix pass (8-bit digit), batched over blocks ---------------------------------
+// seg_base (optional): slot at which segment p starts; default = seg_tile0[p] * SORT_TILE (block layout)
 __global__ void __launch_bounds__(SORT_THREADS) k_rs_hist(const u64 *__restrict__ keys, const u32 *__restrict__ seg_cnt,
                                                           const u32 *__restrict__ seg_tile0, const u32 *__restrict__ tile_blk, int shift,
-                                                          u32 *__restrict__ hist) {
+                                                          u32 *__restrict__ hist, const u32 *__restrict__ seg_base) {
   __shared__ u32 h[256];
   u32 tile = blockIdx.x, p = tile_blk[tile];
   u32 cnt = seg_cnt[p], l0 = (tile - seg_tile0[p]) * SORT_TILE;
-  u64 g0 = (u64)tile * SORT_TILE;
+  u64 g0 = seg_base ? (u64)seg_base[p] + l0 : (u64)tile * SORT_TILE;
   if (threadIdx.x < 256) h[threadIdx.x] = 0;
   __syncthreads();
   for (int e = 0; e < SORT_E; e++) {
@@ -143,12 +144,12 @@ __global__ void __launch_bounds__(256) k_rs_scan(u32 *__restrict__ hist, const u
 __global__ void __launch_bounds__(SORT_THREADS) k_rs_scatter(const u64 *__restrict__ keys_in, u64 *__restrict__ keys_out,
                                                              const u32 *__restrict__ seg_cnt, const u32 *__restrict__ seg_tile0,
                                                              const u32 *__restrict__ tile_blk, int shift, const u32 *__restrict__ hist,
-                                                             const u32 *__restrict__ digit_base) {
+                                                             const u32 *__restrict__ digit_base, const u32 *__restrict__ seg_base) {
   __shared__ u32 wcnt[SORT_THREADS / 32][256];
   __shared__ u32 base[256];
   u32 tile = blockIdx.x, p = tile_blk[tile];
   u32 cnt = seg_cnt[p], l0 = (tile - seg_tile0[p]) * SORT_TILE;
-  u64 g0 = (u64)tile * SORT_TILE, gp = (u64)seg_tile0[p] * SORT_TILE;
+  u64 gp = seg_base ? (u64)seg_base[p] : (u64)seg_tile0[p] * SORT_TILE, g0 = gp + l0;
   int lane = lane_id(), w = warp_id();
   for (int i = threadIdx.x; i < (SORT_THREADS / 32) * 256; i += SORT_THREADS) (&wcnt[0][0])[i] = 0;
   if (threadIdx.x < 256) base[threadIdx.x] = digit_base[(u64)p * 256 + threadIdx.x] + hist[(u64)tile * 256 + threadIdx.x];
@@ -205,13 +206,13 @@ __device__ __forceinline__ void seg_load_flags(const u64 *__restrict__ keys, u64
 // last sub-group head (slot index within the block) of every tile, or -1
 __global__ void __launch_bounds__(SEG_THREADS) k_sub_heads(const u64 *__restrict__ keys, const u32 *__restrict__ seg_cnt,
                                                            const u32 *__restrict__ seg_tile0, const u32 *__restrict__ tile_blk,
-                                                           int *__restrict__ tile_last) {
+                                                           int *__restrict__ tile_last, const u32 *__restrict__ seg_base) {
   __shared__ int ws[33];
   u32 tile = blockIdx.x, p = tile_blk[tile];
   u32 cnt = seg_cnt[p], l0 = (tile - seg_tile0[p]) * SORT_TILE;
   u64 k[SEG_E];
   u32 flags, lbase;
-  seg_load_flags(keys, (u64)tile * SORT_TILE, l0, cnt, k, flags, lbase);
+  seg_load_flags(keys, seg_base ? (u64)seg_base[p] + l0 : (u64)tile * SORT_TILE, l0, cnt, k, flags, lbase);
   int last = flags ? (int)(lbase + (31 - __clz((int)flags))) : -1;
   last = block_max<int>(last, ws);
   if (threadIdx.x == 0) tile_last[tile] = last;
@@ -285,7 +286,7 @@ __global__ void __launch_bounds__(SEG_THREADS) k_compact(const u64 *__restrict__
                                                          const u32 *__restrict__ seg_cnt, const u32 *__restrict__ seg_tile0,
                                                          const u32 *__restrict__ tile_blk, const int *__restrict__ keep_prefix,
                                                          const u32 *__restrict__ seg_tile0_new, u32 *__restrict__ idx_out,
-                                                         u32 *__restrict__ rank_out, u32 *__restrict__ pos_out) {
+                                                         u32 *__restrict__ rank_out, u32 *__restrict__ pos_out, const u32 *__restrict__ sidx) {
   __shared__ int ws[33];
   u32 tile = blockIdx.x, p = tile_blk[tile];
   u32 cnt = seg_cnt[p], l0 = (tile - seg_tile0[p]) * SORT_TILE;
@@ -304,7 +305,7 @@ __global__ void __launch_bounds__(SEG_THREADS) k_compact(const u64 *__restrict__
 #pragma unroll
   for (int e = 0; e < SEG_E; e++) {
     if (r[e] & KEEP_BIT) {
-      idx_out[dst] = (u32)(keys[g + e] & 0xFFFFFu);
+      idx_out[dst] = sidx ? sidx[g + e] : (u32)(keys[g + e] & 0xFFFFFu);
       rank_out[dst] = r[e] & ~KEEP_BIT;
       pos_out[dst] = a_pos[g + e];
       dst++;

@@ -7,6 +7,7 @@
 #include "common.cuh"
 #include "rle1.cuh"
 #include "bwt.cuh"
+#include "refine.cuh"
 #include "mtf.cuh"
 #include "huff.cuh"
 #include "decode.cuh"
@@ -34,6 +35,7 @@ struct Ctx {
   DevBuf isa, keysA, keysB, valsA, valsB, rankA, rankB, posA, posB, rnew, hist, digit_base;
   DevBuf seg_cnt, seg_cnt2, seg_tile0, seg_tile0b, tile_blk, tile_blkb, tile_i0, tile_i1, tile_i2, tile_i3, totals;
   DevBuf Lcol, ranks, lastocc, A, freq, meta, W, bit_off, scrc, out, out_len, used_bits;
+  DevBuf key2, sidx, big_cnt, big_base, big_blk, big_tile0, big_tblk, nbig, totals2;
   // decode-side buffers
   DevBuf d_in, cand, ncand, dmeta, dsyms, dL, dtt, dwalk, dblk, dout, dmisc, dsel, doff, dperm, dmap;
   // host staging (pinned)
@@ -59,6 +61,7 @@ struct Ctx {
                      &isa, &keysA, &keysB, &valsA, &valsB, &rankA, &rankB, &posA, &posB, &rnew, &hist, &digit_base,
                      &seg_cnt, &seg_cnt2, &seg_tile0, &seg_tile0b, &tile_blk, &tile_blkb, &tile_i0, &tile_i1, &tile_i2, &tile_i3, &totals,
                      &Lcol, &ranks, &lastocc, &A, &freq, &meta, &W, &bit_off, &scrc, &out, &out_len, &used_bits,
+                     &key2, &sidx, &big_cnt, &big_base, &big_blk, &big_tile0, &big_tblk, &nbig, &totals2,
                      &d_in, &cand, &ncand, &dmeta, &dsyms, &dL, &dtt, &dwalk, &dblk, &dout, &dmisc, &dsel, &doff, &dperm, &dmap};
     for (DevBuf *b : all) pool.push_back(b);
   }
@@ -235,43 +238,107 @@ int pipe_stages(Ctx *c) {
     u64 totals_active = 0;
     for (auto &r : hrecs) totals_active += r.n;
     c->dom_used = 0;
-    for (int round = 0;; round++) {
+    auto timed_scatter = [&](unsigned grid, const u64 *ki, u64 *ko, const u32 *scnt, const u32 *st0, const u32 *stb, int shift, const u32 *sbase,
+                             u64 slots_now) -> int {
+      if (c->ev_ok) {
+        if (c->dom_used + 2 > c->dom_ev.size()) {
+          cudaEvent_t a, b2;
+          CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b2));
+          c->dom_ev.push_back(a); c->dom_ev.push_back(b2);
+        }
+        CK(cudaEventRecord(c->dom_ev[c->dom_used], c->stream));
+      }
+      LAUNCH(k_rs_scatter, grid, SORT_THREADS, 0, ki, ko, scnt, st0, stb, shift, P<u32>(c->hist), P<u32>(c->digit_base), sbase);
+      if (c->ev_ok) { CK(cudaEventRecord(c->dom_ev[c->dom_used + 1], c->stream)); c->dom_used += 2; }
+      c->st.dom_launches++;
+      c->st.dom_bytes += 16ull * slots_now;
+      return 0;
+    };
+    // ---- round 0: 5-byte prefix, batched global radix sort (5 passes) ----
+    {
       c->st.sort_rounds++;
       c->st.sort_slots += (u64)Ta * SORT_TILE;
       u64 *ki = kA, *ko = kB;
       for (int pass = 0; pass < 5; pass++) {
-        LAUNCH(k_rs_hist, Ta, SORT_THREADS, 0, ki, seg_cnt, tile0, tblk, 20 + pass * 8, P<u32>(c->hist));
+        LAUNCH(k_rs_hist, Ta, SORT_THREADS, 0, ki, seg_cnt, tile0, tblk, 20 + pass * 8, P<u32>(c->hist), (const u32 *)nullptr);
         LAUNCH(k_rs_scan, (unsigned)nb, 256, 0, P<u32>(c->hist), tile0, P<u32>(c->digit_base));
-        if (c->ev_ok) {
-          if (c->dom_used + 2 > c->dom_ev.size()) {
-            cudaEvent_t a, b;
-            CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
-            c->dom_ev.push_back(a); c->dom_ev.push_back(b);
-          }
-          CK(cudaEventRecord(c->dom_ev[c->dom_used], c->stream));
-        }
-        LAUNCH(k_rs_scatter, Ta, SORT_THREADS, 0, ki, ko, seg_cnt, tile0, tblk, 20 + pass * 8, P<u32>(c->hist), P<u32>(c->digit_base));
-        if (c->ev_ok) { CK(cudaEventRecord(c->dom_ev[c->dom_used + 1], c->stream)); c->dom_used += 2; }
-        c->st.dom_launches++;
-        c->st.dom_bytes += 16ull * totals_active;
+        if ((rc = timed_scatter(Ta, ki, ko, seg_cnt, tile0, tblk, 20 + pass * 8, nullptr, totals_active))) return rc;
         u64 *tk = ki; ki = ko; ko = tk;
       }
-      // sorted keys are now in ki == kB
-      LAUNCH(k_sub_heads, Ta, SEG_THREADS, 0, ki, seg_cnt, tile0, tblk, P<int>(c->tile_i0));
+      LAUNCH(k_sub_heads, Ta, SEG_THREADS, 0, ki, seg_cnt, tile0, tblk, P<int>(c->tile_i0), (const u32 *)nullptr);
       LAUNCH(k_seg_scan, (unsigned)nb, 256, 0, tile0, 0, P<int>(c->tile_i0), P<int>(c->tile_i1), (u32 *)nullptr);
       LAUNCH(k_rank_apply, Ta, SEG_THREADS, 0, ki, pos, seg_cnt, tile0, tblk, P<int>(c->tile_i1), P<u32>(c->isa), BS, P<u32>(c->rnew),
              P<int>(c->tile_i2));
       LAUNCH(k_seg_scan, (unsigned)nb, 256, 0, tile0, 1, P<int>(c->tile_i2), P<int>(c->tile_i3), seg_cnt_n);
       LAUNCH(k_tilemap, 1, 1024, 0, seg_cnt_n, nb, tile0_n, tblk_n, P<u64>(c->totals));
-      LAUNCH(k_compact, Ta, SEG_THREADS, 0, ki, pos, P<u32>(c->rnew), seg_cnt, tile0, tblk, P<int>(c->tile_i3), tile0_n, vA, rank_n, pos_n);
+      LAUNCH(k_compact, Ta, SEG_THREADS, 0, ki, pos, P<u32>(c->rnew), seg_cnt, tile0, tblk, P<int>(c->tile_i3), tile0_n, vA, rank_n, pos_n,
+             (const u32 *)nullptr);
       CK(cudaMemcpyAsync(totals, c->totals.p, sizeof totals, cudaMemcpyDeviceToHost, c->stream));
       CK(cudaStreamSynchronize(c->stream));
       { u32 *t; t = seg_cnt; seg_cnt = seg_cnt_n; seg_cnt_n = t; t = tile0; tile0 = tile0_n; tile0_n = t;
         t = tblk; tblk = tblk_n; tblk_n = t; t = rank; rank = rank_n; rank_n = t; t = pos; pos = pos_n; pos_n = t; }
       Ta = (unsigned)totals[0];
       totals_active = totals[1];
-      if (totals[1] == 0) break;
-      LAUNCH(k_keys_round, Ta, SEG_THREADS, 0, P<BlockRec>(c->recs), seg_cnt, tile0, tblk, P<u32>(c->isa), BS, h, vA, rank, kA);
+    }
+    // ---- rounds >= 1: groups sorted in shared memory; big groups through the global path (refine.cuh) ----
+    const u32 big_cap = (u32)(2 * tiles0 + 16);
+    if (totals_active) {
+      ENS(c->key2, 4 * slots); ENS(c->sidx, 4 * slots);
+      ENS(c->big_cnt, 4 * (size_t)big_cap); ENS(c->big_base, 4 * (size_t)big_cap); ENS(c->big_blk, 4 * (size_t)big_cap);
+      ENS(c->big_tile0, 4 * ((size_t)big_cap + 1)); ENS(c->big_tblk, 4 * (3 * tiles0 + 16));
+      ENS(c->tile_i0, 4 * (3 * tiles0 + 16)); ENS(c->tile_i1, 4 * (3 * tiles0 + 16));
+      ENS(c->hist, 4 * 256 * (3 * tiles0 + 16)); ENS(c->digit_base, 4 * 256 * (size_t)(big_cap > (u32)nb ? big_cap : (u32)nb));
+      ENS(c->nbig, 64); ENS(c->totals2, 64);
+#ifndef BZ_SIM
+      static bool attr2 = false;
+      if (!attr2) {
+        CK(cudaFuncSetAttribute(k_refine_local, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RlSmem)));
+        attr2 = true;
+      }
+#endif
+    }
+    while (totals_active) {
+      c->st.sort_rounds++;
+      c->st.sort_slots += (u64)Ta * SORT_TILE;
+      LAUNCH(k_keys2, Ta, SEG_THREADS, 0, P<BlockRec>(c->recs), seg_cnt, tile0, tblk, P<u32>(c->isa), BS, h, vA, P<u32>(c->key2));
+      CK(cudaMemsetAsync(c->nbig.p, 0, 4, c->stream));
+      LAUNCH(k_refine_local, 2 * Ta, RL_THREADS, sizeof(RlSmem), P<u32>(c->key2), vA, rank, pos, seg_cnt, tile0, tblk, P<u32>(c->isa), BS,
+             P<u32>(c->sidx), P<u32>(c->rnew), P<u32>(c->big_cnt), P<u32>(c->big_base), P<u32>(c->big_blk), P<u32>(c->nbig), big_cap);
+      u32 n_big = 0;
+      CK(cudaMemcpyAsync(&n_big, c->nbig.p, 4, cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      if (n_big > big_cap) { c->err = "internal: big-group list overflow"; return BZ2B200_E_CUDA; }
+      if (n_big) {
+        u32 *bcnt = P<u32>(c->big_cnt), *bbase = P<u32>(c->big_base), *bblk = P<u32>(c->big_blk), *bt0 = P<u32>(c->big_tile0), *btb = P<u32>(c->big_tblk);
+        u64 t2[2] = {0, 0};
+        LAUNCH(k_tilemap, 1, 1024, 0, bcnt, (int)n_big, bt0, btb, P<u64>(c->totals2));
+        CK(cudaMemcpyAsync(t2, c->totals2.p, sizeof t2, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        unsigned Tb = (unsigned)t2[0];
+        LAUNCH(k_big_keys, Tb, SEG_THREADS, 0, P<u32>(c->key2), vA, bcnt, bt0, btb, bbase, kA);
+        u64 *ki = kA, *ko = kB;
+        for (int pass = 0; pass < 3; pass++) {  // key2 < 2^20: bits 20..43
+          LAUNCH(k_rs_hist, Tb, SORT_THREADS, 0, ki, bcnt, bt0, btb, 20 + pass * 8, P<u32>(c->hist), bbase);
+          LAUNCH(k_rs_scan, n_big, 256, 0, P<u32>(c->hist), bt0, P<u32>(c->digit_base));
+          if ((rc = timed_scatter(Tb, ki, ko, bcnt, bt0, btb, 20 + pass * 8, bbase, t2[1]))) return rc;
+          u64 *tk = ki; ki = ko; ko = tk;
+        }
+        LAUNCH(k_sub_heads, Tb, SEG_THREADS, 0, ki, bcnt, bt0, btb, P<int>(c->tile_i0), bbase);
+        LAUNCH(k_seg_scan, n_big, 256, 0, bt0, 0, P<int>(c->tile_i0), P<int>(c->tile_i1), (u32 *)nullptr);
+        LAUNCH(k_big_apply, Tb, SEG_THREADS, 0, ki, pos, bcnt, bt0, btb, bbase, bblk, P<int>(c->tile_i1), P<u32>(c->isa), BS, P<u32>(c->sidx),
+               P<u32>(c->rnew));
+      }
+      LAUNCH(k_keep_count, Ta, SEG_THREADS, 0, P<u32>(c->rnew), seg_cnt, tile0, tblk, P<int>(c->tile_i2));
+      LAUNCH(k_seg_scan, (unsigned)nb, 256, 0, tile0, 1, P<int>(c->tile_i2), P<int>(c->tile_i3), seg_cnt_n);
+      LAUNCH(k_tilemap, 1, 1024, 0, seg_cnt_n, nb, tile0_n, tblk_n, P<u64>(c->totals));
+      LAUNCH(k_compact, Ta, SEG_THREADS, 0, kB, pos, P<u32>(c->rnew), seg_cnt, tile0, tblk, P<int>(c->tile_i3), tile0_n, vA, rank_n, pos_n,
+             P<u32>(c->sidx));
+      CK(cudaMemcpyAsync(totals, c->totals.p, sizeof totals, cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      { u32 *t; t = seg_cnt; seg_cnt = seg_cnt_n; seg_cnt_n = t; t = tile0; tile0 = tile0_n; tile0_n = t;
+        t = tblk; tblk = tblk_n; tblk_n = t; t = rank; rank = rank_n; rank_n = t; t = pos; pos = pos_n; pos_n = t; }
+      Ta = (unsigned)totals[0];
+      totals_active = totals[1];
       h = h >= (1u << 24) ? h : h * 2;
     }
     ENS(c->Lcol, (size_t)nb * BS);
