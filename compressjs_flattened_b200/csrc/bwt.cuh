@@ -6,17 +6,18 @@
 // the j-th rotation; origPtr = rank of rotation 0.
 //
 // Algorithm (Larsson-Sadakane doubling, all blocks of the batch at once):
-//   ISA[i]  = current rank of rotation i = SA index of the first slot of its group
-//   active  = compacted list of the slots whose group still has > 1 member, in SA
-//             order: (a_idx = rotation, a_rank = its group rank, a_pos = SA index of the slot)
-//   round h : key = (a_rank << 40) | ISA[(i+h) mod n] << 20 | i  -> batched LSD radix sort of
-//             bits 20..59 (5 passes of 8 bits); the rotation index rides in the low 20 bits, so a
-//             pass moves keys only -> new group heads where keys
-//             change -> ISA update -> singletons leave the active list.
-//   start   : key = first 5 bytes of the rotation (same 40-bit machinery), h = 5.
+//   ISA[i]  = current rank of rotation i = SA index (inside its block) of the first slot of its group
+//   start   : key = (first 5 bytes of the rotation << 20) | i -> batched LSD radix sort of bits 20..59
+//             (5 passes of 8 bits, keys only); every block's slots are padded to a multiple of SORT_TILE so
+//             a tile never straddles two blocks; tile_blk[] maps a tile to its block.  k_rank0 then finds
+//             the groups, writes ISA and emits the ACTIVE LIST: the slots whose group has > 1 member, in
+//             SA order over all blocks, as (gidx = block * stride + rotation, rank = block * stride + SA
+//             index of the group's first slot).  The list is one global array: groups are contiguous runs
+//             of equal rank, nothing else about blocks is needed (block = gidx / stride).
+//   round h : key2 = ISA[(i+h) mod n] for every active slot (k_keys2), then every group is sorted by key2
+//             (refine.cuh), new groups/ranks/ISA, singletons leave the list.  h = 5, 10, 20, ...
 //   h >= n  : remaining ties are identical rotations: key2 = n-1-i (descending index).
-// Every block's active slots are padded to a multiple of SORT_TILE so a tile never
-// straddles two blocks; tile_blk[] maps a tile to its block.
+// Both list-producing kernels compact IN ORDER in a single pass (decoupled look-back, common.cuh).
 #pragma once
 #include "common.cuh"
 #include "rle1.cuh"
@@ -58,10 +59,10 @@ __global__ void k_seg_init(const BlockRec *__restrict__ recs, int nb, u32 *__res
 }
 
 // ---- key construction ------------------------------------------------------------------------
-// mode 0: first five bytes of each rotation; also initialises a_pos/a_rank/vals for the full block.
+// first five bytes of each rotation, rotation index in the low 20 bits
 __global__ void __launch_bounds__(SEG_THREADS) k_keys_init(const u8 *__restrict__ blk, i64 blk_stride, const BlockRec *__restrict__ recs,
                                                            const u32 *__restrict__ seg_tile0, const u32 *__restrict__ tile_blk,
-                                                           u64 *__restrict__ keys, u32 *__restrict__ a_rank, u32 *__restrict__ a_pos) {
+                                                           u64 *__restrict__ keys) {
   u32 tile = blockIdx.x, p = tile_blk[tile];
   u32 n = recs[p].n;
   const u8 *T = blk + (i64)p * blk_stride;
@@ -78,32 +79,8 @@ __global__ void __launch_bounds__(SEG_THREADS) k_keys_init(const u8 *__restrict_
     }
     u64 g = g0 + (lj - l0);
     keys[g] = (key << 20) | lj;
-    a_rank[g] = 0;
-    a_pos[g] = lj;
   }
 }
-// doubling round: key = (group rank << 20) | rank of the rotation h further on (or n-1-i once h >= n)
-__global__ void __launch_bounds__(SEG_THREADS) k_keys_round(const BlockRec *__restrict__ recs, const u32 *__restrict__ seg_cnt,
-                                                            const u32 *__restrict__ seg_tile0, const u32 *__restrict__ tile_blk,
-                                                            const u32 *__restrict__ isa, i64 isa_stride, u32 h,
-                                                            const u32 *__restrict__ a_idx, const u32 *__restrict__ a_rank,
-                                                            u64 *__restrict__ keys) {
-  u32 tile = blockIdx.x, p = tile_blk[tile];
-  u32 n = recs[p].n, cnt = seg_cnt[p];
-  const u32 *I = isa + (i64)p * isa_stride;
-  u32 l0 = (tile - seg_tile0[p]) * SORT_TILE;
-  u64 g0 = (u64)tile * SORT_TILE;
-  for (int e = 0; e < SEG_E; e++) {
-    u32 lj = l0 + e * SEG_THREADS + threadIdx.x;
-    if (lj >= cnt) continue;
-    u64 g = g0 + (lj - l0);
-    u32 i = a_idx[g], k2;
-    if (h >= n) k2 = n - 1 - i;
-    else { u32 x = i + h; if (x >= n) x -= n; k2 = I[x]; }
-    keys[g] = ((u64)a_rank[g] << 40) | ((u64)k2 << 20) | i;
-  }
-}
-
 // ---- one LSD radix pass (8-bit digit), batched over blocks ---------------------------------
 // seg_base (optional): slot at which segment p starts; default = seg_tile0[p] * SORT_TILE (block layout)
 __global__ void __launch_bounds__(SORT_THREADS) k_rs_hist(const u64 *__restrict__ keys, const u32 *__restrict__ seg_cnt,
@@ -189,7 +166,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_rs_scatter(const u64 *__restri
 }
 
 // ---- regrouping after a sort ---------------------------------------------------------------
-__device__ __forceinline__ void seg_load_flags(const u64 *__restrict__ keys, u64 g0, u32 l0, u32 cnt, u64 k[SEG_E], u32 &flags, u32 &lbase) {
+__device__ __forceinline__ void seg_load_flags(const u64 *__restrict__ keys, u64 g0, u32 l0, u32 cnt, int kshift, u64 k[SEG_E], u32 &flags, u32 &lbase) {
   lbase = l0 + threadIdx.x * SEG_E;
   u64 g = g0 + (u64)threadIdx.x * SEG_E;
   flags = 0;
@@ -198,7 +175,7 @@ __device__ __forceinline__ void seg_load_flags(const u64 *__restrict__ keys, u64
   for (int e = 0; e < SEG_E; e++) {
     if (lbase + e < cnt) {
       k[e] = keys[g + e];
-      if (lbase + e == 0 || (k[e] >> 20) != (prev >> 20)) flags |= 1u << e;
+      if (lbase + e == 0 || (k[e] >> kshift) != (prev >> kshift)) flags |= 1u << e;
       prev = k[e];
     }
   }
@@ -206,13 +183,13 @@ __device__ __forceinline__ void seg_load_flags(const u64 *__restrict__ keys, u64
 // last sub-group head (slot index within the block) of every tile, or -1
 __global__ void __launch_bounds__(SEG_THREADS) k_sub_heads(const u64 *__restrict__ keys, const u32 *__restrict__ seg_cnt,
                                                            const u32 *__restrict__ seg_tile0, const u32 *__restrict__ tile_blk,
-                                                           int *__restrict__ tile_last, const u32 *__restrict__ seg_base) {
+                                                           int *__restrict__ tile_last, const u32 *__restrict__ seg_base, int kshift) {
   __shared__ int ws[33];
   u32 tile = blockIdx.x, p = tile_blk[tile];
   u32 cnt = seg_cnt[p], l0 = (tile - seg_tile0[p]) * SORT_TILE;
   u64 k[SEG_E];
   u32 flags, lbase;
-  seg_load_flags(keys, seg_base ? (u64)seg_base[p] + l0 : (u64)tile * SORT_TILE, l0, cnt, k, flags, lbase);
+  seg_load_flags(keys, seg_base ? (u64)seg_base[p] + l0 : (u64)tile * SORT_TILE, l0, cnt, kshift, k, flags, lbase);
   int last = flags ? (int)(lbase + (31 - __clz((int)flags))) : -1;
   last = block_max<int>(last, ws);
   if (threadIdx.x == 0) tile_last[tile] = last;
@@ -241,75 +218,112 @@ __global__ void __launch_bounds__(256) k_seg_scan(const u32 *__restrict__ seg_ti
   }
   if (mode == 1 && threadIdx.x == 0) seg_cnt_new[p] = (u32)carry;
 }
-// new rank of every active slot, ISA update, keep flag, per-tile kept count
-__global__ void __launch_bounds__(SEG_THREADS) k_rank_apply(const u64 *__restrict__ keys, const u32 *__restrict__ a_pos, const u32 *__restrict__ seg_cnt,
-                                                            const u32 *__restrict__ seg_tile0, const u32 *__restrict__ tile_blk,
-                                                            const int *__restrict__ tile_carry, u32 *__restrict__ isa, i64 isa_stride,
-                                                            u32 *__restrict__ r_new, int *__restrict__ tile_keep) {
-  __shared__ int ws[33];
-  u32 tile = blockIdx.x, p = tile_blk[tile];
-  u32 cnt = seg_cnt[p], l0 = (tile - seg_tile0[p]) * SORT_TILE;
-  u64 g0 = (u64)tile * SORT_TILE, gp = (u64)seg_tile0[p] * SORT_TILE;
-  u64 k[SEG_E];
-  u32 flags, lbase;
-  seg_load_flags(keys, g0, l0, cnt, k, flags, lbase);
-  int my_last = flags ? (int)(lbase + (31 - __clz((int)flags))) : -1, tot;
-  int hb = block_excl_max<int>(my_last, -1, tot, ws);
-  int carry = tile_carry[tile];
-  int cur = hb > carry ? hb : carry;
-  u64 g = g0 + (u64)threadIdx.x * SEG_E;
-  // is the slot after my last one a head?  (needed for the singleton test)
-  u32 nxt = lbase + SEG_E;
-  bool next_head = true;
-  if (nxt < cnt && lbase < cnt) next_head = (keys[g + SEG_E] >> 20) != (k[SEG_E - 1] >> 20);
-  int kept = 0;
-  u32 *I = isa + (i64)p * isa_stride;
+// ---- round 0 regroup: groups, ISA, active list (single pass, ordered) -------------------------------
+#define R0_THREADS 512
+#define R0_ROWS (SORT_TILE / R0_THREADS)  // rows of 32 slots per warp: warp w owns slots [w*256, w*256+256)
+#define R0_NOKEY 0xffffffffffffffffull   // differs from every real key in bits 20.. (real keys are < 2^60)
+__global__ void __launch_bounds__(R0_THREADS) k_rank0(const u64 *__restrict__ keys, const u32 *__restrict__ seg_cnt,
+                                                      const u32 *__restrict__ seg_tile0, const u32 *__restrict__ tile_blk,
+                                                      u32 *__restrict__ isa, i64 stride, u32 *__restrict__ act_idx, u32 *__restrict__ act_rank,
+                                                      u64 *__restrict__ status, u32 *__restrict__ ticket, u32 *__restrict__ n_act_out, u32 ntiles) {
+  __shared__ u64 sk[SORT_TILE + 2];  // sk[1 + i] = key of tile slot i; sk[0] / sk[m + 1] = the neighbours
+  __shared__ int wlast[R0_THREADS / 32];
+  __shared__ u32 wkeep[R0_THREADS / 32];
+  __shared__ u32 sh_tile, sh_base;
+  __shared__ int sh_carry;
+  const int lane = lane_id(), w = warp_id();
+  if (threadIdx.x == 0) sh_tile = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const u32 tile = sh_tile, p = tile_blk[tile];
+  const u32 cnt = seg_cnt[p], l0 = (tile - seg_tile0[p]) * SORT_TILE;
+  const u64 gp = (u64)seg_tile0[p] * SORT_TILE;
+  const u32 m = cnt - l0 < SORT_TILE ? cnt - l0 : SORT_TILE;
+  for (u32 i = threadIdx.x; i < m + 2; i += R0_THREADS) {
+    i64 j = (i64)l0 - 1 + i;
+    sk[i] = (j >= 0 && j < (i64)cnt) ? keys[gp + (u64)j] : R0_NOKEY;
+  }
+  __syncthreads();
+  // phase 1: head / keep ballots of this warp's rows
+  u32 hb[R0_ROWS], kb[R0_ROWS];
+  int wl = -1;
+  u32 nkeep = 0;
 #pragma unroll
-  for (int e = 0; e < SEG_E; e++) {
-    u32 lj = lbase + e;
-    if (lj < cnt) {
-      bool head = (flags >> e) & 1u;
-      if (head) cur = (int)lj;
-      bool nh = e + 1 < SEG_E ? (lj + 1 >= cnt || ((flags >> (e + 1)) & 1u)) : (lj + 1 >= cnt || next_head);
-      u32 rank = a_pos[gp + (u32)cur];
-      bool single = head && nh;
-      I[(u32)(k[e] & 0xFFFFFu)] = rank;
-      r_new[g + e] = rank | (single ? 0u : KEEP_BIT);
-      kept += single ? 0 : 1;
+  for (int e = 0; e < R0_ROWS; e++) {
+    u32 i = (u32)w * (32 * R0_ROWS) + e * 32 + lane;
+    bool valid = i < m, head = false, nh = false;
+    if (valid) {
+      u64 k = sk[i + 1] >> 20;
+      head = k != (sk[i] >> 20);
+      nh = k != (sk[i + 2] >> 20);
+    }
+    hb[e] = __ballot_sync(FULL_MASK, head);
+    kb[e] = __ballot_sync(FULL_MASK, valid && !(head && nh));
+    if (hb[e]) wl = (int)(w * (32 * R0_ROWS) + e * 32 + (31 - __clz((int)hb[e])));
+    nkeep += __popc(kb[e]);
+  }
+  if (lane == 0) { wlast[w] = wl; wkeep[w] = nkeep; }
+  if (w == 0) {
+    // head of the group that contains the tile's first slot when that slot is not a head itself
+    int carry = (int)l0;
+    if (l0 > 0 && (sk[1] >> 20) == (sk[0] >> 20)) {
+      const u64 P5 = sk[1] >> 20;
+      const u64 *K = keys + gp;
+      i64 res = -1;
+      for (u32 c0 = 0; c0 < 64 && res < 0; c0 += 32) {  // slot l0-1 has the prefix; test l0-2-c0-lane
+        i64 j = (i64)l0 - 2 - c0 - lane;
+        bool diff = j < 0 || (K[j] >> 20) != P5;
+        u32 b = __ballot_sync(FULL_MASK, diff);
+        if (b) res = (i64)l0 - 1 - c0 - (__ffs((int)b) - 1);
+      }
+      if (res < 0) {  // long group: first slot of the block with prefix >= P5
+        u32 lo = 0, hi = l0 - 1;
+        while (lo < hi) {
+          u32 mid = (lo + hi) >> 1;
+          if ((K[mid] >> 20) < P5) lo = mid + 1; else hi = mid;
+        }
+        res = lo;
+      }
+      carry = (int)res;
+    }
+    if (lane == 0) sh_carry = carry;
+  }
+  __syncthreads();
+  // ordered compaction base of this tile and of this warp
+  if (w == 0) {
+    u32 x = lane < R0_THREADS / 32 ? wkeep[lane] : 0;
+    u32 inc = warp_incl_sum<u32>(x);
+    u32 agg = __shfl_sync(FULL_MASK, inc, 31);
+    u32 base = lookback_warp(status, tile, agg);
+    if (lane < R0_THREADS / 32) wkeep[lane] = inc - x;
+    if (lane == 0) {
+      sh_base = base;
+      if (tile == ntiles - 1) *n_act_out = base + agg;
     }
   }
-  kept = block_sum<int>(kept, ws);
-  if (threadIdx.x == 0) tile_keep[tile] = kept;
-}
-// move the surviving slots to the next round's (re-padded) layout
-__global__ void __launch_bounds__(SEG_THREADS) k_compact(const u64 *__restrict__ keys, const u32 *__restrict__ a_pos, const u32 *__restrict__ r_new,
-                                                         const u32 *__restrict__ seg_cnt, const u32 *__restrict__ seg_tile0,
-                                                         const u32 *__restrict__ tile_blk, const int *__restrict__ keep_prefix,
-                                                         const u32 *__restrict__ seg_tile0_new, u32 *__restrict__ idx_out,
-                                                         u32 *__restrict__ rank_out, u32 *__restrict__ pos_out, const u32 *__restrict__ sidx) {
-  __shared__ int ws[33];
-  u32 tile = blockIdx.x, p = tile_blk[tile];
-  u32 cnt = seg_cnt[p], l0 = (tile - seg_tile0[p]) * SORT_TILE;
-  u64 g = (u64)tile * SORT_TILE + (u64)threadIdx.x * SEG_E;
-  u32 lbase = l0 + threadIdx.x * SEG_E;
-  u32 r[SEG_E];
-  int mine = 0;
+  int cur = sh_carry;  // block-local SA index of the last head before this warp's slots
+  for (int ww = 0; ww < w; ww++) if (wlast[ww] >= 0) cur = (int)l0 + wlast[ww];
+  __syncthreads();
+  // phase 2: ranks, ISA, survivors
+  const u32 pb = (u32)((u64)p * (u64)stride);
+  u32 out = sh_base + wkeep[w];
+  const u32 le = lane == 31 ? 0xffffffffu : ((2u << lane) - 1);  // lanes <= mine
+  const u32 lt = (1u << lane) - 1;
 #pragma unroll
-  for (int e = 0; e < SEG_E; e++) {
-    r[e] = lbase + e < cnt ? r_new[g + e] : 0;
-    mine += (r[e] & KEEP_BIT) ? 1 : 0;
-  }
-  int tot;
-  int pre = block_excl_sum<int>(mine, tot, ws);
-  u64 dst = (u64)seg_tile0_new[p] * SORT_TILE + (u32)keep_prefix[tile] + (u32)pre;
-#pragma unroll
-  for (int e = 0; e < SEG_E; e++) {
-    if (r[e] & KEEP_BIT) {
-      idx_out[dst] = sidx ? sidx[g + e] : (u32)(keys[g + e] & 0xFFFFFu);
-      rank_out[dst] = r[e] & ~KEEP_BIT;
-      pos_out[dst] = a_pos[g + e];
-      dst++;
+  for (int e = 0; e < R0_ROWS; e++) {
+    u32 i = (u32)w * (32 * R0_ROWS) + e * 32 + lane;
+    u32 mk = hb[e] & le;
+    int hp = mk ? (int)(l0 + w * (32 * R0_ROWS) + e * 32 + (31 - __clz((int)mk))) : cur;
+    if (i < m) {
+      u32 idx = (u32)(sk[i + 1] & 0xFFFFFu);
+      isa[pb + idx] = (u32)hp;
+      if ((kb[e] >> lane) & 1u) {
+        u32 o = out + __popc(kb[e] & lt);
+        act_idx[o] = pb + idx;
+        act_rank[o] = pb + (u32)hp;
+      }
     }
+    if (hb[e]) cur = (int)(l0 + w * (32 * R0_ROWS) + e * 32 + (31 - __clz((int)hb[e])));
+    out += __popc(kb[e]);
   }
 }
 

@@ -32,10 +32,10 @@ struct Ctx {
   std::vector<DevBuf *> pool;
   // compress-side buffers
   DevBuf in, tile_last, tile_first, head_carry, tile_emit, g_tile, recs, nblk, blk, crcpart, pow256;
-  DevBuf isa, keysA, keysB, valsA, valsB, rankA, rankB, posA, posB, rnew, hist, digit_base;
-  DevBuf seg_cnt, seg_cnt2, seg_tile0, seg_tile0b, tile_blk, tile_blkb, tile_i0, tile_i1, tile_i2, tile_i3, totals;
+  DevBuf isa, keysA, keysB, valsB, actI0, actI1, actR0, actR1, lb_status, lbm, hist, digit_base;
+  DevBuf seg_cnt, seg_tile0, tile_blk, tile_i0, tile_i1, totals;
   DevBuf Lcol, ranks, lastocc, A, freq, meta, W, bit_off, scrc, out, out_len, used_bits;
-  DevBuf key2, sidx, big_cnt, big_base, big_blk, big_tile0, big_tblk, nbig, totals2;
+  DevBuf key2, big_cnt, big_old, big_new, big_rank, big_tile0, big_tblk, totals2;
   // decode-side buffers
   DevBuf d_in, cand, ncand, dmeta, dsyms, dL, dtt, dwalk, dblk, dout, dmisc, dsel, doff, dperm, dmap;
   // host staging (pinned)
@@ -58,10 +58,10 @@ struct Ctx {
   size_t dom_used = 0;
   Ctx() {
     DevBuf *all[] = {&in, &tile_last, &tile_first, &head_carry, &tile_emit, &g_tile, &recs, &nblk, &blk, &crcpart, &pow256,
-                     &isa, &keysA, &keysB, &valsA, &valsB, &rankA, &rankB, &posA, &posB, &rnew, &hist, &digit_base,
-                     &seg_cnt, &seg_cnt2, &seg_tile0, &seg_tile0b, &tile_blk, &tile_blkb, &tile_i0, &tile_i1, &tile_i2, &tile_i3, &totals,
+                     &isa, &keysA, &keysB, &valsB, &actI0, &actI1, &actR0, &actR1, &lb_status, &lbm, &hist, &digit_base,
+                     &seg_cnt, &seg_tile0, &tile_blk, &tile_i0, &tile_i1, &totals,
                      &Lcol, &ranks, &lastocc, &A, &freq, &meta, &W, &bit_off, &scrc, &out, &out_len, &used_bits,
-                     &key2, &sidx, &big_cnt, &big_base, &big_blk, &big_tile0, &big_tblk, &nbig, &totals2,
+                     &key2, &big_cnt, &big_old, &big_new, &big_rank, &big_tile0, &big_tblk, &totals2,
                      &d_in, &cand, &ncand, &dmeta, &dsyms, &dL, &dtt, &dwalk, &dblk, &dout, &dmisc, &dsel, &doff, &dperm, &dmap};
     for (DevBuf *b : all) pool.push_back(b);
   }
@@ -154,7 +154,7 @@ int pipe_cut(Ctx *c, i64 s_start, i64 own_end) {
   int nb = 0;
   P_.hrecs.clear();
   if (N > 0 && s_start < N && s_start < own_end) {
-    LAUNCH(k_rle_cut, 1, RLE_THREADS, 0, P_.d_in, N, B, P<i64>(c->head_carry), P<i64>(c->tile_first), P<u64>(c->g_tile), T,
+    LAUNCH(k_rle_cut, 1, CUT_THREADS, 0, P_.d_in, N, B, P<i64>(c->head_carry), P<i64>(c->tile_first), P<u64>(c->g_tile), T,
            P<BlockRec>(c->recs), max_blocks, P<int>(c->nblk), s_start, own_end);
     CK(cudaMemcpyAsync(&nb, c->nblk.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
@@ -210,33 +210,34 @@ int pipe_stages(Ctx *c) {
     // ---- S2 BWT ----
     size_t slots = 0;
     for (auto &r : hrecs) slots += (size_t)round_up(r.n, SORT_TILE);
-    size_t tiles0 = slots / SORT_TILE;
+    const size_t tiles0 = slots / SORT_TILE;
+    if ((u64)nb * (u64)BS >= (1ull << 31)) { c->err = "too many bytes for one call (block table * stride must stay below 2^31)"; return BZ2B200_E_ARG; }
+    const size_t big_tiles = 5 * tiles0 + 16;                // big groups have > RF_T0 slots each
+    const u32 big_cap = (u32)(slots / RF_T0 + 16);
+    const size_t lb_tiles = slots / RF_T0 + tiles0 + 16;
     ENS(c->isa, 4 * (size_t)nb * BS);
     ENS(c->keysA, 8 * slots); ENS(c->keysB, 8 * slots);
-    ENS(c->valsA, 4 * slots);
-    ENS(c->rankA, 4 * slots); ENS(c->rankB, 4 * slots);
-    ENS(c->posA, 4 * slots); ENS(c->posB, 4 * slots);
-    ENS(c->rnew, 4 * slots);
-    ENS(c->hist, 4 * 256 * tiles0); ENS(c->digit_base, 4 * 256 * (size_t)nb);
-    ENS(c->seg_cnt, 4 * (size_t)nb); ENS(c->seg_cnt2, 4 * (size_t)nb);
-    ENS(c->seg_tile0, 4 * (size_t)(nb + 1)); ENS(c->seg_tile0b, 4 * (size_t)(nb + 1));
-    ENS(c->tile_blk, 4 * tiles0); ENS(c->tile_blkb, 4 * tiles0);
-    ENS(c->tile_i0, 4 * tiles0); ENS(c->tile_i1, 4 * tiles0); ENS(c->tile_i2, 4 * tiles0); ENS(c->tile_i3, 4 * tiles0);
-    ENS(c->totals, 64);
-    u32 *seg_cnt = P<u32>(c->seg_cnt), *seg_cnt_n = P<u32>(c->seg_cnt2);
-    u32 *tile0 = P<u32>(c->seg_tile0), *tile0_n = P<u32>(c->seg_tile0b);
-    u32 *tblk = P<u32>(c->tile_blk), *tblk_n = P<u32>(c->tile_blkb);
-    u32 *rank = P<u32>(c->rankA), *rank_n = P<u32>(c->rankB), *pos = P<u32>(c->posA), *pos_n = P<u32>(c->posB);
+    ENS(c->actI0, 4 * slots); ENS(c->actI1, 4 * slots); ENS(c->actR0, 4 * slots); ENS(c->actR1, 4 * slots);
+    ENS(c->key2, 4 * slots);
+    ENS(c->hist, 4 * 256 * big_tiles); ENS(c->digit_base, 4 * 256 * (size_t)(big_cap > (u32)nb ? big_cap : (u32)nb));
+    ENS(c->seg_cnt, 4 * (size_t)nb); ENS(c->seg_tile0, 4 * (size_t)(nb + 1)); ENS(c->tile_blk, 4 * tiles0);
+    ENS(c->tile_i0, 4 * big_tiles); ENS(c->tile_i1, 4 * big_tiles);
+    ENS(c->big_cnt, 4 * (size_t)big_cap); ENS(c->big_old, 4 * (size_t)big_cap); ENS(c->big_new, 4 * (size_t)big_cap);
+    ENS(c->big_rank, 4 * (size_t)big_cap); ENS(c->big_tile0, 4 * ((size_t)big_cap + 1)); ENS(c->big_tblk, 4 * big_tiles);
+    ENS(c->lb_status, 8 * lb_tiles); ENS(c->lbm, 64);
+    ENS(c->totals, 64); ENS(c->totals2, 64);
+    u32 *seg_cnt = P<u32>(c->seg_cnt), *tile0 = P<u32>(c->seg_tile0), *tblk = P<u32>(c->tile_blk);
     u64 *kA = P<u64>(c->keysA), *kB = P<u64>(c->keysB);
-    u32 *vA = P<u32>(c->valsA);
-    u64 totals[2] = {0, 0};
+    u32 *actI[2] = {P<u32>(c->actI0), P<u32>(c->actI1)}, *actR[2] = {P<u32>(c->actR0), P<u32>(c->actR1)};
+    u32 *lbm = P<u32>(c->lbm);  // [0] tile ticket, [1] length of the list being written, [2] big groups of the round
+    u64 *status = P<u64>(c->lb_status);
+    const u64 magic = ~0ull / (u64)BS + 1;  // gidx / BS == umul64hi(gidx, magic) for gidx < 2^32
     LAUNCH(k_seg_init, (unsigned)((nb + 255) / 256), 256, 0, P<BlockRec>(c->recs), nb, seg_cnt);
     LAUNCH(k_tilemap, 1, 1024, 0, seg_cnt, nb, tile0, tblk, P<u64>(c->totals));
-    unsigned Ta = (unsigned)tiles0;
-    LAUNCH(k_keys_init, Ta, SEG_THREADS, 0, P<u8>(c->blk), BS, P<BlockRec>(c->recs), tile0, tblk, kA, rank, pos);
-    u32 h = 5;
-    u64 totals_active = 0;
-    for (auto &r : hrecs) totals_active += r.n;
+    const unsigned Ta = (unsigned)tiles0;
+    LAUNCH(k_keys_init, Ta, SEG_THREADS, 0, P<u8>(c->blk), BS, P<BlockRec>(c->recs), tile0, tblk, kA);
+    u64 total_n = 0;
+    for (auto &r : hrecs) total_n += r.n;
     c->dom_used = 0;
     auto timed_scatter = [&](unsigned grid, const u64 *ki, u64 *ko, const u32 *scnt, const u32 *st0, const u32 *stb, int shift, const u32 *sbase,
                              u64 slots_now) -> int {
@@ -254,7 +255,8 @@ int pipe_stages(Ctx *c) {
       c->st.dom_bytes += 16ull * slots_now;
       return 0;
     };
-    // ---- round 0: 5-byte prefix, batched global radix sort (5 passes) ----
+    u32 hv[4] = {0, 0, 0, 0};
+    // ---- round 0: 5-byte prefix, batched global radix sort (5 passes), then groups + ISA + active list ----
     {
       c->st.sort_rounds++;
       c->st.sort_slots += (u64)Ta * SORT_TILE;
@@ -262,83 +264,61 @@ int pipe_stages(Ctx *c) {
       for (int pass = 0; pass < 5; pass++) {
         LAUNCH(k_rs_hist, Ta, SORT_THREADS, 0, ki, seg_cnt, tile0, tblk, 20 + pass * 8, P<u32>(c->hist), (const u32 *)nullptr);
         LAUNCH(k_rs_scan, (unsigned)nb, 256, 0, P<u32>(c->hist), tile0, P<u32>(c->digit_base));
-        if ((rc = timed_scatter(Ta, ki, ko, seg_cnt, tile0, tblk, 20 + pass * 8, nullptr, totals_active))) return rc;
+        if ((rc = timed_scatter(Ta, ki, ko, seg_cnt, tile0, tblk, 20 + pass * 8, nullptr, total_n))) return rc;
         u64 *tk = ki; ki = ko; ko = tk;
       }
-      LAUNCH(k_sub_heads, Ta, SEG_THREADS, 0, ki, seg_cnt, tile0, tblk, P<int>(c->tile_i0), (const u32 *)nullptr);
-      LAUNCH(k_seg_scan, (unsigned)nb, 256, 0, tile0, 0, P<int>(c->tile_i0), P<int>(c->tile_i1), (u32 *)nullptr);
-      LAUNCH(k_rank_apply, Ta, SEG_THREADS, 0, ki, pos, seg_cnt, tile0, tblk, P<int>(c->tile_i1), P<u32>(c->isa), BS, P<u32>(c->rnew),
-             P<int>(c->tile_i2));
-      LAUNCH(k_seg_scan, (unsigned)nb, 256, 0, tile0, 1, P<int>(c->tile_i2), P<int>(c->tile_i3), seg_cnt_n);
-      LAUNCH(k_tilemap, 1, 1024, 0, seg_cnt_n, nb, tile0_n, tblk_n, P<u64>(c->totals));
-      LAUNCH(k_compact, Ta, SEG_THREADS, 0, ki, pos, P<u32>(c->rnew), seg_cnt, tile0, tblk, P<int>(c->tile_i3), tile0_n, vA, rank_n, pos_n,
-             (const u32 *)nullptr);
-      CK(cudaMemcpyAsync(totals, c->totals.p, sizeof totals, cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaMemsetAsync(lbm, 0, 16, c->stream));
+      CK(cudaMemsetAsync(status, 0, 8 * (size_t)Ta, c->stream));
+      LAUNCH(k_rank0, Ta, R0_THREADS, 0, ki, seg_cnt, tile0, tblk, P<u32>(c->isa), BS, actI[0], actR[0], status, lbm, lbm + 1, (u32)Ta);
+      CK(cudaMemcpyAsync(hv, lbm, sizeof hv, cudaMemcpyDeviceToHost, c->stream));
       CK(cudaStreamSynchronize(c->stream));
-      { u32 *t; t = seg_cnt; seg_cnt = seg_cnt_n; seg_cnt_n = t; t = tile0; tile0 = tile0_n; tile0_n = t;
-        t = tblk; tblk = tblk_n; tblk_n = t; t = rank; rank = rank_n; rank_n = t; t = pos; pos = pos_n; pos_n = t; }
-      Ta = (unsigned)totals[0];
-      totals_active = totals[1];
     }
-    // ---- rounds >= 1: groups sorted in shared memory; big groups through the global path (refine.cuh) ----
-    const u32 big_cap = (u32)(2 * tiles0 + 16);
-    if (totals_active) {
-      ENS(c->key2, 4 * slots); ENS(c->sidx, 4 * slots);
-      ENS(c->big_cnt, 4 * (size_t)big_cap); ENS(c->big_base, 4 * (size_t)big_cap); ENS(c->big_blk, 4 * (size_t)big_cap);
-      ENS(c->big_tile0, 4 * ((size_t)big_cap + 1)); ENS(c->big_tblk, 4 * (3 * tiles0 + 16));
-      ENS(c->tile_i0, 4 * (3 * tiles0 + 16)); ENS(c->tile_i1, 4 * (3 * tiles0 + 16));
-      ENS(c->hist, 4 * 256 * (3 * tiles0 + 16)); ENS(c->digit_base, 4 * 256 * (size_t)(big_cap > (u32)nb ? big_cap : (u32)nb));
-      ENS(c->nbig, 64); ENS(c->totals2, 64);
+    // ---- rounds >= 1 (refine.cuh) ----
+    u32 n_act = hv[1], h = 5;
+    int cur = 0;
 #ifndef BZ_SIM
-      static bool attr2 = false;
-      if (!attr2) {
-        CK(cudaFuncSetAttribute(k_refine_local, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RlSmem)));
-        attr2 = true;
-      }
-#endif
+    static bool attr2 = false;
+    if (!attr2) {
+      CK(cudaFuncSetAttribute(k_refine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RfSmem)));
+      attr2 = true;
     }
-    while (totals_active) {
+#endif
+    while (n_act) {
       c->st.sort_rounds++;
-      c->st.sort_slots += (u64)Ta * SORT_TILE;
-      LAUNCH(k_keys2, Ta, SEG_THREADS, 0, P<BlockRec>(c->recs), seg_cnt, tile0, tblk, P<u32>(c->isa), BS, h, vA, P<u32>(c->key2));
-      CK(cudaMemsetAsync(c->nbig.p, 0, 4, c->stream));
-      LAUNCH(k_refine_local, 2 * Ta, RL_THREADS, sizeof(RlSmem), P<u32>(c->key2), vA, rank, pos, seg_cnt, tile0, tblk, P<u32>(c->isa), BS,
-             P<u32>(c->sidx), P<u32>(c->rnew), P<u32>(c->big_cnt), P<u32>(c->big_base), P<u32>(c->big_blk), P<u32>(c->nbig), big_cap);
-      u32 n_big = 0;
-      CK(cudaMemcpyAsync(&n_big, c->nbig.p, 4, cudaMemcpyDeviceToHost, c->stream));
+      c->st.sort_slots += n_act;
+      const u32 ntiles = (n_act + RF_T0 - 1) / RF_T0;
+      LAUNCH(k_keys2, (n_act + 255) / 256, 256, 0, actI[cur], n_act, P<BlockRec>(c->recs), P<u32>(c->isa), (u32)BS, magic, h, P<u32>(c->key2));
+      CK(cudaMemsetAsync(lbm, 0, 16, c->stream));
+      CK(cudaMemsetAsync(status, 0, 8 * (size_t)ntiles, c->stream));
+      LAUNCH(k_refine, ntiles, RF_THREADS, sizeof(RfSmem), P<u32>(c->key2), actI[cur], actR[cur], n_act, P<u32>(c->isa), (u32)BS, magic, actI[cur ^ 1],
+             actR[cur ^ 1], status, lbm, lbm + 1, ntiles, P<u32>(c->big_cnt), P<u32>(c->big_old), P<u32>(c->big_new), P<u32>(c->big_rank), lbm + 2,
+             big_cap);
+      CK(cudaMemcpyAsync(hv, lbm, sizeof hv, cudaMemcpyDeviceToHost, c->stream));
       CK(cudaStreamSynchronize(c->stream));
+      const u32 n_big = hv[2];
       if (n_big > big_cap) { c->err = "internal: big-group list overflow"; return BZ2B200_E_CUDA; }
-      if (n_big) {
-        u32 *bcnt = P<u32>(c->big_cnt), *bbase = P<u32>(c->big_base), *bblk = P<u32>(c->big_blk), *bt0 = P<u32>(c->big_tile0), *btb = P<u32>(c->big_tblk);
+      if (n_big) {  // groups of more than RF_T0 slots: sorted inside the new list by the global radix sort
+        u32 *bcnt = P<u32>(c->big_cnt), *bold = P<u32>(c->big_old), *bnew = P<u32>(c->big_new), *bt0 = P<u32>(c->big_tile0), *btb = P<u32>(c->big_tblk);
         u64 t2[2] = {0, 0};
         LAUNCH(k_tilemap, 1, 1024, 0, bcnt, (int)n_big, bt0, btb, P<u64>(c->totals2));
         CK(cudaMemcpyAsync(t2, c->totals2.p, sizeof t2, cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
-        unsigned Tb = (unsigned)t2[0];
-        LAUNCH(k_big_keys, Tb, SEG_THREADS, 0, P<u32>(c->key2), vA, bcnt, bt0, btb, bbase, kA);
+        const unsigned Tb = (unsigned)t2[0];
+        LAUNCH(k_big_keys, Tb, SEG_THREADS, 0, P<u32>(c->key2), actI[cur ^ 1], bcnt, bt0, btb, bold, bnew, kA);
         u64 *ki = kA, *ko = kB;
-        for (int pass = 0; pass < 3; pass++) {  // key2 < 2^20: bits 20..43
-          LAUNCH(k_rs_hist, Tb, SORT_THREADS, 0, ki, bcnt, bt0, btb, 20 + pass * 8, P<u32>(c->hist), bbase);
+        for (int pass = 0; pass < 3; pass++) {  // key2 < 2^20: bits 32..55
+          LAUNCH(k_rs_hist, Tb, SORT_THREADS, 0, ki, bcnt, bt0, btb, 32 + pass * 8, P<u32>(c->hist), bnew);
           LAUNCH(k_rs_scan, n_big, 256, 0, P<u32>(c->hist), bt0, P<u32>(c->digit_base));
-          if ((rc = timed_scatter(Tb, ki, ko, bcnt, bt0, btb, 20 + pass * 8, bbase, t2[1]))) return rc;
+          if ((rc = timed_scatter(Tb, ki, ko, bcnt, bt0, btb, 32 + pass * 8, bnew, t2[1]))) return rc;
           u64 *tk = ki; ki = ko; ko = tk;
         }
-        LAUNCH(k_sub_heads, Tb, SEG_THREADS, 0, ki, bcnt, bt0, btb, P<int>(c->tile_i0), bbase);
+        LAUNCH(k_sub_heads, Tb, SEG_THREADS, 0, ki, bcnt, bt0, btb, P<int>(c->tile_i0), bnew, 32);
         LAUNCH(k_seg_scan, n_big, 256, 0, bt0, 0, P<int>(c->tile_i0), P<int>(c->tile_i1), (u32 *)nullptr);
-        LAUNCH(k_big_apply, Tb, SEG_THREADS, 0, ki, pos, bcnt, bt0, btb, bbase, bblk, P<int>(c->tile_i1), P<u32>(c->isa), BS, P<u32>(c->sidx),
-               P<u32>(c->rnew));
+        LAUNCH(k_big_apply, Tb, SEG_THREADS, 0, ki, bcnt, bt0, btb, bnew, P<u32>(c->big_rank), P<int>(c->tile_i1), P<u32>(c->isa), (u32)BS, magic,
+               actI[cur ^ 1], actR[cur ^ 1]);
       }
-      LAUNCH(k_keep_count, Ta, SEG_THREADS, 0, P<u32>(c->rnew), seg_cnt, tile0, tblk, P<int>(c->tile_i2));
-      LAUNCH(k_seg_scan, (unsigned)nb, 256, 0, tile0, 1, P<int>(c->tile_i2), P<int>(c->tile_i3), seg_cnt_n);
-      LAUNCH(k_tilemap, 1, 1024, 0, seg_cnt_n, nb, tile0_n, tblk_n, P<u64>(c->totals));
-      LAUNCH(k_compact, Ta, SEG_THREADS, 0, kB, pos, P<u32>(c->rnew), seg_cnt, tile0, tblk, P<int>(c->tile_i3), tile0_n, vA, rank_n, pos_n,
-             P<u32>(c->sidx));
-      CK(cudaMemcpyAsync(totals, c->totals.p, sizeof totals, cudaMemcpyDeviceToHost, c->stream));
-      CK(cudaStreamSynchronize(c->stream));
-      { u32 *t; t = seg_cnt; seg_cnt = seg_cnt_n; seg_cnt_n = t; t = tile0; tile0 = tile0_n; tile0_n = t;
-        t = tblk; tblk = tblk_n; tblk_n = t; t = rank; rank = rank_n; rank_n = t; t = pos; pos = pos_n; pos_n = t; }
-      Ta = (unsigned)totals[0];
-      totals_active = totals[1];
+      cur ^= 1;
+      n_act = hv[1];
       h = h >= (1u << 24) ? h : h * 2;
     }
     ENS(c->Lcol, (size_t)nb * BS);

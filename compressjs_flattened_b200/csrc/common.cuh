@@ -155,6 +155,38 @@ __device__ __forceinline__ T block_sum(T v, T *ws) {
   return x;
 }
 
+// ---- ordered single-pass compaction: decoupled look-back over tiles -----------------------------
+// status[t]: bits 63..62 = state (1: the tile's own count, 2: inclusive prefix), low 32 bits = value.
+// Tiles take their index from an atomic ticket, so every tile a CTA waits for is already running.
+#define LB_AGG (1ull << 62)
+#define LB_INC (2ull << 62)
+// All 32 lanes of ONE warp of the CTA call this; returns the number of items in the tiles before `tile`.
+__device__ __forceinline__ u32 lookback_warp(volatile u64 *status, u32 tile, u32 aggregate) {
+  const int lane = lane_id();
+  if (tile == 0) {
+    if (lane == 0) { __threadfence(); status[0] = LB_INC | aggregate; }
+    return 0;
+  }
+  if (lane == 0) { __threadfence(); status[tile] = LB_AGG | aggregate; }
+  u32 excl = 0;
+  i64 t = (i64)tile - 1;
+  while (true) {
+    i64 my = t - lane;
+    u64 v = LB_INC;  // before tile 0: inclusive prefix 0
+    if (my >= 0) {
+      do { v = status[my]; } while ((v >> 62) == 0);
+    }
+    u32 inc_mask = __ballot_sync(FULL_MASK, (v >> 62) == 2);
+    int first_inc = inc_mask ? __ffs((int)inc_mask) - 1 : 32;
+    u32 contrib = lane <= first_inc ? (u32)(v & 0xffffffffull) : 0u;
+    excl += warp_sum<u32>(contrib);
+    if (inc_mask) break;
+    t -= 32;
+  }
+  if (lane == 0) { __threadfence(); status[tile] = LB_INC | (u64)(excl + aggregate); }
+  return excl;
+}
+
 // ---- bzip2 CRC (MSB-first CRC-32, poly 0x04C11DB7; BJ:1013-1067) algebra ----
 // A register value is a polynomial over GF(2) with the coefficient of x^k in bit k.
 __host__ __device__ __forceinline__ u32 crc_mulmod(u32 a, u32 b) {

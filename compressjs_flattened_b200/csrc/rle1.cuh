@@ -16,8 +16,8 @@
 //   k_rle_heads  : per 4 KiB tile, first/last run head
 //   k_scan_*     : exclusive scans over the tile summaries (one CTA)
 //   k_rle_count  : per tile, number of emitted bytes -> G at tile granularity
-//   k_rle_cut    : one CTA walks the blocks: closed form for the first run, then
-//                  a binary search on G for the cut; O(log tiles) per block
+//   k_rle_cut    : one CTA walks the blocks, 32 speculated blocks per round (one warp each): closed
+//                  form for the first run, then a 32-ary search on G for the cut
 //   k_rle_emit   : every input position writes its 0-2 output bytes
 //   k_crc_*      : chunked CRC with x^n mod P recombination
 #pragma once
@@ -48,8 +48,8 @@ struct RleView {
   u32 gpre;         // emitted bytes in this tile before p0
 };
 
-__device__ __forceinline__ void rle_load(const u8 *__restrict__ in, i64 N, i64 tile, RleView &v) {
-  v.p0 = tile * RLE_TILE + (i64)threadIdx.x * 16;
+__device__ __forceinline__ void rle_load_at(const u8 *__restrict__ in, i64 N, i64 p0, RleView &v) {
+  v.p0 = p0;
   i64 left = N - v.p0;
   v.nvalid = left >= 16 ? 16 : (left > 0 ? (int)left : 0);
   if (v.nvalid == 16) {
@@ -71,17 +71,11 @@ __device__ __forceinline__ void rle_load(const u8 *__restrict__ in, i64 N, i64 t
   }
   v.flags = f;
 }
-
-// Full per-thread view of a tile: run heads, emitted-byte counts and their prefix.
-// ws64/ws32: >= 33 entries of shared memory each.  All RLE_THREADS threads call it.
-__device__ __forceinline__ void rle_view(const u8 *__restrict__ in, i64 N, i64 tile, const i64 *__restrict__ head_carry,
-                                         RleView &v, u32 &tile_total, i64 *ws64, u32 *ws32) {
-  rle_load(in, N, tile, v);
-  i64 my_last = v.flags ? v.p0 + (31 - __clz((int)v.flags)) : (i64)-1;
-  i64 tot;
-  i64 hb = block_excl_max<i64>(my_last, (i64)-1, tot, ws64);
-  i64 carry = head_carry[tile];
-  v.head_before = hb > carry ? hb : carry;
+__device__ __forceinline__ void rle_load(const u8 *__restrict__ in, i64 N, i64 tile, RleView &v) {
+  rle_load_at(in, N, tile * RLE_TILE + (i64)threadIdx.x * 16, v);
+}
+// emitted bytes (global-fresh coordinates) of the 16 positions of a view whose head_before is known
+__device__ __forceinline__ u32 rle_emits(RleView &v) {
   i64 cur = v.head_before;
   u32 em = 0, cnt = 0;
 #pragma unroll
@@ -95,6 +89,20 @@ __device__ __forceinline__ void rle_view(const u8 *__restrict__ in, i64 N, i64 t
     }
   }
   v.em = em;
+  return cnt;
+}
+
+// Full per-thread view of a tile: run heads, emitted-byte counts and their prefix.
+// ws64/ws32: >= 33 entries of shared memory each.  All RLE_THREADS threads call it.
+__device__ __forceinline__ void rle_view(const u8 *__restrict__ in, i64 N, i64 tile, const i64 *__restrict__ head_carry,
+                                         RleView &v, u32 &tile_total, i64 *ws64, u32 *ws32) {
+  rle_load(in, N, tile, v);
+  i64 my_last = v.flags ? v.p0 + (31 - __clz((int)v.flags)) : (i64)-1;
+  i64 tot;
+  i64 hb = block_excl_max<i64>(my_last, (i64)-1, tot, ws64);
+  i64 carry = head_carry[tile];
+  v.head_before = hb > carry ? hb : carry;
+  u32 cnt = rle_emits(v);
   v.gpre = block_excl_sum<u32>(cnt, tile_total, ws32);
 }
 
@@ -150,108 +158,189 @@ __global__ void __launch_bounds__(1024) k_scan_excl_sum_u32_u64(const u32 *__res
   if (threadIdx.x == 0) out[n] = carry;
 }
 
-// Sequential walk over the blocks (one CTA).  See the file header.
-__global__ void __launch_bounds__(RLE_THREADS) k_rle_cut(const u8 *__restrict__ in, i64 N, u32 B, const i64 *__restrict__ head_carry,
-                                                         const i64 *__restrict__ tile_first, const u64 *__restrict__ g_tile, i64 T,
-                                                         BlockRec *__restrict__ recs, int max_blocks, int *__restrict__ n_blocks, i64 s_start,
-                                                         i64 own_end) {
-  __shared__ i64 ws64[33];
-  __shared__ u32 ws32[33];
-  __shared__ u64 sh_u64;
-  __shared__ i64 sh_i64;
+// ---- block cut points ------------------------------------------------------------------------
+// The chain s_{k+1} = f(s_k) is sequential, but for a "regular" start (one where the fresh automaton and the
+// global-fresh coordinates agree, i.e. any start that is not inside a run of >= 4) a block simply spans B units
+// of G.  One CTA of 32 warps therefore SPECULATES: warp j assumes block k+j starts at the first position whose
+// G reaches G(s_k) + j*B, and runs the exact step f() from there.  The chain is then validated link by link
+// (f(c_j) == c_{j+1}); everything up to the first broken link is committed and the walk restarts from the last
+// exact block end.  Every round commits at least one exactly computed block, so adversarial inputs (cuts inside
+// long runs, count bytes straddling a cut) degrade to the sequential walk and never to a wrong answer.
+#define CUT_WARPS 32
+#define CUT_THREADS (CUT_WARPS * 32)
+#define RLE_CHUNK 512  // bytes a warp looks at per step (16 per lane)
+
+// One warp walks tile `tile` chunk by chunk.  want_pos >= 0: returns the number of bytes emitted inside the tile
+// before position want_pos.  want_pos < 0: returns the first position whose inclusive cumulative emission
+// gbase + ... reaches `target` (INF when the tile ends first).
+__device__ __forceinline__ i64 warp_tile_walk(const u8 *__restrict__ in, i64 N, i64 tile, i64 head_carry_t, u64 gbase, i64 want_pos,
+                                              u64 target) {
   const i64 INF = (i64)0x7fffffffffffffffLL;
-  i64 s = s_start;  // shards: the walk starts at a known cut point and owns the blocks that start before own_end
-  int k = 0;
-  RleView v;
-  u32 tt;
-  while (s < N && s < own_end && k < max_blocks) {
-    // (1) end of the run that contains s
-    i64 ts = s / RLE_TILE;
-    rle_load(in, N, ts, v);
+  const int lane = lane_id();
+  i64 carry_head = head_carry_t;
+  u32 gacc = 0;
+  for (int c = 0; c < RLE_TILE / RLE_CHUNK; c++) {
+    RleView v;
+    rle_load_at(in, N, tile * RLE_TILE + (i64)c * RLE_CHUNK + (i64)lane * 16, v);
+    i64 my_last = v.flags ? v.p0 + (31 - __clz((int)v.flags)) : (i64)-1;
+    i64 inc = warp_incl_max<i64>(my_last);
+    i64 prev = __shfl_up_sync(FULL_MASK, inc, 1);
+    if (lane == 0) prev = -1;
+    v.head_before = prev > carry_head ? prev : carry_head;
+    u32 cnt = rle_emits(v);
+    u32 inc_c = warp_incl_sum<u32>(cnt);
+    v.gpre = gacc + inc_c - cnt;
+    if (want_pos >= 0) {
+      bool mine = want_pos >= v.p0 && want_pos < v.p0 + 16;
+      u32 g = v.gpre;
+      if (mine)
+        for (int j = 0; j < (int)(want_pos - v.p0); j++) g += (v.em >> (2 * j)) & 3u;
+      u32 bal = __ballot_sync(FULL_MASK, mine);
+      g = __shfl_sync(FULL_MASK, g, bal ? __ffs((int)bal) - 1 : 0);
+      if (bal) return (i64)g;
+    } else {
+      u64 run = gbase + v.gpre;
+      i64 c3 = INF;
+      for (int j = 0; j < v.nvalid; j++) {
+        run += (v.em >> (2 * j)) & 3u;
+        if (run >= target) { c3 = v.p0 + j; break; }
+      }
+      c3 = warp_min<i64>(c3);
+      if (c3 != INF) return c3;
+    }
+    i64 last_inc = __shfl_sync(FULL_MASK, inc, 31);
+    if (last_inc > carry_head) carry_head = last_inc;
+    gacc += __shfl_sync(FULL_MASK, inc_c, 31);
+  }
+  return want_pos >= 0 ? (i64)gacc : INF;
+}
+// last t in [lo, hi] with g[t] < target (g non-decreasing, g[lo] < target): 32-ary search by one warp
+__device__ __forceinline__ i64 warp_search_tile(const u64 *__restrict__ g, i64 lo, i64 hi, u64 target) {
+  const int lane = lane_id();
+  while (lo < hi) {
+    i64 step = (hi - lo + 31) / 32;
+    i64 pr = lo + (i64)(lane + 1) * step;
+    bool tr = pr <= hi && g[pr] < target;
+    int cnt = __popc(__ballot_sync(FULL_MASK, tr));
+    lo += (i64)cnt * step;
+    if (lo + step - 1 < hi) hi = lo + step - 1;
+  }
+  return lo;
+}
+// The exact step of the reference's block loop from start s (one warp; every lane returns the same record).
+__device__ __forceinline__ void warp_cut_step(const u8 *__restrict__ in, i64 N, u32 B, const i64 *__restrict__ head_carry,
+                                              const i64 *__restrict__ tile_first, const u64 *__restrict__ g_tile, i64 T, i64 s, BlockRec &r) {
+  const i64 INF = (i64)0x7fffffffffffffffLL;
+  const int lane = lane_id();
+  // (1) end of the run that contains s
+  const i64 ts = s / RLE_TILE;
+  i64 e = INF;
+  for (i64 p = s & ~(i64)(RLE_CHUNK - 1); e == INF && p < (ts + 1) * RLE_TILE && p < N; p += RLE_CHUNK) {
+    RleView v;
+    rle_load_at(in, N, p + (i64)lane * 16, v);
     i64 cand = INF;
     for (int j = 0; j < v.nvalid; j++)
       if ((v.flags & (1u << j)) && v.p0 + j > s) { cand = v.p0 + j; break; }
-    i64 e = block_min<i64>(cand, ws64);
-    for (i64 t0 = ts + 1; e == INF && t0 < T; t0 += RLE_THREADS) {
-      i64 t = t0 + threadIdx.x;
-      i64 c2 = INF;
-      if (t < T) { i64 f = tile_first[t]; if (f >= 0) c2 = f; }
-      e = block_min<i64>(c2, ws64);
-    }
-    if (e == INF) e = N;
-    // (2) closed form for the fresh run [s, e)
-    u64 R = (u64)(e - s);
-    u64 kfull = R / 255;
-    u32 rem = (u32)(R % 255), c = B, out = 0;
-    u64 consumed = 0;
-    u64 fit = c >= 6 ? (u64)((c - 1) / 5) : 0;
-    u64 ncons = kfull < fit ? kfull : fit;
-    out = (u32)(5 * ncons);
-    c -= (u32)(5 * ncons);
-    consumed = 255 * ncons;
-    u32 l = ncons < kfull ? 255u : rem;
-    if (l == 0) {
-    } else if (l <= 3) {
-      if (c > l) { out += l; c -= l; consumed += l; }
-      else { out += c; consumed += c; c = 0; }
+    e = warp_min<i64>(cand);
+  }
+  for (i64 t0 = ts + 1; e == INF && t0 < T; t0 += 32) {
+    i64 t = t0 + lane;
+    i64 c2 = INF;
+    if (t < T) { i64 f = tile_first[t]; if (f >= 0) c2 = f; }
+    e = warp_min<i64>(c2);
+  }
+  if (e == INF) e = N;
+  // (2) closed form for the fresh run [s, e)
+  u64 R = (u64)(e - s);
+  u64 kfull = R / 255;
+  u32 rem = (u32)(R % 255), c = B, out = 0;
+  u64 consumed = 0;
+  u64 fit = c >= 6 ? (u64)((c - 1) / 5) : 0;
+  u64 ncons = kfull < fit ? kfull : fit;
+  out = (u32)(5 * ncons);
+  c -= (u32)(5 * ncons);
+  consumed = 255 * ncons;
+  u32 l = ncons < kfull ? 255u : rem;
+  if (l == 0) {
+  } else if (l <= 3) {
+    if (c > l) { out += l; c -= l; consumed += l; }
+    else { out += c; consumed += c; c = 0; }
+  } else {
+    if (c >= 6) { out += 5; c -= 5; consumed += l; }
+    else if (c == 5) { out += 5; consumed += 4; c = 0; }
+    else if (c == 4) { out += 4; consumed += 4; c = 0; }
+    else { out += c; consumed += c; c = 0; }
+  }
+  r.s = s; r.e_true = e; r.Ge = 0; r.outR = out; r.crc = 0; r.orig_ptr = 0;
+  if (c == 0) {
+    r.p = s + (i64)consumed;
+    r.n = out;
+  } else if (e >= N) {
+    r.p = N;
+    r.n = out;
+  } else {
+    // (3) global-fresh coordinates from e with c bytes of room
+    const i64 te = e / RLE_TILE;
+    const u64 Ge = g_tile[te] + (u64)warp_tile_walk(in, N, te, head_carry[te], 0, e, 0);
+    r.Ge = Ge;
+    const u64 target = Ge + c;
+    if (target > g_tile[T]) {
+      r.p = N;
+      r.n = out + (u32)(g_tile[T] - Ge);
     } else {
-      if (c >= 6) { out += 5; c -= 5; consumed += l; }
-      else if (c == 5) { out += 5; consumed += 4; c = 0; }
-      else if (c == 4) { out += 4; consumed += 4; c = 0; }
-      else { out += c; consumed += c; c = 0; }
+      i64 lo = te + (i64)((c - 1) / 5120u);  // a tile emits at most 5/4 of its bytes, so g_tile[lo] < target
+      if (lo > T - 1) lo = T - 1;
+      const i64 tc = warp_search_tile(g_tile, lo, T - 1, target);
+      const i64 icut = warp_tile_walk(in, N, tc, head_carry[tc], g_tile[tc], -1, target);
+      r.p = icut + 1;
+      r.n = B;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(CUT_THREADS) k_rle_cut(const u8 *__restrict__ in, i64 N, u32 B, const i64 *__restrict__ head_carry,
+                                                         const i64 *__restrict__ tile_first, const u64 *__restrict__ g_tile, i64 T,
+                                                         BlockRec *__restrict__ recs, int max_blocks, int *__restrict__ n_blocks, i64 s_start,
+                                                         i64 own_end) {
+  __shared__ BlockRec sh_rec[CUT_WARPS];
+  __shared__ i64 sh_cand[CUT_WARPS];
+  const i64 INF = (i64)0x7fffffffffffffffLL;
+  const int lane = lane_id(), w = warp_id();
+  const u64 Gtot = g_tile[T];
+  i64 s = s_start;  // shards: the walk starts at a known cut point and owns the blocks that start before own_end
+  int k = 0;
+  while (s < N && s < own_end && k < max_blocks) {
+    // this warp's candidate start
+    i64 cand = INF;
+    if (w == 0) cand = s;
+    else {
+      const i64 tsb = s / RLE_TILE;
+      const u64 gs = g_tile[tsb] + (u64)warp_tile_walk(in, N, tsb, head_carry[tsb], 0, s, 0);
+      const u64 span = (u64)w * B, target = gs + span;
+      if (target <= Gtot) {
+        i64 lo = tsb + (i64)((span - 1) / 5120u);
+        if (lo > T - 1) lo = T - 1;
+        const i64 tc = warp_search_tile(g_tile, lo, T - 1, target);
+        const i64 icut = warp_tile_walk(in, N, tc, head_carry[tc], g_tile[tc], -1, target);
+        if (icut != INF && icut + 1 < N) cand = icut + 1;
+      }
     }
     BlockRec r;
-    r.s = s; r.e_true = e; r.Ge = 0; r.outR = out; r.crc = 0; r.orig_ptr = 0;
-    if (c == 0) {
-      r.p = s + (i64)consumed;
-      r.n = out;
-    } else if (e >= N) {
-      r.p = N;
-      r.n = out;
-    } else {
-      // (3) global-fresh coordinates from e with c bytes of room
-      i64 te = e / RLE_TILE;
-      rle_view(in, N, te, head_carry, v, tt, ws64, ws32);
-      if (e >= v.p0 && e < v.p0 + 16) {
-        u32 g = v.gpre;
-        for (int j = 0; j < (int)(e - v.p0); j++) g += (v.em >> (2 * j)) & 3u;
-        sh_u64 = g_tile[te] + g;
-      }
-      __syncthreads();
-      u64 Ge = sh_u64;
-      __syncthreads();
-      r.Ge = Ge;
-      u64 target = Ge + c;
-      if (target > g_tile[T]) {
-        r.p = N;
-        r.n = out + (u32)(g_tile[T] - Ge);
-      } else {
-        if (threadIdx.x == 0) {  // last tile whose base is below the target
-          i64 lo = te, hi = T - 1;
-          while (lo < hi) {
-            i64 mid = (lo + hi + 1) >> 1;
-            if (g_tile[mid] < target) lo = mid; else hi = mid - 1;
-          }
-          sh_i64 = lo;
-        }
-        __syncthreads();
-        i64 tc = sh_i64;
-        __syncthreads();
-        rle_view(in, N, tc, head_carry, v, tt, ws64, ws32);
-        u64 run = g_tile[tc] + v.gpre;
-        i64 c3 = INF;
-        for (int j = 0; j < v.nvalid; j++) {
-          run += (v.em >> (2 * j)) & 3u;
-          if (run >= target) { c3 = v.p0 + j; break; }
-        }
-        i64 icut = block_min<i64>(c3, ws64);
-        r.p = icut + 1;
-        r.n = B;
-      }
+    r.s = cand; r.p = INF; r.e_true = 0; r.Ge = 0; r.outR = 0; r.n = 0; r.crc = 0; r.orig_ptr = 0;
+    if (cand != INF) warp_cut_step(in, N, B, head_carry, tile_first, g_tile, T, cand, r);
+    if (lane == 0) { sh_cand[w] = cand; sh_rec[w] = r; }
+    __syncthreads();
+    // follow the links that hold
+    int m = 0;
+    while (m + 1 < CUT_WARPS && k + m + 1 < max_blocks) {
+      const i64 nx = sh_rec[m].p;
+      if (!(nx < N && nx < own_end) || sh_cand[m + 1] != nx) break;
+      m++;
     }
-    if (threadIdx.x == 0) recs[k] = r;
-    s = r.p;
-    k++;
+    if ((int)threadIdx.x <= m) recs[k + threadIdx.x] = sh_rec[threadIdx.x];
+    s = sh_rec[m].p;
+    k += m + 1;
+    __syncthreads();
   }
   if (threadIdx.x == 0) *n_blocks = (s < N && s < own_end) ? -1 : k;  // -1: max_blocks too small (cannot happen with the host's bound)
 }

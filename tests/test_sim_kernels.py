@@ -25,6 +25,20 @@ def test_compress_parity_small(sim_engine, oracle, name):
         assert sim_engine.decompressFile(exp) == data
 
 
+def test_bwt_group_classes(sim_engine, oracle):
+    """Small (counting), medium (dense shared-memory radix) and big (global radix, passed through) groups of the
+    doubling rounds, alone and mixed inside one tile; periodic blocks end with the descending-index tie rule."""
+    rng = np.random.default_rng(5)
+    cases = {
+        "ab5000": b"ab" * 5000, "abc3000": b"abc" * 3000, "two50k": bytes(rng.integers(0, 2, 50000, dtype=np.uint8)),
+        "mix": b"ab" * 3000 + bytes(rng.integers(97, 123, 20000, dtype=np.uint8)) + b"xyz" * 2500 + bytes(rng.integers(0, 2, 9000, dtype=np.uint8)),
+        "period97": bytes(rng.integers(97, 123, 97, dtype=np.uint8)) * 400,
+        "three": bytes(rng.integers(0, 3, 30000, dtype=np.uint8)),
+    }
+    for name, data in cases.items():
+        assert sim_engine.compressFile(data, None, 9) == oracle.compress(data, 9), name
+
+
 def test_compress_parity_multiblock_level1(sim_engine, oracle):
     data = fixture_bytes("sample5.ref")[:230_000]
     exp = oracle.compress(data, 1)
@@ -77,6 +91,27 @@ def test_cut_points_stress_tiny_blocks(sim_engine, oracle):
             starts, lens, crcs = oracle.cut_points(data, 9)
             recs = sim_engine.block_table()
             assert [(r.s, r.n, r.crc) for r in recs] == list(zip(starts[:-1], lens, crcs))
+    finally:
+        oracle.set_block_cap(0)
+        sim_engine.debug_set_block_cap(0)
+
+
+def test_cut_points_many_tiles_speculation(sim_engine, oracle):
+    """More blocks than the cut kernel speculates per round, spread over many 4 KiB tiles: text-like stretches
+    (every speculated link holds), stretches of long runs (links break) and mixed."""
+    rng = np.random.default_rng(19)
+    text = rng.integers(97, 123, 120_000, dtype=np.uint8).tobytes()
+    runs = _runny(rng, 60_000, 3, 0.5)
+    zeros = bytes(70_000)
+    data = text[:50_000] + runs[:30_000] + zeros + text[50_000:] + runs[30_000:] + b"x" * 9000 + text[:20_000]
+    try:
+        for cap in (997, 4099, 20_011):
+            oracle.set_block_cap(cap)
+            sim_engine.debug_set_block_cap(cap)
+            starts, lens, crcs = oracle.cut_points(data, 9)
+            sim_engine.compressFile(data, None, 9)
+            recs = sim_engine.block_table()
+            assert [(r.s, r.n, r.crc) for r in recs] == list(zip(starts[:-1], lens, crcs)), f"cap={cap}"
     finally:
         oracle.set_block_cap(0)
         sim_engine.debug_set_block_cap(0)
