@@ -35,7 +35,7 @@ struct Ctx {
   DevBuf isa, keysA, keysB, valsB, actI0, actI1, actR0, actR1, lb_status, lbm, hist, digit_base;
   DevBuf seg_cnt, seg_tile0, tile_blk, tile_i0, tile_i1, totals;
   DevBuf Lcol, ranks, lastocc, A, freq, meta, W, bit_off, scrc, out, out_len, used_bits;
-  DevBuf key2, big_cnt, big_old, big_new, big_rank, big_tile0, big_tblk, totals2;
+  DevBuf key2, big_cnt, big_old, big_rank, big_tile0, big_tblk, totals2;
   // decode-side buffers
   DevBuf d_in, cand, ncand, dmeta, dsyms, dL, dtt, dwalk, dblk, dout, dmisc, dsel, doff, dperm, dmap;
   // host staging (pinned)
@@ -61,7 +61,7 @@ struct Ctx {
                      &isa, &keysA, &keysB, &valsB, &actI0, &actI1, &actR0, &actR1, &lb_status, &lbm, &hist, &digit_base,
                      &seg_cnt, &seg_tile0, &tile_blk, &tile_i0, &tile_i1, &totals,
                      &Lcol, &ranks, &lastocc, &A, &freq, &meta, &W, &bit_off, &scrc, &out, &out_len, &used_bits,
-                     &key2, &big_cnt, &big_old, &big_new, &big_rank, &big_tile0, &big_tblk, &totals2,
+                     &key2, &big_cnt, &big_old, &big_rank, &big_tile0, &big_tblk, &totals2,
                      &d_in, &cand, &ncand, &dmeta, &dsyms, &dL, &dtt, &dwalk, &dblk, &dout, &dmisc, &dsel, &doff, &dperm, &dmap};
     for (DevBuf *b : all) pool.push_back(b);
   }
@@ -222,7 +222,7 @@ int pipe_stages(Ctx *c) {
     ENS(c->hist, 4 * 256 * big_tiles); ENS(c->digit_base, 4 * 256 * (size_t)(big_cap > (u32)nb ? big_cap : (u32)nb));
     ENS(c->seg_cnt, 4 * (size_t)nb); ENS(c->seg_tile0, 4 * (size_t)(nb + 1)); ENS(c->tile_blk, 4 * tiles0);
     ENS(c->tile_i0, 4 * big_tiles); ENS(c->tile_i1, 4 * big_tiles);
-    ENS(c->big_cnt, 4 * (size_t)big_cap); ENS(c->big_old, 4 * (size_t)big_cap); ENS(c->big_new, 4 * (size_t)big_cap);
+    ENS(c->big_cnt, 4 * (size_t)big_cap); ENS(c->big_old, 4 * (size_t)big_cap);
     ENS(c->big_rank, 4 * (size_t)big_cap); ENS(c->big_tile0, 4 * ((size_t)big_cap + 1)); ENS(c->big_tblk, 4 * big_tiles);
     ENS(c->lb_status, 8 * lb_tiles); ENS(c->lbm, 64);
     ENS(c->totals, 64); ENS(c->totals2, 64);
@@ -273,53 +273,54 @@ int pipe_stages(Ctx *c) {
       CK(cudaMemcpyAsync(hv, lbm, sizeof hv, cudaMemcpyDeviceToHost, c->stream));
       CK(cudaStreamSynchronize(c->stream));
     }
-    // ---- rounds >= 1 (refine.cuh) ----
+    // ---- rounds >= 1 (refine.cuh): list A (+ key2) -> sorted staging list B -> compacted list A ----
     u32 n_act = hv[1], h = 5;
-    int cur = 0;
 #ifndef BZ_SIM
     static bool attr2 = false;
     if (!attr2) {
-      CK(cudaFuncSetAttribute(k_refine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RfSmem)));
+      CK(cudaFuncSetAttribute(k_sort_groups, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RfSmem)));
       attr2 = true;
     }
 #endif
+    if (n_act) LAUNCH(k_keys2, (n_act + 255) / 256, 256, 0, actI[0], n_act, P<BlockRec>(c->recs), P<u32>(c->isa), (u32)BS, magic, h, P<u32>(c->key2));
     while (n_act) {
       c->st.sort_rounds++;
       c->st.sort_slots += n_act;
-      const u32 ntiles = (n_act + RF_T0 - 1) / RF_T0;
-      LAUNCH(k_keys2, (n_act + 255) / 256, 256, 0, actI[cur], n_act, P<BlockRec>(c->recs), P<u32>(c->isa), (u32)BS, magic, h, P<u32>(c->key2));
+      const u32 ntiles = (n_act + RF_T0 - 1) / RF_T0, ctiles = (n_act + CK_TILE - 1) / CK_TILE;
       CK(cudaMemsetAsync(lbm, 0, 16, c->stream));
-      CK(cudaMemsetAsync(status, 0, 8 * (size_t)ntiles, c->stream));
-      LAUNCH(k_refine, ntiles, RF_THREADS, sizeof(RfSmem), P<u32>(c->key2), actI[cur], actR[cur], n_act, P<u32>(c->isa), (u32)BS, magic, actI[cur ^ 1],
-             actR[cur ^ 1], status, lbm, lbm + 1, ntiles, P<u32>(c->big_cnt), P<u32>(c->big_old), P<u32>(c->big_new), P<u32>(c->big_rank), lbm + 2,
-             big_cap);
+      CK(cudaMemsetAsync(status, 0, 8 * (size_t)ctiles, c->stream));
+      LAUNCH(k_sort_groups, ntiles, RF_THREADS, sizeof(RfSmem), P<u32>(c->key2), actI[0], actR[0], n_act, P<u32>(c->isa), (u32)BS, magic, actI[1],
+             actR[1], P<u32>(c->big_cnt), P<u32>(c->big_old), P<u32>(c->big_rank), lbm + 2, big_cap);
       CK(cudaMemcpyAsync(hv, lbm, sizeof hv, cudaMemcpyDeviceToHost, c->stream));
       CK(cudaStreamSynchronize(c->stream));
       const u32 n_big = hv[2];
       if (n_big > big_cap) { c->err = "internal: big-group list overflow"; return BZ2B200_E_CUDA; }
-      if (n_big) {  // groups of more than RF_T0 slots: sorted inside the new list by the global radix sort
-        u32 *bcnt = P<u32>(c->big_cnt), *bold = P<u32>(c->big_old), *bnew = P<u32>(c->big_new), *bt0 = P<u32>(c->big_tile0), *btb = P<u32>(c->big_tblk);
+      if (n_big) {  // groups of more than RF_T0 slots: the global radix sort
+        u32 *bcnt = P<u32>(c->big_cnt), *bbase = P<u32>(c->big_old), *bt0 = P<u32>(c->big_tile0), *btb = P<u32>(c->big_tblk);
         u64 t2[2] = {0, 0};
         LAUNCH(k_tilemap, 1, 1024, 0, bcnt, (int)n_big, bt0, btb, P<u64>(c->totals2));
         CK(cudaMemcpyAsync(t2, c->totals2.p, sizeof t2, cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
         const unsigned Tb = (unsigned)t2[0];
-        LAUNCH(k_big_keys, Tb, SEG_THREADS, 0, P<u32>(c->key2), actI[cur ^ 1], bcnt, bt0, btb, bold, bnew, kA);
+        LAUNCH(k_big_keys, Tb, SEG_THREADS, 0, P<u32>(c->key2), actI[0], bcnt, bt0, btb, bbase, kA);
         u64 *ki = kA, *ko = kB;
         for (int pass = 0; pass < 3; pass++) {  // key2 < 2^20: bits 32..55
-          LAUNCH(k_rs_hist, Tb, SORT_THREADS, 0, ki, bcnt, bt0, btb, 32 + pass * 8, P<u32>(c->hist), bnew);
+          LAUNCH(k_rs_hist, Tb, SORT_THREADS, 0, ki, bcnt, bt0, btb, 32 + pass * 8, P<u32>(c->hist), bbase);
           LAUNCH(k_rs_scan, n_big, 256, 0, P<u32>(c->hist), bt0, P<u32>(c->digit_base));
-          if ((rc = timed_scatter(Tb, ki, ko, bcnt, bt0, btb, 32 + pass * 8, bnew, t2[1]))) return rc;
+          if ((rc = timed_scatter(Tb, ki, ko, bcnt, bt0, btb, 32 + pass * 8, bbase, t2[1]))) return rc;
           u64 *tk = ki; ki = ko; ko = tk;
         }
-        LAUNCH(k_sub_heads, Tb, SEG_THREADS, 0, ki, bcnt, bt0, btb, P<int>(c->tile_i0), bnew, 32);
+        LAUNCH(k_sub_heads, Tb, SEG_THREADS, 0, ki, bcnt, bt0, btb, P<int>(c->tile_i0), bbase, 32);
         LAUNCH(k_seg_scan, n_big, 256, 0, bt0, 0, P<int>(c->tile_i0), P<int>(c->tile_i1), (u32 *)nullptr);
-        LAUNCH(k_big_apply, Tb, SEG_THREADS, 0, ki, bcnt, bt0, btb, bnew, P<u32>(c->big_rank), P<int>(c->tile_i1), P<u32>(c->isa), (u32)BS, magic,
-               actI[cur ^ 1], actR[cur ^ 1]);
+        LAUNCH(k_big_apply, Tb, SEG_THREADS, 0, ki, bcnt, bt0, btb, bbase, P<u32>(c->big_rank), P<int>(c->tile_i1), P<u32>(c->isa), (u32)BS, magic,
+               actI[1], actR[1]);
       }
-      cur ^= 1;
-      n_act = hv[1];
       h = h >= (1u << 24) ? h : h * 2;
+      LAUNCH(k_compact_keys, ctiles, CK_THREADS, 0, actI[1], actR[1], n_act, P<BlockRec>(c->recs), P<u32>(c->isa), (u32)BS, magic, h, actI[0], actR[0],
+             P<u32>(c->key2), status, lbm, lbm + 1, ctiles);
+      CK(cudaMemcpyAsync(hv, lbm, sizeof hv, cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      n_act = hv[1];
     }
     ENS(c->Lcol, (size_t)nb * BS);
     LAUNCH(k_bwt_gather, dim3(64, (unsigned)nb), 256, 0, P<u8>(c->blk), BS, P<BlockRec>(c->recs), P<u32>(c->isa), BS, P<u8>(c->Lcol), BS);
