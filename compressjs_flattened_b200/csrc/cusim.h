@@ -233,6 +233,7 @@ static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned s) {
 static inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned sh) { sh &= 31; return sh ? (hi << sh) | (lo >> (32 - sh)) : hi; }
 static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned sh) { sh &= 31; return sh ? (lo >> sh) | (hi << (32 - sh)) : lo; }
 template <typename T> static inline T __ldg(const T *p) { return *p; }
+static inline unsigned __vcmpne4(unsigned a, unsigned b) { unsigned r = 0; for (int i = 0; i < 4; i++) if (((a >> (8 * i)) & 0xff) != ((b >> (8 * i)) & 0xff)) r |= 0xffu << (8 * i); return r; }
 static inline unsigned long long __umul64hi(unsigned long long a, unsigned long long b) { return (unsigned long long)(((unsigned __int128)a * b) >> 64); }
 
 template <typename T> static inline T atomicAdd(T *p, T v) { T o = *p; *p = o + v; return o; }

@@ -5,9 +5,9 @@
 //                  value in the segment; used-byte bitmap of the block
 //   k_mtf_scan     (one CTA per block) alphabetSize, exclusive max-scan of those tables over the segments:
 //                  the MTF list at a segment start is "bytes by last occurrence, unseen bytes ascending"
-//   k_mtf_ranks    (grid-wide, one warp per segment) start list by rank counting, then the sequential MTF
-//                  with the list striped over the warp: row 0 in one register per lane (rank < 32 = one
-//                  ballot + one shuffle), rows 1..7 packed in a u64 per lane (SWAR search, rare)
+//   k_mtf_ranks    (grid-wide, one warp per segment, one THREAD per 128-byte sub-segment) start list of the segment
+//                  by rank counting, start lists of the sub-segments by 31 cooperative composition steps, then
+//                  every lane runs the sequential MTF of its own bytes, list packed in u64 words (SWAR)
 //   k_mtf_rle2     (one CTA per block) zero-rank runs -> bijective base-2 RUNA/RUNB digits, other ranks ->
 //                  rank+1, end-of-block; positions from a block-wide prefix sum; histogram in shared memory
 #pragma once
@@ -100,95 +100,216 @@ __global__ void __launch_bounds__(256) k_mtf_scan(const BlockRec *__restrict__ r
   }
 }
 
-// ---- K-S3c: MTF ranks, one warp per segment ----
-// The list is striped over the warp: entry 32*r + lane lives in lane `lane`, row r.  Row 0 ("hot") is a register of
-// its own: a rank below 32 costs one ballot and one shuffle.  Rows 1..7 are the bytes of a u64 ("cold").
-__global__ void __launch_bounds__(256) k_mtf_ranks(const u8 *__restrict__ L, i64 l_stride, const BlockRec *__restrict__ recs,
-                                                   const int *__restrict__ lastocc, i64 lastocc_stride, u8 *__restrict__ ranks) {
-  __shared__ int tbl[8][256];
-  __shared__ u8 lst[8][256];
+// ---- K-S3c: MTF ranks: one warp per 4 KiB segment, one THREAD per 128-byte sub-segment ----
+// 1. the warp sorts the segment's last-occurrence table (bitonic, 8 keys per lane): the start list;
+// 2. every lane lists the distinct bytes of its sub-segment, most recent first (backward pass + bitmap);
+// 3. 31 warp-cooperative steps give every lane ITS start list: the MTF state after a chunk is
+//    [bytes seen in the chunk, most recent first] ++ [the previous list without them];
+// 4. every lane runs the sequential MTF of its 128 bytes (staged in shared memory, ranks written in place)
+//    with the list as 32 little-endian u64 words: entries 0..15 in two registers, the rest in shared memory
+//    ([word][lane]).  Finding a byte is the SWAR zero-byte test (the lowest flagged byte is exact); moving it
+//    to the front is one shift per word with a byte carried into the next word.  More than half of the bytes
+//    of a BWT'd text repeat their predecessor (rank 0, list untouched): only run heads are stepped.
+#define MTR_SUB (MTF_SEG / 32)
+#define MTR_WARPS 4
+#define MTR_PITCH (MTR_SUB + 4)   // bytes per lane in the staging buffer: lanes in step hit different banks
+struct MtrSmem {
+  u64 lst[32][32];          // [word][lane]: lane's list, 8 entries per word
+  u32 bm[32][9];            // [lane][word]: bitmap of the bytes seen in lane's sub-segment
+  u8 buf[32 * MTR_PITCH];   // step 2/3: lane's distinct bytes, most recent first; step 4: its bytes -> its ranks
+};
+__device__ __forceinline__ u32 mtf_step(u64 &hot0, u64 &hot1, u64 (*lst)[32], int lane, u32 b) {
+  const u64 ONES = 0x0101010101010101ULL, HIGHS = 0x8080808080808080ULL;
+  const u64 pat = ONES * b;
+  u64 x = hot0 ^ pat, z = (x - ONES) & ~x & HIGHS;
+  if (z) {
+    u32 pos = (u32)(__ffsll((long long)z) - 1) >> 3;
+    u64 m = (2ULL << (8 * pos + 7)) - 1;
+    hot0 = (hot0 & ~m) | (((hot0 << 8) | b) & m);
+    return pos;
+  }
+  u64 c = hot0 >> 56;
+  hot0 = (hot0 << 8) | b;
+  x = hot1 ^ pat; z = (x - ONES) & ~x & HIGHS;
+  if (z) {
+    u32 pos = (u32)(__ffsll((long long)z) - 1) >> 3;
+    u64 m = (2ULL << (8 * pos + 7)) - 1;
+    hot1 = (hot1 & ~m) | (((hot1 << 8) | c) & m);
+    return 8 + pos;
+  }
+  u64 c2 = hot1 >> 56;
+  hot1 = (hot1 << 8) | c;
+  c = c2;
+  for (u32 k = 2;; k++) {  // every byte value is somewhere in the list
+    u64 w = lst[k][lane];
+    x = w ^ pat; z = (x - ONES) & ~x & HIGHS;
+    if (z) {
+      u32 pos = (u32)(__ffsll((long long)z) - 1) >> 3;
+      u64 m = (2ULL << (8 * pos + 7)) - 1;
+      lst[k][lane] = (w & ~m) | (((w << 8) | c) & m);
+      return 8 * k + pos;
+    }
+    lst[k][lane] = (w << 8) | c;
+    c = w >> 56;
+  }
+}
+// grid (ceil(nseg_max / MTR_WARPS), nb), MTR_WARPS * 32 threads, dynamic shared memory MTR_WARPS * sizeof(MtrSmem)
+__global__ void __launch_bounds__(MTR_WARPS * 32) k_mtf_ranks(const u8 *__restrict__ L, i64 l_stride, const BlockRec *__restrict__ recs,
+                                                              const int *__restrict__ lastocc, i64 lastocc_stride, u8 *__restrict__ ranks) {
+  DYN_SMEM(MtrSmem, smw);
   const u32 p = blockIdx.y;
   const u32 n = recs[p].n;
-  const int lane = lane_id(), w = warp_id();
-  const u32 s = blockIdx.x * 8 + w;
-  const u32 b0 = s * MTF_SEG;
-  if (b0 >= n) return;
+  const int lane = lane_id();
+  MtrSmem &sm = smw[warp_id()];
+  const u32 s = blockIdx.x * MTR_WARPS + warp_id();
+  const u32 seg0 = s * MTF_SEG;
+  if (seg0 >= n) return;
   const u8 *Lp = L + (i64)p * l_stride;
   u8 *Rp = ranks + (i64)p * l_stride;
-  const int *occ = lastocc + (i64)p * lastocc_stride + (i64)s * 256;
-  for (int c = lane; c < 256; c += 32) tbl[w][c] = occ[c];
-  __syncwarp();
+  // 1. start list of the segment -> column 0: byte values by last occurrence, descending (all keys distinct)
   {
-    int mine[8], rank[8];
+    const int *occ = lastocc + (i64)p * lastocc_stride + (i64)s * 256;
+    u32 v[8];
 #pragma unroll
-    for (int k = 0; k < 8; k++) { mine[k] = tbl[w][lane + 32 * k]; rank[k] = 0; }
-    for (int o = 0; o < 256; o++) {
-      int t = tbl[w][o];
+    for (int k = 0; k < 8; k++) v[k] = ((u32)(occ[lane * 8 + k] + 131072) << 8) | (u32)(lane * 8 + k);
+    // bitonic network over e = lane*8+k, final order descending
 #pragma unroll
-      for (int k = 0; k < 8; k++) rank[k] += t > mine[k] ? 1 : 0;
-    }
+    for (int size = 2; size <= 256; size <<= 1) {
 #pragma unroll
-    for (int k = 0; k < 8; k++) lst[w][rank[k]] = (u8)(lane + 32 * k);
-  }
-  __syncwarp();
-  u32 hot = lst[w][lane];
-  u64 cold = 0;
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        if (stride >= 8) {
+          const int dl = stride >> 3;
+          const bool up = ((lane * 8) & size) != 0;        // this run sorts ascending (only when size < 256)
+          const bool low = (lane & dl) == 0;               // I hold the lower index of the pair
 #pragma unroll
-  for (int r = 7; r >= 1; r--) cold = (cold << 8) | lst[w][32 * r + lane];
-  u32 front = lst[w][0];
-  const u32 *L32 = reinterpret_cast<const u32 *>(Lp + b0);
-  u32 *R32 = reinterpret_cast<u32 *>(Rp + b0);
-  for (u32 ch = 0; ch < MTF_SEG / 128 && b0 + ch * 128 < n; ch++) {
-    u32 w4 = L32[ch * 32 + lane];  // buffers are padded: reading past n inside the stride is fine
-    u32 mine = 0;
-    u32 lim = n - (b0 + ch * 128);
-    u32 nwords = lim >= 128 ? 32u : (lim + 3) / 4;
-    for (u32 wq = 0; wq < nwords; wq++) {
-      u32 word = __shfl_sync(FULL_MASK, w4, (int)wq);
-      u32 acc = 0;
+          for (int k = 0; k < 8; k++) {
+            u32 o = __shfl_xor_sync(FULL_MASK, v[k], dl);
+            bool take_max = (low != up);                   // descending run: lower index keeps the max
+            v[k] = take_max ? (v[k] > o ? v[k] : o) : (v[k] < o ? v[k] : o);
+          }
+        } else {
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
-        u32 b = (word >> (8 * k)) & 0xffu;
-        u32 j = 0;
-        if (b != front) {
-          u32 m = __ballot_sync(FULL_MASK, hot == b);
-          if (m) {
-            int l = __ffs((int)m) - 1;
-            j = (u32)l;
-            u32 up = __shfl_up_sync(FULL_MASK, hot, 1);
-            if (lane <= l) hot = lane == 0 ? b : up;
-          } else {
-            u64 x = cold ^ (0x0101010101010101ULL * b);
-            u64 z = (x - 0x0101010101010101ULL) & ~x & 0x0080808080808080ULL;
-            u32 mm = __ballot_sync(FULL_MASK, z != 0);
-            int l = __ffs((int)mm) - 1;
-            u64 zz = __shfl_sync(FULL_MASK, z, l);
-            int row = 1 + ((__ffsll((long long)zz) - 1) >> 3);
-            j = (u32)(32 * row + l);
-            // every entry before (row, l) moves one place down the list; b becomes the front
-            u32 carry = b;  // what enters lane 0 of the row being shifted
-            {
-              u32 last = __shfl_sync(FULL_MASK, hot, 31);
-              u32 up = __shfl_up_sync(FULL_MASK, hot, 1);
-              hot = lane == 0 ? carry : up;
-              carry = last;
-            }
-            for (int r = 1; r <= row; r++) {
-              u32 cur = (u32)(cold >> (8 * (r - 1))) & 0xffu;
-              u32 last = __shfl_sync(FULL_MASK, cur, 31);
-              u32 up = __shfl_up_sync(FULL_MASK, cur, 1);
-              u32 nv = lane == 0 ? carry : up;
-              if (r < row || lane <= l) cold = (cold & ~(0xffULL << (8 * (r - 1)))) | ((u64)nv << (8 * (r - 1)));
-              carry = last;
+          for (int k = 0; k < 8; k++) {
+            if ((k & stride) == 0) {
+              const int e = lane * 8 + k;
+              const bool up = (e & size) != 0;
+              u32 a = v[k], bb = v[k | stride];
+              u32 hi = a > bb ? a : bb, lo = a > bb ? bb : a;
+              v[k] = up ? lo : hi;
+              v[k | stride] = up ? hi : lo;
             }
           }
-          front = b;
         }
-        acc |= j << (8 * k);
       }
-      if (lane == (int)wq) mine = acc;
     }
-    R32[ch * 32 + lane] = mine;  // bytes past n are garbage ranks inside the padded stride; never read
+    u64 w = 0;
+#pragma unroll
+    for (int k = 7; k >= 0; k--) w = (w << 8) | (v[k] & 0xffu);
+    sm.lst[lane][0] = w;
+  }
+  // 2. distinct bytes of my sub-segment, most recent first
+  const u32 b0 = seg0 + (u32)lane * MTR_SUB;
+  const u32 len = b0 >= n ? 0u : (n - b0 < MTR_SUB ? n - b0 : (u32)MTR_SUB);
+  const uint4 *L16 = reinterpret_cast<const uint4 *>(Lp + b0);  // buffers are padded: reading past n inside the stride is fine
+  u8 *mybuf = sm.buf + lane * MTR_PITCH;
+#pragma unroll
+  for (int q = 0; q < 8; q++) sm.bm[lane][q] = 0;
+  u32 nseen = 0;
+  for (int ch = (int)((len + 15) / 16) - 1; ch >= 0; ch--) {
+    uint4 in = L16[ch];
+    u32 wi[4] = {in.x, in.y, in.z, in.w};
+#pragma unroll
+    for (int q = 3; q >= 0; q--) {
+#pragma unroll
+      for (int k = 3; k >= 0; k--) {
+        if ((u32)ch * 16 + q * 4 + k < len) {
+          u32 c = (wi[q] >> (8 * k)) & 0xffu;
+          u32 bw = sm.bm[lane][c >> 5];
+          if (!((bw >> (c & 31)) & 1u)) {
+            sm.bm[lane][c >> 5] = bw | (1u << (c & 31));
+            mybuf[nseen++] = (u8)c;
+          }
+        }
+      }
+    }
+  }
+  __syncwarp();
+  // 3. lane l+1's start list = seen[l] ++ (lane l's start list without the bytes of seen[l])
+  for (int l = 0; l < 31; l++) {
+    const u32 cnt = __shfl_sync(FULL_MASK, nseen, l);
+    const u64 w = sm.lst[lane][l];  // my 8 entries of lane l's list
+    if (cnt == 0) { sm.lst[lane][l + 1] = w; __syncwarp(); continue; }
+    const u32 bmw = sm.bm[l][lane & 7];  // lanes 0..7 hold lane l's bitmap words
+    u32 keep = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      u32 c = (u32)(w >> (8 * k)) & 0xffu;
+      u32 word = __shfl_sync(FULL_MASK, bmw, (int)(c >> 5));
+      if (!((word >> (c & 31)) & 1u)) keep |= 1u << k;
+    }
+    u32 nk = __popc(keep);
+    u32 dst = cnt + warp_incl_sum<u32>(nk) - nk;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      if ((keep >> k) & 1u) {
+        reinterpret_cast<u8 *>(&sm.lst[dst >> 3][l + 1])[dst & 7] = (u8)(w >> (8 * k));
+        dst++;
+      }
+    }
+    const u8 *sl = sm.buf + l * MTR_PITCH;
+    for (u32 i = lane; i < cnt; i += 32) reinterpret_cast<u8 *>(&sm.lst[i >> 3][l + 1])[i & 7] = sl[i];
+    __syncwarp();
+  }
+  // 4. sequential MTF of my sub-segment, in place in the staging buffer.  A byte equal to its predecessor has
+  // rank 0 without touching the list (the predecessor is at the front), so only run heads are stepped.
+  if (len == 0) return;
+  u32 *B32 = reinterpret_cast<u32 *>(mybuf);  // the pitch is a multiple of 4, not of 16
+  u32 hm[MTR_SUB / 32];                        // head bit per byte; the first byte always counts as a head
+  {
+    u32 prev = 0x100;  // differs from every byte
+#pragma unroll
+    for (int ch = 0; ch < MTR_SUB / 16; ch++) {
+      u32 bits16 = 0;
+      if ((u32)ch * 16 < len) {
+        uint4 in = L16[ch];
+        u32 wi[4] = {in.x, in.y, in.z, in.w};
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          B32[4 * ch + q] = wi[q];
+          u32 ne = __vcmpne4(wi[q], (wi[q] << 8) | (prev & 0xffu));
+          if (prev == 0x100) ne |= 0xffu;
+          bits16 |= (((ne & 0x01010101u) * 0x01020408u) >> 24) << (4 * q);
+          prev = wi[q] >> 24;
+        }
+      }
+      if (ch & 1) hm[ch >> 1] |= bits16 << 16; else hm[ch >> 1] = bits16;
+    }
+  }
+  u64 hot0 = sm.lst[0][lane], hot1 = sm.lst[1][lane];
+#pragma unroll
+  for (int q = 0; q < MTR_SUB / 32; q++) {
+    u32 mask = hm[q];
+    if (len < (u32)(q + 1) * 32) mask &= len > (u32)q * 32 ? (1u << (len - q * 32)) - 1 : 0u;
+    while (mask) {
+      u32 i = (u32)q * 32 + (u32)(__ffs((int)mask) - 1);
+      mask &= mask - 1;
+      mybuf[i] = (u8)mtf_step(hot0, hot1, sm.lst, lane, mybuf[i]);
+    }
+  }
+  {
+    uint4 *R16 = reinterpret_cast<uint4 *>(Rp + b0);
+#pragma unroll
+    for (int ch = 0; ch < MTR_SUB / 16; ch++) {  // bytes past n: garbage inside the padded stride, never read
+      if ((u32)ch * 16 < len) {
+        u32 bits16 = (hm[ch >> 1] >> (16 * (ch & 1))) & 0xffffu, wo[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          u32 keep = ((((bits16 >> (4 * q)) & 0xfu) * 0x00204081u) & 0x01010101u) * 0xffu;
+          wo[q] = B32[4 * ch + q] & keep;  // non-heads: rank 0
+        }
+        R16[ch] = make_uint4(wo[0], wo[1], wo[2], wo[3]);
+      }
+    }
   }
 }
 
