@@ -14,7 +14,7 @@
 #include "common.cuh"
 #include "rle1.cuh"
 
-#define MTF_SEG 4096
+#define MTF_SEG 8192
 #define MTF_THREADS 1024
 #define MTF_WARPS 32
 #define MTF_ABSENT (-2000000000)  // below every initial-order key
