@@ -36,6 +36,7 @@ struct Ctx {
   DevBuf seg_cnt, seg_tile0, tile_blk, tile_i0, tile_i1, totals;
   DevBuf Lcol, ranks, lastocc, A, freq, meta, W, bit_off, scrc, out, out_len, used_bits;
   DevBuf key2, big_cnt, big_old, big_rank, big_tile0, big_tblk, totals2;
+  DevBuf hfreq, hlens, hplen, hcodes, hsel, hcost, hgoff, hblk;
   // decode-side buffers
   DevBuf d_in, cand, ncand, dmeta, dsyms, dL, dtt, dwalk, dblk, dout, dmisc, dsel, doff, dperm, dmap;
   // host staging (pinned)
@@ -62,6 +63,7 @@ struct Ctx {
                      &seg_cnt, &seg_tile0, &tile_blk, &tile_i0, &tile_i1, &totals,
                      &Lcol, &ranks, &lastocc, &A, &freq, &meta, &W, &bit_off, &scrc, &out, &out_len, &used_bits,
                      &key2, &big_cnt, &big_old, &big_rank, &big_tile0, &big_tblk, &totals2,
+                     &hfreq, &hlens, &hplen, &hcodes, &hsel, &hcost, &hgoff, &hblk,
                      &d_in, &cand, &ncand, &dmeta, &dsyms, &dL, &dtt, &dwalk, &dblk, &dout, &dmisc, &dsel, &doff, &dperm, &dmap};
     for (DevBuf *b : all) pool.push_back(b);
   }
@@ -349,20 +351,42 @@ int pipe_stages(Ctx *c) {
     LAUNCH(k_mtf_rle2, (unsigned)nb, MTF_THREADS, 0, P<BlockRec>(c->recs), P<u8>(c->ranks), BS, P<u16>(c->A), AS, P<u32>(c->freq), P<BlockMeta>(c->meta));
     if ((rc = mark(c, 3))) return rc;
 
-    // ---- S4/S5 Huffman + emission ----
+    // ---- S4/S5 Huffman + emission (huff.cuh) ----
     u64 maxbits = 80 + 25 + 16 + 256 + 18 + 7ull * ((B + 1 + 49) / 50) + 6ull * (5 + 258 * 39) + 20ull * (B + 1);
     WS = round_up((i64)((maxbits + 31) / 32) + 2, 64);
-    ENS(c->W, 4 * (size_t)nb * WS);
-    CK(cudaMemsetAsync(c->W.p, 0, 4 * (size_t)nb * WS, c->stream));
+    ENS(c->W, 4 * (size_t)nb * WS);  // zeroed per block by k_huf_codes, only as far as the block's bits reach
+    const u32 max_nsel = (B + 1 + BZ_GROUP - 1) / BZ_GROUP;
+    HufArrays ha;
+    ha.sel_stride = round_up((i64)max_nsel + 1, 16);
+    ENS(c->hfreq, 4 * (size_t)nb * BZ_MAX_GROUPS * BZ_MAX_SYMS);
+    ENS(c->hlens, (size_t)nb * BZ_MAX_GROUPS * HUF_LSTRIDE);
+    ENS(c->hplen, 8 * (size_t)nb * BZ_MAX_SYMS);
+    ENS(c->hcodes, 4 * (size_t)nb * BZ_MAX_GROUPS * BZ_MAX_SYMS);
+    ENS(c->hsel, (size_t)nb * ha.sel_stride);
+    ENS(c->hcost, 2 * (size_t)nb * ha.sel_stride);
+    ENS(c->hgoff, 4 * (size_t)nb * ha.sel_stride);
+    ENS(c->hblk, sizeof(HufBlk) * (size_t)nb);
+    ha.freq = P<u32>(c->hfreq); ha.lens = P<u8>(c->hlens); ha.plen = P<u64>(c->hplen); ha.codes = P<u32>(c->hcodes);
+    ha.sel = P<u8>(c->hsel); ha.cost = P<u16>(c->hcost); ha.goff = P<u32>(c->hgoff); ha.hb = P<HufBlk>(c->hblk);
 #ifndef BZ_SIM
     static bool attr_set = false;
     if (!attr_set) {
-      CK(cudaFuncSetAttribute(k_huff_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HufSmem)));
+      CK(cudaFuncSetAttribute(k_huf_init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HufBuildSmem)));
+      CK(cudaFuncSetAttribute(k_huf_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HufBuildSmem)));
       attr_set = true;
     }
 #endif
-    LAUNCH(k_huff_encode, (unsigned)nb, HUF_THREADS, sizeof(HufSmem), P<u16>(c->A), AS, P<u32>(c->freq), P<BlockRec>(c->recs),
-           P<BlockMeta>(c->meta), P<u32>(c->W), WS);
+    const dim3 ggrid((max_nsel + HUF_GT - 1) / HUF_GT, (unsigned)nb);
+    LAUNCH(k_huf_init, (unsigned)nb, HUF_BT, sizeof(HufBuildSmem), ha, P<u32>(c->freq), P<BlockMeta>(c->meta));
+    for (int it = 0; it < BZ_MAX_GROUPS - 2; it++) {  // 2 -> 6 tables; blocks at their target skip
+      LAUNCH(k_huf_assign, ggrid, HUF_GT, 0, ha, P<u16>(c->A), AS, 0);
+      LAUNCH(k_huf_split, (unsigned)nb, HUF_BT, 0, ha);
+      LAUNCH(k_huf_hist, ggrid, HUF_GT, 0, ha, P<u16>(c->A), AS);
+      LAUNCH(k_huf_build, (unsigned)nb, HUF_BT, sizeof(HufBuildSmem), ha);
+    }
+    LAUNCH(k_huf_assign, ggrid, HUF_GT, 0, ha, P<u16>(c->A), AS, 1);  // BJ:2163
+    LAUNCH(k_huf_codes, (unsigned)nb, HUF_CT, 0, ha, P<BlockRec>(c->recs), P<BlockMeta>(c->meta), P<u32>(c->W), WS);
+    LAUNCH(k_huf_emit, ggrid, HUF_GT, 0, ha, P<u16>(c->A), AS, P<u32>(c->W), WS);
   } else {
     for (int i = 1; i <= 3; i++) if ((rc = mark(c, i))) return rc;
   }

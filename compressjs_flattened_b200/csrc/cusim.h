@@ -37,7 +37,7 @@ static inline uint2 make_uint2(unsigned a, unsigned b) { return uint2{a, b}; }
 #define __shared__ static
 #define __launch_bounds__(...)
 #define __constant__ static
-#define __align__(x) alignas(x)
+#define __align__(x) __attribute__((aligned(x)))
 
 typedef int cudaError_t;
 typedef void *cudaStream_t;

@@ -9,29 +9,42 @@
 //     (positions >= len>>>1) to a new table, recount ALL histograms, rebuild ALL tables;
 //   - code lengths: keys (freq<<9)|sym ascending through the in-place length-limited
 //     allocator with limit 20; canonical codes by (length, symbol).
-// One CTA per block; tables, selectors and group costs live in shared memory, the symbol
-// array streams from L2.  The allocator itself is sequential (<= 258 leaves) and runs on one
-// thread per table.
+// The optimiser is a chain of small kernels so that the passes over the symbols run grid-wide:
+//   k_huf_init    (per block)  first two tables {global histogram, flat}
+//   k_huf_assign  (grid-wide)  cost of every group of 50 symbols under every table (all six lengths of a symbol
+//                              packed in one u64, so one add per symbol), winner + its cost
+//   k_huf_split   (per block)  most-used table, stable median split (counting sort over costs), new selector ids
+//   k_huf_hist    (grid-wide)  histograms of all tables from the selectors
+//   k_huf_build   (per block)  code lengths of all tables (the allocator is sequential: one thread per table)
+//   k_huf_codes   (per block)  canonical codes, block header, selector + table bits, bit offset of every group
+//   k_huf_emit    (grid-wide)  every thread packs one group of 50 symbols at its bit offset
+// A block leaves the loop when it has its target number of tables (BJ:2150); the host launches the
+// assign/split/hist/build round four times (2 -> 6 tables) and finished blocks skip.
 #pragma once
 #include "common.cuh"
 #include "mtf.cuh"
 
-#define HUF_THREADS 1024
-#define HUF_MAX_SEL 18016
 #define HUF_LSTRIDE 260
+#define HUF_GT 256                       // groups per CTA of the grid-wide kernels (one per thread)
+#define HUF_GT_SYMS (HUF_GT * BZ_GROUP)  // symbols staged per CTA
+#define HUF_BT 256                       // threads of the per-block kernels
+#define HUF_CT 1024                      // threads of k_huf_codes
 
-struct HufSmem {
-  u32 freq[BZ_MAX_GROUPS][BZ_MAX_SYMS];
-  u32 keys[BZ_MAX_GROUPS][BZ_MAX_SYMS];
-  int work[BZ_MAX_GROUPS][BZ_MAX_SYMS];
-  u32 code[BZ_MAX_GROUPS][BZ_MAX_SYMS];
-  u32 chist[1024];
-  u32 ws[34];
-  u32 counts[8];
-  u32 bcast[8];
-  u16 cost[HUF_MAX_SEL];
-  u8 sel[HUF_MAX_SEL];
-  u8 lens[BZ_MAX_GROUPS][HUF_LSTRIDE];
+struct HufBlk {   // optimiser state of one block
+  int ng, target, S, active;
+  u32 m, nsel, pad0, pad1;
+};
+// per-block arrays in global memory (strides in elements)
+struct HufArrays {
+  u32 *freq;     // [nb][6][BZ_MAX_SYMS]
+  u8 *lens;      // [nb][6][HUF_LSTRIDE]
+  u64 *plen;     // [nb][BZ_MAX_SYMS]: the six lengths of a symbol, 10 bits each
+  u32 *codes;    // [nb][6][BZ_MAX_SYMS]: length << 24 | canonical code
+  u8 *sel;       // [nb][sel_stride]
+  u16 *cost;     // [nb][sel_stride]: first the winning cost of the group, finally the selector MTF rank
+  u32 *goff;     // [nb][sel_stride]: bit offset of the group inside the block's stream
+  HufBlk *hb;    // [nb]
+  i64 sel_stride;
 };
 
 // ---- in-place length-limited code-length allocation (BJ:1135-1298) -------------------------
@@ -96,9 +109,15 @@ __device__ inline void ha_allocate(int *a, int N, int maxlen) {
   }
 }
 
-// rebuild tables [0, ng) from sm.freq (StaticHuffman ctor, BJ:1866-1894)
-__device__ inline void huf_build(HufSmem &sm, int ng, int S) {
-  for (int x = threadIdx.x; x < ng * S; x += HUF_THREADS) {
+// rebuild tables [0, ng) from freq (StaticHuffman ctor, BJ:1866-1894); blockDim.x == HUF_BT
+struct HufBuildSmem {
+  u32 freq[BZ_MAX_GROUPS][BZ_MAX_SYMS];
+  u32 keys[BZ_MAX_GROUPS][BZ_MAX_SYMS];
+  int work[BZ_MAX_GROUPS][BZ_MAX_SYMS];
+  u8 lens[BZ_MAX_GROUPS][HUF_LSTRIDE];
+};
+__device__ inline void huf_build(HufBuildSmem &sm, int ng, int S, u8 *__restrict__ lens_g, u64 *__restrict__ plen_g) {
+  for (int x = threadIdx.x; x < ng * S; x += HUF_BT) {
     int t = x / S, i = x - t * S;
     u32 key = (sm.freq[t][i] << 9) | (u32)i;
     int rank = 0;
@@ -106,39 +125,198 @@ __device__ inline void huf_build(HufSmem &sm, int ng, int S) {
     sm.keys[t][rank] = key;
   }
   __syncthreads();
-  for (int x = threadIdx.x; x < ng * S; x += HUF_THREADS) {
+  for (int x = threadIdx.x; x < ng * S; x += HUF_BT) {
     int t = x / S, i = x - t * S;
     sm.work[t][i] = (int)(sm.keys[t][i] >> 9);
   }
   __syncthreads();
   if ((threadIdx.x & 31) == 0 && (int)(threadIdx.x >> 5) < ng) ha_allocate(sm.work[threadIdx.x >> 5], S, BZ_MAX_CODE);
   __syncthreads();
-  for (int x = threadIdx.x; x < ng * S; x += HUF_THREADS) {
+  for (int x = threadIdx.x; x < ng * S; x += HUF_BT) {
     int t = x / S, i = x - t * S;
     sm.lens[t][sm.keys[t][i] & 0x1ffu] = (u8)sm.work[t][i];
   }
   __syncthreads();
+  for (int x = threadIdx.x; x < ng * S; x += HUF_BT) {
+    int t = x / S, i = x - t * S;
+    lens_g[t * HUF_LSTRIDE + i] = sm.lens[t][i];
+  }
+  for (int i = threadIdx.x; i < S; i += HUF_BT) {
+    u64 v = 0;
+    for (int t = 0; t < ng; t++) v |= (u64)sm.lens[t][i] << (10 * t);
+    plen_g[i] = v;
+  }
 }
 
-// BJ:1989-2004; also records each group's winning cost
-__device__ inline void huf_assign(HufSmem &sm, int ng, const u16 *__restrict__ Ap, u32 m, u32 nsel) {
-  for (u32 g = threadIdx.x; g < nsel; g += HUF_THREADS) {
-    u32 i0 = g * BZ_GROUP, i1 = i0 + BZ_GROUP < m ? i0 + BZ_GROUP : m;
-    u32 c[BZ_MAX_GROUPS] = {0, 0, 0, 0, 0, 0};
-    for (u32 i = i0; i < i1; i++) {
-      u32 sym = Ap[i];
-#pragma unroll
-      for (int t = 0; t < BZ_MAX_GROUPS; t++)
-        if (t < ng) c[t] += sm.lens[t][sym];
-    }
-    u32 best = 0, bc = c[0];
-#pragma unroll
-    for (int t = 1; t < BZ_MAX_GROUPS; t++)
-      if (t < ng && c[t] < bc) { best = t; bc = c[t]; }
-    sm.sel[g] = (u8)best;
-    sm.cost[g] = (u16)bc;
+// initial tables: global histogram and flat (BJ:2155-2157)
+__global__ void __launch_bounds__(HUF_BT) k_huf_init(HufArrays ha, const u32 *__restrict__ freq_in, const BlockMeta *__restrict__ meta) {
+  DYN_SMEM(HufBuildSmem, smp);
+  HufBuildSmem &sm = *smp;
+  const u32 p = blockIdx.x;
+  const u32 m = meta[p].m, alpha = meta[p].alpha;
+  const int S = (int)alpha + 2;
+  for (int i = threadIdx.x; i < S; i += HUF_BT) {
+    sm.freq[0][i] = freq_in[(i64)p * BZ_MAX_SYMS + i];
+    sm.freq[1][i] = 1;
+  }
+  if (threadIdx.x == 0) {
+    HufBlk h;
+    h.ng = 2;
+    h.target = m >= 2400 ? 6 : m >= 1200 ? 5 : m >= 600 ? 4 : m >= 200 ? 3 : 2;  // BJ:2150
+    h.S = S; h.active = 0; h.m = m; h.nsel = (m + BZ_GROUP - 1) / BZ_GROUP; h.pad0 = h.pad1 = 0;
+    ha.hb[p] = h;
   }
   __syncthreads();
+  huf_build(sm, 2, S, ha.lens + (i64)p * BZ_MAX_GROUPS * HUF_LSTRIDE, ha.plen + (i64)p * BZ_MAX_SYMS);
+}
+
+// BJ:1989-2004; also records each group's winning cost.  grid (ceil(max nsel / HUF_GT), nb)
+__global__ void __launch_bounds__(HUF_GT) k_huf_assign(HufArrays ha, const u16 *__restrict__ A, i64 a_stride, int final_pass) {
+  __align__(16) __shared__ u16 sy[HUF_GT_SYMS];
+  __shared__ u64 pl[BZ_MAX_SYMS];
+  const u32 p = blockIdx.y;
+  const HufBlk h = ha.hb[p];
+  if (!final_pass && h.ng >= h.target) return;
+  const u32 g0 = blockIdx.x * HUF_GT;
+  if (g0 >= h.nsel) return;
+  const u16 *Ap = A + (i64)p * a_stride;
+  const u32 i0 = g0 * BZ_GROUP, cnt = h.m - i0 < HUF_GT_SYMS ? h.m - i0 : (u32)HUF_GT_SYMS;
+  {
+    const uint4 *src = reinterpret_cast<const uint4 *>(Ap + i0);  // 16-byte aligned: the stride and i0 are multiples of 8 symbols
+    uint4 *dst = reinterpret_cast<uint4 *>(sy);
+    for (u32 x = threadIdx.x; x < (cnt + 7) / 8; x += HUF_GT) dst[x] = src[x];
+  }
+  for (int i = threadIdx.x; i < h.S; i += HUF_GT) pl[i] = ha.plen[(i64)p * BZ_MAX_SYMS + i];
+  __syncthreads();
+  const u32 g = g0 + threadIdx.x;
+  if (g >= h.nsel) return;
+  const u32 j0 = threadIdx.x * BZ_GROUP, j1 = j0 + BZ_GROUP < cnt ? j0 + BZ_GROUP : cnt;
+  u64 acc = 0;
+  for (u32 j = j0; j < j1; j++) acc += pl[sy[j]];
+  u32 best = 0, bc = (u32)(acc & 1023u);
+#pragma unroll
+  for (int t = 1; t < BZ_MAX_GROUPS; t++) {
+    u32 ct = (u32)(acc >> (10 * t)) & 1023u;
+    if (t < h.ng && ct < bc) { best = t; bc = ct; }
+  }
+  ha.sel[(i64)p * ha.sel_stride + g] = (u8)best;
+  ha.cost[(i64)p * ha.sel_stride + g] = (u16)bc;
+}
+
+// BJ:2014-2036: first most-used table, stable median split; zeroes the histograms for k_huf_hist
+__global__ void __launch_bounds__(HUF_BT) k_huf_split(HufArrays ha) {
+  __shared__ u32 chist[1024];
+  __shared__ u32 counts[8];
+  __shared__ u32 bcast[2];
+  __shared__ u32 ws[34];
+  const u32 p = blockIdx.x;
+  const HufBlk h = ha.hb[p];
+  if (h.ng >= h.target) {
+    if (threadIdx.x == 0 && h.active) ha.hb[p].active = 0;
+    return;
+  }
+  u8 *sel = ha.sel + (i64)p * ha.sel_stride;
+  const u16 *cost = ha.cost + (i64)p * ha.sel_stride;
+  const u32 nsel = h.nsel;
+  const int ng = h.ng;
+  if (threadIdx.x < 8) counts[threadIdx.x] = 0;
+  for (int i = threadIdx.x; i < 1024; i += HUF_BT) chist[i] = 0;
+  __syncthreads();
+  {
+    u32 loc[BZ_MAX_GROUPS] = {0, 0, 0, 0, 0, 0};
+    for (u32 g = threadIdx.x; g < nsel; g += HUF_BT) {
+      u32 s = sel[g];
+#pragma unroll
+      for (int t = 0; t < BZ_MAX_GROUPS; t++) loc[t] += s == (u32)t ? 1u : 0u;
+    }
+#pragma unroll
+    for (int t = 0; t < BZ_MAX_GROUPS; t++) {
+      u32 v = warp_sum<u32>(loc[t]);
+      if (lane_id() == 0 && v) atomicAdd(&counts[t], v);
+    }
+  }
+  __syncthreads();
+  int which = 0;
+  for (int t = 1; t < ng; t++) if (counts[t] > counts[which]) which = t;  // first maximum (BJ:2019)
+  for (u32 g = threadIdx.x; g < nsel; g += HUF_BT)
+    if (sel[g] == which) atomicAdd(&chist[cost[g]], 1u);
+  __syncthreads();
+  const u32 len = counts[which], half = len >> 1;
+  if (threadIdx.x == 0) {  // cost bin that straddles the median position
+    u32 cum = 0, c = 0;
+    for (; c < 1024; c++) {
+      if (cum + chist[c] > half) break;
+      cum += chist[c];
+    }
+    bcast[0] = c;    // 1024 when len == 0 (cannot happen: the most-used table has a group)
+    bcast[1] = cum;  // groups strictly cheaper than that bin
+  }
+  __syncthreads();
+  const u32 cstar = bcast[0], below = bcast[1];
+  u32 carry = 0;
+  for (u32 base = 0; base < nsel; base += HUF_BT) {
+    u32 g = base + threadIdx.x;
+    bool mine = g < nsel && sel[g] == which;
+    u32 cg = mine ? cost[g] : 0;
+    u32 flag = (mine && cg == cstar) ? 1u : 0u, tot;
+    u32 occ = carry + block_excl_sum<u32>(flag, tot, ws);
+    if (mine && (cg > cstar || (cg == cstar && below + occ >= half))) sel[g] = (u8)ng;
+    carry += tot;
+  }
+  u32 *fq = ha.freq + (i64)p * BZ_MAX_GROUPS * BZ_MAX_SYMS;
+  for (int i = threadIdx.x; i < (ng + 1) * BZ_MAX_SYMS; i += HUF_BT) fq[i] = 0;
+  if (threadIdx.x == 0) { ha.hb[p].ng = ng + 1; ha.hb[p].active = 1; }
+}
+
+// BJ:2037-2048: histograms of all tables.  grid (ceil(max nsel / HUF_GT), nb)
+__global__ void __launch_bounds__(HUF_GT) k_huf_hist(HufArrays ha, const u16 *__restrict__ A, i64 a_stride) {
+  __shared__ u32 hs[BZ_MAX_GROUPS][BZ_MAX_SYMS];
+  __shared__ u8 ss[HUF_GT];
+  const u32 p = blockIdx.y;
+  const HufBlk h = ha.hb[p];
+  if (!h.active) return;
+  const u32 g0 = blockIdx.x * HUF_GT;
+  if (g0 >= h.nsel) return;
+  const u16 *Ap = A + (i64)p * a_stride;
+  const u32 i0 = g0 * BZ_GROUP, cnt = h.m - i0 < HUF_GT_SYMS ? h.m - i0 : (u32)HUF_GT_SYMS;
+  for (int i = threadIdx.x; i < h.ng * BZ_MAX_SYMS; i += HUF_GT) (&hs[0][0])[i] = 0;
+  ss[threadIdx.x] = g0 + threadIdx.x < h.nsel ? ha.sel[(i64)p * ha.sel_stride + g0 + threadIdx.x] : 0;
+  __syncthreads();
+  {
+    const uint4 *src = reinterpret_cast<const uint4 *>(Ap + i0);
+    for (u32 x = threadIdx.x; x < (cnt + 7) / 8; x += HUF_GT) {
+      uint4 v = src[x];
+      u32 wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        u32 j = x * 8 + q;
+        if (j < cnt) atomicAdd(&hs[ss[j / BZ_GROUP]][(wv[q >> 1] >> (16 * (q & 1))) & 0xffffu], 1u);
+      }
+    }
+  }
+  __syncthreads();
+  u32 *fq = ha.freq + (i64)p * BZ_MAX_GROUPS * BZ_MAX_SYMS;
+  for (int x = threadIdx.x; x < h.ng * h.S; x += HUF_GT) {
+    int t = x / h.S, i = x - t * h.S;
+    u32 v = hs[t][i];
+    if (v) atomicAdd(&fq[t * BZ_MAX_SYMS + i], v);
+  }
+}
+
+// BJ:2050-2052: rebuild every table
+__global__ void __launch_bounds__(HUF_BT) k_huf_build(HufArrays ha) {
+  DYN_SMEM(HufBuildSmem, smp);
+  HufBuildSmem &sm = *smp;
+  const u32 p = blockIdx.x;
+  const HufBlk h = ha.hb[p];
+  if (!h.active) return;
+  const u32 *fq = ha.freq + (i64)p * BZ_MAX_GROUPS * BZ_MAX_SYMS;
+  for (int x = threadIdx.x; x < h.ng * h.S; x += HUF_BT) {
+    int t = x / h.S, i = x - t * h.S;
+    sm.freq[t][i] = fq[t * BZ_MAX_SYMS + i];
+  }
+  __syncthreads();
+  huf_build(sm, h.ng, h.S, ha.lens + (i64)p * BZ_MAX_GROUPS * HUF_LSTRIDE, ha.plen + (i64)p * BZ_MAX_SYMS);
 }
 
 __device__ __forceinline__ void put_bits(u32 *W, u64 o, u64 val, u32 len) {
@@ -159,88 +337,58 @@ __device__ __forceinline__ u64 emit_items(u32 *W, u64 bitpos, u64 val, u32 len, 
   return bitpos + tot;
 }
 
-__global__ void __launch_bounds__(HUF_THREADS) k_huff_encode(const u16 *__restrict__ A, i64 a_stride, const u32 *__restrict__ freq_in,
-                                                             const BlockRec *__restrict__ recs, BlockMeta *__restrict__ meta,
-                                                             u32 *__restrict__ W, i64 w_stride) {
-  DYN_SMEM(HufSmem, smp);
-  HufSmem &sm = *smp;
+// canonical codes, block header, selectors, tables, bit offset of every group.  One CTA per block.
+struct HufCodesSmem {
+  u8 lens[BZ_MAX_GROUPS][HUF_LSTRIDE];
+  int first[BZ_MAX_GROUPS][BZ_MAX_CODE + 2];
+  u32 ws[34];
+  u32 bcast[4];
+};
+__global__ void __launch_bounds__(HUF_CT) k_huf_codes(HufArrays ha, const BlockRec *__restrict__ recs, BlockMeta *__restrict__ meta,
+                                                      u32 *__restrict__ W, i64 w_stride) {
+  __shared__ HufCodesSmem sm;
   const u32 p = blockIdx.x;
-  const u16 *Ap = A + (i64)p * a_stride;
+  const HufBlk h = ha.hb[p];
+  const int ng = h.ng, S = h.S;
+  const u32 nsel = h.nsel, alpha = (u32)S - 2;
   u32 *Wp = W + (i64)p * w_stride;
-  const u32 m = meta[p].m, alpha = meta[p].alpha;
-  const int S = (int)alpha + 2;
-  const u32 nsel = (m + BZ_GROUP - 1) / BZ_GROUP;
-  const int target = m >= 2400 ? 6 : m >= 1200 ? 5 : m >= 600 ? 4 : m >= 200 ? 3 : 2;  // BJ:2150
-
-  // initial tables: global histogram and flat (BJ:2155-2157)
-  for (int i = threadIdx.x; i < S; i += HUF_THREADS) {
-    sm.freq[0][i] = freq_in[(i64)p * BZ_MAX_SYMS + i];
-    sm.freq[1][i] = 1;
+  u8 *sel = ha.sel + (i64)p * ha.sel_stride;
+  u16 *cost = ha.cost + (i64)p * ha.sel_stride;
+  u32 *goff = ha.goff + (i64)p * ha.sel_stride;
+  const u8 *lens_g = ha.lens + (i64)p * BZ_MAX_GROUPS * HUF_LSTRIDE;
+  for (int x = threadIdx.x; x < ng * HUF_LSTRIDE; x += HUF_CT) (&sm.lens[0][0])[x] = lens_g[x];
+  // total bits of the symbol data = sum of the winning costs; zero exactly the words this block will touch
+  u32 data_bits = 0;
+  for (u32 g = threadIdx.x; g < nsel; g += HUF_CT) data_bits += cost[g];
+  {
+    u32 tot;
+    block_excl_sum<u32>(data_bits, tot, sm.ws);
+    data_bits = tot;
+  }
+  {
+    u64 maxbits = 80 + 25 + 16 + 256 + 18 + 7ull * nsel + 6ull * (5 + 258 * 39) + data_bits;
+    u32 nw = (u32)((maxbits + 31) >> 5) + 2;
+    if ((i64)nw > w_stride) nw = (u32)w_stride;
+    for (u32 x = threadIdx.x; x < nw; x += HUF_CT) Wp[x] = 0;
   }
   __syncthreads();
-  huf_build(sm, 2, S);
-  int ng = 2;
-  while (ng < target) {  // BJ:2012-2053
-    huf_assign(sm, ng, Ap, m, nsel);
-    if (threadIdx.x < 8) sm.counts[threadIdx.x] = 0;
-    for (int i = threadIdx.x; i < 1024; i += HUF_THREADS) sm.chist[i] = 0;
-    __syncthreads();
-    for (u32 g = threadIdx.x; g < nsel; g += HUF_THREADS) atomicAdd(&sm.counts[sm.sel[g]], 1u);
-    __syncthreads();
-    int which = 0;
-    for (int t = 1; t < ng; t++) if (sm.counts[t] > sm.counts[which]) which = t;  // first maximum
-    for (u32 g = threadIdx.x; g < nsel; g += HUF_THREADS)
-      if (sm.sel[g] == which) atomicAdd(&sm.chist[sm.cost[g]], 1u);
-    __syncthreads();
-    const u32 len = sm.counts[which], half = len >> 1;
-    if (threadIdx.x == 0) {  // cost bin that straddles the median position
-      u32 cum = 0, c = 0;
-      for (; c < 1024; c++) {
-        if (cum + sm.chist[c] > half) break;
-        cum += sm.chist[c];
-      }
-      sm.bcast[0] = c;    // 1024 when len == 0 (cannot happen: the most-used table has a group)
-      sm.bcast[1] = cum;  // groups strictly cheaper than that bin
-    }
-    __syncthreads();
-    const u32 cstar = sm.bcast[0], below = sm.bcast[1];
-    u32 carry = 0;
-    for (u32 base = 0; base < nsel; base += HUF_THREADS) {
-      u32 g = base + threadIdx.x;
-      bool mine = g < nsel && sm.sel[g] == which;
-      u32 cg = mine ? sm.cost[g] : 0;
-      u32 flag = (mine && cg == cstar) ? 1u : 0u, tot;
-      u32 occ = carry + block_excl_sum<u32>(flag, tot, sm.ws);
-      if (mine && (cg > cstar || (cg == cstar && below + occ >= half))) sm.sel[g] = (u8)ng;
-      carry += tot;
-    }
-    ng++;
-    for (int i = threadIdx.x; i < ng * BZ_MAX_SYMS; i += HUF_THREADS) (&sm.freq[0][0])[i] = 0;
-    __syncthreads();
-    for (u32 i = threadIdx.x; i < m; i += HUF_THREADS) atomicAdd(&sm.freq[sm.sel[i / BZ_GROUP]][Ap[i]], 1u);
-    __syncthreads();
-    huf_build(sm, ng, S);
-  }
-  huf_assign(sm, ng, Ap, m, nsel);  // BJ:2163
-
   // canonical codes (BJ:1896-1916): first code of each length, then rank among equal lengths
   if ((threadIdx.x & 31) == 0 && (int)(threadIdx.x >> 5) < ng) {
     int t = threadIdx.x >> 5;
     u32 cnt[BZ_MAX_CODE + 2];
-    for (int L = 0; L <= BZ_MAX_CODE + 1; L++) cnt[L] = 0;
+    for (int Lq = 0; Lq <= BZ_MAX_CODE + 1; Lq++) cnt[Lq] = 0;
     for (int i = 0; i < S; i++) cnt[sm.lens[t][i]]++;
     u32 code = 0;
-    for (int L = 1; L <= BZ_MAX_CODE; L++) { sm.work[t][L] = (int)code; code = (code + cnt[L]) << 1; }
+    for (int Lq = 1; Lq <= BZ_MAX_CODE; Lq++) { sm.first[t][Lq] = (int)code; code = (code + cnt[Lq]) << 1; }
   }
   __syncthreads();
-  for (int x = threadIdx.x; x < ng * S; x += HUF_THREADS) {
-    int t = x / S, i = x - t * S, L = sm.lens[t][i], r = 0;
-    for (int j = 0; j < i; j++) r += sm.lens[t][j] == L ? 1 : 0;
-    sm.code[t][i] = (u32)sm.work[t][L] + (u32)r;
+  u32 *codes = ha.codes + (i64)p * BZ_MAX_GROUPS * BZ_MAX_SYMS;
+  for (int x = threadIdx.x; x < ng * S; x += HUF_CT) {
+    int t = x / S, i = x - t * S, Lq = sm.lens[t][i], r = 0;
+    for (int j = 0; j < i; j++) r += sm.lens[t][j] == Lq ? 1 : 0;
+    codes[t * BZ_MAX_SYMS + i] = ((u32)Lq << 24) | ((u32)sm.first[t][Lq] + (u32)r);
   }
-  __syncthreads();
-
-  // ---- emission ----
+  // ---- header ----
   u64 bp = 0;
   if (threadIdx.x == 0) {
     put_bits(Wp, 0, BZ_MAGIC_BLOCK, 48);                 // BJ:2238
@@ -264,21 +412,53 @@ __global__ void __launch_bounds__(HUF_THREADS) k_huff_encode(const u16 *__restri
   }
   __syncthreads();
   bp = sm.bcast[2];
-  // selector MTF ranks (BJ:2170-2182) into sm.cost[]
+  // group bit offsets need the winning costs, which the selector ranks are about to overwrite: scan them first
+  // (relative to the start of the symbol data; the base is added below)
+  {
+    u32 carry = 0;
+    for (u32 base = 0; base < nsel; base += HUF_CT) {
+      u32 g = base + threadIdx.x;
+      u32 c = g < nsel ? cost[g] : 0, tot;
+      u32 e = block_excl_sum<u32>(c, tot, sm.ws);
+      if (g < nsel) goff[g] = carry + e;
+      carry += tot;
+    }
+  }
+  // selector MTF ranks (BJ:2170-2182) into cost[]: the rank of table s is the number of tables used more
+  // recently than s; a table not used yet sits at its initial place (virtual last use -1-v).  Every thread
+  // owns a contiguous run of groups; the last use of each table before the run comes from six max-scans.
   const bool d1 = (int)alpha < ng;
   if (!d1) {
-    for (u32 g = threadIdx.x; g < nsel; g += HUF_THREADS) {
-      u32 s = sm.sel[g], seen = 0;
-      int q = (int)g - 1;
-      for (; q >= 0; q--) {
-        u32 v = sm.sel[q];
-        if (v == s) break;
-        seen |= 1u << v;
+    const u32 per = (nsel + HUF_CT - 1) / HUF_CT;
+    const u32 gb = threadIdx.x * per < nsel ? threadIdx.x * per : nsel, ge = gb + per < nsel ? gb + per : nsel;
+    const int NONE = -1000000;
+    int last[BZ_MAX_GROUPS];
+#pragma unroll
+    for (int v = 0; v < BZ_MAX_GROUPS; v++) last[v] = NONE;
+    for (u32 g = gb; g < ge; g++) {
+      u32 sv = sel[g];
+#pragma unroll
+      for (int v = 0; v < BZ_MAX_GROUPS; v++) if (sv == (u32)v) last[v] = (int)g;
+    }
+    int cur[BZ_MAX_GROUPS];
+#pragma unroll
+    for (int v = 0; v < BZ_MAX_GROUPS; v++) {
+      int tot;
+      int e = block_excl_max<int>(last[v], NONE, tot, reinterpret_cast<int *>(sm.ws));
+      cur[v] = e == NONE ? -1 - v : e;
+    }
+    for (u32 g = gb; g < ge; g++) {
+      u32 sv = sel[g];
+      int mine = 0;
+#pragma unroll
+      for (int v = 0; v < BZ_MAX_GROUPS; v++) if (sv == (u32)v) mine = cur[v];
+      u32 j = 0;
+#pragma unroll
+      for (int v = 0; v < BZ_MAX_GROUPS; v++) {
+        j += (v < ng && cur[v] > mine) ? 1u : 0u;
+        if (sv == (u32)v) cur[v] = (int)g;
       }
-      u32 j;
-      if (q >= 0) j = __popc(seen);
-      else j = __popc(seen) + __popc(~seen & ((1u << s) - 1));  // never used before: still in initial order
-      sm.cost[g] = (u16)j;
+      cost[g] = (u16)j;
     }
   } else if (threadIdx.x == 0) {
     // Reference defect D1: the MTF list is a Uint8Array(alpha) shorter
@@ -286,18 +466,18 @@ __global__ void __launch_bounds__(HUF_THREADS) k_huff_encode(const u16 *__restri
     u8 ML[8];
     for (int i = 0; i < 8; i++) ML[i] = (u8)i;
     for (u32 g = 0; g < nsel; g++) {
-      int s = sm.sel[g], j;
+      int s = sel[g], j;
       for (j = 0; j < ng; j++) if (j < (int)alpha && ML[j] == s) break;
       int src = j < (int)alpha ? ML[j] : 0;
       for (int q = j; q > 0; q--) if (q < (int)alpha) ML[q] = ML[q - 1];
       ML[0] = (u8)src;
-      sm.cost[g] = (u16)j;
+      cost[g] = (u16)j;
     }
   }
   __syncthreads();
-  for (u32 base = 0; base < nsel; base += HUF_THREADS) {
+  for (u32 base = 0; base < nsel; base += HUF_CT) {
     u32 g = base + threadIdx.x;
-    u32 j = g < nsel ? sm.cost[g] : 0;
+    u32 j = g < nsel ? cost[g] : 0;
     bp = emit_items(Wp, bp, ((1ULL << j) - 1) << 1, g < nsel ? j + 1 : 0, sm.ws);
   }
   // tables (BJ:1926-1947)
@@ -317,24 +497,59 @@ __global__ void __launch_bounds__(HUF_THREADS) k_huff_encode(const u16 *__restri
     }
     bp = emit_items(Wp, bp, val, len, sm.ws);
   }
-  // data (BJ:2189-2194)
-  for (u32 base = 0; base < m; base += HUF_THREADS) {
-    u32 i = base + threadIdx.x;
-    u64 val = 0;
-    u32 len = 0;
-    if (i < m) {
-      u32 t = sm.sel[i / BZ_GROUP], sym = Ap[i];
-      val = sm.code[t][sym];
-      len = sm.lens[t][sym];
-    }
-    bp = emit_items(Wp, bp, val, len, sm.ws);
-  }
+  // the symbol data starts at bp
+  for (u32 g = threadIdx.x; g < nsel; g += HUF_CT) goff[g] += (u32)bp;
   if (threadIdx.x == 0) {
     meta[p].n_groups = (u32)ng;
     meta[p].n_sel = nsel;
-    meta[p].bits = bp;
+    meta[p].bits = bp + data_bits;
     meta[p].d1 = d1 ? 1u : 0u;
   }
+}
+
+// data (BJ:2189-2194): one thread per group of 50 symbols.  grid (ceil(max nsel / HUF_GT), nb)
+__global__ void __launch_bounds__(HUF_GT) k_huf_emit(HufArrays ha, const u16 *__restrict__ A, i64 a_stride, u32 *__restrict__ W, i64 w_stride) {
+  __align__(16) __shared__ u16 sy[HUF_GT_SYMS];
+  __shared__ u32 cd[BZ_MAX_GROUPS][BZ_MAX_SYMS];
+  const u32 p = blockIdx.y;
+  const HufBlk h = ha.hb[p];
+  const u32 g0 = blockIdx.x * HUF_GT;
+  if (g0 >= h.nsel) return;
+  const u16 *Ap = A + (i64)p * a_stride;
+  u32 *Wp = W + (i64)p * w_stride;
+  const u32 i0 = g0 * BZ_GROUP, cnt = h.m - i0 < HUF_GT_SYMS ? h.m - i0 : (u32)HUF_GT_SYMS;
+  {
+    const uint4 *src = reinterpret_cast<const uint4 *>(Ap + i0);
+    uint4 *dst = reinterpret_cast<uint4 *>(sy);
+    for (u32 x = threadIdx.x; x < (cnt + 7) / 8; x += HUF_GT) dst[x] = src[x];
+  }
+  {
+    const u32 *codes = ha.codes + (i64)p * BZ_MAX_GROUPS * BZ_MAX_SYMS;
+    for (int x = threadIdx.x; x < h.ng * BZ_MAX_SYMS; x += HUF_GT) (&cd[0][0])[x] = codes[x];
+  }
+  __syncthreads();
+  const u32 g = g0 + threadIdx.x;
+  if (g >= h.nsel) return;
+  const u32 j0 = threadIdx.x * BZ_GROUP, j1 = j0 + BZ_GROUP < cnt ? j0 + BZ_GROUP : cnt;
+  const u32 *tab = cd[ha.sel[(i64)p * ha.sel_stride + g]];
+  const u32 o = ha.goff[(i64)p * ha.sel_stride + g];
+  u32 wi = o >> 5, nbits = o & 31;  // nbits: bits already in the accumulator (the leading ones are not mine: zeros)
+  u64 acc = 0;
+  bool first = true;
+  for (u32 j = j0; j < j1; j++) {
+    u32 e = tab[sy[j]], len = e >> 24;
+    acc = (acc << len) | (u64)(e & 0xffffffu);
+    nbits += len;
+    if (nbits >= 32) {
+      nbits -= 32;
+      u32 word = (u32)(acc >> nbits);
+      if (first) { atomicOr(&Wp[wi], word); first = false; }  // shares its leading bits with the previous group
+      else Wp[wi] = word;                                       // wholly mine
+      wi++;
+      acc &= (1ULL << nbits) - 1;
+    }
+  }
+  if (nbits) atomicOr(&Wp[wi], (u32)(acc << (32 - nbits)));
 }
 
 // ---- K-S6: bit-granular concatenation of the per-block streams --------------------------
