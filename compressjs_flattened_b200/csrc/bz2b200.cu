@@ -36,7 +36,7 @@ struct Ctx {
   DevBuf seg_cnt, seg_tile0, tile_blk, tile_i0, tile_i1, totals;
   DevBuf Lcol, ranks, lastocc, A, freq, meta, W, bit_off, scrc, out, out_len, used_bits;
   DevBuf key2, big_cnt, big_old, big_rank, big_tile0, big_tblk, totals2;
-  DevBuf hfreq, hlens, hplen, hcodes, hsel, hcost, hgoff, hblk;
+  DevBuf r2_status, hfreq, hlens, hplen, hcodes, hsel, hcost, hgoff, hblk;
   // decode-side buffers
   DevBuf d_in, cand, ncand, dmeta, dsyms, dL, dtt, dwalk, dblk, dout, dmisc, dsel, doff, dperm, dmap;
   // host staging (pinned)
@@ -63,7 +63,7 @@ struct Ctx {
                      &seg_cnt, &seg_tile0, &tile_blk, &tile_i0, &tile_i1, &totals,
                      &Lcol, &ranks, &lastocc, &A, &freq, &meta, &W, &bit_off, &scrc, &out, &out_len, &used_bits,
                      &key2, &big_cnt, &big_old, &big_rank, &big_tile0, &big_tblk, &totals2,
-                     &hfreq, &hlens, &hplen, &hcodes, &hsel, &hcost, &hgoff, &hblk,
+                     &r2_status, &hfreq, &hlens, &hplen, &hcodes, &hsel, &hcost, &hgoff, &hblk,
                      &d_in, &cand, &ncand, &dmeta, &dsyms, &dL, &dtt, &dwalk, &dblk, &dout, &dmisc, &dsel, &doff, &dperm, &dmap};
     for (DevBuf *b : all) pool.push_back(b);
   }
@@ -348,7 +348,14 @@ int pipe_stages(Ctx *c) {
 #endif
     LAUNCH(k_mtf_ranks, dim3((unsigned)((nseg_max + MTR_WARPS - 1) / MTR_WARPS), (unsigned)nb), MTR_WARPS * 32, MTR_WARPS * sizeof(MtrSmem), P<u8>(c->Lcol),
            BS, P<BlockRec>(c->recs), P<int>(c->lastocc), nseg_max * 256, P<u8>(c->ranks));
-    LAUNCH(k_mtf_rle2, (unsigned)nb, MTF_THREADS, 0, P<BlockRec>(c->recs), P<u8>(c->ranks), BS, P<u16>(c->A), AS, P<u32>(c->freq), P<BlockMeta>(c->meta));
+    {
+      const i64 r2_tiles = (BS + R2_TILE - 1) / R2_TILE;
+      ENS(c->r2_status, 8 * (size_t)nb * r2_tiles + 4 * (size_t)nb);
+      CK(cudaMemsetAsync(c->r2_status.p, 0, 8 * (size_t)nb * r2_tiles + 4 * (size_t)nb, c->stream));
+      CK(cudaMemsetAsync(c->freq.p, 0, 4 * BZ_MAX_SYMS * (size_t)nb, c->stream));
+      LAUNCH(k_mtf_rle2, dim3((unsigned)r2_tiles, (unsigned)nb), R2_THREADS, 0, P<BlockRec>(c->recs), P<u8>(c->ranks), BS, P<u16>(c->A), AS, P<u32>(c->freq),
+             P<BlockMeta>(c->meta), P<u64>(c->r2_status), r2_tiles, reinterpret_cast<u32 *>(P<u64>(c->r2_status) + (size_t)nb * r2_tiles));
+    }
     if ((rc = mark(c, 3))) return rc;
 
     // ---- S4/S5 Huffman + emission (huff.cuh) ----

@@ -268,10 +268,11 @@ __global__ void __launch_bounds__(HUF_BT) k_huf_split(HufArrays ha) {
   if (threadIdx.x == 0) { ha.hb[p].ng = ng + 1; ha.hb[p].active = 1; }
 }
 
-// BJ:2037-2048: histograms of all tables.  grid (ceil(max nsel / HUF_GT), nb)
+// BJ:2037-2048: histograms of all tables.  grid (ceil(max nsel / HUF_GT), nb); one thread per group of 50 symbols
+// (one table), RUNA / RUNB / rank 1 counted in registers
 __global__ void __launch_bounds__(HUF_GT) k_huf_hist(HufArrays ha, const u16 *__restrict__ A, i64 a_stride) {
+  __align__(16) __shared__ u16 sy[HUF_GT_SYMS];
   __shared__ u32 hs[BZ_MAX_GROUPS][BZ_MAX_SYMS];
-  __shared__ u8 ss[HUF_GT];
   const u32 p = blockIdx.y;
   const HufBlk h = ha.hb[p];
   if (!h.active) return;
@@ -280,19 +281,24 @@ __global__ void __launch_bounds__(HUF_GT) k_huf_hist(HufArrays ha, const u16 *__
   const u16 *Ap = A + (i64)p * a_stride;
   const u32 i0 = g0 * BZ_GROUP, cnt = h.m - i0 < HUF_GT_SYMS ? h.m - i0 : (u32)HUF_GT_SYMS;
   for (int i = threadIdx.x; i < h.ng * BZ_MAX_SYMS; i += HUF_GT) (&hs[0][0])[i] = 0;
-  ss[threadIdx.x] = g0 + threadIdx.x < h.nsel ? ha.sel[(i64)p * ha.sel_stride + g0 + threadIdx.x] : 0;
-  __syncthreads();
   {
     const uint4 *src = reinterpret_cast<const uint4 *>(Ap + i0);
-    for (u32 x = threadIdx.x; x < (cnt + 7) / 8; x += HUF_GT) {
-      uint4 v = src[x];
-      u32 wv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-      for (int q = 0; q < 8; q++) {
-        u32 j = x * 8 + q;
-        if (j < cnt) atomicAdd(&hs[ss[j / BZ_GROUP]][(wv[q >> 1] >> (16 * (q & 1))) & 0xffffu], 1u);
-      }
+    uint4 *dst = reinterpret_cast<uint4 *>(sy);
+    for (u32 x = threadIdx.x; x < (cnt + 7) / 8; x += HUF_GT) dst[x] = src[x];
+  }
+  __syncthreads();
+  const u32 g = g0 + threadIdx.x;
+  if (g < h.nsel) {
+    const u32 j0 = threadIdx.x * BZ_GROUP, j1 = j0 + BZ_GROUP < cnt ? j0 + BZ_GROUP : cnt;
+    u32 *ht = hs[ha.sel[(i64)p * ha.sel_stride + g]];
+    u32 hot[3] = {0, 0, 0};
+    for (u32 j = j0; j < j1; j++) {
+      u32 sym = sy[j];
+      if (sym < 3) { hot[0] += sym == 0; hot[1] += sym == 1; hot[2] += sym == 2; }
+      else atomicAdd(&ht[sym], 1u);
     }
+#pragma unroll
+    for (int q = 0; q < 3; q++) if (hot[q]) atomicAdd(&ht[q], hot[q]);
   }
   __syncthreads();
   u32 *fq = ha.freq + (i64)p * BZ_MAX_GROUPS * BZ_MAX_SYMS;

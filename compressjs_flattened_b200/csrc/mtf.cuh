@@ -8,15 +8,13 @@
 //   k_mtf_ranks    (grid-wide, one warp per segment, one THREAD per 128-byte sub-segment) start list of the segment
 //                  by rank counting, start lists of the sub-segments by 31 cooperative composition steps, then
 //                  every lane runs the sequential MTF of its own bytes, list packed in u64 words (SWAR)
-//   k_mtf_rle2     (one CTA per block) zero-rank runs -> bijective base-2 RUNA/RUNB digits, other ranks ->
-//                  rank+1, end-of-block; positions from a block-wide prefix sum; histogram in shared memory
+//   k_mtf_rle2     (grid-wide, 4 KiB tiles) zero-rank runs -> bijective base-2 RUNA/RUNB digits, other ranks ->
+//                  rank+1, end-of-block; positions from a look-back over the block's tiles; histogram in shared memory
 #pragma once
 #include "common.cuh"
 #include "rle1.cuh"
 
 #define MTF_SEG 8192
-#define MTF_THREADS 1024
-#define MTF_WARPS 32
 #define MTF_ABSENT (-2000000000)  // below every initial-order key
 
 struct BlockMeta {
@@ -313,56 +311,94 @@ __global__ void __launch_bounds__(MTR_WARPS * 32) k_mtf_ranks(const u8 *__restri
   }
 }
 
-// ---- K-S3d: RLE2 + symbol compaction + histogram, one CTA per block ----
-__global__ void __launch_bounds__(MTF_THREADS) k_mtf_rle2(const BlockRec *__restrict__ recs, const u8 *__restrict__ ranks, i64 l_stride,
-                                                          u16 *__restrict__ A, i64 a_stride, u32 *__restrict__ freq_out,
-                                                          BlockMeta *__restrict__ meta) {
+// ---- K-S3d: RLE2 + symbol compaction + histogram, grid-wide ----
+// grid (ceil(stride / R2_TILE), nb), R2_THREADS threads.  A zero run emits its RUNA/RUNB digits where it ENDS, so a
+// tile only has to know where the run that is open at its first rank began: a backward scan over the ranks
+// (each run is scanned once).  Output positions come from a look-back over the tiles of the block (tiles take
+// their index from a per-block ticket); the histogram is accumulated in shared memory and flushed with atomics.
+#define R2_TILE 8192
+#define R2_THREADS 512
+#define R2_E (R2_TILE / R2_THREADS)
+__global__ void __launch_bounds__(R2_THREADS) k_mtf_rle2(const BlockRec *__restrict__ recs, const u8 *__restrict__ ranks, i64 l_stride,
+                                                         u16 *__restrict__ A, i64 a_stride, u32 *__restrict__ freq_out,
+                                                         BlockMeta *__restrict__ meta, u64 *__restrict__ status, i64 status_stride,
+                                                         u32 *__restrict__ tickets) {
   __shared__ u32 hist[BZ_MAX_SYMS + 2];
   __shared__ u32 ws[33];
   __shared__ int wsi[33];
-  const u32 p = blockIdx.x;
+  __shared__ u32 sh_tile, sh_base;
+  __shared__ int sh_nz;
+  const u32 p = blockIdx.y;
   const u32 n = recs[p].n;
+  if (threadIdx.x == 0) sh_tile = atomicAdd(&tickets[p], 1u);
+  for (int i = threadIdx.x; i < BZ_MAX_SYMS + 2; i += R2_THREADS) hist[i] = 0;
+  __syncthreads();
+  const u32 tile = sh_tile, t0 = tile * R2_TILE;
+  if (t0 >= n) return;
+  const u32 ntiles = (n + R2_TILE - 1) / R2_TILE;
   const u8 *Rp = ranks + (i64)p * l_stride;
   u16 *Ap = A + (i64)p * a_stride;
-  const u32 alpha = meta[p].alpha;
-  for (int i = threadIdx.x; i < BZ_MAX_SYMS + 2; i += MTF_THREADS) hist[i] = 0;
-  __syncthreads();
-  // ---- phase D ----
-  int carry_nz = -1;  // last position with a non-zero rank
-  u32 carry_m = 0;    // symbols emitted so far
-  const u32 *Rw = reinterpret_cast<const u32 *>(Rp);
-  for (u32 base = 0; base < n; base += MTF_THREADS * 4) {
-    u32 i0 = base + threadIdx.x * 4;
-    u32 rw = i0 < n ? Rw[i0 >> 2] : 0;
-    u32 r[5];
-    for (int k = 0; k < 4; k++) r[k] = (rw >> (8 * k)) & 0xffu;
-    r[4] = (i0 + 4 < n) ? Rp[i0 + 4] : 1u;  // sentinel: the position after the block ends any run
-    int my_nz = -1;
-    for (int k = 0; k < 4; k++) if (i0 + k < n && r[k]) my_nz = (int)(i0 + k);
-    int tot_nz;
-    int nz = block_excl_max<int>(my_nz, -1, tot_nz, wsi);
-    if (carry_nz > nz) nz = carry_nz;
-    u32 cnt = 0;
-    {
-      int cur = nz;
-      for (int k = 0; k < 4; k++) {
-        u32 i = i0 + k;
-        if (i >= n) break;
+  const u32 i0 = t0 + threadIdx.x * R2_E;
+  u32 r[R2_E + 1];
+  {
+    uint4 v = i0 < n ? *reinterpret_cast<const uint4 *>(Rp + i0) : make_uint4(0, 0, 0, 0);  // padded stride: reading past n is fine
+    u32 wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < R2_E; k++) r[k] = (wv[k >> 2] >> (8 * (k & 3))) & 0xffu;
+    r[R2_E] = (i0 + R2_E < n) ? Rp[i0 + R2_E] : 1u;  // sentinel: the position after the block ends any run
+  }
+  // last non-zero rank before the tile (-1: none), found only when a run is open at the tile's first rank
+  if (threadIdx.x < 32) {
+    int res = -1;
+    if (t0 > 0 && Rp[t0] == 0) {
+      const int lane = threadIdx.x;
+      for (i64 j0 = (i64)t0 - 1; j0 >= 0 && res < 0; j0 -= 32) {
+        i64 j = j0 - lane;
+        bool nzq = j >= 0 && Rp[j] != 0;
+        u32 b = __ballot_sync(FULL_MASK, nzq);
+        if (b) res = (int)(j0 - (__ffs((int)b) - 1));
+      }
+    } else if (t0 > 0) res = (int)t0 - 1;
+    if (threadIdx.x == 0) sh_nz = res;
+  }
+  int my_nz = -1;
+#pragma unroll
+  for (int k = 0; k < R2_E; k++) if (i0 + k < n && r[k]) my_nz = (int)(i0 + k);
+  int tot_nz;
+  int nz = block_excl_max<int>(my_nz, -1, tot_nz, wsi);
+  if (sh_nz > nz) nz = sh_nz;
+  u32 cnt = 0;
+  {
+    int cur = nz;
+#pragma unroll
+    for (int k = 0; k < R2_E; k++) {
+      u32 i = i0 + k;
+      if (i < n) {
         if (r[k]) { cnt++; cur = (int)i; }
         else if (i + 1 >= n || r[k + 1]) cnt += 31 - __clz((int)(i - (u32)cur) + 1);
       }
     }
-    u32 tot_m;
-    u32 o = carry_m + block_excl_sum<u32>(cnt, tot_m, ws);
-    {
-      int cur = nz;
-      for (int k = 0; k < 4; k++) {
-        u32 i = i0 + k;
-        if (i >= n) break;
+  }
+  u32 tot_m;
+  u32 o = block_excl_sum<u32>(cnt, tot_m, ws);
+  if (threadIdx.x < 32) {
+    u32 base = lookback_warp(status + (i64)p * status_stride, tile, tot_m);
+    if (threadIdx.x == 0) sh_base = base;
+  }
+  __syncthreads();
+  o += sh_base;
+  {
+    int cur = nz;
+    u32 hot0 = 0, hot1 = 0, hot2 = 0;  // RUNA, RUNB and rank 1 are most of the symbols: counted in registers, one atomic per warp
+#pragma unroll
+    for (int k = 0; k < R2_E; k++) {
+      u32 i = i0 + k;
+      if (i < n) {
         if (r[k]) {
           cur = (int)i;
           Ap[o++] = (u16)(r[k] + 1);
-          atomicAdd(&hist[r[k] + 1], 1u);
+          if (r[k] == 1) hot2++;
+          else atomicAdd(&hist[r[k] + 1], 1u);
         } else if (i + 1 >= n || r[k + 1]) {
           u32 run = i - (u32)cur;  // BJ:2107-2118
           while (run) {
@@ -370,20 +406,24 @@ __global__ void __launch_bounds__(MTF_THREADS) k_mtf_rle2(const BlockRec *__rest
             run -= sym + 1;
             run >>= 1;
             Ap[o++] = (u16)sym;
-            atomicAdd(&hist[sym], 1u);
+            hot0 += sym ^ 1u; hot1 += sym;
           }
         }
       }
     }
-    if (tot_nz > carry_nz) carry_nz = tot_nz;
-    carry_m += tot_m;
+    hot0 = warp_sum<u32>(hot0); hot1 = warp_sum<u32>(hot1); hot2 = warp_sum<u32>(hot2);
+    if (lane_id() == 0) {
+      if (hot0) atomicAdd(&hist[0], hot0);
+      if (hot1) atomicAdd(&hist[1], hot1);
+      if (hot2) atomicAdd(&hist[2], hot2);
+    }
+  }
+  if (tile == ntiles - 1 && threadIdx.x == 0) {
+    const u32 alpha = meta[p].alpha, mm = sh_base + tot_m;
+    Ap[mm] = (u16)(alpha + 1);  // end of block, BJ:2138
+    atomicAdd(&hist[alpha + 1], 1u);
+    meta[p].m = mm + 1;
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    Ap[carry_m] = (u16)(alpha + 1);  // end of block, BJ:2138
-    hist[alpha + 1] += 1;
-    meta[p].m = carry_m + 1;
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < BZ_MAX_SYMS; i += MTF_THREADS) freq_out[(i64)p * BZ_MAX_SYMS + i] = hist[i];
+  for (int i = threadIdx.x; i < BZ_MAX_SYMS; i += R2_THREADS) if (hist[i]) atomicAdd(&freq_out[(i64)p * BZ_MAX_SYMS + i], hist[i]);
 }
