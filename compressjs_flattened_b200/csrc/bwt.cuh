@@ -218,6 +218,17 @@ __global__ void __launch_bounds__(256) k_seg_scan(const u32 *__restrict__ seg_ti
   }
   if (mode == 1 && threadIdx.x == 0) seg_cnt_new[p] = (u32)carry;
 }
+// A rotation whose rank is final writes its byte of the L column (the byte before the rotation) and, for
+// rotation 0, origPtr.  gidx = block base pb + rotation index; rank is global too (same stride everywhere).
+__device__ __forceinline__ void bwt_emit_final(const u8 *__restrict__ T, u8 *__restrict__ L, BlockRec *__restrict__ recs, u32 p, u32 pb, u32 gidx,
+                                               u32 rank) {
+  if (gidx != pb) L[rank] = T[gidx - 1];
+  else {
+    L[rank] = T[pb + recs[p].n - 1];
+    recs[p].orig_ptr = rank - pb;
+  }
+}
+
 // ---- round 0 regroup: groups, ISA, active list (single pass, ordered) -------------------------------
 #define R0_THREADS 512
 #define R0_ROWS (SORT_TILE / R0_THREADS)  // rows of 32 slots per warp: warp w owns slots [w*256, w*256+256)
@@ -225,7 +236,8 @@ __global__ void __launch_bounds__(256) k_seg_scan(const u32 *__restrict__ seg_ti
 __global__ void __launch_bounds__(R0_THREADS) k_rank0(const u64 *__restrict__ keys, const u32 *__restrict__ seg_cnt,
                                                       const u32 *__restrict__ seg_tile0, const u32 *__restrict__ tile_blk,
                                                       u32 *__restrict__ isa, i64 stride, u32 *__restrict__ act_idx, u32 *__restrict__ act_rank,
-                                                      u64 *__restrict__ status, u32 *__restrict__ ticket, u32 *__restrict__ n_act_out, u32 ntiles) {
+                                                      u64 *__restrict__ status, u32 *__restrict__ ticket, u32 *__restrict__ n_act_out, u32 ntiles,
+                                                      const u8 *__restrict__ T, u8 *__restrict__ L, BlockRec *__restrict__ recs) {
   __shared__ u64 sk[SORT_TILE + 2];  // sk[1 + i] = key of tile slot i; sk[0] / sk[m + 1] = the neighbours
   __shared__ int wlast[R0_THREADS / 32];
   __shared__ u32 wkeep[R0_THREADS / 32];
@@ -288,6 +300,26 @@ __global__ void __launch_bounds__(R0_THREADS) k_rank0(const u64 *__restrict__ ke
     if (lane == 0) sh_carry = carry;
   }
   __syncthreads();
+  int cur = sh_carry;  // block-local SA index of the last head before this warp's slots
+  for (int ww = 0; ww < w; ww++) if (wlast[ww] >= 0) cur = (int)l0 + wlast[ww];
+  // phase 2a: ranks + ISA (before the look-back, whose latency these scattered stores hide)
+  const u32 pb = (u32)((u64)p * (u64)stride);
+  const u32 le = lane == 31 ? 0xffffffffu : ((2u << lane) - 1);  // lanes <= mine
+  const u32 lt = (1u << lane) - 1;
+  u32 hpv[R0_ROWS];
+#pragma unroll
+  for (int e = 0; e < R0_ROWS; e++) {
+    u32 i = (u32)w * (32 * R0_ROWS) + e * 32 + lane;
+    u32 mk = hb[e] & le;
+    int hp = mk ? (int)(l0 + w * (32 * R0_ROWS) + e * 32 + (31 - __clz((int)mk))) : cur;
+    hpv[e] = (u32)hp;
+    if (i < m) {
+      const u32 gidx = pb + (u32)(sk[i + 1] & 0xFFFFFu);
+      isa[gidx] = (u32)hp;
+      if (!((kb[e] >> lane) & 1u)) bwt_emit_final(T, L, recs, p, pb, gidx, pb + (u32)hp);  // a singleton: final
+    }
+    if (hb[e]) cur = (int)(l0 + w * (32 * R0_ROWS) + e * 32 + (31 - __clz((int)hb[e])));
+  }
   // ordered compaction base of this tile and of this warp
   if (w == 0) {
     u32 x = lane < R0_THREADS / 32 ? wkeep[lane] : 0;
@@ -300,44 +332,18 @@ __global__ void __launch_bounds__(R0_THREADS) k_rank0(const u64 *__restrict__ ke
       if (tile == ntiles - 1) *n_act_out = base + agg;
     }
   }
-  int cur = sh_carry;  // block-local SA index of the last head before this warp's slots
-  for (int ww = 0; ww < w; ww++) if (wlast[ww] >= 0) cur = (int)l0 + wlast[ww];
   __syncthreads();
-  // phase 2: ranks, ISA, survivors
-  const u32 pb = (u32)((u64)p * (u64)stride);
+  // phase 2b: survivors
   u32 out = sh_base + wkeep[w];
-  const u32 le = lane == 31 ? 0xffffffffu : ((2u << lane) - 1);  // lanes <= mine
-  const u32 lt = (1u << lane) - 1;
 #pragma unroll
   for (int e = 0; e < R0_ROWS; e++) {
     u32 i = (u32)w * (32 * R0_ROWS) + e * 32 + lane;
-    u32 mk = hb[e] & le;
-    int hp = mk ? (int)(l0 + w * (32 * R0_ROWS) + e * 32 + (31 - __clz((int)mk))) : cur;
-    if (i < m) {
-      u32 idx = (u32)(sk[i + 1] & 0xFFFFFu);
-      isa[pb + idx] = (u32)hp;
-      if ((kb[e] >> lane) & 1u) {
-        u32 o = out + __popc(kb[e] & lt);
-        act_idx[o] = pb + idx;
-        act_rank[o] = pb + (u32)hp;
-      }
+    if (i < m && ((kb[e] >> lane) & 1u)) {
+      u32 o = out + __popc(kb[e] & lt);
+      act_idx[o] = pb + (u32)(sk[i + 1] & 0xFFFFFu);
+      act_rank[o] = pb + hpv[e];
     }
-    if (hb[e]) cur = (int)(l0 + w * (32 * R0_ROWS) + e * 32 + (31 - __clz((int)hb[e])));
     out += __popc(kb[e]);
   }
 }
 
-// ---- final: L column and origPtr from the inverse suffix array -----------------------------
-__global__ void __launch_bounds__(256) k_bwt_gather(const u8 *__restrict__ blk, i64 blk_stride, BlockRec *__restrict__ recs,
-                                                    const u32 *__restrict__ isa, i64 isa_stride, u8 *__restrict__ L, i64 l_stride) {
-  u32 p = blockIdx.y;
-  u32 n = recs[p].n;
-  const u8 *T = blk + (i64)p * blk_stride;
-  const u32 *I = isa + (i64)p * isa_stride;
-  u8 *out = L + (i64)p * l_stride;
-  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    u32 r = I[i];
-    out[r] = T[i == 0 ? n - 1 : i - 1];
-    if (i == 0) recs[p].orig_ptr = r;
-  }
-}

@@ -218,6 +218,7 @@ int pipe_stages(Ctx *c) {
     const u32 big_cap = (u32)(slots / RF_T0 + 16);
     const size_t lb_tiles = slots / RF_T0 + tiles0 + 16;
     ENS(c->isa, 4 * (size_t)nb * BS);
+    ENS(c->Lcol, (size_t)nb * BS);  // written by whichever kernel makes a rotation's rank final
     ENS(c->keysA, 8 * slots); ENS(c->keysB, 8 * slots);
     ENS(c->actI0, 4 * slots); ENS(c->actI1, 4 * slots); ENS(c->actR0, 4 * slots); ENS(c->actR1, 4 * slots);
     ENS(c->key2, 4 * slots);
@@ -271,7 +272,8 @@ int pipe_stages(Ctx *c) {
       }
       CK(cudaMemsetAsync(lbm, 0, 16, c->stream));
       CK(cudaMemsetAsync(status, 0, 8 * (size_t)Ta, c->stream));
-      LAUNCH(k_rank0, Ta, R0_THREADS, 0, ki, seg_cnt, tile0, tblk, P<u32>(c->isa), BS, actI[0], actR[0], status, lbm, lbm + 1, (u32)Ta);
+      LAUNCH(k_rank0, Ta, R0_THREADS, 0, ki, seg_cnt, tile0, tblk, P<u32>(c->isa), BS, actI[0], actR[0], status, lbm, lbm + 1, (u32)Ta, P<u8>(c->blk),
+             P<u8>(c->Lcol), P<BlockRec>(c->recs));
       CK(cudaMemcpyAsync(hv, lbm, sizeof hv, cudaMemcpyDeviceToHost, c->stream));
       CK(cudaStreamSynchronize(c->stream));
     }
@@ -292,7 +294,7 @@ int pipe_stages(Ctx *c) {
       CK(cudaMemsetAsync(lbm, 0, 16, c->stream));
       CK(cudaMemsetAsync(status, 0, 8 * (size_t)ctiles, c->stream));
       LAUNCH(k_sort_groups, ntiles, RF_THREADS, sizeof(RfSmem), P<u32>(c->key2), actI[0], actR[0], n_act, P<u32>(c->isa), (u32)BS, magic, actI[1],
-             actR[1], P<u32>(c->big_cnt), P<u32>(c->big_old), P<u32>(c->big_rank), lbm + 2, big_cap);
+             actR[1], P<u32>(c->big_cnt), P<u32>(c->big_old), P<u32>(c->big_rank), lbm + 2, big_cap, P<u8>(c->blk), P<u8>(c->Lcol), P<BlockRec>(c->recs));
       CK(cudaMemcpyAsync(hv, lbm, sizeof hv, cudaMemcpyDeviceToHost, c->stream));
       CK(cudaStreamSynchronize(c->stream));
       const u32 n_big = hv[2];
@@ -315,7 +317,7 @@ int pipe_stages(Ctx *c) {
         LAUNCH(k_sub_heads, Tb, SEG_THREADS, 0, ki, bcnt, bt0, btb, P<int>(c->tile_i0), bbase, 32);
         LAUNCH(k_seg_scan, n_big, 256, 0, bt0, 0, P<int>(c->tile_i0), P<int>(c->tile_i1), (u32 *)nullptr);
         LAUNCH(k_big_apply, Tb, SEG_THREADS, 0, ki, bcnt, bt0, btb, bbase, P<u32>(c->big_rank), P<int>(c->tile_i1), P<u32>(c->isa), (u32)BS, magic,
-               actI[1], actR[1]);
+               actI[1], actR[1], P<u8>(c->blk), P<u8>(c->Lcol), P<BlockRec>(c->recs));
       }
       h = h >= (1u << 24) ? h : h * 2;
       LAUNCH(k_compact_keys, ctiles, CK_THREADS, 0, actI[1], actR[1], n_act, P<BlockRec>(c->recs), P<u32>(c->isa), (u32)BS, magic, h, actI[0], actR[0],
@@ -324,8 +326,6 @@ int pipe_stages(Ctx *c) {
       CK(cudaStreamSynchronize(c->stream));
       n_act = hv[1];
     }
-    ENS(c->Lcol, (size_t)nb * BS);
-    LAUNCH(k_bwt_gather, dim3(64, (unsigned)nb), 256, 0, P<u8>(c->blk), BS, P<BlockRec>(c->recs), P<u32>(c->isa), BS, P<u8>(c->Lcol), BS);
     if ((rc = mark(c, 2))) return rc;
 
     // ---- S3 MTF + RLE2 ----

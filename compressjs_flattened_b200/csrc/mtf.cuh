@@ -316,8 +316,8 @@ __global__ void __launch_bounds__(MTR_WARPS * 32) k_mtf_ranks(const u8 *__restri
 // tile only has to know where the run that is open at its first rank began: a backward scan over the ranks
 // (each run is scanned once).  Output positions come from a look-back over the tiles of the block (tiles take
 // their index from a per-block ticket); the histogram is accumulated in shared memory and flushed with atomics.
-#define R2_TILE 8192
-#define R2_THREADS 512
+#define R2_TILE 16384
+#define R2_THREADS 1024
 #define R2_E (R2_TILE / R2_THREADS)
 __global__ void __launch_bounds__(R2_THREADS) k_mtf_rle2(const BlockRec *__restrict__ recs, const u8 *__restrict__ ranks, i64 l_stride,
                                                          u16 *__restrict__ A, i64 a_stride, u32 *__restrict__ freq_out,

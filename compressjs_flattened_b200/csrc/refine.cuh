@@ -129,7 +129,8 @@ __device__ __forceinline__ void warp_radix_group(RfSmem &sm, u32 a, u32 s) {
 __global__ void __launch_bounds__(RF_THREADS) k_sort_groups(const u32 *__restrict__ key2, const u32 *__restrict__ a_idx, const u32 *__restrict__ a_rank,
                                                             u32 n_act, u32 *__restrict__ isa, u32 stride, u64 magic, u32 *__restrict__ s_idx,
                                                             u32 *__restrict__ s_rank, u32 *__restrict__ big_cnt, u32 *__restrict__ big_base,
-                                                            u32 *__restrict__ big_rank, u32 *__restrict__ n_big, u32 big_cap) {
+                                                            u32 *__restrict__ big_rank, u32 *__restrict__ n_big, u32 big_cap,
+                                                            const u8 *__restrict__ T, u8 *__restrict__ L, BlockRec *__restrict__ recs) {
   DYN_SMEM(RfSmem, smp);
   RfSmem &sm = *smp;
   const int lane = lane_id(), w = warp_id();
@@ -250,9 +251,14 @@ __global__ void __launch_bounds__(RF_THREADS) k_sort_groups(const u32 *__restric
         const bool next_head = d + 1 >= m || g[e + 1] != g[e] || (sc[e + 2] >> RF_SBITS) != (sc[e + 1] >> RF_SBITS);
         const u32 gi = sm.I[sc[e + 1] & (RF_CAP - 1)];
         const u32 off = (u32)cur - g[e], nr = sm.RK[g[e]] + off;
-        if (off) isa[gi] = nr - blk_of(gi, magic) * stride;
+        const bool single = head && next_head;
+        if (off || single) {
+          const u32 p = blk_of(gi, magic), pb = p * stride;
+          if (off) isa[gi] = nr - pb;
+          if (single) bwt_emit_final(T, L, recs, p, pb, gi, nr);
+        }
         s_idx[lo + d] = gi;
-        s_rank[lo + d] = nr | ((head && next_head) ? 0u : KEEP_BIT);
+        s_rank[lo + d] = nr | (single ? 0u : KEEP_BIT);
       }
     }
   }
@@ -280,6 +286,20 @@ __global__ void __launch_bounds__(CK_THREADS) k_compact_keys(const u32 *__restri
     nk += __popc(kb[e]);
   }
   if (lane == 0) wk[w] = nk;
+  // the survivors' gidx and next-round key2 (ISA gathers) are fetched before the look-back wait
+  u32 gi[CK_ROWS], k2v[CK_ROWS];
+#pragma unroll
+  for (int e = 0; e < CK_ROWS; e++) {
+    gi[e] = 0; k2v[e] = 0;
+    if ((kb[e] >> lane) & 1u) {
+      u32 pos = tile * CK_TILE + (u32)w * (32 * CK_ROWS) + e * 32 + lane;
+      u32 gidx = s_idx[pos];
+      u32 p = blk_of(gidx, magic), pb = p * stride, i = gidx - pb, n = recs[p].n, k2;
+      if (h_next >= n) k2 = n - 1 - i;
+      else { u32 x = i + h_next; if (x >= n) x -= n; k2 = isa[pb + x]; }
+      gi[e] = gidx; k2v[e] = k2;
+    }
+  }
   __syncthreads();
   if (w == 0) {
     u32 x = lane < CK_THREADS / 32 ? wk[lane] : 0;
@@ -298,15 +318,10 @@ __global__ void __launch_bounds__(CK_THREADS) k_compact_keys(const u32 *__restri
 #pragma unroll
   for (int e = 0; e < CK_ROWS; e++) {
     if ((kb[e] >> lane) & 1u) {
-      u32 pos = tile * CK_TILE + (u32)w * (32 * CK_ROWS) + e * 32 + lane;
       u32 o = out + __popc(kb[e] & lt);
-      u32 gidx = s_idx[pos];
-      u32 p = blk_of(gidx, magic), pb = p * stride, i = gidx - pb, n = recs[p].n, k2;
-      if (h_next >= n) k2 = n - 1 - i;
-      else { u32 x = i + h_next; if (x >= n) x -= n; k2 = isa[pb + x]; }
-      o_idx[o] = gidx;
+      o_idx[o] = gi[e];
       o_rank[o] = r[e] & ~KEEP_BIT;
-      o_key2[o] = k2;
+      o_key2[o] = k2v[e];
     }
     out += __popc(kb[e]);
   }
@@ -330,7 +345,8 @@ __global__ void __launch_bounds__(SEG_THREADS) k_big_apply(const u64 *__restrict
                                                            const u32 *__restrict__ seg_tile0, const u32 *__restrict__ tile_blk,
                                                            const u32 *__restrict__ big_base, const u32 *__restrict__ big_rank,
                                                            const int *__restrict__ tile_carry, u32 *__restrict__ isa, u32 stride, u64 magic,
-                                                           u32 *__restrict__ s_idx, u32 *__restrict__ s_rank) {
+                                                           u32 *__restrict__ s_idx, u32 *__restrict__ s_rank, const u8 *__restrict__ T,
+                                                           u8 *__restrict__ L, BlockRec *__restrict__ recs) {
   __shared__ int ws[33];
   u32 tile = blockIdx.x, s = tile_blk[tile];
   u32 cnt = seg_cnt[s], l0 = (tile - seg_tile0[s]) * SORT_TILE;
@@ -355,9 +371,14 @@ __global__ void __launch_bounds__(SEG_THREADS) k_big_apply(const u64 *__restrict
       if (head) cur = (int)lj;
       bool nh = e + 1 < SEG_E ? (lj + 1 >= cnt || ((flags >> (e + 1)) & 1u)) : (lj + 1 >= cnt || next_head);
       u32 gi = (u32)(k[e] & 0xffffffffull), nr = r0 + (u32)cur;
+      const bool single = head && nh;
       s_idx[g + e] = gi;
-      s_rank[g + e] = nr | ((head && nh) ? 0u : KEEP_BIT);
-      if (cur) isa[gi] = nr - blk_of(gi, magic) * stride;
+      s_rank[g + e] = nr | (single ? 0u : KEEP_BIT);
+      if (cur || single) {
+        const u32 p = blk_of(gi, magic), pb = p * stride;
+        if (cur) isa[gi] = nr - pb;
+        if (single) bwt_emit_final(T, L, recs, p, pb, gi, nr);
+      }
     }
   }
 }
