@@ -25,6 +25,7 @@
 #define RF_E (RF_CAP / RF_THREADS)
 #define RF_WARPS (RF_THREADS / 32)
 #define RF_SMALL 32
+#define RF_COOP 256                      // larger groups (up to RF_T0) are sorted by the whole CTA
 #define RF_SBITS 11                     // slot bits below key2 in the composite sort word (RF_CAP == 1 << RF_SBITS)
 #define RF_MAXMED (RF_CAP / (RF_SMALL + 1) + 1)
 #define CK_TILE 2048                    // slots per CTA of k_compact_keys
@@ -55,7 +56,9 @@ struct RfSmem {
   u16 gs[RF_CAP];   // first slot of the slot's group
   u16 ge[RF_CAP];   // at a group's first slot: one past its last slot
   u32 wc[RF_WARPS][128];       // warp-private digit counters
-  u16 med_a[RF_MAXMED + 1];    // first slot of every medium group
+  u16 med_a[RF_MAXMED + 1];    // first slot of every medium group (<= RF_COOP slots)
+  u16 lrg_a[RF_CAP / RF_COOP + 1];  // first slot of every large group
+  u32 dbase[128];
   u32 ws[34];
   int wsi[34];
   u32 bc[8];
@@ -72,11 +75,15 @@ __device__ __forceinline__ u32 lower_bound_u32(const u32 *a, u32 lo, u32 hi, u32
 // RF_T0 + 32 slots, 32 at a time; a longer group falls back to a binary search.  Called by a whole warp.
 __device__ __forceinline__ u32 group_start_warp(const u32 *__restrict__ R, u32 j) {
   const int lane = lane_id();
-  const u32 v = R[j];
-  for (u32 c0 = 0; c0 <= RF_T0; c0 += 32) {
+  // one load covers slots j-31 .. j: lane l looks at slot j-l (lane 0 holds the group's rank)
+  u32 mine = (u32)lane <= j ? R[j - (u32)lane] : 0;
+  const u32 v = __shfl_sync(FULL_MASK, mine, 0);
+  u32 b = __ballot_sync(FULL_MASK, (u32)lane > j || mine != v);
+  if (b) return j - ((u32)__ffs((int)b) - 1) + 1;
+  for (u32 c0 = 31; c0 <= RF_T0; c0 += 32) {
     u32 back = c0 + (u32)lane + 1;  // slot j - back
     bool diff = back > j ? true : R[j - back] != v;
-    u32 b = __ballot_sync(FULL_MASK, diff);
+    b = __ballot_sync(FULL_MASK, diff);
     if (b) return j - (c0 + (u32)__ffs((int)b) - 1);
   }
   return lower_bound_u32(R, 0, j, v);
@@ -126,6 +133,56 @@ __device__ __forceinline__ void warp_radix_group(RfSmem &sm, u32 a, u32 s) {
   }
 }
 
+// The whole CTA sorts sm.C[a .. a+s) by key2 into sm.SC[a .. a+s): same passes, every warp ranks a contiguous chunk.
+// Called by all threads; ends with a barrier.
+__device__ __forceinline__ void cta_radix_group(RfSmem &sm, u32 a, u32 s) {
+  const int lane = lane_id(), w = warp_id();
+  const u32 lt = (1u << lane) - 1;
+  const u32 chunk = ((s + RF_WARPS - 1) / RF_WARPS + 31) & ~31u;  // <= RF_T0 / RF_WARPS rounded up
+  u32 *src = sm.C + a, *dst = sm.SC + a;
+  for (int pass = 0; pass < 3; pass++) {
+    const int shift = RF_SBITS + 7 * pass;
+    for (int i = threadIdx.x; i < RF_WARPS * 128; i += RF_THREADS) (&sm.wc[0][0])[i] = 0;
+    __syncthreads();
+    u32 key[RF_T0 / RF_WARPS / 32 + 1], rkk[RF_T0 / RF_WARPS / 32 + 1];
+#pragma unroll
+    for (int e = 0; e < RF_T0 / RF_WARPS / 32 + 1; e++) {
+      u32 o = (u32)w * chunk + e * 32 + lane;
+      bool ok = (u32)e * 32 < chunk && o < s;
+      key[e] = ok ? src[o] : 0;
+      u32 d = ok ? ((key[e] >> shift) & 127u) : 0xffffu;
+      u32 peers = __match_any_sync(FULL_MASK, d);
+      int leader = __ffs((int)peers) - 1;
+      u32 old = 0;
+      if (ok && lane == leader) { old = sm.wc[w][d]; sm.wc[w][d] = old + __popc(peers); }
+      old = __shfl_sync(FULL_MASK, old, leader);
+      rkk[e] = old + __popc(peers & lt);
+      __syncwarp();
+    }
+    __syncthreads();
+    u32 tot_d = 0;
+    if (threadIdx.x < 128) {
+      u32 acc = 0;
+      for (int ww = 0; ww < RF_WARPS; ww++) { u32 t = sm.wc[ww][threadIdx.x]; sm.wc[ww][threadIdx.x] = acc; acc += t; }
+      tot_d = acc;
+    }
+    u32 tot;
+    u32 db = block_excl_sum<u32>(tot_d, tot, sm.ws);
+    if (threadIdx.x < 128) sm.dbase[threadIdx.x] = db;
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < RF_T0 / RF_WARPS / 32 + 1; e++) {
+      u32 o = (u32)w * chunk + e * 32 + lane;
+      if ((u32)e * 32 < chunk && o < s) {
+        u32 d = (key[e] >> shift) & 127u;
+        dst[sm.dbase[d] + sm.wc[w][d] + rkk[e]] = key[e];
+      }
+    }
+    __syncthreads();
+    u32 *t = src; src = dst; dst = t;
+  }
+}
+
 __global__ void __launch_bounds__(RF_THREADS) k_sort_groups(const u32 *__restrict__ key2, const u32 *__restrict__ a_idx, const u32 *__restrict__ a_rank,
                                                             u32 n_act, u32 *__restrict__ isa, u32 stride, u64 magic, u32 *__restrict__ s_idx,
                                                             u32 *__restrict__ s_rank, u32 *__restrict__ big_cnt, u32 *__restrict__ big_base,
@@ -137,6 +194,14 @@ __global__ void __launch_bounds__(RF_THREADS) k_sort_groups(const u32 *__restric
   const u32 tile = blockIdx.x;
   const u32 j0 = tile * RF_T0, j1 = j0 + RF_T0 < n_act ? j0 + RF_T0 : n_act;
   const u32 *R = a_rank;
+  // the nominal slots [j0, j1) are fetched first so that their latency overlaps the search for the bounds
+  u32 pk[RF_T0 / RF_THREADS], pi[RF_T0 / RF_THREADS], pr[RF_T0 / RF_THREADS];
+#pragma unroll
+  for (int e = 0; e < RF_T0 / RF_THREADS; e++) {
+    u32 j = j0 + e * RF_THREADS + threadIdx.x;
+    pk[e] = pi[e] = pr[e] = 0;
+    if (j < j1) { pk[e] = key2[j]; pi[e] = a_idx[j]; pr[e] = R[j]; }
+  }
   // ---- tile bounds [lo, hi): whole groups only ----
   if (w < 2) {
     const u32 j = w == 0 ? j0 : j1;
@@ -155,17 +220,21 @@ __global__ void __launch_bounds__(RF_THREADS) k_sort_groups(const u32 *__restric
       }
       lo = e < hi ? e : hi;
     }
-    sm.bc[0] = lo; sm.bc[1] = hi; sm.bc[2] = 0;
+    sm.bc[0] = lo; sm.bc[1] = hi; sm.bc[2] = 0; sm.bc[3] = 0; sm.bc[4] = 0;
   }
   __syncthreads();
   const u32 lo = sm.bc[0], hi = sm.bc[1];
   const u32 m = hi - lo;  // < 2 * RF_T0
   if (m == 0) return;
-  // ---- load (striped) ----
+  // ---- into shared memory: the prefetched slots that fall into [lo, hi), then the slots before j0 ----
 #pragma unroll
-  for (int e = 0; e < RF_E; e++) {
-    u32 t = e * RF_THREADS + threadIdx.x;
-    if (t < m) { sm.C[t] = (key2[lo + t] << RF_SBITS) | t; sm.I[t] = a_idx[lo + t]; sm.RK[t] = R[lo + t]; }
+  for (int e = 0; e < RF_T0 / RF_THREADS; e++) {
+    u32 j = j0 + e * RF_THREADS + threadIdx.x;
+    if (j >= lo && j < hi) { u32 t = j - lo; sm.C[t] = (pk[e] << RF_SBITS) | t; sm.I[t] = pi[e]; sm.RK[t] = pr[e]; }
+  }
+  if (lo < j0) {
+    const u32 pre = j0 - lo < m ? j0 - lo : m;
+    for (u32 t = threadIdx.x; t < pre; t += RF_THREADS) { sm.C[t] = (key2[lo + t] << RF_SBITS) | t; sm.I[t] = a_idx[lo + t]; sm.RK[t] = R[lo + t]; }
   }
   __syncthreads();
   // ---- group structure (blocked: thread owns slots t0 .. t0+RF_E-1) ----
@@ -207,16 +276,28 @@ __global__ void __launch_bounds__(RF_THREADS) k_sort_groups(const u32 *__restric
         for (u32 x = a; x < b; x++) before += sm.C[x] < cj ? 1u : 0u;
         sm.SC[a + before] = cj;
       } else if (t == a) {
-        u32 q = atomicAdd(&sm.bc[2], 1u);
-        sm.med_a[q] = (u16)a;
+        if (b - a > RF_COOP) { u32 q = atomicAdd(&sm.bc[3], 1u); sm.lrg_a[q] = (u16)a; }
+        else { u32 q = atomicAdd(&sm.bc[2], 1u); sm.med_a[q] = (u16)a; }
       }
     }
   }
   __syncthreads();
-  // ---- medium groups: one warp per group ----
+  // ---- large groups (> RF_COOP slots): the whole CTA sorts one group at a time ----
+  {
+    const u32 n_lrg = sm.bc[3];
+    for (u32 g = 0; g < n_lrg; g++) {
+      const u32 a = sm.lrg_a[g];
+      cta_radix_group(sm, a, (u32)sm.ge[a] - a);
+    }
+  }
+  // ---- medium groups: one warp per group, handed out dynamically ----
   {
     const u32 n_med = sm.bc[2];
-    for (u32 g = w; g < n_med; g += RF_WARPS) {
+    for (;;) {
+      u32 g = 0;
+      if (lane == 0) g = atomicAdd(&sm.bc[4], 1u);
+      g = __shfl_sync(FULL_MASK, g, 0);
+      if (g >= n_med) break;
       const u32 a = sm.med_a[g];
       warp_radix_group(sm, a, (u32)sm.ge[a] - a);
     }
