@@ -31,7 +31,7 @@ struct Ctx {
   bz2b200_stats st{};
   std::vector<DevBuf *> pool;
   // compress-side buffers
-  DevBuf in, tile_last, tile_first, head_carry, tile_emit, g_tile, recs, nblk, blk, crcpart, pow256;
+  DevBuf in, tile_last, tile_first, head_carry, tile_emit, g_sub, h_sub, g_tile, recs, nblk, blk, crcpart, pow256;
   DevBuf isa, keysA, keysB, valsB, actI0, actI1, actR0, actR1, lb_status, lbm, hist, digit_base;
   DevBuf seg_cnt, seg_tile0, tile_blk, tile_i0, tile_i1, totals;
   DevBuf Lcol, ranks, lastocc, A, freq, meta, W, bit_off, scrc, out, out_len, used_bits;
@@ -58,7 +58,7 @@ struct Ctx {
   std::vector<cudaEvent_t> dom_ev;  // start/stop pairs around the dominant kernel's launches
   size_t dom_used = 0;
   Ctx() {
-    DevBuf *all[] = {&in, &tile_last, &tile_first, &head_carry, &tile_emit, &g_tile, &recs, &nblk, &blk, &crcpart, &pow256,
+    DevBuf *all[] = {&in, &tile_last, &tile_first, &head_carry, &tile_emit, &g_sub, &h_sub, &g_tile, &recs, &nblk, &blk, &crcpart, &pow256,
                      &isa, &keysA, &keysB, &valsB, &actI0, &actI1, &actR0, &actR1, &lb_status, &lbm, &hist, &digit_base,
                      &seg_cnt, &seg_tile0, &tile_blk, &tile_i0, &tile_i1, &totals,
                      &Lcol, &ranks, &lastocc, &A, &freq, &meta, &W, &bit_off, &scrc, &out, &out_len, &used_bits,
@@ -140,7 +140,8 @@ int pipe_begin(Ctx *c, const u8 *d_in, size_t n_, int level) {
     ENS(c->tile_emit, 4 * T); ENS(c->g_tile, 8 * (T + 1));
     LAUNCH(k_rle_heads, (unsigned)T, RLE_THREADS, 0, d_in, N, P<i64>(c->tile_last), P<i64>(c->tile_first));
     LAUNCH(k_scan_excl_max_i64, 1, 1024, 0, P<i64>(c->tile_last), P<i64>(c->head_carry), T);
-    LAUNCH(k_rle_count, (unsigned)T, RLE_THREADS, 0, d_in, N, P<i64>(c->head_carry), P<u32>(c->tile_emit));
+    ENS(c->g_sub, 4 * (size_t)T * (RLE_THREADS / 32)); ENS(c->h_sub, 8 * (size_t)T * (RLE_THREADS / 32));
+    LAUNCH(k_rle_count, (unsigned)T, RLE_THREADS, 0, d_in, N, P<i64>(c->head_carry), P<u32>(c->tile_emit), P<u32>(c->g_sub), P<i64>(c->h_sub));
     LAUNCH(k_scan_excl_sum_u32_u64, 1, 1024, 0, P<u32>(c->tile_emit), P<u64>(c->g_tile), T);
   }
   return BZ2B200_OK;
@@ -156,7 +157,7 @@ int pipe_cut(Ctx *c, i64 s_start, i64 own_end) {
   int nb = 0;
   P_.hrecs.clear();
   if (N > 0 && s_start < N && s_start < own_end) {
-    LAUNCH(k_rle_cut, 1, CUT_THREADS, 0, P_.d_in, N, B, P<i64>(c->head_carry), P<i64>(c->tile_first), P<u64>(c->g_tile), T,
+    LAUNCH(k_rle_cut, 1, CUT_THREADS, 0, P_.d_in, N, B, P<u32>(c->g_sub), P<i64>(c->h_sub), P<i64>(c->tile_first), P<u64>(c->g_tile), T,
            P<BlockRec>(c->recs), max_blocks, P<int>(c->nblk), s_start, own_end);
     CK(cudaMemcpyAsync(&nb, c->nblk.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));

@@ -123,13 +123,17 @@ __global__ void __launch_bounds__(RLE_THREADS) k_rle_heads(const u8 *__restrict_
 }
 
 __global__ void __launch_bounds__(RLE_THREADS) k_rle_count(const u8 *__restrict__ in, i64 N, const i64 *__restrict__ head_carry,
-                                                           u32 *__restrict__ tile_emit) {
+                                                           u32 *__restrict__ tile_emit, u32 *__restrict__ g_sub, i64 *__restrict__ h_sub) {
   __shared__ i64 ws64[33];
   __shared__ u32 ws32[33];
   RleView v;
   u32 total;
   rle_view(in, N, blockIdx.x, head_carry, v, total, ws64, ws32);
   if (threadIdx.x == 0) tile_emit[blockIdx.x] = total;
+  if (lane_id() == 0) {  // per 512-byte chunk (one warp): bytes emitted in the tile before it, last run head before it
+    g_sub[(i64)blockIdx.x * (RLE_THREADS / 32) + warp_id()] = v.gpre;
+    h_sub[(i64)blockIdx.x * (RLE_THREADS / 32) + warp_id()] = v.head_before;
+  }
 }
 
 // out[i] = max(in[0..i)) (identity -1); single CTA of 1024 threads
@@ -170,49 +174,50 @@ __global__ void __launch_bounds__(1024) k_scan_excl_sum_u32_u64(const u32 *__res
 #define CUT_THREADS (CUT_WARPS * 32)
 #define RLE_CHUNK 512  // bytes a warp looks at per step (16 per lane)
 
-// One warp walks tile `tile` chunk by chunk.  want_pos >= 0: returns the number of bytes emitted inside the tile
-// before position want_pos.  want_pos < 0: returns the first position whose inclusive cumulative emission
-// gbase + ... reaches `target` (INF when the tile ends first).
-__device__ __forceinline__ i64 warp_tile_walk(const u8 *__restrict__ in, i64 N, i64 tile, i64 head_carry_t, u64 gbase, i64 want_pos,
-                                              u64 target) {
+// One warp answers a query about tile `tile` from the chunk summaries of k_rle_count and ONE 512-byte chunk.
+// want_pos >= 0: returns the number of bytes emitted inside the tile before position want_pos.  want_pos < 0: returns
+// the first position whose inclusive cumulative emission gbase + ... reaches `target` (INF when the tile ends first).
+__device__ __forceinline__ i64 warp_tile_walk(const u8 *__restrict__ in, i64 N, i64 tile, const u32 *__restrict__ g_sub,
+                                              const i64 *__restrict__ h_sub, u64 gbase, i64 want_pos, u64 target) {
   const i64 INF = (i64)0x7fffffffffffffffLL;
   const int lane = lane_id();
-  i64 carry_head = head_carry_t;
-  u32 gacc = 0;
-  for (int c = 0; c < RLE_TILE / RLE_CHUNK; c++) {
-    RleView v;
-    rle_load_at(in, N, tile * RLE_TILE + (i64)c * RLE_CHUNK + (i64)lane * 16, v);
-    i64 my_last = v.flags ? v.p0 + (31 - __clz((int)v.flags)) : (i64)-1;
-    i64 inc = warp_incl_max<i64>(my_last);
-    i64 prev = __shfl_up_sync(FULL_MASK, inc, 1);
-    if (lane == 0) prev = -1;
-    v.head_before = prev > carry_head ? prev : carry_head;
-    u32 cnt = rle_emits(v);
-    u32 inc_c = warp_incl_sum<u32>(cnt);
-    v.gpre = gacc + inc_c - cnt;
-    if (want_pos >= 0) {
-      bool mine = want_pos >= v.p0 && want_pos < v.p0 + 16;
-      u32 g = v.gpre;
-      if (mine)
-        for (int j = 0; j < (int)(want_pos - v.p0); j++) g += (v.em >> (2 * j)) & 3u;
-      u32 bal = __ballot_sync(FULL_MASK, mine);
-      g = __shfl_sync(FULL_MASK, g, bal ? __ffs((int)bal) - 1 : 0);
-      if (bal) return (i64)g;
-    } else {
-      u64 run = gbase + v.gpre;
-      i64 c3 = INF;
-      for (int j = 0; j < v.nvalid; j++) {
-        run += (v.em >> (2 * j)) & 3u;
-        if (run >= target) { c3 = v.p0 + j; break; }
-      }
-      c3 = warp_min<i64>(c3);
-      if (c3 != INF) return c3;
-    }
-    i64 last_inc = __shfl_sync(FULL_MASK, inc, 31);
-    if (last_inc > carry_head) carry_head = last_inc;
-    gacc += __shfl_sync(FULL_MASK, inc_c, 31);
+  const int NCH = RLE_TILE / RLE_CHUNK;
+  int c;
+  if (want_pos >= 0) c = (int)((want_pos - tile * RLE_TILE) / RLE_CHUNK);
+  else {  // last chunk whose start is still below the target
+    u32 gs = lane < NCH ? g_sub[tile * NCH + lane] : 0;
+    u32 b = __ballot_sync(FULL_MASK, lane < NCH && gbase + gs < target);
+    c = __popc(b) - 1;
+    if (c < 0) c = 0;
   }
-  return want_pos >= 0 ? (i64)gacc : INF;
+  const u32 gacc = g_sub[tile * NCH + c];
+  const i64 carry_head = h_sub[tile * NCH + c];
+  RleView v;
+  rle_load_at(in, N, tile * RLE_TILE + (i64)c * RLE_CHUNK + (i64)lane * 16, v);
+  i64 my_last = v.flags ? v.p0 + (31 - __clz((int)v.flags)) : (i64)-1;
+  i64 inc = warp_incl_max<i64>(my_last);
+  i64 prev = __shfl_up_sync(FULL_MASK, inc, 1);
+  if (lane == 0) prev = -1;
+  v.head_before = prev > carry_head ? prev : carry_head;
+  u32 cnt = rle_emits(v);
+  u32 inc_c = warp_incl_sum<u32>(cnt);
+  v.gpre = gacc + inc_c - cnt;
+  if (want_pos >= 0) {
+    bool mine = want_pos >= v.p0 && want_pos < v.p0 + 16;
+    u32 g = v.gpre;
+    if (mine)
+      for (int j = 0; j < (int)(want_pos - v.p0); j++) g += (v.em >> (2 * j)) & 3u;
+    u32 bal = __ballot_sync(FULL_MASK, mine);
+    g = __shfl_sync(FULL_MASK, g, bal ? __ffs((int)bal) - 1 : 0);
+    return bal ? (i64)g : (i64)(gacc + __shfl_sync(FULL_MASK, inc_c, 31));
+  }
+  u64 run = gbase + v.gpre;
+  i64 c3 = INF;
+  for (int j = 0; j < v.nvalid; j++) {
+    run += (v.em >> (2 * j)) & 3u;
+    if (run >= target) { c3 = v.p0 + j; break; }
+  }
+  return warp_min<i64>(c3);
 }
 // last t in [lo, hi] with g[t] < target (g non-decreasing, g[lo] < target): 32-ary search by one warp
 __device__ __forceinline__ i64 warp_search_tile(const u64 *__restrict__ g, i64 lo, i64 hi, u64 target) {
@@ -228,7 +233,7 @@ __device__ __forceinline__ i64 warp_search_tile(const u64 *__restrict__ g, i64 l
   return lo;
 }
 // The exact step of the reference's block loop from start s (one warp; every lane returns the same record).
-__device__ __forceinline__ void warp_cut_step(const u8 *__restrict__ in, i64 N, u32 B, const i64 *__restrict__ head_carry,
+__device__ __forceinline__ void warp_cut_step(const u8 *__restrict__ in, i64 N, u32 B, const u32 *__restrict__ g_sub, const i64 *__restrict__ h_sub,
                                               const i64 *__restrict__ tile_first, const u64 *__restrict__ g_tile, i64 T, i64 s, BlockRec &r) {
   const i64 INF = (i64)0x7fffffffffffffffLL;
   const int lane = lane_id();
@@ -281,7 +286,7 @@ __device__ __forceinline__ void warp_cut_step(const u8 *__restrict__ in, i64 N, 
   } else {
     // (3) global-fresh coordinates from e with c bytes of room
     const i64 te = e / RLE_TILE;
-    const u64 Ge = g_tile[te] + (u64)warp_tile_walk(in, N, te, head_carry[te], 0, e, 0);
+    const u64 Ge = g_tile[te] + (u64)warp_tile_walk(in, N, te, g_sub, h_sub, 0, e, 0);
     r.Ge = Ge;
     const u64 target = Ge + c;
     if (target > g_tile[T]) {
@@ -291,14 +296,14 @@ __device__ __forceinline__ void warp_cut_step(const u8 *__restrict__ in, i64 N, 
       i64 lo = te + (i64)((c - 1) / 5120u);  // a tile emits at most 5/4 of its bytes, so g_tile[lo] < target
       if (lo > T - 1) lo = T - 1;
       const i64 tc = warp_search_tile(g_tile, lo, T - 1, target);
-      const i64 icut = warp_tile_walk(in, N, tc, head_carry[tc], g_tile[tc], -1, target);
+      const i64 icut = warp_tile_walk(in, N, tc, g_sub, h_sub, g_tile[tc], -1, target);
       r.p = icut + 1;
       r.n = B;
     }
   }
 }
 
-__global__ void __launch_bounds__(CUT_THREADS) k_rle_cut(const u8 *__restrict__ in, i64 N, u32 B, const i64 *__restrict__ head_carry,
+__global__ void __launch_bounds__(CUT_THREADS) k_rle_cut(const u8 *__restrict__ in, i64 N, u32 B, const u32 *__restrict__ g_sub, const i64 *__restrict__ h_sub,
                                                          const i64 *__restrict__ tile_first, const u64 *__restrict__ g_tile, i64 T,
                                                          BlockRec *__restrict__ recs, int max_blocks, int *__restrict__ n_blocks, i64 s_start,
                                                          i64 own_end) {
@@ -315,19 +320,19 @@ __global__ void __launch_bounds__(CUT_THREADS) k_rle_cut(const u8 *__restrict__ 
     if (w == 0) cand = s;
     else {
       const i64 tsb = s / RLE_TILE;
-      const u64 gs = g_tile[tsb] + (u64)warp_tile_walk(in, N, tsb, head_carry[tsb], 0, s, 0);
+      const u64 gs = g_tile[tsb] + (u64)warp_tile_walk(in, N, tsb, g_sub, h_sub, 0, s, 0);
       const u64 span = (u64)w * B, target = gs + span;
       if (target <= Gtot) {
         i64 lo = tsb + (i64)((span - 1) / 5120u);
         if (lo > T - 1) lo = T - 1;
         const i64 tc = warp_search_tile(g_tile, lo, T - 1, target);
-        const i64 icut = warp_tile_walk(in, N, tc, head_carry[tc], g_tile[tc], -1, target);
+        const i64 icut = warp_tile_walk(in, N, tc, g_sub, h_sub, g_tile[tc], -1, target);
         if (icut != INF && icut + 1 < N) cand = icut + 1;
       }
     }
     BlockRec r;
     r.s = cand; r.p = INF; r.e_true = 0; r.Ge = 0; r.outR = 0; r.n = 0; r.crc = 0; r.orig_ptr = 0;
-    if (cand != INF) warp_cut_step(in, N, B, head_carry, tile_first, g_tile, T, cand, r);
+    if (cand != INF) warp_cut_step(in, N, B, g_sub, h_sub, tile_first, g_tile, T, cand, r);
     if (lane == 0) { sh_cand[w] = cand; sh_rec[w] = r; }
     __syncthreads();
     // follow the links that hold
@@ -405,13 +410,20 @@ __global__ void __launch_bounds__(RLE_THREADS) k_rle_emit(const u8 *__restrict__
   }
 }
 
-// raw CRC (register starts at 0) of every 64 KiB chunk of every block's input range
+// raw CRC (register starts at 0) of every 64 KiB chunk of every block's input range.  256 threads, 256 bytes per
+// thread, four bytes per step (slicing-by-4: tab[k][b] = CRC register after byte b and k zero bytes).
 __global__ void __launch_bounds__(256) k_crc_chunks(const u8 *__restrict__ in, const BlockRec *__restrict__ recs,
                                                     const u32 *__restrict__ pow256, u32 *__restrict__ part, int max_chunks) {
-  __shared__ u32 tab[256];
+  __shared__ u32 tab[4][256];
   __shared__ u32 ws[33];
   int k = blockIdx.y, c = blockIdx.x;
-  tab[threadIdx.x] = crc_table_entry(threadIdx.x);
+  {
+    u32 t0 = crc_table_entry(threadIdx.x), t = t0;
+    tab[0][threadIdx.x] = t;
+    __syncthreads();
+#pragma unroll
+    for (int q = 1; q < 4; q++) { t = (t << 8) ^ tab[0][t >> 24]; tab[q][threadIdx.x] = t; }
+  }
   __syncthreads();
   i64 s = recs[k].s, p = recs[k].p;
   i64 c0 = s + (i64)c * CRC_CHUNK;
@@ -421,7 +433,16 @@ __global__ void __launch_bounds__(256) k_crc_chunks(const u8 *__restrict__ in, c
   i64 b = a + 256 < c1 ? a + 256 : c1;
   u32 crc = 0;
   if (a < b) {
-    for (i64 i = a; i < b; i++) crc = (crc << 8) ^ tab[(crc >> 24) ^ in[i]];
+    i64 i = a;
+    for (; i < b && (i & 3); i++) crc = (crc << 8) ^ tab[0][(crc >> 24) ^ in[i]];  // up to an aligned word
+    const u32 *w32 = reinterpret_cast<const u32 *>(in + i);
+    i64 nw = (b - i) >> 2;
+    for (i64 q = 0; q < nw; q++) {
+      u32 w = w32[q];  // little-endian load: the first byte is the low one
+      crc = tab[3][(crc >> 24) ^ (w & 0xffu)] ^ tab[2][((crc >> 16) & 0xffu) ^ ((w >> 8) & 0xffu)] ^
+            tab[1][((crc >> 8) & 0xffu) ^ ((w >> 16) & 0xffu)] ^ tab[0][(crc & 0xffu) ^ (w >> 24)];
+    }
+    for (i += nw * 4; i < b; i++) crc = (crc << 8) ^ tab[0][(crc >> 24) ^ in[i]];
     u64 after = (u64)(c1 - b);
     u32 shift = (c1 - c0 == CRC_CHUNK) ? pow256[255 - threadIdx.x] : crc_xpow(8 * after);
     crc = crc_mulmod(crc, shift);
