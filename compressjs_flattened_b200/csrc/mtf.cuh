@@ -312,24 +312,52 @@ __global__ void __launch_bounds__(MTR_WARPS * 32) k_mtf_ranks(const u8 *__restri
 }
 
 // ---- K-S3d: RLE2 + symbol compaction + histogram, grid-wide ----
-// grid (ceil(stride / R2_TILE), nb), R2_THREADS threads.  A zero run emits its RUNA/RUNB digits where it ENDS, so a
-// tile only has to know where the run that is open at its first rank began: a backward scan over the ranks
-// (each run is scanned once).  Output positions come from a look-back over the tiles of the block (tiles take
-// their index from a per-block ticket); the histogram is accumulated in shared memory and flushed with atomics.
-#define R2_TILE 16384
-#define R2_THREADS 1024
-#define R2_E (R2_TILE / R2_THREADS)
+// grid (ceil(stride / R2_TILE), nb), R2_THREADS threads.  A warp owns 1024 consecutive ranks as 8 rows of 128
+// (one u32 = 4 ranks per lane, coalesced); symbol counts become output offsets by warp scans, so neighbouring
+// lanes write neighbouring symbols.  A zero run emits its RUNA/RUNB digits where it ENDS, so a tile only has to
+// know where the run that is open at its first rank began: a backward scan over the ranks (each run is scanned
+// once).  Output positions of a tile come from a look-back over the tiles of the block (tiles take their index
+// from a per-block ticket); the histogram is accumulated in shared memory and flushed with atomics.
+#define R2_THREADS 256
+#define R2_WARPS (R2_THREADS / 32)
+#define R2_ROWS 8
+#define R2_TILE (R2_WARPS * R2_ROWS * 128)
+// The 4 ranks of word `wv` at positions i0.. as output ITEMS (cur: last non-zero position before i0, -1 none;
+// nxt: the rank after the word is non-zero or past the block).  A non-zero rank r is one symbol r+1; the last
+// zero of a run of length L is floor(log2(L+1)) RUNA/RUNB digits, digit k = bit k of L+1 (BJ:2107-2118 in
+// closed form).  cnt[k] = symbols of item k, pay[k] = r+1, or (L+1) | 0x80000000 for a run.
+__device__ __forceinline__ u32 r2_items(u32 wv, u32 i0, u32 n, int cur, bool nxt, u32 cnt[4], u32 pay[4]) {
+  u32 total = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const u32 i = i0 + k, r = (wv >> (8 * k)) & 0xffu;
+    cnt[k] = 0; pay[k] = 0;
+    if (i < n) {
+      const bool next_nz = k < 3 ? (((wv >> (8 * k + 8)) & 0xffu) != 0) : nxt;
+      if (r) { cur = (int)i; cnt[k] = 1; pay[k] = r + 1; }
+      else if (i + 1 >= n || next_nz) {
+        u32 v = i - (u32)cur + 1;
+        cnt[k] = 31 - __clz((int)v);
+        pay[k] = v | 0x80000000u;
+      }
+    }
+    total += cnt[k];
+  }
+  return total;
+}
 __global__ void __launch_bounds__(R2_THREADS) k_mtf_rle2(const BlockRec *__restrict__ recs, const u8 *__restrict__ ranks, i64 l_stride,
                                                          u16 *__restrict__ A, i64 a_stride, u32 *__restrict__ freq_out,
                                                          BlockMeta *__restrict__ meta, u64 *__restrict__ status, i64 status_stride,
                                                          u32 *__restrict__ tickets) {
   __shared__ u32 hist[BZ_MAX_SYMS + 2];
-  __shared__ u32 ws[33];
-  __shared__ int wsi[33];
+  __shared__ int wl[R2_WARPS];
+  __shared__ u32 wc[R2_WARPS];
   __shared__ u32 sh_tile, sh_base;
   __shared__ int sh_nz;
+  __shared__ u32 it_off[R2_WARPS][129], it_pay[R2_WARPS][128];
   const u32 p = blockIdx.y;
   const u32 n = recs[p].n;
+  const int lane = lane_id(), w = warp_id();
   if (threadIdx.x == 0) sh_tile = atomicAdd(&tickets[p], 1u);
   for (int i = threadIdx.x; i < BZ_MAX_SYMS + 2; i += R2_THREADS) hist[i] = 0;
   __syncthreads();
@@ -338,20 +366,34 @@ __global__ void __launch_bounds__(R2_THREADS) k_mtf_rle2(const BlockRec *__restr
   const u32 ntiles = (n + R2_TILE - 1) / R2_TILE;
   const u8 *Rp = ranks + (i64)p * l_stride;
   u16 *Ap = A + (i64)p * a_stride;
-  const u32 i0 = t0 + threadIdx.x * R2_E;
-  u32 r[R2_E + 1];
-  {
-    uint4 v = i0 < n ? *reinterpret_cast<const uint4 *>(Rp + i0) : make_uint4(0, 0, 0, 0);  // padded stride: reading past n is fine
-    u32 wv[4] = {v.x, v.y, v.z, v.w};
+  const u32 w0 = t0 + (u32)w * (R2_ROWS * 128);  // first rank of this warp
+  u32 wv[R2_ROWS];
 #pragma unroll
-    for (int k = 0; k < R2_E; k++) r[k] = (wv[k >> 2] >> (8 * (k & 3))) & 0xffu;
-    r[R2_E] = (i0 + R2_E < n) ? Rp[i0 + R2_E] : 1u;  // sentinel: the position after the block ends any run
+  for (int q = 0; q < R2_ROWS; q++) {
+    const u32 i0 = w0 + q * 128 + lane * 4;
+    u32 v = i0 < n ? *reinterpret_cast<const u32 *>(Rp + i0) : 0u;  // padded stride: reading past n inside a word is fine
+    if (i0 + 4 > n && i0 < n) v &= (1u << (8 * (n - i0))) - 1;     // ranks past the block count as zero
+    wv[q] = v;
   }
-  // last non-zero rank before the tile (-1: none), found only when a run is open at the tile's first rank
-  if (threadIdx.x < 32) {
+  // is the rank after this warp's last one non-zero (or past the block)?
+  bool warp_nxt = true;
+  if (w0 + R2_ROWS * 128 < n) warp_nxt = Rp[w0 + R2_ROWS * 128] != 0;
+  // last non-zero position inside this warp's ranks
+  int mylast = -1;
+#pragma unroll
+  for (int q = 0; q < R2_ROWS; q++) {
+    u32 b = __ballot_sync(FULL_MASK, wv[q] != 0);
+    if (b) {
+      int L = 31 - __clz((int)b);
+      u32 x = __shfl_sync(FULL_MASK, wv[q], L);
+      mylast = (int)(w0 + q * 128 + L * 4 + ((31 - __clz((int)x)) >> 3));
+    }
+  }
+  if (lane == 0) wl[w] = mylast;
+  // last non-zero rank before the tile (-1: none), needed only when a run is open at the tile's first rank
+  if (w == 0) {
     int res = -1;
     if (t0 > 0 && Rp[t0] == 0) {
-      const int lane = threadIdx.x;
       for (i64 j0 = (i64)t0 - 1; j0 >= 0 && res < 0; j0 -= 32) {
         i64 j = j0 - lane;
         bool nzq = j >= 0 && Rp[j] != 0;
@@ -359,70 +401,106 @@ __global__ void __launch_bounds__(R2_THREADS) k_mtf_rle2(const BlockRec *__restr
         if (b) res = (int)(j0 - (__ffs((int)b) - 1));
       }
     } else if (t0 > 0) res = (int)t0 - 1;
-    if (threadIdx.x == 0) sh_nz = res;
-  }
-  int my_nz = -1;
-#pragma unroll
-  for (int k = 0; k < R2_E; k++) if (i0 + k < n && r[k]) my_nz = (int)(i0 + k);
-  int tot_nz;
-  int nz = block_excl_max<int>(my_nz, -1, tot_nz, wsi);
-  if (sh_nz > nz) nz = sh_nz;
-  u32 cnt = 0;
-  {
-    int cur = nz;
-#pragma unroll
-    for (int k = 0; k < R2_E; k++) {
-      u32 i = i0 + k;
-      if (i < n) {
-        if (r[k]) { cnt++; cur = (int)i; }
-        else if (i + 1 >= n || r[k + 1]) cnt += 31 - __clz((int)(i - (u32)cur) + 1);
-      }
-    }
-  }
-  u32 tot_m;
-  u32 o = block_excl_sum<u32>(cnt, tot_m, ws);
-  if (threadIdx.x < 32) {
-    u32 base = lookback_warp(status + (i64)p * status_stride, tile, tot_m);
-    if (threadIdx.x == 0) sh_base = base;
+    if (lane == 0) sh_nz = res;
   }
   __syncthreads();
-  o += sh_base;
+  int carry0 = sh_nz;
+  for (int ww = 0; ww < w; ww++) if (wl[ww] > carry0) carry0 = wl[ww];
+  // pass 1: symbols per lane and row
+  u32 rowcnt[R2_ROWS];
+  int rowcur[R2_ROWS];
+  bool rownxt[R2_ROWS];
+  u32 total = 0;
   {
-    int cur = nz;
-    u32 hot0 = 0, hot1 = 0, hot2 = 0;  // RUNA, RUNB and rank 1 are most of the symbols: counted in registers, one atomic per warp
+    int carry = carry0;
 #pragma unroll
-    for (int k = 0; k < R2_E; k++) {
-      u32 i = i0 + k;
-      if (i < n) {
-        if (r[k]) {
-          cur = (int)i;
-          Ap[o++] = (u16)(r[k] + 1);
-          if (r[k] == 1) hot2++;
-          else atomicAdd(&hist[r[k] + 1], 1u);
-        } else if (i + 1 >= n || r[k + 1]) {
-          u32 run = i - (u32)cur;  // BJ:2107-2118
-          while (run) {
-            u32 sym = (run & 1) ? 0u : 1u;
-            run -= sym + 1;
-            run >>= 1;
-            Ap[o++] = (u16)sym;
-            hot0 += sym ^ 1u; hot1 += sym;
-          }
-        }
+    for (int q = 0; q < R2_ROWS; q++) {
+      const u32 i0 = w0 + q * 128 + lane * 4;
+      // last non-zero before my word: the nearest lower lane of this row that has one, else the running carry
+      u32 b = __ballot_sync(FULL_MASK, wv[q] != 0);
+      int hi_in_word = wv[q] ? (int)(i0 + ((31 - __clz((int)wv[q])) >> 3)) : -1;
+      u32 lower = b & ((1u << lane) - 1);
+      int src = lower ? 31 - __clz((int)lower) : 0;
+      int from_lane = __shfl_sync(FULL_MASK, hi_in_word, src);
+      int cur = lower ? from_lane : carry;
+      // the rank after my word
+      u32 nx = __shfl_down_sync(FULL_MASK, wv[q], 1);
+      u32 nrow0 = q + 1 < R2_ROWS ? __shfl_sync(FULL_MASK, wv[q + 1 < R2_ROWS ? q + 1 : q], 0) : 0u;
+      bool nxt = lane < 31 ? (nx & 0xffu) != 0 : (q + 1 < R2_ROWS ? (nrow0 & 0xffu) != 0 : warp_nxt);
+      if (i0 + 4 >= n) nxt = true;
+      rowcur[q] = cur;
+      rownxt[q] = nxt;
+      { u32 c4[4], p4[4]; rowcnt[q] = r2_items(wv[q], i0, n, cur, nxt, c4, p4); }
+      total += rowcnt[q];
+      if (b) {
+        int L = 31 - __clz((int)b);
+        carry = __shfl_sync(FULL_MASK, hi_in_word, L);
       }
     }
-    hot0 = warp_sum<u32>(hot0); hot1 = warp_sum<u32>(hot1); hot2 = warp_sum<u32>(hot2);
-    if (lane_id() == 0) {
-      if (hot0) atomicAdd(&hist[0], hot0);
-      if (hot1) atomicAdd(&hist[1], hot1);
-      if (hot2) atomicAdd(&hist[2], hot2);
+  }
+  u32 wtot = warp_sum<u32>(total);
+  if (lane == 0) wc[w] = wtot;
+  __syncthreads();
+  if (w == 0) {
+    u32 x = lane < R2_WARPS ? wc[lane] : 0;
+    u32 inc = warp_incl_sum<u32>(x);
+    u32 agg = __shfl_sync(FULL_MASK, inc, 31);
+    u32 base = lookback_warp(status + (i64)p * status_stride, tile, agg);
+    if (lane < R2_WARPS) wc[lane] = inc - x;
+    if (lane == 0) {
+      sh_base = base;
+      if (tile == ntiles - 1) {
+        const u32 alpha = meta[p].alpha, mm = base + agg;
+        Ap[mm] = (u16)(alpha + 1);  // end of block, BJ:2138
+        atomicAdd(&hist[alpha + 1], 1u);
+        meta[p].m = mm + 1;
+      }
     }
   }
-  if (tile == ntiles - 1 && threadIdx.x == 0) {
-    const u32 alpha = meta[p].alpha, mm = sh_base + tot_m;
-    Ap[mm] = (u16)(alpha + 1);  // end of block, BJ:2138
-    atomicAdd(&hist[alpha + 1], 1u);
-    meta[p].m = mm + 1;
+  __syncthreads();
+  // pass 2: emit.  Per row the items' offsets and payloads go to shared memory; then output symbol s is produced by
+  // lane s % 32 (binary search for its item), so the stores are coalesced and no lane loops over a long run.
+  u32 o = sh_base + wc[w];
+  u32 hot0 = 0, hot1 = 0, hot2 = 0;  // RUNA, RUNB and rank 1 are most of the symbols: counted in registers
+  u32 *ioff = it_off[w], *ipay = it_pay[w];
+#pragma unroll 1
+  for (int q = 0; q < R2_ROWS; q++) {
+    const u32 i0 = w0 + q * 128 + lane * 4;
+    u32 c4[4], p4[4];
+    r2_items(wv[q], i0, n, rowcur[q], rownxt[q], c4, p4);
+    u32 inc = warp_incl_sum<u32>(rowcnt[q]);
+    u32 e = inc - rowcnt[q];
+    const u32 trow = __shfl_sync(FULL_MASK, inc, 31);
+#pragma unroll
+    for (int k = 0; k < 4; k++) { ioff[lane * 4 + k] = e; ipay[lane * 4 + k] = p4[k]; e += c4[k]; }
+    if (lane == 31) ioff[128] = trow;
+    __syncwarp();
+    for (u32 sidx = lane; sidx < trow; sidx += 32) {
+      u32 lo_i = 0, hi_i = 128;  // last item with ioff[item] <= sidx (items without symbols share their offset with the next)
+#pragma unroll
+      for (int st = 0; st < 7; st++) {
+        u32 mid = (lo_i + hi_i) >> 1;
+        if (ioff[mid] <= sidx) lo_i = mid; else hi_i = mid;
+      }
+      const u32 py = ipay[lo_i];
+      u32 sym;
+      if (py & 0x80000000u) {
+        sym = ((py & 0x7fffffffu) >> (sidx - ioff[lo_i])) & 1u;
+        hot0 += sym ^ 1u; hot1 += sym;
+      } else {
+        sym = py;
+        if (sym == 2) hot2++; else atomicAdd(&hist[sym], 1u);
+      }
+      Ap[o + sidx] = (u16)sym;
+    }
+    o += trow;
+    __syncwarp();
+  }
+  hot0 = warp_sum<u32>(hot0); hot1 = warp_sum<u32>(hot1); hot2 = warp_sum<u32>(hot2);
+  if (lane == 0) {
+    if (hot0) atomicAdd(&hist[0], hot0);
+    if (hot1) atomicAdd(&hist[1], hot1);
+    if (hot2) atomicAdd(&hist[2], hot2);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < BZ_MAX_SYMS; i += R2_THREADS) if (hist[i]) atomicAdd(&freq_out[(i64)p * BZ_MAX_SYMS + i], hist[i]);
