@@ -7,15 +7,15 @@
 //
 // Algorithm (Larsson-Sadakane doubling, all blocks of the batch at once):
 //   ISA[i]  = current rank of rotation i = SA index (inside its block) of the first slot of its group
-//   start   : key = (first 5 bytes of the rotation << 20) | i -> batched LSD radix sort of bits 20..59
-//             (5 passes of 8 bits, keys only); every block's slots are padded to a multiple of SORT_TILE so
+//   start   : key = (first L symbols of the rotation, dense codes, 44 bits) << 20 | i -> batched LSD radix sort of
+//             bits 20..63 (5 passes of 9 bits, keys only); every block's slots are padded to a multiple of SORT_TILE so
 //             a tile never straddles two blocks; tile_blk[] maps a tile to its block.  k_rank0 then finds
 //             the groups, writes ISA and emits the ACTIVE LIST: the slots whose group has > 1 member, in
 //             SA order over all blocks, as (gidx = block * stride + rotation, rank = block * stride + SA
 //             index of the group's first slot).  The list is one global array: groups are contiguous runs
 //             of equal rank, nothing else about blocks is needed (block = gidx / stride).
 //   round h : key2 = ISA[(i+h) mod n] for every active slot (k_keys2), then every group is sorted by key2
-//             (refine.cuh), new groups/ranks/ISA, singletons leave the list.  h = 5, 10, 20, ...
+//             (refine.cuh), new groups/ranks/ISA, singletons leave the list.  h = L, 2L, 4L, ... (per block)
 //   h >= n  : remaining ties are identical rotations: key2 = n-1-i (descending index).
 // Both list-producing kernels compact IN ORDER in a single pass (decoupled look-back, common.cuh).
 #pragma once
@@ -59,12 +59,70 @@ __global__ void k_seg_init(const BlockRec *__restrict__ recs, int nb, u32 *__res
 }
 
 // ---- key construction ------------------------------------------------------------------------
-// first five bytes of each rotation, rotation index in the low 20 bits
+// The first sort covers as many symbols as fit 44 bits: the bytes of a block are first renumbered densely
+// (order-preserving), b = bits per symbol, L = 44 / b symbols (5 for binary data, 6 for text, 22 for DNA).
+struct BlkSort {
+  u32 used[8];  // bitmap of the byte values of the block
+  u32 b, L;     // bits per symbol, symbols in the first key (= h of the first doubling round)
+  u32 pad[6];
+  u8 code[256]; // byte -> dense code
+};
+// grid (32, nb): used-byte bitmap of every block
+__global__ void __launch_bounds__(256) k_sym_used(const u8 *__restrict__ blk, i64 blk_stride, const BlockRec *__restrict__ recs,
+                                                  BlkSort *__restrict__ bs) {
+  __shared__ u32 bm[8];
+  const u32 p = blockIdx.y, n = recs[p].n;
+  const u8 *T = blk + (i64)p * blk_stride;
+  if (threadIdx.x < 8) bm[threadIdx.x] = 0;
+  __syncthreads();
+  u32 loc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const u32 nw = (n + 3) / 4;  // padded stride: whole words; bytes past n are masked
+  for (u32 x = blockIdx.x * 256 + threadIdx.x; x < nw; x += gridDim.x * 256) {
+    u32 wv = reinterpret_cast<const u32 *>(T)[x];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      u32 c = (wv >> (8 * k)) & 0xffu;
+      if (4 * x + k < n) {
+#pragma unroll
+        for (int q = 0; q < 8; q++) if ((c >> 5) == (u32)q) loc[q] |= 1u << (c & 31);
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 8; q++) {
+    u32 v = loc[q];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v |= __shfl_xor_sync(FULL_MASK, v, d);
+    if (lane_id() == 0 && v) atomicOr(&bm[q], v);
+  }
+  __syncthreads();
+  if (threadIdx.x < 8 && bm[threadIdx.x]) atomicOr(&bs[p].used[threadIdx.x], bm[threadIdx.x]);
+}
+// nb CTAs of 256 threads: dense codes, b and L
+__global__ void __launch_bounds__(256) k_sym_tab(BlkSort *__restrict__ bs) {
+  __shared__ u32 ws[33];
+  BlkSort &B = bs[blockIdx.x];
+  const u32 c = threadIdx.x;
+  u32 used = (B.used[c >> 5] >> (c & 31)) & 1u, alpha;
+  u32 idx = block_excl_sum<u32>(used, alpha, ws);
+  B.code[c] = (u8)idx;
+  if (c == 0) {
+    u32 b = 1;
+    while ((1u << b) < alpha) b++;
+    B.b = b;
+    B.L = 44 / b;
+  }
+}
+// dense codes of the first L symbols of each rotation, left-aligned in bits 20..63; rotation index in the low 20 bits
 __global__ void __launch_bounds__(SEG_THREADS) k_keys_init(const u8 *__restrict__ blk, i64 blk_stride, const BlockRec *__restrict__ recs,
                                                            const u32 *__restrict__ seg_tile0, const u32 *__restrict__ tile_blk,
-                                                           u64 *__restrict__ keys) {
+                                                           const BlkSort *__restrict__ bs, u64 *__restrict__ keys) {
+  __shared__ u8 code[256];
   u32 tile = blockIdx.x, p = tile_blk[tile];
   u32 n = recs[p].n;
+  code[threadIdx.x] = bs[p].code[threadIdx.x];
+  const u32 b = bs[p].b, L = bs[p].L;
+  __syncthreads();
   const u8 *T = blk + (i64)p * blk_stride;
   u32 l0 = (tile - seg_tile0[p]) * SORT_TILE;
   u64 g0 = (u64)tile * SORT_TILE;
@@ -73,63 +131,68 @@ __global__ void __launch_bounds__(SEG_THREADS) k_keys_init(const u8 *__restrict_
     if (lj >= n) continue;
     u64 key = 0;
     u32 x = lj;
-    for (int k = 0; k < 5; k++) {
-      key = (key << 8) | T[x];
+    for (u32 k = 0; k < L; k++) {
+      key = (key << b) | code[T[x]];
       x = x + 1 == n ? 0 : x + 1;
     }
-    u64 g = g0 + (lj - l0);
-    keys[g] = (key << 20) | lj;
+    keys[g0 + (lj - l0)] = (key << (64 - L * b)) | lj;
   }
 }
-// ---- one LSD radix pass (8-bit digit), batched over blocks ---------------------------------
+// ---- one LSD radix pass (BITS-bit digit, 8 or 9), batched over blocks ---------------------------
 // seg_base (optional): slot at which segment p starts; default = seg_tile0[p] * SORT_TILE (block layout)
+template <int BITS>
 __global__ void __launch_bounds__(SORT_THREADS) k_rs_hist(const u64 *__restrict__ keys, const u32 *__restrict__ seg_cnt,
                                                           const u32 *__restrict__ seg_tile0, const u32 *__restrict__ tile_blk, int shift,
                                                           u32 *__restrict__ hist, const u32 *__restrict__ seg_base) {
-  __shared__ u32 h[256];
+  constexpr int NB = 1 << BITS;
+  __shared__ u32 h[NB];
   u32 tile = blockIdx.x, p = tile_blk[tile];
   u32 cnt = seg_cnt[p], l0 = (tile - seg_tile0[p]) * SORT_TILE;
   u64 g0 = seg_base ? (u64)seg_base[p] + l0 : (u64)tile * SORT_TILE;
-  if (threadIdx.x < 256) h[threadIdx.x] = 0;
+  for (int i = threadIdx.x; i < NB; i += SORT_THREADS) h[i] = 0;
   __syncthreads();
   for (int e = 0; e < SORT_E; e++) {
     u32 o = e * SORT_THREADS + threadIdx.x;
-    if (l0 + o < cnt) atomicAdd(&h[(u32)(keys[g0 + o] >> shift) & 255u], 1u);
+    if (l0 + o < cnt) atomicAdd(&h[(u32)(keys[g0 + o] >> shift) & (NB - 1)], 1u);
   }
   __syncthreads();
-  if (threadIdx.x < 256) hist[(u64)tile * 256 + threadIdx.x] = h[threadIdx.x];
+  for (int i = threadIdx.x; i < NB; i += SORT_THREADS) hist[(u64)tile * NB + i] = h[i];
 }
-// per block: column-wise exclusive prefix over its tiles (in place) + exclusive digit bases
-__global__ void __launch_bounds__(256) k_rs_scan(u32 *__restrict__ hist, const u32 *__restrict__ seg_tile0, u32 *__restrict__ digit_base) {
+// per block: column-wise exclusive prefix over its tiles (in place) + exclusive digit bases; 1 << BITS threads
+template <int BITS>
+__global__ void __launch_bounds__(1 << BITS) k_rs_scan(u32 *__restrict__ hist, const u32 *__restrict__ seg_tile0, u32 *__restrict__ digit_base) {
+  constexpr int NB = 1 << BITS;
   __shared__ u32 ws[33];
   u32 p = blockIdx.x, d = threadIdx.x;
   u32 t0 = seg_tile0[p], t1 = seg_tile0[p + 1];
   u32 acc = 0;
   u32 t = t0;
   for (; t + 4 <= t1; t += 4) {  // 4 independent loads in flight
-    u32 a = hist[(u64)t * 256 + d], b = hist[(u64)(t + 1) * 256 + d], c = hist[(u64)(t + 2) * 256 + d], e = hist[(u64)(t + 3) * 256 + d];
-    hist[(u64)t * 256 + d] = acc; acc += a;
-    hist[(u64)(t + 1) * 256 + d] = acc; acc += b;
-    hist[(u64)(t + 2) * 256 + d] = acc; acc += c;
-    hist[(u64)(t + 3) * 256 + d] = acc; acc += e;
+    u32 a = hist[(u64)t * NB + d], b = hist[(u64)(t + 1) * NB + d], c = hist[(u64)(t + 2) * NB + d], e = hist[(u64)(t + 3) * NB + d];
+    hist[(u64)t * NB + d] = acc; acc += a;
+    hist[(u64)(t + 1) * NB + d] = acc; acc += b;
+    hist[(u64)(t + 2) * NB + d] = acc; acc += c;
+    hist[(u64)(t + 3) * NB + d] = acc; acc += e;
   }
-  for (; t < t1; t++) { u32 a = hist[(u64)t * 256 + d]; hist[(u64)t * 256 + d] = acc; acc += a; }
+  for (; t < t1; t++) { u32 a = hist[(u64)t * NB + d]; hist[(u64)t * NB + d] = acc; acc += a; }
   u32 tot;
   u32 base = block_excl_sum<u32>(acc, tot, ws);
-  digit_base[(u64)p * 256 + d] = base;
+  digit_base[(u64)p * NB + d] = base;
 }
+template <int BITS>
 __global__ void __launch_bounds__(SORT_THREADS) k_rs_scatter(const u64 *__restrict__ keys_in, u64 *__restrict__ keys_out,
                                                              const u32 *__restrict__ seg_cnt, const u32 *__restrict__ seg_tile0,
                                                              const u32 *__restrict__ tile_blk, int shift, const u32 *__restrict__ hist,
                                                              const u32 *__restrict__ digit_base, const u32 *__restrict__ seg_base) {
-  __shared__ u32 wcnt[SORT_THREADS / 32][256];
-  __shared__ u32 base[256];
+  constexpr int NB = 1 << BITS;
+  __shared__ u16 wcnt[SORT_THREADS / 32][NB];  // a warp ranks 256 keys: counts fit 16 bits
+  __shared__ u32 base[NB];
   u32 tile = blockIdx.x, p = tile_blk[tile];
   u32 cnt = seg_cnt[p], l0 = (tile - seg_tile0[p]) * SORT_TILE;
   u64 gp = seg_base ? (u64)seg_base[p] : (u64)seg_tile0[p] * SORT_TILE, g0 = gp + l0;
   int lane = lane_id(), w = warp_id();
-  for (int i = threadIdx.x; i < (SORT_THREADS / 32) * 256; i += SORT_THREADS) (&wcnt[0][0])[i] = 0;
-  if (threadIdx.x < 256) base[threadIdx.x] = digit_base[(u64)p * 256 + threadIdx.x] + hist[(u64)tile * 256 + threadIdx.x];
+  for (int i = threadIdx.x; i < (SORT_THREADS / 32) * NB / 2; i += SORT_THREADS) reinterpret_cast<u32 *>(&wcnt[0][0])[i] = 0;
+  for (int i = threadIdx.x; i < NB; i += SORT_THREADS) base[i] = digit_base[(u64)p * NB + i] + hist[(u64)tile * NB + i];
   __syncthreads();
   u64 key[SORT_E];
   u32 rk[SORT_E];
@@ -139,26 +202,26 @@ __global__ void __launch_bounds__(SORT_THREADS) k_rs_scatter(const u64 *__restri
     u32 o = (u32)w * (32 * SORT_E) + e * 32 + lane;
     bool ok = l0 + o < cnt;
     key[e] = ok ? keys_in[g0 + o] : 0;
-    u32 d = ok ? ((u32)(key[e] >> shift) & 255u) : 256u;
+    u32 d = ok ? ((u32)(key[e] >> shift) & (NB - 1)) : (u32)NB;
     u32 peers = __match_any_sync(FULL_MASK, d);
     int leader = __ffs((int)peers) - 1;
     u32 old = 0;
-    if (lane == leader && ok) { old = wcnt[w][d]; wcnt[w][d] = old + __popc(peers); }
+    if (lane == leader && ok) { old = wcnt[w][d]; wcnt[w][d] = (u16)(old + __popc(peers)); }
     old = __shfl_sync(FULL_MASK, old, leader);
     rk[e] = old + __popc(peers & lt);
     __syncwarp();
   }
   __syncthreads();
-  if (threadIdx.x < 256) {  // exclusive prefix of each digit over the warps
+  for (int d = threadIdx.x; d < NB; d += SORT_THREADS) {  // exclusive prefix of each digit over the warps
     u32 acc = 0;
-    for (int ww = 0; ww < SORT_THREADS / 32; ww++) { u32 t = wcnt[ww][threadIdx.x]; wcnt[ww][threadIdx.x] = acc; acc += t; }
+    for (int ww = 0; ww < SORT_THREADS / 32; ww++) { u32 t = wcnt[ww][d]; wcnt[ww][d] = (u16)acc; acc += t; }
   }
   __syncthreads();
 #pragma unroll
   for (int e = 0; e < SORT_E; e++) {
     u32 o = (u32)w * (32 * SORT_E) + e * 32 + lane;
     if (l0 + o < cnt) {
-      u32 d = (u32)(key[e] >> shift) & 255u;
+      u32 d = (u32)(key[e] >> shift) & (NB - 1);
       u64 dst = gp + base[d] + wcnt[w][d] + rk[e];
       keys_out[dst] = key[e];
     }
@@ -232,7 +295,7 @@ __device__ __forceinline__ void bwt_emit_final(const u8 *__restrict__ T, u8 *__r
 // ---- round 0 regroup: groups, ISA, active list (single pass, ordered) -------------------------------
 #define R0_THREADS 512
 #define R0_ROWS (SORT_TILE / R0_THREADS)  // rows of 32 slots per warp: warp w owns slots [w*256, w*256+256)
-#define R0_NOKEY 0xffffffffffffffffull   // differs from every real key in bits 20.. (real keys are < 2^60)
+#define R0_NOKEY 0xffffffffffffffffull   // filler outside the block; the block's ends are tested explicitly
 __global__ void __launch_bounds__(R0_THREADS) k_rank0(const u64 *__restrict__ keys, const u32 *__restrict__ seg_cnt,
                                                       const u32 *__restrict__ seg_tile0, const u32 *__restrict__ tile_blk,
                                                       u32 *__restrict__ isa, i64 stride, u32 *__restrict__ act_idx, u32 *__restrict__ act_rank,
@@ -265,8 +328,8 @@ __global__ void __launch_bounds__(R0_THREADS) k_rank0(const u64 *__restrict__ ke
     bool valid = i < m, head = false, nh = false;
     if (valid) {
       u64 k = sk[i + 1] >> 20;
-      head = k != (sk[i] >> 20);
-      nh = k != (sk[i + 2] >> 20);
+      head = l0 + i == 0 || k != (sk[i] >> 20);
+      nh = l0 + i + 1 >= cnt || k != (sk[i + 2] >> 20);
     }
     hb[e] = __ballot_sync(FULL_MASK, head);
     kb[e] = __ballot_sync(FULL_MASK, valid && !(head && nh));

@@ -36,7 +36,7 @@ struct Ctx {
   DevBuf seg_cnt, seg_tile0, tile_blk, tile_i0, tile_i1, totals;
   DevBuf Lcol, ranks, lastocc, A, freq, meta, W, bit_off, scrc, out, out_len, used_bits;
   DevBuf key2, big_cnt, big_old, big_rank, big_tile0, big_tblk, totals2;
-  DevBuf r2_status, hfreq, hlens, hplen, hcodes, hsel, hcost, hgoff, hblk;
+  DevBuf blksort, r2_status, hfreq, hlens, hplen, hcodes, hsel, hcost, hgoff, hblk;
   // decode-side buffers
   DevBuf d_in, cand, ncand, dmeta, dsyms, dL, dtt, dwalk, dblk, dout, dmisc, dsel, doff, dperm, dmap;
   // host staging (pinned)
@@ -63,7 +63,7 @@ struct Ctx {
                      &seg_cnt, &seg_tile0, &tile_blk, &tile_i0, &tile_i1, &totals,
                      &Lcol, &ranks, &lastocc, &A, &freq, &meta, &W, &bit_off, &scrc, &out, &out_len, &used_bits,
                      &key2, &big_cnt, &big_old, &big_rank, &big_tile0, &big_tblk, &totals2,
-                     &r2_status, &hfreq, &hlens, &hplen, &hcodes, &hsel, &hcost, &hgoff, &hblk,
+                     &blksort, &r2_status, &hfreq, &hlens, &hplen, &hcodes, &hsel, &hcost, &hgoff, &hblk,
                      &d_in, &cand, &ncand, &dmeta, &dsyms, &dL, &dtt, &dwalk, &dblk, &dout, &dmisc, &dsel, &doff, &dperm, &dmap};
     for (DevBuf *b : all) pool.push_back(b);
   }
@@ -223,7 +223,7 @@ int pipe_stages(Ctx *c) {
     ENS(c->keysA, 8 * slots); ENS(c->keysB, 8 * slots);
     ENS(c->actI0, 4 * slots); ENS(c->actI1, 4 * slots); ENS(c->actR0, 4 * slots); ENS(c->actR1, 4 * slots);
     ENS(c->key2, 4 * slots);
-    ENS(c->hist, 4 * 256 * big_tiles); ENS(c->digit_base, 4 * 256 * (size_t)(big_cap > (u32)nb ? big_cap : (u32)nb));
+    ENS(c->hist, 4 * 512 * big_tiles); ENS(c->digit_base, 4 * 512 * (size_t)(big_cap > (u32)nb ? big_cap : (u32)nb));
     ENS(c->seg_cnt, 4 * (size_t)nb); ENS(c->seg_tile0, 4 * (size_t)(nb + 1)); ENS(c->tile_blk, 4 * tiles0);
     ENS(c->tile_i0, 4 * big_tiles); ENS(c->tile_i1, 4 * big_tiles);
     ENS(c->big_cnt, 4 * (size_t)big_cap); ENS(c->big_old, 4 * (size_t)big_cap);
@@ -239,12 +239,16 @@ int pipe_stages(Ctx *c) {
     LAUNCH(k_seg_init, (unsigned)((nb + 255) / 256), 256, 0, P<BlockRec>(c->recs), nb, seg_cnt);
     LAUNCH(k_tilemap, 1, 1024, 0, seg_cnt, nb, tile0, tblk, P<u64>(c->totals));
     const unsigned Ta = (unsigned)tiles0;
-    LAUNCH(k_keys_init, Ta, SEG_THREADS, 0, P<u8>(c->blk), BS, P<BlockRec>(c->recs), tile0, tblk, kA);
+    ENS(c->blksort, sizeof(BlkSort) * (size_t)nb);
+    CK(cudaMemsetAsync(c->blksort.p, 0, sizeof(BlkSort) * (size_t)nb, c->stream));
+    LAUNCH(k_sym_used, dim3(32, (unsigned)nb), 256, 0, P<u8>(c->blk), BS, P<BlockRec>(c->recs), P<BlkSort>(c->blksort));
+    LAUNCH(k_sym_tab, (unsigned)nb, 256, 0, P<BlkSort>(c->blksort));
+    LAUNCH(k_keys_init, Ta, SEG_THREADS, 0, P<u8>(c->blk), BS, P<BlockRec>(c->recs), tile0, tblk, P<BlkSort>(c->blksort), kA);
     u64 total_n = 0;
     for (auto &r : hrecs) total_n += r.n;
     c->dom_used = 0;
-    auto timed_scatter = [&](unsigned grid, const u64 *ki, u64 *ko, const u32 *scnt, const u32 *st0, const u32 *stb, int shift, const u32 *sbase,
-                             u64 slots_now) -> int {
+    auto timed_scatter = [&](bool bits9, unsigned grid, const u64 *ki, u64 *ko, const u32 *scnt, const u32 *st0, const u32 *stb, int shift,
+                             const u32 *sbase, u64 slots_now) -> int {
       if (c->ev_ok) {
         if (c->dom_used + 2 > c->dom_ev.size()) {
           cudaEvent_t a, b2;
@@ -253,7 +257,8 @@ int pipe_stages(Ctx *c) {
         }
         CK(cudaEventRecord(c->dom_ev[c->dom_used], c->stream));
       }
-      LAUNCH(k_rs_scatter, grid, SORT_THREADS, 0, ki, ko, scnt, st0, stb, shift, P<u32>(c->hist), P<u32>(c->digit_base), sbase);
+      if (bits9) LAUNCH(k_rs_scatter<9>, grid, SORT_THREADS, 0, ki, ko, scnt, st0, stb, shift, P<u32>(c->hist), P<u32>(c->digit_base), sbase);
+      else LAUNCH(k_rs_scatter<8>, grid, SORT_THREADS, 0, ki, ko, scnt, st0, stb, shift, P<u32>(c->hist), P<u32>(c->digit_base), sbase);
       if (c->ev_ok) { CK(cudaEventRecord(c->dom_ev[c->dom_used + 1], c->stream)); c->dom_used += 2; }
       c->st.dom_launches++;
       c->st.dom_bytes += 16ull * slots_now;
@@ -265,10 +270,10 @@ int pipe_stages(Ctx *c) {
       c->st.sort_rounds++;
       c->st.sort_slots += (u64)Ta * SORT_TILE;
       u64 *ki = kA, *ko = kB;
-      for (int pass = 0; pass < 5; pass++) {
-        LAUNCH(k_rs_hist, Ta, SORT_THREADS, 0, ki, seg_cnt, tile0, tblk, 20 + pass * 8, P<u32>(c->hist), (const u32 *)nullptr);
-        LAUNCH(k_rs_scan, (unsigned)nb, 256, 0, P<u32>(c->hist), tile0, P<u32>(c->digit_base));
-        if ((rc = timed_scatter(Ta, ki, ko, seg_cnt, tile0, tblk, 20 + pass * 8, nullptr, total_n))) return rc;
+      for (int pass = 0; pass < 5; pass++) {  // bits 20..63, 9 bits a pass
+        LAUNCH(k_rs_hist<9>, Ta, SORT_THREADS, 0, ki, seg_cnt, tile0, tblk, 20 + pass * 9, P<u32>(c->hist), (const u32 *)nullptr);
+        LAUNCH(k_rs_scan<9>, (unsigned)nb, 512, 0, P<u32>(c->hist), tile0, P<u32>(c->digit_base));
+        if ((rc = timed_scatter(true, Ta, ki, ko, seg_cnt, tile0, tblk, 20 + pass * 9, nullptr, total_n))) return rc;
         u64 *tk = ki; ki = ko; ko = tk;
       }
       CK(cudaMemsetAsync(lbm, 0, 16, c->stream));
@@ -279,7 +284,7 @@ int pipe_stages(Ctx *c) {
       CK(cudaStreamSynchronize(c->stream));
     }
     // ---- rounds >= 1 (refine.cuh): list A (+ key2) -> sorted staging list B -> compacted list A ----
-    u32 n_act = hv[1], h = 5;
+    u32 n_act = hv[1], round = 0;  // doubling round r compares h = L << r symbols further on (L per block)
 #ifndef BZ_SIM
     static bool attr2 = false;
     if (!attr2) {
@@ -287,7 +292,8 @@ int pipe_stages(Ctx *c) {
       attr2 = true;
     }
 #endif
-    if (n_act) LAUNCH(k_keys2, (n_act + 255) / 256, 256, 0, actI[0], n_act, P<BlockRec>(c->recs), P<u32>(c->isa), (u32)BS, magic, h, P<u32>(c->key2));
+    if (n_act) LAUNCH(k_keys2, (n_act + 255) / 256, 256, 0, actI[0], n_act, P<BlockRec>(c->recs), P<u32>(c->isa), (u32)BS, magic, P<BlkSort>(c->blksort), round,
+                      P<u32>(c->key2));
     while (n_act) {
       c->st.sort_rounds++;
       c->st.sort_slots += n_act;
@@ -310,9 +316,9 @@ int pipe_stages(Ctx *c) {
         LAUNCH(k_big_keys, Tb, SEG_THREADS, 0, P<u32>(c->key2), actI[0], bcnt, bt0, btb, bbase, kA);
         u64 *ki = kA, *ko = kB;
         for (int pass = 0; pass < 3; pass++) {  // key2 < 2^20: bits 32..55
-          LAUNCH(k_rs_hist, Tb, SORT_THREADS, 0, ki, bcnt, bt0, btb, 32 + pass * 8, P<u32>(c->hist), bbase);
-          LAUNCH(k_rs_scan, n_big, 256, 0, P<u32>(c->hist), bt0, P<u32>(c->digit_base));
-          if ((rc = timed_scatter(Tb, ki, ko, bcnt, bt0, btb, 32 + pass * 8, bbase, t2[1]))) return rc;
+          LAUNCH(k_rs_hist<8>, Tb, SORT_THREADS, 0, ki, bcnt, bt0, btb, 32 + pass * 8, P<u32>(c->hist), bbase);
+          LAUNCH(k_rs_scan<8>, n_big, 256, 0, P<u32>(c->hist), bt0, P<u32>(c->digit_base));
+          if ((rc = timed_scatter(false, Tb, ki, ko, bcnt, bt0, btb, 32 + pass * 8, bbase, t2[1]))) return rc;
           u64 *tk = ki; ki = ko; ko = tk;
         }
         LAUNCH(k_sub_heads, Tb, SEG_THREADS, 0, ki, bcnt, bt0, btb, P<int>(c->tile_i0), bbase, 32);
@@ -320,8 +326,9 @@ int pipe_stages(Ctx *c) {
         LAUNCH(k_big_apply, Tb, SEG_THREADS, 0, ki, bcnt, bt0, btb, bbase, P<u32>(c->big_rank), P<int>(c->tile_i1), P<u32>(c->isa), (u32)BS, magic,
                actI[1], actR[1], P<u8>(c->blk), P<u8>(c->Lcol), P<BlockRec>(c->recs));
       }
-      h = h >= (1u << 24) ? h : h * 2;
-      LAUNCH(k_compact_keys, ctiles, CK_THREADS, 0, actI[1], actR[1], n_act, P<BlockRec>(c->recs), P<u32>(c->isa), (u32)BS, magic, h, actI[0], actR[0],
+      round = round < 30 ? round + 1 : round;
+      LAUNCH(k_compact_keys, ctiles, CK_THREADS, 0, actI[1], actR[1], n_act, P<BlockRec>(c->recs), P<u32>(c->isa), (u32)BS, magic, P<BlkSort>(c->blksort), round,
+             actI[0], actR[0],
              P<u32>(c->key2), status, lbm, lbm + 1, ctiles);
       CK(cudaMemcpyAsync(hv, lbm, sizeof hv, cudaMemcpyDeviceToHost, c->stream));
       CK(cudaStreamSynchronize(c->stream));

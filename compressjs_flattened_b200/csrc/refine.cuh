@@ -37,12 +37,19 @@
 __device__ __forceinline__ u32 blk_of(u32 gidx, u64 magic) { return (u32)__umul64hi((u64)gidx, magic); }
 
 // key2 of every active slot
+// h of block p in doubling round `round`: L, 2L, 4L, ... (anything >= n means "compare whole rotations")
+__device__ __forceinline__ u32 round_h(const BlkSort *__restrict__ bs, u32 p, u32 round) {
+  u64 h = (u64)bs[p].L << round;
+  return h > (1u << 24) ? (1u << 24) : (u32)h;
+}
 __global__ void __launch_bounds__(256) k_keys2(const u32 *__restrict__ act_idx, u32 n_act, const BlockRec *__restrict__ recs,
-                                               const u32 *__restrict__ isa, u32 stride, u64 magic, u32 h, u32 *__restrict__ key2) {
+                                               const u32 *__restrict__ isa, u32 stride, u64 magic, const BlkSort *__restrict__ bs, u32 round,
+                                               u32 *__restrict__ key2) {
   u32 g = blockIdx.x * 256u + threadIdx.x;
   if (g >= n_act) return;
   u32 gidx = act_idx[g];
   u32 p = blk_of(gidx, magic), pb = p * stride, i = gidx - pb, n = recs[p].n, k2;
+  const u32 h = round_h(bs, p, round);
   if (h >= n) k2 = n - 1 - i;  // identical rotations: descending index
   else { u32 x = i + h; if (x >= n) x -= n; k2 = isa[pb + x]; }
   key2[g] = k2;
@@ -348,7 +355,8 @@ __global__ void __launch_bounds__(RF_THREADS) k_sort_groups(const u32 *__restric
 // ---- ordered compaction of the staging list + key2 of the survivors for the next round ------------------
 __global__ void __launch_bounds__(CK_THREADS) k_compact_keys(const u32 *__restrict__ s_idx, const u32 *__restrict__ s_rank, u32 n_act,
                                                              const BlockRec *__restrict__ recs, const u32 *__restrict__ isa, u32 stride, u64 magic,
-                                                             u32 h_next, u32 *__restrict__ o_idx, u32 *__restrict__ o_rank, u32 *__restrict__ o_key2,
+                                                             const BlkSort *__restrict__ bs, u32 round_next, u32 *__restrict__ o_idx,
+                                                             u32 *__restrict__ o_rank, u32 *__restrict__ o_key2,
                                                              u64 *__restrict__ status, u32 *__restrict__ ticket, u32 *__restrict__ n_act_out,
                                                              u32 ntiles) {
   __shared__ u32 wk[CK_THREADS / 32];
@@ -376,6 +384,7 @@ __global__ void __launch_bounds__(CK_THREADS) k_compact_keys(const u32 *__restri
       u32 pos = tile * CK_TILE + (u32)w * (32 * CK_ROWS) + e * 32 + lane;
       u32 gidx = s_idx[pos];
       u32 p = blk_of(gidx, magic), pb = p * stride, i = gidx - pb, n = recs[p].n, k2;
+      const u32 h_next = round_h(bs, p, round_next);
       if (h_next >= n) k2 = n - 1 - i;
       else { u32 x = i + h_next; if (x >= n) x -= n; k2 = isa[pb + x]; }
       gi[e] = gidx; k2v[e] = k2;
