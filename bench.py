@@ -289,7 +289,7 @@ def main():
             "ms_per_step": round(dev_ms_max / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic", "config": workload_desc(args.level, args.mb, world),
             "e2e": {"value": round(total_mb / (e2e_ms_max / 1e3), 2), "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": int(e2e_out),
-                    "ms_per_step": round(e2e_ms_max / args.steps, 3), "api": "bz2b200_compress (N=1) / bz2b200_shard_begin..emit (N>1): pinned host input, malloc'd host output"},
+                    "ms_per_step": round(e2e_ms_max / args.steps, 3), "api": "bz2b200_compress (N=1) / bz2b200_shard_begin..emit (N>1): pinned host input, page-locked host output from the library's result pool"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_rs_scatter (BWT radix-sort scatter pass)", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,

@@ -13,10 +13,61 @@
 #include "decode.cuh"
 
 #include <algorithm>
+#include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace {
+
+// ---- results handed to the caller ------------------------------------------------------------
+// Large results live in page-locked memory (the device-to-host copy then runs at PCIe speed instead of through
+// the driver's pageable staging).  bz2b200_free() recognises them and keeps a few for reuse, so a caller that
+// compresses in a loop does not pay cudaMallocHost every time.  Small results are plain malloc.
+struct ResultPool {
+  std::mutex mu;
+  std::vector<std::pair<void *, size_t>> live, idle;  // (pointer, capacity)
+  static const size_t kMinPinned = 1 << 20, kMaxIdle = 4;
+  void *get(size_t bytes) {
+    if (bytes < kMinPinned) return malloc(bytes ? bytes : 1);
+    std::lock_guard<std::mutex> g(mu);
+    size_t best = idle.size();
+    for (size_t i = 0; i < idle.size(); i++)
+      if (idle[i].second >= bytes && (best == idle.size() || idle[i].second < idle[best].second)) best = i;
+    if (best < idle.size()) {
+      auto e = idle[best];
+      idle.erase(idle.begin() + (long)best);
+      live.push_back(e);
+      return e.first;
+    }
+    void *p = nullptr;
+    size_t cap = bytes + bytes / 4 + 4096;
+#ifndef BZ_SIM
+    if (cudaMallocHost(&p, cap) != cudaSuccess) { cudaGetLastError(); p = nullptr; }
+#endif
+    if (!p) return malloc(bytes);  // page-locking failed: fall back to pageable memory
+    live.push_back({p, cap});
+    return p;
+  }
+  void put(void *p) {
+    if (!p) return;
+    {
+      std::lock_guard<std::mutex> g(mu);
+      for (size_t i = 0; i < live.size(); i++)
+        if (live[i].first == p) {
+          auto e = live[i];
+          live.erase(live.begin() + (long)i);
+          if (idle.size() < kMaxIdle) { idle.push_back(e); return; }
+#ifndef BZ_SIM
+          cudaFreeHost(p);
+#endif
+          return;
+        }
+    }
+    free(p);
+  }
+};
+ResultPool &result_pool() { static ResultPool rp; return rp; }
 
 struct DevBuf {
   void *p = nullptr;
@@ -522,7 +573,7 @@ int bz2b200_compress(bz2b200_ctx *ctx, const uint8_t *in, size_t n, int level, u
   size_t olen = 0;
   int rc = compress_device(c, P<u8>(c->in), n, level, nullptr, 0, &olen, true);
   if (rc) return rc;
-  uint8_t *res = (uint8_t *)malloc(olen ? olen : 1);
+  uint8_t *res = (uint8_t *)result_pool().get(olen);
   if (!res) return BZ2B200_E_OUT_OF_MEMORY;
   CK(cudaMemcpy(res, c->out.p, olen, cudaMemcpyDeviceToHost));
   *out = res;
@@ -587,7 +638,7 @@ int bz2b200_shard_emit(bz2b200_ctx *ctx, int bit_phase, bz2b200_shard_info *info
   info->bit_phase = (uint32_t)bit_phase;
   *seg_bytes = olen;
   if (!seg) return BZ2B200_OK;  // segment stays in HBM (device-resident timing)
-  uint8_t *res = (uint8_t *)malloc(olen ? olen : 1);
+  uint8_t *res = (uint8_t *)result_pool().get(olen);
   if (!res) return BZ2B200_E_OUT_OF_MEMORY;
   if (olen) CK(cudaMemcpy(res, c->out.p, olen, cudaMemcpyDeviceToHost));
   *seg = res;
@@ -636,7 +687,7 @@ size_t bz2b200_compress_bound(size_t n, int level) {
   return (n + n / 4 + nblocks) * 20 / 8 + nblocks * (10 + 4 + 32 + 3 + 18001 + 6 * 1300) + 64;
 }
 
-void bz2b200_free(void *p) { free(p); }
+void bz2b200_free(void *p) { result_pool().put(p); }
 
 const char *bz2b200_strerror(int rc) {
   switch (rc) {  // messages of BJ:1376-1383

@@ -1,7 +1,7 @@
 // decode_abi.inl -- C ABI of the decompress path (included inside extern "C" by bz2b200.cu)
 
 static int take_output(Ctx *c, const DecodeResult &R, uint8_t **out, size_t *out_len) {
-  uint8_t *res = (uint8_t *)malloc(R.out_len ? (size_t)R.out_len : 1);
+  uint8_t *res = (uint8_t *)result_pool().get((size_t)R.out_len);
   if (!res) return BZ2B200_E_OUT_OF_MEMORY;
   if (R.out_len) CK(cudaMemcpy(res, c->dout.p, (size_t)R.out_len, cudaMemcpyDeviceToHost));
   *out = res;
