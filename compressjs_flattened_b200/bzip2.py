@@ -239,6 +239,12 @@ class Bzip2Engine:
         if rc:
             self._raise(rc)
 
+    def debug_set_batch_blocks(self, blocks):
+        """tests only: blocks per batch of the per-block stages, 0 restores the automatic limit"""
+        rc = self._L.bz2b200_debug_set_batch_blocks(self._ctx, blocks)
+        if rc:
+            self._raise(rc)
+
     def block_table(self):
         nb = self.stats().n_blocks
         raw = self.debug_fetch(0, 0, C.sizeof(_native.BlockRec) * nb)

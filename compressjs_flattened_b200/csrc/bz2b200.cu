@@ -87,7 +87,7 @@ struct Ctx {
   DevBuf seg_cnt, seg_tile0, tile_blk, tile_i0, tile_i1, totals;
   DevBuf Lcol, ranks, lastocc, A, freq, meta, W, bit_off, scrc, out, out_len, used_bits;
   DevBuf key2, big_cnt, big_old, big_rank, big_tile0, big_tblk, totals2;
-  DevBuf blksort, r2_status, hfreq, hlens, hplen, hcodes, hsel, hcost, hgoff, hblk;
+  DevBuf out2, recs_all, blksort, r2_status, hfreq, hlens, hplen, hcodes, hsel, hcost, hgoff, hblk;
   // decode-side buffers
   DevBuf d_in, cand, ncand, dmeta, dsyms, dL, dtt, dwalk, dblk, dout, dmisc, dsel, doff, dperm, dmap;
   // host staging (pinned)
@@ -101,7 +101,10 @@ struct Ctx {
     int level = 9, nb = 0;
     std::vector<BlockRec> hrecs;
   } pipe;
-  u32 cap_override = 0;  // tests only
+  u32 cap_override = 0;    // tests only
+  u32 batch_override = 0;  // tests only: blocks per batch
+  u64 shard_bits = 0;      // bit length of the last shard segment (phase 0 in `out`)
+  bool recs_batched = false;  // the last call ran in batches: the full block table is in recs_all
   int last_nb = 0;
   i64 last_bs = 0, last_as = 0;
   cudaEvent_t ev[10]{};
@@ -114,7 +117,7 @@ struct Ctx {
                      &seg_cnt, &seg_tile0, &tile_blk, &tile_i0, &tile_i1, &totals,
                      &Lcol, &ranks, &lastocc, &A, &freq, &meta, &W, &bit_off, &scrc, &out, &out_len, &used_bits,
                      &key2, &big_cnt, &big_old, &big_rank, &big_tile0, &big_tblk, &totals2,
-                     &blksort, &r2_status, &hfreq, &hlens, &hplen, &hcodes, &hsel, &hcost, &hgoff, &hblk,
+                     &out2, &recs_all, &blksort, &r2_status, &hfreq, &hlens, &hplen, &hcodes, &hsel, &hcost, &hgoff, &hblk,
                      &d_in, &cand, &ncand, &dmeta, &dsyms, &dL, &dtt, &dwalk, &dblk, &dout, &dmisc, &dsel, &doff, &dperm, &dmap};
     for (DevBuf *b : all) pool.push_back(b);
   }
@@ -514,12 +517,128 @@ int pipe_emit(Ctx *c, u64 base_bits, bool whole, u32 *d_out, size_t out_cap, boo
   return BZ2B200_OK;
 }
 
+// ---- batches of blocks --------------------------------------------------------------------------
+// The per-block state is ~45 bytes per input byte and global indices are 31 bits, so a call with more blocks than
+// fit is run as consecutive batches of whole blocks: the stages see one batch at a time (c->recs = its slice of the
+// block table) and every batch is stitched behind the previous one at the running bit offset.
+int batch_limit(Ctx *c) {
+  if (c->batch_override) return (int)c->batch_override;
+  const i64 BS = round_up((i64)c->pipe.B + 1, 256);
+  i64 by_index = ((1ll << 31) - 1) / BS;
+  size_t free_b = 0, total_b = 0;
+  i64 by_mem = by_index;
+#ifndef BZ_SIM
+  if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+    size_t pooled = 0;
+    for (DevBuf *b : c->pool) pooled += b->cap;  // already ours: reusable
+    by_mem = (i64)((free_b + pooled) / 10 * 7 / (size_t)(BS * 52));
+  }
+#endif
+  i64 lim = by_index < by_mem ? by_index : by_mem;
+  return (int)(lim < 1 ? 1 : lim);
+}
+
+// one batch: bit offsets from `base_bits`, the output words this batch touches are cleared (the word that holds
+// base_bits keeps the previous batch's bits unless this is the first batch), then the funnel-shift stitch
+int pipe_emit_part(Ctx *c, u64 base_bits, bool first, u32 *d_out, size_t out_cap, u64 *bits_out, u32 *crc_fold) {
+  Ctx::Pipe &P_ = c->pipe;
+  const int nb = P_.nb;
+  LAUNCH(k_stitch_offsets, 1, 1024, 0, P<BlockMeta>(c->meta), P<BlockRec>(c->recs), nb, P<u64>(c->bit_off), P<u32>(c->scrc), base_bits);
+  u64 end_bits = 0;
+  u32 fold = 0;
+  CK(cudaMemcpyAsync(&end_bits, P<u64>(c->bit_off) + nb, 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(&fold, c->scrc.p, 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  *bits_out = end_bits - base_bits;
+  *crc_fold = fold;
+  const u64 w_first = first ? 0 : (base_bits >> 5) + 1, w_end = ((end_bits + 80 + 31) >> 5) + 2;  // room for the footer too
+  if (w_end * 4 > out_cap) { c->err = "output buffer too small"; return BZ2B200_E_UNEXPECTED_OUTPUT_EOF; }
+  if (w_end > w_first) CK(cudaMemsetAsync(d_out + w_first, 0, (size_t)(w_end - w_first) * 4, c->stream));
+  if (nb) LAUNCH(k_stitch, dim3(32, (unsigned)nb), 256, 0, P<u32>(c->W), P_.WS, P<u64>(c->bit_off), d_out);
+  int rc;
+  if ((rc = mark(c, 5))) return rc;
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaGetLastError());
+  return BZ2B200_OK;
+}
+
+// stages + emission of every block in the table, in one batch or several
+int pipe_run(Ctx *c, u64 base_bits, bool whole, u32 *d_out, size_t out_cap, bool own_out, size_t *out_len, u64 *bits_out, u32 *crc_fold) {
+  Ctx::Pipe &P_ = c->pipe;
+  const int nb_total = P_.nb, maxb = batch_limit(c);
+  int rc;
+  c->recs_batched = false;
+  if (nb_total <= maxb) {
+    if ((rc = pipe_stages(c))) return rc;
+    return pipe_emit(c, base_bits, whole, d_out, out_cap, own_out, out_len, bits_out, crc_fold);
+  }
+  std::vector<BlockRec> all = P_.hrecs;
+  ENS(c->recs_all, sizeof(BlockRec) * (size_t)nb_total);
+  CK(cudaMemcpyAsync(c->recs_all.p, c->recs.p, sizeof(BlockRec) * (size_t)nb_total, cudaMemcpyDeviceToDevice, c->stream));
+  if (own_out) {
+    out_cap = bz2b200_compress_bound((size_t)P_.N, P_.level) + 64;
+    ENS(c->out, out_cap);
+    d_out = P<u32>(c->out);
+  }
+  u64 running = base_bits, mtf_syms = 0;
+  u32 fold = 0, d1 = 0;
+  float ms_stage[5] = {0, 0, 0, 0, 0}, ms_total = 0, dom_ms = 0;
+  bz2b200_stats keep = c->st;
+  for (int b0 = 0; b0 < nb_total; b0 += maxb) {
+    const int bn = nb_total - b0 < maxb ? nb_total - b0 : maxb;
+    CK(cudaMemcpyAsync(c->recs.p, P<BlockRec>(c->recs_all) + b0, sizeof(BlockRec) * (size_t)bn, cudaMemcpyDeviceToDevice, c->stream));
+    P_.hrecs.assign(all.begin() + b0, all.begin() + b0 + bn);
+    P_.nb = bn;
+    if (b0) { if ((rc = mark(c, 0))) return rc; if ((rc = mark(c, 1))) return rc; }  // S1 of later batches: emit + CRC only, counted from here
+    if ((rc = pipe_stages(c))) return rc;
+    u64 bits = 0;
+    u32 foldb = 0;
+    if ((rc = pipe_emit_part(c, running, b0 == 0, d_out, out_cap, &bits, &foldb))) return rc;
+    CK(cudaMemcpyAsync(P<BlockRec>(c->recs_all) + b0, c->recs.p, sizeof(BlockRec) * (size_t)bn, cudaMemcpyDeviceToDevice, c->stream));
+    const u32 m = (u32)bn & 31u;
+    fold = (m ? ((fold << m) | (fold >> (32 - m))) : fold) ^ foldb;  // BJ:2237 over the batch's blocks
+    running += bits;
+    {
+      std::vector<BlockMeta> hm((size_t)bn);
+      CK(cudaMemcpy(hm.data(), c->meta.p, sizeof(BlockMeta) * (size_t)bn, cudaMemcpyDeviceToHost));
+      for (auto &mm : hm) { mtf_syms += mm.m; d1 |= mm.d1; }
+    }
+    if (c->ev_ok) {
+      for (int i = 0; i < 5; i++) { float t = 0; CK(cudaEventElapsedTime(&t, c->ev[i], c->ev[i + 1])); ms_stage[i] += t; ms_total += t; }
+      for (size_t i = 0; i + 1 < c->dom_used; i += 2) { float t = 0; CK(cudaEventElapsedTime(&t, c->dom_ev[i], c->dom_ev[i + 1])); dom_ms += t; }
+    }
+  }
+  P_.hrecs = all;
+  P_.nb = nb_total;
+  c->recs_batched = true;
+  c->st.n_blocks = (u32)nb_total;
+  (void)keep;
+  if (bits_out) *bits_out = running - base_bits;
+  if (crc_fold) *crc_fold = fold;
+  u64 olen = (running + 7) / 8;
+  if (whole) {
+    u64 endb = running;
+    CK(cudaMemcpyAsync(c->bit_off.p, &endb, 8, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->scrc.p, &fold, 4, cudaMemcpyHostToDevice, c->stream));
+    LAUNCH(k_stream_ends, 1, 32, 0, d_out, P<u64>(c->bit_off), 0, P<u32>(c->scrc), P_.level, P<u64>(c->out_len));
+    CK(cudaMemcpyAsync(&olen, c->out_len.p, 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  *out_len = (size_t)olen;
+  c->st.out_bytes = olen;
+  c->st.mtf_syms = mtf_syms;
+  c->st.d1_triggered = d1;
+  for (int i = 0; i < 5; i++) c->st.ms_stage[i] = ms_stage[i];
+  c->st.ms_total = ms_total;
+  c->st.dom_ms = dom_ms;
+  return BZ2B200_OK;
+}
+
 int compress_device(Ctx *c, const u8 *d_in, size_t n_, int level, u32 *d_out, size_t out_cap, size_t *out_len, bool own_out) {
   int rc;
   if ((rc = pipe_begin(c, d_in, n_, level))) return rc;
   if ((rc = pipe_cut(c, 0, (i64)n_))) return rc;
-  if ((rc = pipe_stages(c))) return rc;
-  return pipe_emit(c, 32, true, d_out, out_cap, own_out, out_len, nullptr, nullptr);
+  return pipe_run(c, 32, true, d_out, out_cap, own_out, out_len, nullptr, nullptr);
 }
 
 #include "decode_host.inl"
@@ -615,14 +734,13 @@ int bz2b200_shard_compress(bz2b200_ctx *ctx, bz2b200_shard_info *info) {
   Ctx *c = reinterpret_cast<Ctx *>(ctx);
   if (!c || !info) return BZ2B200_E_ARG;
   CK(cudaSetDevice(c->device));
-  int rc = pipe_stages(c);
-  if (rc) return rc;
-  LAUNCH(k_stitch_offsets, 1, 1024, 0, P<BlockMeta>(c->meta), P<BlockRec>(c->recs), c->pipe.nb, P<u64>(c->bit_off), P<u32>(c->scrc), (u64)0);
+  // the segment is stitched at bit phase 0 now (in batches if need be); shard_emit moves it to its real phase
+  size_t olen = 0;
   u64 bits = 0;
   u32 fold = 0;
-  CK(cudaMemcpyAsync(&bits, P<u64>(c->bit_off) + c->pipe.nb, 8, cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaMemcpyAsync(&fold, c->scrc.p, 4, cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
+  int rc = pipe_run(c, 0, false, nullptr, 0, true, &olen, &bits, &fold);
+  if (rc) return rc;
+  c->shard_bits = bits;
   info->bits = bits;
   info->crc_fold = fold;
   return BZ2B200_OK;
@@ -632,15 +750,21 @@ int bz2b200_shard_emit(bz2b200_ctx *ctx, int bit_phase, bz2b200_shard_info *info
   Ctx *c = reinterpret_cast<Ctx *>(ctx);
   if (!c || !info || !seg_bytes || bit_phase < 0 || bit_phase > 7) return BZ2B200_E_ARG;
   CK(cudaSetDevice(c->device));
-  size_t olen = 0;
-  int rc = pipe_emit(c, (u64)bit_phase, false, nullptr, 0, true, &olen, nullptr, nullptr);
-  if (rc) return rc;
+  const u64 bits = c->shard_bits, nsrc = (bits + 7) / 8;
+  const size_t olen = (size_t)(((u64)bit_phase + bits + 7) / 8);
+  const u8 *d_seg = P<u8>(c->out);
+  if (bit_phase && bits) {
+    ENS(c->out2, nsrc + 16);
+    LAUNCH(k_shift_bytes, (unsigned)((nsrc + 256) / 256), 256, 0, P<u8>(c->out), nsrc, (u32)bit_phase, P<u8>(c->out2));
+    d_seg = P<u8>(c->out2);
+  }
+  CK(cudaStreamSynchronize(c->stream));
   info->bit_phase = (uint32_t)bit_phase;
   *seg_bytes = olen;
   if (!seg) return BZ2B200_OK;  // segment stays in HBM (device-resident timing)
   uint8_t *res = (uint8_t *)result_pool().get(olen);
   if (!res) return BZ2B200_E_OUT_OF_MEMORY;
-  if (olen) CK(cudaMemcpy(res, c->out.p, olen, cudaMemcpyDeviceToHost));
+  if (olen) CK(cudaMemcpy(res, d_seg, olen, cudaMemcpyDeviceToHost));
   *seg = res;
   *seg_bytes = olen;
   return BZ2B200_OK;
@@ -726,7 +850,10 @@ long long bz2b200_debug_fetch(bz2b200_ctx *ctx, int what, int blk, void *dst, si
   int nb = c->last_nb;
   if (what != 0 && what != 4 && (blk < 0 || blk >= nb)) return BZ2B200_E_ARG;
   switch (what) {
-    case 0: src = c->recs.p; bytes = sizeof(BlockRec) * (size_t)nb; break;
+    case 0:
+      if (c->recs_batched) { src = c->recs_all.p; bytes = sizeof(BlockRec) * (size_t)c->pipe.nb; }
+      else { src = c->recs.p; bytes = sizeof(BlockRec) * (size_t)nb; }
+      break;
     case 1: src = P<u8>(c->blk) + (i64)blk * c->last_bs; bytes = (size_t)c->last_bs; break;
     case 2: src = P<u8>(c->Lcol) + (i64)blk * c->last_bs; bytes = (size_t)c->last_bs; break;
     case 3: src = P<u16>(c->A) + (i64)blk * c->last_as; bytes = 2 * (size_t)c->last_as; break;
@@ -736,6 +863,13 @@ long long bz2b200_debug_fetch(bz2b200_ctx *ctx, int what, int blk, void *dst, si
   if (bytes > cap) bytes = cap;
   if (bytes && cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) return BZ2B200_E_CUDA;
   return (long long)bytes;
+}
+
+int bz2b200_debug_set_batch_blocks(bz2b200_ctx *ctx, uint32_t blocks) {
+  Ctx *c = reinterpret_cast<Ctx *>(ctx);
+  if (!c) return BZ2B200_E_ARG;
+  c->batch_override = blocks;
+  return BZ2B200_OK;
 }
 
 int bz2b200_debug_set_block_cap(bz2b200_ctx *ctx, uint32_t cap) {

@@ -598,6 +598,14 @@ __global__ void __launch_bounds__(256) k_stitch(const u32 *__restrict__ W, i64 w
     }
   }
 }
+// a shard's segment was stitched at bit phase 0; moved to its real phase (0..7) once the bit lengths of the earlier
+// shards are known: dst[i] = src[i] >> phase | src[i-1] << (8 - phase), one byte more than the source
+__global__ void __launch_bounds__(256) k_shift_bytes(const u8 *__restrict__ src, u64 nbytes, u32 phase, u8 *__restrict__ dst) {
+  u64 i = (u64)blockIdx.x * 256 + threadIdx.x;
+  if (i > nbytes) return;
+  u32 cur = i < nbytes ? src[i] : 0u, prev = i ? src[i - 1] : 0u;
+  dst[i] = (u8)((cur >> phase) | (prev << (8 - phase)));
+}
 // header, footer (BJ:2223-2226, 2245-2247) and the final length
 __global__ void k_stream_ends(u32 *__restrict__ out, const u64 *__restrict__ bit_off, int nb, const u32 *__restrict__ stream_crc, int level,
                               u64 *__restrict__ out_len) {

@@ -116,6 +116,9 @@ int bz2b200_last_stats(bz2b200_ctx *ctx, bz2b200_stats *st);
 long long bz2b200_debug_fetch(bz2b200_ctx *ctx, int what, int blk, void *dst, size_t cap);
 /* tests/ only: override the block capacity B (0 = level*100000-19) to stress the cut-point logic. */
 int bz2b200_debug_set_block_cap(bz2b200_ctx *ctx, uint32_t cap);
+/* tests/ only: run the per-block stages in batches of at most `blocks` blocks (0 = as many as fit the
+ * 31-bit index space and 70 % of the free device memory).  Stage dumps then show the last batch. */
+int bz2b200_debug_set_batch_blocks(bz2b200_ctx *ctx, uint32_t blocks);
 
 #ifdef __cplusplus
 }

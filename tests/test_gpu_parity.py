@@ -160,3 +160,45 @@ def test_full_size_configs(gpu_engine, key):
     rows = []
     gpu_engine.table(comp, lambda p, s: rows.append((p, s)))
     assert [s for _, s in rows] == sizes_enc and rows[0][0] == 32
+
+
+def test_batched_blocks_same_stream(gpu_engine):
+    """A call with more blocks than one batch holds (forced here: 7 blocks per batch at level 1): same bytes,
+    same block table, as the single-batch run and the oracle's golden."""
+    from compressjs_flattened_b200.corpus import gen_text
+    data = gen_text(10_000_000, 8)
+    whole = gpu_engine.compressFile(data, None, 1)
+    recs_whole = [(r.s, r.p, r.n, r.crc, r.orig_ptr) for r in gpu_engine.block_table()]
+    try:
+        for per in (7, 64):
+            gpu_engine.debug_set_batch_blocks(per)
+            assert gpu_engine.compressFile(data, None, 1) == whole
+            assert [(r.s, r.p, r.n, r.crc, r.orig_ptr) for r in gpu_engine.block_table()] == recs_whole
+    finally:
+        gpu_engine.debug_set_batch_blocks(0)
+    assert gpu_engine.decompressFile(whole) == data.tobytes()
+    g = GOLD["text:10000000:8:L9"]
+    assert hashlib.sha256(gpu_engine.compressFile(data, None, 9)).hexdigest() == g["out_sha256"]
+
+
+def test_shards_in_process_equal_whole_stream(gpu_engine):
+    """The multi-GPU protocol (begin / cut / compress / emit / stitch) driven on one device: 4 shards of a
+    20 MB stream, every segment emitted at its bit phase, stitched on the host == the single-call stream."""
+    from compressjs_flattened_b200.corpus import gen_text
+    data = gen_text(20_000_000, 8).tobytes()
+    whole = gpu_engine.compressFile(data, None, 9)
+    n, world = len(data), 4
+    slice_len = (n + world - 1) // world
+    start, bitpos, segs, infos = 0, 32, [], []
+    for r in range(world):
+        base = r * slice_len
+        own = max(0, min(slice_len, n - base))
+        gpu_engine.shard_begin(data[base:min(n, base + own + 1_200_000)], 9)
+        info = gpu_engine.shard_cut(max(start - base, 0), own, r == world - 1)
+        assert info.complete
+        start = max(base + info.next_start, start)
+        gpu_engine.shard_compress(info)
+        segs.append(gpu_engine.shard_emit(info, bitpos & 7))
+        infos.append(info)
+        bitpos += info.bits
+    assert gpu_engine.stitch_shards(9, segs, infos) == whole

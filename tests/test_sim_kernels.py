@@ -117,6 +117,24 @@ def test_cut_points_many_tiles_speculation(sim_engine, oracle):
         sim_engine.debug_set_block_cap(0)
 
 
+def test_batched_blocks_same_stream(sim_engine, oracle):
+    """More blocks than one batch holds: the batches are stitched behind one another at the running bit offset."""
+    data = fixture_bytes("sample5.ref")[:150_000] + bytes(3000) + b"ab" * 4000
+    try:
+        oracle.set_block_cap(9000)
+        sim_engine.debug_set_block_cap(9000)
+        exp = oracle.compress(data, 9)
+        for per in (1, 3, 7, 100):
+            sim_engine.debug_set_batch_blocks(per)
+            assert sim_engine.compressFile(data, None, 9) == exp, per
+            starts, lens, crcs = oracle.cut_points(data, 9)
+            assert [(r.s, r.n, r.crc) for r in sim_engine.block_table()] == list(zip(starts[:-1], lens, crcs))
+    finally:
+        oracle.set_block_cap(0)
+        sim_engine.debug_set_block_cap(0)
+        sim_engine.debug_set_batch_blocks(0)
+
+
 def test_decode_fixtures_and_random_access(sim_engine):
     for n in (0, 3):
         assert sim_engine.decompressFile(fixture_bytes(f"sample{n}.bz2")) == fixture_bytes(f"sample{n}.ref")
