@@ -168,7 +168,9 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
         ctl = dist.new_group(backend="gloo")   # the per-rank scalars (first-block offset, bit length) travel host-side
     eng = Bzip2Engine(local)
-    from compressjs_flattened_b200.sharded import compress_shard, gather_and_stitch
+    from compressjs_flattened_b200.sharded import HostMailbox, compress_shard, gather_and_stitch
+    # one node: the three scalars per rank go through shared memory (microseconds) instead of the TCP-backed group
+    mbox = HostMailbox(rank, world, os.environ.get("MASTER_PORT", "0")) if world > 1 else None
     nbytes = args.mb * 1_000_000
     chunks = args.mb
     halo_mb = 2 if (world > 1 and rank < world - 1) else 0   # bytes after the slice that the last owned block may need
@@ -192,7 +194,7 @@ def main():
         if world == 1:
             return eng.compress_device(d_in[i % 2].data_ptr(), nbytes, args.level, d_out.data_ptr(), d_out.numel())
         n, _, _ = compress_shard(eng, None, rank * nbytes, nbytes, args.level, rank == world - 1, rank=rank, world=world, group=ctl,
-                                 device_ptr=d_in[i % 2].data_ptr(), nbytes=navail, to_host=False)
+                                 device_ptr=d_in[i % 2].data_ptr(), nbytes=navail, to_host=False, mailbox=mbox)
         return n
 
     # ---------------- device-resident: `value` ----------------
@@ -230,8 +232,10 @@ def main():
 
     def host_call(j):
         if world > 1:  # host slice+halo in, host segment out, through the shard API
-            seg, _, _ = compress_shard(eng, pinned[j].numpy(), rank * nbytes, nbytes, args.level, rank == world - 1, rank=rank, world=world, group=ctl)
-            return len(seg)
+            (ptr, n), _, _ = compress_shard(eng, pinned[j].numpy(), rank * nbytes, nbytes, args.level, rank == world - 1, rank=rank, world=world,
+                                            group=ctl, to_host="raw", mailbox=mbox)
+            eng.free_raw(ptr)
+            return n
         rc = L.bz2b200_compress(eng._ctx, pinned[j].data_ptr(), nbytes, args.level, ctypes.byref(out_p), ctypes.byref(out_n))
         if rc:
             eng._raise(rc)

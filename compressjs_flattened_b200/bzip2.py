@@ -217,11 +217,18 @@ class Bzip2Engine:
         return info
 
     def shard_emit(self, info, bit_phase, to_host=True):
+        """to_host: True -> bytes; False -> the segment stays in HBM, its length is returned;
+        "raw" -> (pointer, length) in the library's page-locked result memory, released with free_raw."""
         out, n = C.POINTER(C.c_uint8)(), C.c_size_t()
         rc = self._L.bz2b200_shard_emit(self._ctx, bit_phase, C.byref(info), C.byref(out) if to_host else None, C.byref(n))
         if rc:
             self._raise(rc)
+        if to_host == "raw":
+            return out, n.value
         return self._take(out, n.value) if to_host else n.value
+
+    def free_raw(self, ptr):
+        self._L.bz2b200_free(ptr)
 
     def stitch_shards(self, level, segs, infos):
         n = len(segs)

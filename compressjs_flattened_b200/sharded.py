@@ -1,7 +1,8 @@
 """Block-range sharding of one bzip2 stream over the ranks of a torch.distributed group.
 
 Each rank holds `buf` = its slice of the input followed by a halo (the bytes after the slice that its last block may
-need).  Cross-rank traffic is three scalars per rank -- no collective on the data path:
+need).  Cross-rank traffic is three scalars per rank -- no collective on the data path (they travel through the
+process group, or through a shared-memory HostMailbox when all ranks are on one node):
   1. chain   : global offset of the first block of rank r, sent by rank r-1 after its cut walk
   2. exscan  : bit lengths of the segments (all_gather of one int64), giving each segment's bit offset
   3. fold    : (n_blocks, crc_fold) of each segment, for the combined CRC (rotations compose)
@@ -13,34 +14,98 @@ import torch.distributed as dist
 from . import _native
 
 
+class HostMailbox:
+    """Scalars between the ranks of ONE node through a page of shared memory (/dev/shm): a slot per rank holding
+    (sequence number, value) pairs; a reader spins on the sequence number.  A few microseconds per hop, against
+    a millisecond for a TCP-backed process group -- the chain of first-block offsets is N-1 hops long."""
+    FIELDS = 4  # (chain, bits) x 2 alternating slots
+
+    def __init__(self, rank, world, key):
+        import numpy as np
+        self.rank, self.world, self.seq = rank, world, 0
+        self.path = f"/dev/shm/bz2b200_mailbox_{key}"
+        shape = (world, self.FIELDS * 2)
+        if rank == 0:
+            m = np.lib.format.open_memmap(self.path, mode="w+", dtype=np.int64, shape=shape)
+            m[:] = 0
+            m.flush()
+        if world > 1:
+            dist.barrier()
+        self.m = np.lib.format.open_memmap(self.path, mode="r+") if rank else m
+
+    def next_round(self):
+        self.seq += 1
+        return self.seq
+
+    # Two slots per field, used alternately: a rank cannot finish round k+1 before every rank has published its
+    # round-k+1 bit length, which each does only after reading everything of round k -- so a slot is never
+    # overwritten while a reader of the round before last still needs it.
+    def put(self, field, value):
+        f = 2 * field + (self.seq & 1)
+        self.m[self.rank, 2 * f + 1] = value
+        self.m[self.rank, 2 * f] = self.seq
+
+    def get(self, src, field):
+        f = 2 * field + (self.seq & 1)
+        row = self.m[src]
+        while int(row[2 * f]) != self.seq:
+            pass
+        return int(row[2 * f + 1])
+
+    def close(self):
+        import os
+        if self.world > 1:
+            dist.barrier()
+        if self.rank == 0:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass
+
+
 def compress_shard(engine, buf, base, own_len, level, is_last, rank=None, world=None, device=None, group=None,
-                   device_ptr=None, nbytes=None, to_host=True):
+                   device_ptr=None, nbytes=None, to_host=True, mailbox=None):
     """Compress the blocks that start inside [base, base+own_len) of the global input.
 
     buf: bytes-like slice+halo (host) -- or pass device_ptr/nbytes for data already in HBM.
-    Returns (segment_bytes, ShardInfo, bit_offset_of_segment_in_stream)."""
+    mailbox: a HostMailbox (single node) carries the scalars instead of the process group.
+    to_host: True -> bytes, False -> the segment stays in HBM (length returned), "raw" -> (pointer, length) owned
+    by the caller (engine.free_raw).
+    Returns (segment, ShardInfo, bit_offset_of_segment_in_stream)."""
     rank = dist.get_rank(group) if rank is None else rank
     world = dist.get_world_size(group) if world is None else world
     dev = device or torch.device("cpu")
     engine.shard_begin(buf, level, device_ptr=device_ptr, nbytes=nbytes)   # summaries: no dependency on other ranks
-    start = torch.zeros(1, dtype=torch.int64, device=dev)
-    if rank > 0:
-        dist.recv(start, src=rank - 1, group=group)                       # (1) first-block offset, global coordinates
-    s_local = max(int(start.item()) - base, 0)
+    if mailbox is not None:
+        mailbox.next_round()
+        start_v = mailbox.get(rank - 1, 0) if rank > 0 else 0                # (1) first-block offset, global coordinates
+    else:
+        start = torch.zeros(1, dtype=torch.int64, device=dev)
+        if rank > 0:
+            dist.recv(start, src=rank - 1, group=group)
+        start_v = int(start.item())
+    s_local = max(start_v - base, 0)
     info = engine.shard_cut(s_local, own_len, is_last)
     if not info.complete:
         raise RuntimeError("halo too short: the last owned block needs input beyond the buffer")
-    if rank + 1 < world:
-        nxt = torch.tensor([max(base + int(info.next_start), int(start.item()))], dtype=torch.int64, device=dev)
-        dist.send(nxt, dst=rank + 1, group=group)
+    nxt_v = max(base + int(info.next_start), start_v)
+    if mailbox is not None:
+        mailbox.put(0, nxt_v)
+    elif rank + 1 < world:
+        dist.send(torch.tensor([nxt_v], dtype=torch.int64, device=dev), dst=rank + 1, group=group)
     engine.shard_compress(info)
-    mine = torch.tensor([int(info.bits)], dtype=torch.int64, device=dev)
-    allbits = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-    if world > 1:
-        dist.all_gather(allbits, mine, group=group)                       # (2) exclusive scan of bit lengths
+    if mailbox is not None:
+        mailbox.put(1, int(info.bits))                                       # (2) exclusive scan of bit lengths
+        allb = [mailbox.get(r, 1) for r in range(world)]                     # everybody reads everybody: keeps the ranks within a round
+        bit_off = 32 + sum(allb[:rank])
     else:
-        allbits = [mine]
-    bit_off = 32 + sum(int(b.item()) for b in allbits[:rank])
+        mine = torch.tensor([int(info.bits)], dtype=torch.int64, device=dev)
+        allbits = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+        if world > 1:
+            dist.all_gather(allbits, mine, group=group)
+        else:
+            allbits = [mine]
+        bit_off = 32 + sum(int(b.item()) for b in allbits[:rank])
     seg = engine.shard_emit(info, bit_off & 7, to_host=to_host)
     return seg, info, bit_off
 

@@ -86,3 +86,42 @@ def test_single_rank_shards_equal_whole_stream(sim_engine, oracle):
     finally:
         oracle.set_block_cap(0)
         sim_engine.debug_set_block_cap(0)
+
+
+MAILBOX_WORKER = textwrap.dedent("""
+    import os, sys, numpy as np
+    sys.path.insert(0, {root!r}); sys.path.insert(0, {here!r})
+    import torch.distributed as dist
+    import oracle_binding as O
+    from compressjs_flattened_b200 import _native
+    from compressjs_flattened_b200.bzip2 import Bzip2Engine
+    from compressjs_flattened_b200.sharded import HostMailbox, compress_shard, gather_and_stitch
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    eng = Bzip2Engine(0, _native.Library(os.path.join({here!r}, "sim", "libbz2b200_sim.so")))
+    mb = HostMailbox(rank, world, os.environ["MASTER_PORT"])
+    rng = np.random.default_rng(5)
+    eng.debug_set_block_cap(300)
+    for rnd in range(3):   # several rounds through the same mailbox: the alternating slots must not mix rounds up
+        data = bytes(np.repeat(rng.integers(0, 4, 4000, dtype=np.uint8), rng.choice([1, 1, 2, 5, 300], 4000)))[:30000]
+        n = len(data); sl = (n + world - 1) // world; base = rank * sl; own = max(0, min(sl, n - base))
+        seg, info, off = compress_shard(eng, data[base:min(n, base + own + 20000)], base, own, 9, rank == world - 1, mailbox=mb)
+        out = gather_and_stitch(eng, seg, info, 9)
+        if rank == 0:
+            O.set_block_cap(300)
+            assert out == O.compress(data, 9), rnd
+            print("MAILBOX_OK", rnd)
+    mb.close()
+    dist.destroy_process_group()
+""")
+
+
+def test_sharded_stream_through_host_mailbox(tmp_path, sim_engine, oracle):
+    """Same protocol, scalars through the shared-memory mailbox (what bench.py uses on one node), 3 ranks, 3 rounds."""
+    script = tmp_path / "worker_mb.py"
+    script.write_text(MAILBOX_WORKER.format(root=ROOT, here=HERE))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=3", "--master-addr", "127.0.0.1",
+                        "--master-port", "29541", str(script)], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("MAILBOX_OK") == 3
