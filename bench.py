@@ -46,16 +46,42 @@ def workload_desc(level, mb, n_gpus):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md asks for the nvidia-smi clocks line).
+    In-process NVML (nvidia_ml_py) polled every 50 ms: a looping `nvidia-smi --query-gpu=... -lms 100` beside a
+    2-rank run cost rank 0 about 3 ms per step (driver locks); the NVML reads below do not.  Falls back to that
+    nvidia-smi loop when NVML cannot be imported."""
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.samples, self.stop_flag, self.thread = index, None, [], [], False, None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            R = pynvml
+            bits = {"hw_slowdown": R.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": R.nvmlClocksThrottleReasonHwThermalSlowdown,
+                    "sw_thermal_slowdown": R.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": R.nvmlClocksThrottleReasonSwPowerCap}
+
+            def poll():
+                while not self.stop_flag:
+                    try:
+                        sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                        rs = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                        self.samples.append((time.time(), float(sm), float(mx), [k for k, b in bits.items() if rs & b]))
+                    except Exception:
+                        pass
+                    time.sleep(0.05)
+            self.thread = threading.Thread(target=poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -66,9 +92,15 @@ class ClockSampler:
             self.lines.append((time.time(), line.strip()))
 
     def stop(self, t0, t1):
+        self.stop_flag = True
         if self.proc:
             self.proc.terminate()
         sm, mx, reasons = [], 0, set()
+        for t, s_, m_, rs in self.samples:
+            if t0 - 0.05 <= t <= t1 + 0.15:
+                sm.append(s_)
+                mx = max(mx, m_)
+                reasons.update(rs)
         for t, line in self.lines:
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9 or not (t0 - 0.05 <= t <= t1 + 0.15):
@@ -81,7 +113,8 @@ class ClockSampler:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm),
+                "source": "nvml" if self.thread else "nvidia-smi"}
 
 
 def peaks():
@@ -201,7 +234,7 @@ def main():
     for i in range(args.warmup):
         out_len = dev_step(i)
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("BENCH_NO_SAMPLER"):
         sampler.start()
         time.sleep(0.25)
     barrier()

@@ -8,6 +8,8 @@ process group, or through a shared-memory HostMailbox when all ranks are on one 
   3. fold    : (n_blocks, crc_fold) of each segment, for the combined CRC (rotations compose)
 The result is byte-identical to compressing the whole input on one GPU.
 """
+import time
+
 import torch
 import torch.distributed as dist
 
@@ -49,7 +51,7 @@ class HostMailbox:
         f = 2 * field + (self.seq & 1)
         row = self.m[src]
         while int(row[2 * f]) != self.seq:
-            pass
+            time.sleep(0)   # let other threads of this process have the interpreter
         return int(row[2 * f + 1])
 
     def close(self):
