@@ -46,42 +46,19 @@ def workload_desc(level, mb, n_gpus):
 
 
 class ClockSampler:
-    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md asks for the nvidia-smi clocks line).
-    In-process NVML (nvidia_ml_py) polled every 50 ms: a looping `nvidia-smi --query-gpu=... -lms 100` beside a
-    2-rank run cost rank 0 about 3 ms per step (driver locks); the NVML reads below do not.  Falls back to that
-    nvidia-smi loop when NVML cannot be imported."""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe).  The query is kept to
+    clocks.sm, clocks.max.sm and the clocks_event_reasons.active bitmask (decoded below): measured beside this
+    bench, the recipe's full line (power.draw + one field per reason) every 100 ms costs 3.6 - 5.6 ms per 17 ms step,
+    this one 0.2 ms (tests/gpu_sampler_probe.py); in-process NVML polling was worse still."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake"}
 
     def __init__(self, index):
-        self.index, self.proc, self.lines, self.samples, self.stop_flag, self.thread = index, None, [], [], False, None
+        self.index, self.proc, self.lines = index, None, []
 
     def start(self):
+        q = "index,clocks.sm,clocks.max.sm,clocks_event_reasons.active"
         try:
-            import pynvml
-            pynvml.nvmlInit()
-            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
-            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
-            R = pynvml
-            bits = {"hw_slowdown": R.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": R.nvmlClocksThrottleReasonHwThermalSlowdown,
-                    "sw_thermal_slowdown": R.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": R.nvmlClocksThrottleReasonSwPowerCap}
-
-            def poll():
-                while not self.stop_flag:
-                    try:
-                        sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
-                        rs = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                        self.samples.append((time.time(), float(sm), float(mx), [k for k, b in bits.items() if rs & b]))
-                    except Exception:
-                        pass
-                    time.sleep(0.05)
-            self.thread = threading.Thread(target=poll, daemon=True)
-            self.thread.start()
-            return
-        except Exception:
-            self.thread = None
-        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.index)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -92,29 +69,23 @@ class ClockSampler:
             self.lines.append((time.time(), line.strip()))
 
     def stop(self, t0, t1):
-        self.stop_flag = True
         if self.proc:
             self.proc.terminate()
         sm, mx, reasons = [], 0, set()
-        for t, s_, m_, rs in self.samples:
-            if t0 - 0.05 <= t <= t1 + 0.15:
-                sm.append(s_)
-                mx = max(mx, m_)
-                reasons.update(rs)
         for t, line in self.lines:
             f = [x.strip() for x in line.split(",")]
-            if len(f) < 9 or not (t0 - 0.05 <= t <= t1 + 0.15):
+            if len(f) < 4 or not (t0 - 0.05 <= t <= t1 + 0.15):
                 continue
             try:
                 sm.append(float(f[1]))
                 mx = max(mx, float(f[2]))
+                mask = int(f[3], 16)
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
+            for bit, name in self.REASONS.items():
+                if mask & bit:
                     reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm),
-                "source": "nvml" if self.thread else "nvidia-smi"}
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
 def peaks():
