@@ -524,14 +524,17 @@ int pipe_emit(Ctx *c, u64 base_bits, bool whole, u32 *d_out, size_t out_cap, boo
 int batch_limit(Ctx *c) {
   if (c->batch_override) return (int)c->batch_override;
   const i64 BS = round_up((i64)c->pipe.B + 1, 256);
-  i64 by_index = ((1ll << 31) - 1) / BS;
-  size_t free_b = 0, total_b = 0;
+  const i64 by_index = ((1ll << 31) - 1) / BS;
   i64 by_mem = by_index;
 #ifndef BZ_SIM
-  if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
-    size_t pooled = 0;
-    for (DevBuf *b : c->pool) pooled += b->cap;  // already ours: reusable
-    by_mem = (i64)((free_b + pooled) / 10 * 7 / (size_t)(BS * 52));
+  // cudaMemGetInfo takes the driver lock and was seen to cost milliseconds: asked only when this call needs more
+  // than the context already holds from earlier calls
+  size_t pooled = 0;
+  for (DevBuf *b : c->pool) pooled += b->cap;
+  const size_t need = (size_t)c->pipe.nb * (size_t)BS * 52;
+  if (need > pooled) {
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) by_mem = (i64)((free_b + pooled) / 10 * 7 / (size_t)(BS * 52));
   }
 #endif
   i64 lim = by_index < by_mem ? by_index : by_mem;
