@@ -46,10 +46,10 @@ def workload_desc(level, mb, n_gpus):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe).  The query is kept to
-    clocks.sm, clocks.max.sm and the clocks_event_reasons.active bitmask (decoded below): measured beside this
-    bench, the recipe's full line (power.draw + one field per reason) every 100 ms costs 3.6 - 5.6 ms per 17 ms step,
-    this one 0.2 ms (tests/gpu_sampler_probe.py); in-process NVML polling was worse still."""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe): clocks.sm,
+    clocks.max.sm and the clocks_event_reasons.active bitmask (decoded below), every 100 ms.  Measured beside this
+    bench (tests/gpu_sampler_probe.py) the loop costs nothing as long as the timed path makes no driver-lock calls:
+    a per-call cudaMemGetInfo in the library used to collide with it (+3..24 ms per step) and was removed."""
     REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake"}
 
     def __init__(self, index):
