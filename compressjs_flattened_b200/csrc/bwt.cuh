@@ -151,39 +151,51 @@ __global__ void __launch_bounds__(SORT_THREADS) k_rs_hist(const u64 *__restrict_
   u64 g0 = seg_base ? (u64)seg_base[p] + l0 : (u64)tile * SORT_TILE;
   for (int i = threadIdx.x; i < NB; i += SORT_THREADS) h[i] = 0;
   __syncthreads();
+  u64 k[SORT_E];
+#pragma unroll
+  for (int e = 0; e < SORT_E; e++) {  // all loads first
+    u32 o = e * SORT_THREADS + threadIdx.x;
+    k[e] = l0 + o < cnt ? keys[g0 + o] : 0;
+  }
+#pragma unroll
   for (int e = 0; e < SORT_E; e++) {
     u32 o = e * SORT_THREADS + threadIdx.x;
-    if (l0 + o < cnt) atomicAdd(&h[(u32)(keys[g0 + o] >> shift) & (NB - 1)], 1u);
+    if (l0 + o < cnt) atomicAdd(&h[(u32)(k[e] >> shift) & (NB - 1)], 1u);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < NB; i += SORT_THREADS) hist[(u64)tile * NB + i] = h[i];
 }
-// per block: column-wise exclusive prefix over its tiles (in place) + exclusive digit bases; 1 << BITS threads
+// per block: column-wise exclusive prefix over its tiles (in place) and the digit totals.  grid (nb, NB / 32), 512
+// threads: a CTA owns 32 digits (lane = digit), its 16 warps split the block's tiles into contiguous ranges: sum of
+// the own range, exclusive scan over the warps in shared memory, then the prefixes of the own range.
+#define RSS_WARPS 16
 template <int BITS>
-__global__ void __launch_bounds__(1 << BITS) k_rs_scan(u32 *__restrict__ hist, const u32 *__restrict__ seg_tile0, u32 *__restrict__ digit_base) {
+__global__ void __launch_bounds__(RSS_WARPS * 32) k_rs_scan(u32 *__restrict__ hist, const u32 *__restrict__ seg_tile0, u32 *__restrict__ digit_tot) {
   constexpr int NB = 1 << BITS;
-  __shared__ u32 ws[33];
-  u32 p = blockIdx.x, d = threadIdx.x;
-  u32 t0 = seg_tile0[p], t1 = seg_tile0[p + 1];
+  __shared__ u32 part[RSS_WARPS][32];
+  const u32 p = blockIdx.x, d = blockIdx.y * 32 + lane_id();
+  const int w = warp_id();
+  const u32 t0 = seg_tile0[p], t1 = seg_tile0[p + 1], nt = t1 - t0;
+  const u32 per = (nt + RSS_WARPS - 1) / RSS_WARPS;
+  const u32 a = t0 + (u32)w * per < t1 ? t0 + (u32)w * per : t1, b = a + per < t1 ? a + per : t1;
+  u32 sum = 0;
+  for (u32 t = a; t < b; t++) sum += hist[(u64)t * NB + d];
+  part[w][lane_id()] = sum;
+  __syncthreads();
   u32 acc = 0;
-  u32 t = t0;
-  for (; t + 4 <= t1; t += 4) {  // 4 independent loads in flight
-    u32 a = hist[(u64)t * NB + d], b = hist[(u64)(t + 1) * NB + d], c = hist[(u64)(t + 2) * NB + d], e = hist[(u64)(t + 3) * NB + d];
-    hist[(u64)t * NB + d] = acc; acc += a;
-    hist[(u64)(t + 1) * NB + d] = acc; acc += b;
-    hist[(u64)(t + 2) * NB + d] = acc; acc += c;
-    hist[(u64)(t + 3) * NB + d] = acc; acc += e;
+  for (int ww = 0; ww < w; ww++) acc += part[ww][lane_id()];
+  if (w == RSS_WARPS - 1) digit_tot[(u64)p * NB + d] = acc + sum;
+  for (u32 t = a; t < b; t++) {
+    u32 v = hist[(u64)t * NB + d];
+    hist[(u64)t * NB + d] = acc;
+    acc += v;
   }
-  for (; t < t1; t++) { u32 a = hist[(u64)t * NB + d]; hist[(u64)t * NB + d] = acc; acc += a; }
-  u32 tot;
-  u32 base = block_excl_sum<u32>(acc, tot, ws);
-  digit_base[(u64)p * NB + d] = base;
 }
 template <int BITS>
-__global__ void __launch_bounds__(SORT_THREADS) k_rs_scatter(const u64 *__restrict__ keys_in, u64 *__restrict__ keys_out,
+__global__ void __launch_bounds__(SORT_THREADS, 3) k_rs_scatter(const u64 *__restrict__ keys_in, u64 *__restrict__ keys_out,
                                                              const u32 *__restrict__ seg_cnt, const u32 *__restrict__ seg_tile0,
                                                              const u32 *__restrict__ tile_blk, int shift, const u32 *__restrict__ hist,
-                                                             const u32 *__restrict__ digit_base, const u32 *__restrict__ seg_base) {
+                                                             const u32 *__restrict__ digit_tot, const u32 *__restrict__ seg_base) {
   constexpr int NB = 1 << BITS;
   __shared__ u16 wcnt[SORT_THREADS / 32][NB];  // a warp ranks 256 keys: counts fit 16 bits
   __shared__ u32 base[NB];
@@ -192,16 +204,26 @@ __global__ void __launch_bounds__(SORT_THREADS) k_rs_scatter(const u64 *__restri
   u64 gp = seg_base ? (u64)seg_base[p] : (u64)seg_tile0[p] * SORT_TILE, g0 = gp + l0;
   int lane = lane_id(), w = warp_id();
   for (int i = threadIdx.x; i < (SORT_THREADS / 32) * NB / 2; i += SORT_THREADS) reinterpret_cast<u32 *>(&wcnt[0][0])[i] = 0;
-  for (int i = threadIdx.x; i < NB; i += SORT_THREADS) base[i] = digit_base[(u64)p * NB + i] + hist[(u64)tile * NB + i];
+  {  // base of digit d = keys of the block with a smaller digit (scan of the totals) + keys with digit d in earlier tiles
+    static_assert(NB <= SORT_THREADS, "one digit per thread");
+    __shared__ u32 ws[33];
+    u32 tot_d = threadIdx.x < NB ? digit_tot[(u64)p * NB + threadIdx.x] : 0u, tot;
+    u32 ex = block_excl_sum<u32>(tot_d, tot, ws);
+    if (threadIdx.x < NB) base[threadIdx.x] = ex + hist[(u64)tile * NB + threadIdx.x];
+  }
   __syncthreads();
   u64 key[SORT_E];
   u32 rk[SORT_E];
   u32 lt = (1u << lane) - 1;
 #pragma unroll
+  for (int e = 0; e < SORT_E; e++) {  // all loads first: eight independent requests in flight per thread
+    u32 o = (u32)w * (32 * SORT_E) + e * 32 + lane;
+    key[e] = l0 + o < cnt ? keys_in[g0 + o] : 0;
+  }
+#pragma unroll
   for (int e = 0; e < SORT_E; e++) {
     u32 o = (u32)w * (32 * SORT_E) + e * 32 + lane;
     bool ok = l0 + o < cnt;
-    key[e] = ok ? keys_in[g0 + o] : 0;
     u32 d = ok ? ((u32)(key[e] >> shift) & (NB - 1)) : (u32)NB;
     u32 peers = __match_any_sync(FULL_MASK, d);
     int leader = __ffs((int)peers) - 1;

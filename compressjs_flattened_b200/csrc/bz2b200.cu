@@ -326,7 +326,7 @@ int pipe_stages(Ctx *c) {
       u64 *ki = kA, *ko = kB;
       for (int pass = 0; pass < 5; pass++) {  // bits 20..63, 9 bits a pass
         LAUNCH(k_rs_hist<9>, Ta, SORT_THREADS, 0, ki, seg_cnt, tile0, tblk, 20 + pass * 9, P<u32>(c->hist), (const u32 *)nullptr);
-        LAUNCH(k_rs_scan<9>, (unsigned)nb, 512, 0, P<u32>(c->hist), tile0, P<u32>(c->digit_base));
+        LAUNCH(k_rs_scan<9>, dim3((unsigned)nb, 512 / 32), RSS_WARPS * 32, 0, P<u32>(c->hist), tile0, P<u32>(c->digit_base));
         if ((rc = timed_scatter(true, Ta, ki, ko, seg_cnt, tile0, tblk, 20 + pass * 9, nullptr, total_n))) return rc;
         u64 *tk = ki; ki = ko; ko = tk;
       }
@@ -371,7 +371,7 @@ int pipe_stages(Ctx *c) {
         u64 *ki = kA, *ko = kB;
         for (int pass = 0; pass < 3; pass++) {  // key2 < 2^20: bits 32..55
           LAUNCH(k_rs_hist<8>, Tb, SORT_THREADS, 0, ki, bcnt, bt0, btb, 32 + pass * 8, P<u32>(c->hist), bbase);
-          LAUNCH(k_rs_scan<8>, n_big, 256, 0, P<u32>(c->hist), bt0, P<u32>(c->digit_base));
+          LAUNCH(k_rs_scan<8>, dim3(n_big, 256 / 32), RSS_WARPS * 32, 0, P<u32>(c->hist), bt0, P<u32>(c->digit_base));
           if ((rc = timed_scatter(false, Tb, ki, ko, bcnt, bt0, btb, 32 + pass * 8, bbase, t2[1]))) return rc;
           u64 *tk = ki; ki = ko; ko = tk;
         }

@@ -181,7 +181,7 @@ static int decode_device(Ctx *c, const u8 *d_in, size_t n, int multistream, int 
     LAUNCH(k_dec_keys, (unsigned)tiles, SEG_THREADS, 0, P<u8>(c->dL), LS, d_order, P<u32>(c->seg_cnt), P<u32>(c->seg_tile0), P<u32>(c->tile_blk),
            P<u64>(c->keysA));
     LAUNCH(k_rs_hist<8>, (unsigned)tiles, SORT_THREADS, 0, P<u64>(c->keysA), P<u32>(c->seg_cnt), P<u32>(c->seg_tile0), P<u32>(c->tile_blk), 20, P<u32>(c->hist), (const u32 *)nullptr);
-    LAUNCH(k_rs_scan<8>, (unsigned)nb, 256, 0, P<u32>(c->hist), P<u32>(c->seg_tile0), P<u32>(c->digit_base));
+    LAUNCH(k_rs_scan<8>, dim3((unsigned)nb, 256 / 32), RSS_WARPS * 32, 0, P<u32>(c->hist), P<u32>(c->seg_tile0), P<u32>(c->digit_base));
     LAUNCH(k_rs_scatter<8>, (unsigned)tiles, SORT_THREADS, 0, P<u64>(c->keysA), P<u64>(c->keysB), P<u32>(c->seg_cnt),
            P<u32>(c->seg_tile0), P<u32>(c->tile_blk), 20, P<u32>(c->hist), P<u32>(c->digit_base), (const u32 *)nullptr);
     LAUNCH(k_dec_extract, (unsigned)((slots + 255) / 256), 256, 0, P<u64>(c->keysB), P<u32>(c->valsB), (u64)slots);
