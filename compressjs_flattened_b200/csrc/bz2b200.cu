@@ -101,6 +101,13 @@ struct Ctx {
     int level = 9, nb = 0;
     std::vector<BlockRec> hrecs;
   } pipe;
+  bool trace = false;      // BZ2B200_TRACE
+  std::vector<cudaEvent_t> trace_ev, trace_pool;
+  std::vector<const char *> trace_names;
+  void *rb_pin = nullptr;  // page-locked scratch of rb_add / rb_sync
+  void *rb_dst[8];
+  size_t rb_off[8], rb_len[8], rb_used = 0;
+  int rb_n = 0;
   u32 cap_override = 0;    // tests only
   u32 batch_override = 0;  // tests only: blocks per batch
   u64 shard_bits = 0;      // bit length of the last shard segment (phase 0 in `out`)
@@ -132,6 +139,70 @@ struct Ctx {
     }                                                                                    \
   } while (0)
 
+// Small device -> host read-backs (block / slot counts) land in page-locked scratch: a copy to pageable memory goes
+// through the driver's staging path and costs several microseconds more per round trip.
+int rb_add(Ctx *c, void *dst, const void *dev_src, size_t bytes) {
+  if (!c->rb_pin) CK(cudaMallocHost(&c->rb_pin, 1024));
+  if (c->rb_n >= 8 || c->rb_used + bytes > 1024) { c->err = "internal: read-back scratch full"; return BZ2B200_E_CUDA; }
+  CK(cudaMemcpyAsync((char *)c->rb_pin + c->rb_used, dev_src, bytes, cudaMemcpyDeviceToHost, c->stream));
+  c->rb_dst[c->rb_n] = dst; c->rb_off[c->rb_n] = c->rb_used; c->rb_len[c->rb_n] = bytes;
+  c->rb_n++;
+  c->rb_used += (bytes + 15) & ~(size_t)15;
+  return 0;
+}
+int rb_sync(Ctx *c) {
+  CK(cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < c->rb_n; i++) memcpy(c->rb_dst[i], (char *)c->rb_pin + c->rb_off[i], c->rb_len[i]);
+  c->rb_n = 0;
+  c->rb_used = 0;
+  return 0;
+}
+#define RC(call)               \
+  do {                         \
+    int _r = (call);           \
+    if (_r) return _r;         \
+  } while (0)
+
+void trace_mark(Ctx *c, const char *name, bool begin) {
+#ifndef BZ_SIM
+  cudaEvent_t e;
+  if (c->trace_pool.size() > c->trace_ev.size()) e = c->trace_pool[c->trace_ev.size()];
+  else { if (cudaEventCreate(&e) != cudaSuccess) return; c->trace_pool.push_back(e); }
+  cudaEventRecord(e, c->stream);
+  c->trace_ev.push_back(e);
+  if (begin) c->trace_names.push_back(name);
+#else
+  (void)c; (void)name; (void)begin;
+#endif
+}
+void trace_report(Ctx *c) {
+#ifndef BZ_SIM
+  if (!c->trace || c->trace_ev.empty()) return;
+  cudaStreamSynchronize(c->stream);
+  std::vector<std::pair<std::string, std::pair<int, float>>> agg;
+  float gaps = 0, total = 0;
+  for (size_t i = 0; i + 1 < c->trace_ev.size(); i += 2) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->trace_ev[i], c->trace_ev[i + 1]);
+    const std::string nm = c->trace_names[i / 2];
+    size_t k = 0;
+    for (; k < agg.size(); k++) if (agg[k].first == nm) break;
+    if (k == agg.size()) agg.push_back({nm, {0, 0.f}});
+    agg[k].second.first++;
+    agg[k].second.second += ms;
+    total += ms;
+    if (i + 2 < c->trace_ev.size()) { float g = 0; cudaEventElapsedTime(&g, c->trace_ev[i + 1], c->trace_ev[i + 2]); gaps += g; }
+  }
+  std::sort(agg.begin(), agg.end(), [](const auto &a, const auto &b) { return a.second.second > b.second.second; });
+  fprintf(stderr, "[bz2b200 trace] %zu launches, kernels %.3f ms, gaps between launches %.3f ms\n", c->trace_names.size(), total, gaps);
+  for (auto &a : agg) fprintf(stderr, "[bz2b200 trace] %-28s x%-3d %8.3f ms\n", a.first.c_str(), a.second.first, a.second.second);
+  c->trace_ev.clear();
+  c->trace_names.clear();
+#else
+  (void)c;
+#endif
+}
+
 int ensure(Ctx *c, DevBuf &b, size_t bytes) {
   if (bytes <= b.cap) return 0;
   if (b.p) CK(cudaFree(b.p));
@@ -158,9 +229,13 @@ int ensure_pinned(Ctx *c, size_t bytes) {
   } while (0)
 template <typename T> T *P(DevBuf &b) { return reinterpret_cast<T *>(b.p); }
 
+// BZ2B200_TRACE=1 in the environment: CUDA events around every launch, per-kernel totals printed by trace_report()
+// at the end of a compress call (development aid; the extra events serialise nothing but cost a few microseconds each)
 #define LAUNCH(kern, grid, block, smem, ...)                        \
   do {                                                              \
+    if (c->trace) trace_mark(c, #kern, true);                       \
     KLAUNCH(kern, grid, block, smem, c->stream, __VA_ARGS__);       \
+    if (c->trace) trace_mark(c, #kern, false);                      \
     c->st.kernel_launches++;                                        \
   } while (0)
 
@@ -213,8 +288,8 @@ int pipe_cut(Ctx *c, i64 s_start, i64 own_end) {
   if (N > 0 && s_start < N && s_start < own_end) {
     LAUNCH(k_rle_cut, 1, CUT_THREADS, 0, P_.d_in, N, B, P<u32>(c->g_sub), P<i64>(c->h_sub), P<i64>(c->tile_first), P<u64>(c->g_tile), T,
            P<BlockRec>(c->recs), max_blocks, P<int>(c->nblk), s_start, own_end);
-    CK(cudaMemcpyAsync(&nb, c->nblk.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    RC(rb_add(c, &nb, c->nblk.p, sizeof(int)));
+    RC(rb_sync(c));
     if (nb < 0) { c->err = "internal: block table overflow"; return BZ2B200_E_CUDA; }
     P_.hrecs.resize((size_t)nb);
     if (nb) CK(cudaMemcpy(P_.hrecs.data(), c->recs.p, sizeof(BlockRec) * (size_t)nb, cudaMemcpyDeviceToHost));
@@ -334,8 +409,8 @@ int pipe_stages(Ctx *c) {
       CK(cudaMemsetAsync(status, 0, 8 * (size_t)Ta, c->stream));
       LAUNCH(k_rank0, Ta, R0_THREADS, 0, ki, seg_cnt, tile0, tblk, P<u32>(c->isa), BS, actI[0], actR[0], status, lbm, lbm + 1, (u32)Ta, P<u8>(c->blk),
              P<u8>(c->Lcol), P<BlockRec>(c->recs));
-      CK(cudaMemcpyAsync(hv, lbm, sizeof hv, cudaMemcpyDeviceToHost, c->stream));
-      CK(cudaStreamSynchronize(c->stream));
+      RC(rb_add(c, hv, lbm, sizeof hv));
+      RC(rb_sync(c));
     }
     // ---- rounds >= 1 (refine.cuh): list A (+ key2) -> sorted staging list B -> compacted list A ----
     u32 n_act = hv[1], round = 0;  // doubling round r compares h = L << r symbols further on (L per block)
@@ -356,16 +431,16 @@ int pipe_stages(Ctx *c) {
       CK(cudaMemsetAsync(status, 0, 8 * (size_t)ctiles, c->stream));
       LAUNCH(k_sort_groups, ntiles, RF_THREADS, sizeof(RfSmem), P<u32>(c->key2), actI[0], actR[0], n_act, P<u32>(c->isa), (u32)BS, magic, actI[1],
              actR[1], P<u32>(c->big_cnt), P<u32>(c->big_old), P<u32>(c->big_rank), lbm + 2, big_cap, P<u8>(c->blk), P<u8>(c->Lcol), P<BlockRec>(c->recs));
-      CK(cudaMemcpyAsync(hv, lbm, sizeof hv, cudaMemcpyDeviceToHost, c->stream));
-      CK(cudaStreamSynchronize(c->stream));
+      RC(rb_add(c, hv, lbm, sizeof hv));
+      RC(rb_sync(c));
       const u32 n_big = hv[2];
       if (n_big > big_cap) { c->err = "internal: big-group list overflow"; return BZ2B200_E_CUDA; }
       if (n_big) {  // groups of more than RF_T0 slots: the global radix sort
         u32 *bcnt = P<u32>(c->big_cnt), *bbase = P<u32>(c->big_old), *bt0 = P<u32>(c->big_tile0), *btb = P<u32>(c->big_tblk);
         u64 t2[2] = {0, 0};
         LAUNCH(k_tilemap, 1, 1024, 0, bcnt, (int)n_big, bt0, btb, P<u64>(c->totals2));
-        CK(cudaMemcpyAsync(t2, c->totals2.p, sizeof t2, cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaStreamSynchronize(c->stream));
+        RC(rb_add(c, t2, c->totals2.p, sizeof t2));
+        RC(rb_sync(c));
         const unsigned Tb = (unsigned)t2[0];
         LAUNCH(k_big_keys, Tb, SEG_THREADS, 0, P<u32>(c->key2), actI[0], bcnt, bt0, btb, bbase, kA);
         u64 *ki = kA, *ko = kB;
@@ -384,8 +459,8 @@ int pipe_stages(Ctx *c) {
       LAUNCH(k_compact_keys, ctiles, CK_THREADS, 0, actI[1], actR[1], n_act, P<BlockRec>(c->recs), P<u32>(c->isa), (u32)BS, magic, P<BlkSort>(c->blksort), round,
              actI[0], actR[0],
              P<u32>(c->key2), status, lbm, lbm + 1, ctiles);
-      CK(cudaMemcpyAsync(hv, lbm, sizeof hv, cudaMemcpyDeviceToHost, c->stream));
-      CK(cudaStreamSynchronize(c->stream));
+      RC(rb_add(c, hv, lbm, sizeof hv));
+      RC(rb_sync(c));
       n_act = hv[1];
     }
     if ((rc = mark(c, 2))) return rc;
@@ -471,9 +546,9 @@ int pipe_emit(Ctx *c, u64 base_bits, bool whole, u32 *d_out, size_t out_cap, boo
   LAUNCH(k_stitch_offsets, 1, 1024, 0, P<BlockMeta>(c->meta), P<BlockRec>(c->recs), nb, P<u64>(c->bit_off), P<u32>(c->scrc), base_bits);
   u64 end_bits = 0;
   u32 fold = 0;
-  CK(cudaMemcpyAsync(&end_bits, P<u64>(c->bit_off) + nb, 8, cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaMemcpyAsync(&fold, c->scrc.p, 4, cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
+  RC(rb_add(c, &end_bits, P<u64>(c->bit_off) + nb, 8));
+  RC(rb_add(c, &fold, c->scrc.p, 4));
+  RC(rb_sync(c));
   if (bits_out) *bits_out = end_bits - base_bits;
   if (crc_fold) *crc_fold = fold;
   size_t need = (size_t)((end_bits + (whole ? 80 : 0) + 7) / 8);
@@ -490,11 +565,11 @@ int pipe_emit(Ctx *c, u64 base_bits, bool whole, u32 *d_out, size_t out_cap, boo
   u64 olen = need;
   if (whole) {
     LAUNCH(k_stream_ends, 1, 32, 0, d_out, P<u64>(c->bit_off), nb, P<u32>(c->scrc), P_.level, P<u64>(c->out_len));
-    CK(cudaMemcpyAsync(&olen, c->out_len.p, 8, cudaMemcpyDeviceToHost, c->stream));
+    RC(rb_add(c, &olen, c->out_len.p, 8));
   }
   int rc;
   if ((rc = mark(c, 5))) return rc;
-  CK(cudaStreamSynchronize(c->stream));
+  RC(rb_sync(c));
   CK(cudaGetLastError());
   *out_len = (size_t)olen;
   c->st.out_bytes = olen;
@@ -549,9 +624,9 @@ int pipe_emit_part(Ctx *c, u64 base_bits, bool first, u32 *d_out, size_t out_cap
   LAUNCH(k_stitch_offsets, 1, 1024, 0, P<BlockMeta>(c->meta), P<BlockRec>(c->recs), nb, P<u64>(c->bit_off), P<u32>(c->scrc), base_bits);
   u64 end_bits = 0;
   u32 fold = 0;
-  CK(cudaMemcpyAsync(&end_bits, P<u64>(c->bit_off) + nb, 8, cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaMemcpyAsync(&fold, c->scrc.p, 4, cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
+  RC(rb_add(c, &end_bits, P<u64>(c->bit_off) + nb, 8));
+  RC(rb_add(c, &fold, c->scrc.p, 4));
+  RC(rb_sync(c));
   *bits_out = end_bits - base_bits;
   *crc_fold = fold;
   const u64 w_first = first ? 0 : (base_bits >> 5) + 1, w_end = ((end_bits + 80 + 31) >> 5) + 2;  // room for the footer too
@@ -624,8 +699,8 @@ int pipe_run(Ctx *c, u64 base_bits, bool whole, u32 *d_out, size_t out_cap, bool
     CK(cudaMemcpyAsync(c->bit_off.p, &endb, 8, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->scrc.p, &fold, 4, cudaMemcpyHostToDevice, c->stream));
     LAUNCH(k_stream_ends, 1, 32, 0, d_out, P<u64>(c->bit_off), 0, P<u32>(c->scrc), P_.level, P<u64>(c->out_len));
-    CK(cudaMemcpyAsync(&olen, c->out_len.p, 8, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    RC(rb_add(c, &olen, c->out_len.p, 8));
+    RC(rb_sync(c));
   }
   *out_len = (size_t)olen;
   c->st.out_bytes = olen;
@@ -641,7 +716,9 @@ int compress_device(Ctx *c, const u8 *d_in, size_t n_, int level, u32 *d_out, si
   int rc;
   if ((rc = pipe_begin(c, d_in, n_, level))) return rc;
   if ((rc = pipe_cut(c, 0, (i64)n_))) return rc;
-  return pipe_run(c, 32, true, d_out, out_cap, own_out, out_len, nullptr, nullptr);
+  rc = pipe_run(c, 32, true, d_out, out_cap, own_out, out_len, nullptr, nullptr);
+  trace_report(c);
+  return rc;
 }
 
 #include "decode_host.inl"
@@ -661,6 +738,7 @@ int bz2b200_create(int device, bz2b200_ctx **ctx) {
   c->device = device;
   if (cudaStreamCreate(&c->stream) != cudaSuccess) { delete c; return BZ2B200_E_CUDA; }
   c->ev_ok = true;
+  { const char *t = getenv("BZ2B200_TRACE"); c->trace = t && *t && *t != '0'; }
   for (auto &e : c->ev) if (cudaEventCreate(&e) != cudaSuccess) c->ev_ok = false;
   *ctx = reinterpret_cast<bz2b200_ctx *>(c);
   return BZ2B200_OK;
@@ -672,6 +750,7 @@ void bz2b200_destroy(bz2b200_ctx *ctx) {
   cudaSetDevice(c->device);
   for (DevBuf *b : c->pool) if (b->p) cudaFree(b->p);
   if (c->h_pin) cudaFreeHost(c->h_pin);
+  if (c->rb_pin) cudaFreeHost(c->rb_pin);
   if (c->ev_ok) for (auto &e : c->ev) cudaEventDestroy(e);
   for (auto &e : c->dom_ev) cudaEventDestroy(e);
   cudaStreamDestroy(c->stream);
