@@ -113,30 +113,43 @@ __global__ void __launch_bounds__(256) k_sym_tab(BlkSort *__restrict__ bs) {
     B.L = 44 / b;
   }
 }
-// dense codes of the first L symbols of each rotation, left-aligned in bits 20..63; rotation index in the low 20 bits
+// dense codes of the first L symbols of each rotation, left-aligned in bits 20..63; rotation index in the low 20 bits.
+// The tile's bytes (+ L-1 more, cyclically) are staged in shared memory as codes; the histogram of the first radix
+// digit (bits 20..28) is counted on the way, so pass 0 needs no k_rs_hist.
 __global__ void __launch_bounds__(SEG_THREADS) k_keys_init(const u8 *__restrict__ blk, i64 blk_stride, const BlockRec *__restrict__ recs,
                                                            const u32 *__restrict__ seg_tile0, const u32 *__restrict__ tile_blk,
-                                                           const BlkSort *__restrict__ bs, u64 *__restrict__ keys) {
+                                                           const BlkSort *__restrict__ bs, u64 *__restrict__ keys, u32 *__restrict__ hist0) {
   __shared__ u8 code[256];
+  __shared__ u8 sc[SORT_TILE + 48];
+  __shared__ u32 h[512];
   u32 tile = blockIdx.x, p = tile_blk[tile];
   u32 n = recs[p].n;
   code[threadIdx.x] = bs[p].code[threadIdx.x];
+  for (int i = threadIdx.x; i < 512; i += SEG_THREADS) h[i] = 0;
   const u32 b = bs[p].b, L = bs[p].L;
   __syncthreads();
   const u8 *T = blk + (i64)p * blk_stride;
   u32 l0 = (tile - seg_tile0[p]) * SORT_TILE;
   u64 g0 = (u64)tile * SORT_TILE;
-  for (int e = 0; e < SEG_E; e++) {
-    u32 lj = l0 + e * SEG_THREADS + threadIdx.x;
-    if (lj >= n) continue;
-    u64 key = 0;
-    u32 x = lj;
-    for (u32 k = 0; k < L; k++) {
-      key = (key << b) | code[T[x]];
-      x = x + 1 == n ? 0 : x + 1;
-    }
-    keys[g0 + (lj - l0)] = (key << (64 - L * b)) | lj;
+  const u32 m = n - l0 < SORT_TILE ? n - l0 : SORT_TILE;
+  for (u32 j = threadIdx.x; j < m + L - 1; j += SEG_THREADS) {
+    u32 x = l0 + j;
+    while (x >= n) x -= n;
+    sc[j] = code[T[x]];
   }
+  __syncthreads();
+  const int shift = 64 - (int)(L * b);
+  for (int e = 0; e < SEG_E; e++) {
+    u32 j = e * SEG_THREADS + threadIdx.x;
+    if (j >= m) continue;
+    u64 key = 0;
+    for (u32 k = 0; k < L; k++) key = (key << b) | sc[j + k];
+    key = (key << shift) | (l0 + j);
+    keys[g0 + j] = key;
+    atomicAdd(&h[(u32)(key >> 20) & 511u], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 512; i += SEG_THREADS) hist0[(u64)tile * 512 + i] = h[i];
 }
 // ---- one LSD radix pass (BITS-bit digit, 8 or 9), batched over blocks ---------------------------
 // seg_base (optional): slot at which segment p starts; default = seg_tile0[p] * SORT_TILE (block layout)

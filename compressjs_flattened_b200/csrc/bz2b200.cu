@@ -372,7 +372,7 @@ int pipe_stages(Ctx *c) {
     CK(cudaMemsetAsync(c->blksort.p, 0, sizeof(BlkSort) * (size_t)nb, c->stream));
     LAUNCH(k_sym_used, dim3(32, (unsigned)nb), 256, 0, P<u8>(c->blk), BS, P<BlockRec>(c->recs), P<BlkSort>(c->blksort));
     LAUNCH(k_sym_tab, (unsigned)nb, 256, 0, P<BlkSort>(c->blksort));
-    LAUNCH(k_keys_init, Ta, SEG_THREADS, 0, P<u8>(c->blk), BS, P<BlockRec>(c->recs), tile0, tblk, P<BlkSort>(c->blksort), kA);
+    LAUNCH(k_keys_init, Ta, SEG_THREADS, 0, P<u8>(c->blk), BS, P<BlockRec>(c->recs), tile0, tblk, P<BlkSort>(c->blksort), kA, P<u32>(c->hist));
     u64 total_n = 0;
     for (auto &r : hrecs) total_n += r.n;
     c->dom_used = 0;
@@ -400,7 +400,7 @@ int pipe_stages(Ctx *c) {
       c->st.sort_slots += (u64)Ta * SORT_TILE;
       u64 *ki = kA, *ko = kB;
       for (int pass = 0; pass < 5; pass++) {  // bits 20..63, 9 bits a pass
-        LAUNCH(k_rs_hist<9>, Ta, SORT_THREADS, 0, ki, seg_cnt, tile0, tblk, 20 + pass * 9, P<u32>(c->hist), (const u32 *)nullptr);
+        if (pass) LAUNCH(k_rs_hist<9>, Ta, SORT_THREADS, 0, ki, seg_cnt, tile0, tblk, 20 + pass * 9, P<u32>(c->hist), (const u32 *)nullptr);  // pass 0: k_keys_init
         LAUNCH(k_rs_scan<9>, dim3((unsigned)nb, 512 / 32), RSS_WARPS * 32, 0, P<u32>(c->hist), tile0, P<u32>(c->digit_base));
         if ((rc = timed_scatter(true, Ta, ki, ko, seg_cnt, tile0, tblk, 20 + pass * 9, nullptr, total_n))) return rc;
         u64 *tk = ki; ki = ko; ko = tk;

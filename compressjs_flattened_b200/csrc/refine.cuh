@@ -19,14 +19,26 @@
 #include "common.cuh"
 #include "bwt.cuh"
 
+#ifndef RF_T0
 #define RF_T0 1024
+#endif
+#ifndef RF_CAP
 #define RF_CAP 2048
+#endif
+#ifndef RF_THREADS
 #define RF_THREADS 256
+#endif
 #define RF_E (RF_CAP / RF_THREADS)
 #define RF_WARPS (RF_THREADS / 32)
+#ifndef RF_SMALL
 #define RF_SMALL 32
+#endif
+#ifndef RF_COOP
 #define RF_COOP 256                      // larger groups (up to RF_T0) are sorted by the whole CTA
+#endif
+#ifndef RF_SBITS
 #define RF_SBITS 11                     // slot bits below key2 in the composite sort word (RF_CAP == 1 << RF_SBITS)
+#endif
 #define RF_MAXMED (RF_CAP / (RF_SMALL + 1) + 1)
 #define CK_TILE 2048                    // slots per CTA of k_compact_keys
 #define CK_THREADS 256
