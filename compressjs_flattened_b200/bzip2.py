@@ -210,6 +210,21 @@ class Bzip2Engine:
             self._raise(rc)
         return info
 
+    def shard_gtotal(self, pos):
+        g = C.c_uint64()
+        rc = self._L.bz2b200_shard_gtotal(self._ctx, pos, C.byref(g))
+        if rc:
+            self._raise(rc)
+        return g.value
+
+    def shard_cut_g(self, g_before, own_len, is_last):
+        """Speculative cut walk (g_before = G of the earlier shards); returns (info, first_start or None)."""
+        info, first = _native.ShardInfo(), C.c_uint64()
+        rc = self._L.bz2b200_shard_cut_g(self._ctx, g_before, own_len, int(is_last), C.byref(info), C.byref(first))
+        if rc:
+            self._raise(rc)
+        return info, (None if first.value == 0xFFFFFFFFFFFFFFFF else first.value)
+
     def shard_compress(self, info):
         rc = self._L.bz2b200_shard_compress(self._ctx, C.byref(info))
         if rc:

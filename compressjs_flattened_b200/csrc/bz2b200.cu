@@ -276,7 +276,7 @@ int pipe_begin(Ctx *c, const u8 *d_in, size_t n_, int level) {
   return BZ2B200_OK;
 }
 
-int pipe_cut(Ctx *c, i64 s_start, i64 own_end) {
+int pipe_cut(Ctx *c, i64 s_start, i64 own_end, i64 g_start = -1) {
   Ctx::Pipe &P_ = c->pipe;
   const i64 N = P_.N, T = P_.T;
   const u32 B = P_.B;
@@ -285,9 +285,9 @@ int pipe_cut(Ctx *c, i64 s_start, i64 own_end) {
   ENS(c->nblk, 64);
   int nb = 0;
   P_.hrecs.clear();
-  if (N > 0 && s_start < N && s_start < own_end) {
+  if (N > 0 && (g_start >= 0 || (s_start < N && s_start < own_end))) {
     LAUNCH(k_rle_cut, 1, CUT_THREADS, 0, P_.d_in, N, B, P<u32>(c->g_sub), P<i64>(c->h_sub), P<i64>(c->tile_first), P<u64>(c->g_tile), T,
-           P<BlockRec>(c->recs), max_blocks, P<int>(c->nblk), s_start, own_end);
+           P<BlockRec>(c->recs), max_blocks, P<int>(c->nblk), s_start, own_end, g_start);
     RC(rb_add(c, &nb, c->nblk.p, sizeof(int)));
     RC(rb_sync(c));
     if (nb < 0) { c->err = "internal: block table overflow"; return BZ2B200_E_CUDA; }
@@ -796,20 +796,51 @@ int bz2b200_shard_begin(bz2b200_ctx *ctx, const void *in, size_t n_avail, int on
   return pipe_begin(c, d_in, n_avail, level);
 }
 
-int bz2b200_shard_cut(bz2b200_ctx *ctx, uint64_t s_start, uint64_t own_len, int is_last, bz2b200_shard_info *info) {
-  Ctx *c = reinterpret_cast<Ctx *>(ctx);
-  if (!c || !info) return BZ2B200_E_ARG;
-  CK(cudaSetDevice(c->device));
+static int shard_cut_common(Ctx *c, i64 s_start, i64 g_start, uint64_t own_len, int is_last, bz2b200_shard_info *info, uint64_t *first_start) {
   if ((i64)own_len > c->pipe.N) own_len = (uint64_t)c->pipe.N;
-  int rc = pipe_cut(c, (i64)s_start, (i64)own_len);
+  int rc = pipe_cut(c, s_start, (i64)own_len, g_start);
   if (rc) return rc;
   *info = bz2b200_shard_info{};
   const auto &h = c->pipe.hrecs;
   info->n_blocks = (uint32_t)h.size();
-  info->next_start = h.empty() ? s_start : (uint64_t)h.back().p;
+  info->next_start = h.empty() ? (uint64_t)(s_start < 0 ? 0 : s_start) : (uint64_t)h.back().p;
   info->complete = 1;
   if (!is_last && !h.empty() && h.back().p == c->pipe.N && h.back().n < c->pipe.B) info->complete = 0;  // halo too short
+  if (first_start) *first_start = h.empty() ? ~0ull : (uint64_t)h.front().s;
   return BZ2B200_OK;
+}
+
+int bz2b200_shard_cut(bz2b200_ctx *ctx, uint64_t s_start, uint64_t own_len, int is_last, bz2b200_shard_info *info) {
+  Ctx *c = reinterpret_cast<Ctx *>(ctx);
+  if (!c || !info) return BZ2B200_E_ARG;
+  CK(cudaSetDevice(c->device));
+  return shard_cut_common(c, (i64)s_start, -1, own_len, is_last, info, nullptr);
+}
+
+int bz2b200_shard_gtotal(bz2b200_ctx *ctx, uint64_t pos, uint64_t *g) {
+  Ctx *c = reinterpret_cast<Ctx *>(ctx);
+  if (!c || !g) return BZ2B200_E_ARG;
+  CK(cudaSetDevice(c->device));
+  const i64 N = c->pipe.N;
+  *g = 0;
+  if (N == 0) return BZ2B200_OK;
+  ENS(c->nblk, 64);
+  LAUNCH(k_rle_gquery, 1, 32, 0, c->pipe.d_in, N, P<u32>(c->g_sub), P<i64>(c->h_sub), P<u64>(c->g_tile), c->pipe.T, (i64)(pos > (uint64_t)N ? (uint64_t)N : pos),
+         P<u64>(c->nblk) + 1);
+  u64 v = 0;
+  RC(rb_add(c, &v, P<u64>(c->nblk) + 1, 8));
+  RC(rb_sync(c));
+  *g = v;
+  return BZ2B200_OK;
+}
+
+int bz2b200_shard_cut_g(bz2b200_ctx *ctx, uint64_t g_before, uint64_t own_len, int is_last, bz2b200_shard_info *info, uint64_t *first_start) {
+  Ctx *c = reinterpret_cast<Ctx *>(ctx);
+  if (!c || !info || !first_start) return BZ2B200_E_ARG;
+  CK(cudaSetDevice(c->device));
+  if (c->pipe.N == 0) { *info = bz2b200_shard_info{}; info->complete = 1; *first_start = ~0ull; c->pipe.nb = 0; c->pipe.hrecs.clear(); return BZ2B200_OK; }
+  const u64 B = c->pipe.B, g_start = (B - g_before % B) % B;  // G still missing to the next multiple of B
+  return shard_cut_common(c, 0, (i64)g_start, own_len, is_last, info, first_start);
 }
 
 int bz2b200_shard_compress(bz2b200_ctx *ctx, bz2b200_shard_info *info) {

@@ -306,13 +306,24 @@ __device__ __forceinline__ void warp_cut_step(const u8 *__restrict__ in, i64 N, 
 __global__ void __launch_bounds__(CUT_THREADS) k_rle_cut(const u8 *__restrict__ in, i64 N, u32 B, const u32 *__restrict__ g_sub, const i64 *__restrict__ h_sub,
                                                          const i64 *__restrict__ tile_first, const u64 *__restrict__ g_tile, i64 T,
                                                          BlockRec *__restrict__ recs, int max_blocks, int *__restrict__ n_blocks, i64 s_start,
-                                                         i64 own_end) {
+                                                         i64 own_end, i64 g_start) {
   __shared__ BlockRec sh_rec[CUT_WARPS];
   __shared__ i64 sh_cand[CUT_WARPS];
   const i64 INF = (i64)0x7fffffffffffffffLL;
   const int lane = lane_id(), w = warp_id();
   const u64 Gtot = g_tile[T];
   i64 s = s_start;  // shards: the walk starts at a known cut point and owns the blocks that start before own_end
+  if (g_start >= 0) {  // speculative shard start: the first position whose G reaches g_start (every warp computes it)
+    s = 0;
+    if (g_start > 0) {
+      if ((u64)g_start > Gtot) s = N;
+      else {
+        const i64 tc = warp_search_tile(g_tile, 0, T - 1, (u64)g_start);
+        const i64 icut = warp_tile_walk(in, N, tc, g_sub, h_sub, g_tile[tc], -1, (u64)g_start);
+        s = icut == INF ? N : icut + 1;
+      }
+    }
+  }
   int k = 0;
   while (s < N && s < own_end && k < max_blocks) {
     // this warp's candidate start
@@ -348,6 +359,17 @@ __global__ void __launch_bounds__(CUT_THREADS) k_rle_cut(const u8 *__restrict__ 
     __syncthreads();
   }
   if (threadIdx.x == 0) *n_blocks = (s < N && s < own_end) ? -1 : k;  // -1: max_blocks too small (cannot happen with the host's bound)
+}
+
+// G(pos): bytes emitted before input position pos (global-fresh coordinates of this buffer); one warp
+__global__ void __launch_bounds__(32) k_rle_gquery(const u8 *__restrict__ in, i64 N, const u32 *__restrict__ g_sub, const i64 *__restrict__ h_sub,
+                                                   const u64 *__restrict__ g_tile, i64 T, i64 pos, u64 *__restrict__ out) {
+  u64 g = g_tile[T];
+  if (pos < N) {
+    const i64 t = pos / RLE_TILE;
+    g = g_tile[t] + (u64)warp_tile_walk(in, N, t, g_sub, h_sub, 0, pos, 0);
+  }
+  if (threadIdx.x == 0) *out = g;
 }
 
 __global__ void __launch_bounds__(RLE_THREADS) k_rle_emit(const u8 *__restrict__ in, i64 N, u32 B, const i64 *__restrict__ head_carry,

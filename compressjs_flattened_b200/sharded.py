@@ -20,7 +20,7 @@ class HostMailbox:
     """Scalars between the ranks of ONE node through a page of shared memory (/dev/shm): a slot per rank holding
     (sequence number, value) pairs; a reader spins on the sequence number.  A few microseconds per hop, against
     a millisecond for a TCP-backed process group -- the chain of first-block offsets is N-1 hops long."""
-    FIELDS = 4  # (chain, bits) x 2 alternating slots
+    FIELDS = 6  # (chain, bits, G) x 2 alternating slots
 
     def __init__(self, rank, world, key):
         import numpy as np
@@ -79,18 +79,28 @@ def compress_shard(engine, buf, base, own_len, level, is_last, rank=None, world=
     dev = device or torch.device("cpu")
     engine.shard_begin(buf, level, device_ptr=device_ptr, nbytes=nbytes)   # summaries: no dependency on other ranks
     if mailbox is not None:
+        # All ranks cut AT ONCE from a speculated start (blocks begin where G reaches a multiple of B when no cut falls
+        # inside a run); the chain of true first-block offsets then only has to be compared, one scalar hop per rank.
         mailbox.next_round()
-        start_v = mailbox.get(rank - 1, 0) if rank > 0 else 0                # (1) first-block offset, global coordinates
+        mailbox.put(2, engine.shard_gtotal(own_len))                        # (0) what this shard adds to G
+        g_before = sum(mailbox.get(r, 2) for r in range(rank))
+        info, first = engine.shard_cut_g(g_before, own_len, is_last)
+        start_v = mailbox.get(rank - 1, 0) if rank > 0 else 0               # (1) first-block offset, global coordinates
+        s_local = max(start_v - base, 0)
+        guess_ok = (first is not None and first == s_local and s_local < own_len) or (first is None and s_local >= own_len)
+        compress_shard.guesses[guess_ok] += 1
+        if not guess_ok:
+            info = engine.shard_cut(s_local, own_len, is_last)              # the guess was wrong: cut from the true start
     else:
         start = torch.zeros(1, dtype=torch.int64, device=dev)
         if rank > 0:
             dist.recv(start, src=rank - 1, group=group)
         start_v = int(start.item())
-    s_local = max(start_v - base, 0)
-    info = engine.shard_cut(s_local, own_len, is_last)
+        s_local = max(start_v - base, 0)
+        info = engine.shard_cut(s_local, own_len, is_last)
     if not info.complete:
         raise RuntimeError("halo too short: the last owned block needs input beyond the buffer")
-    nxt_v = max(base + int(info.next_start), start_v)
+    nxt_v = max(base + int(info.next_start), start_v) if info.n_blocks else start_v
     if mailbox is not None:
         mailbox.put(0, nxt_v)
     elif rank + 1 < world:
@@ -110,6 +120,9 @@ def compress_shard(engine, buf, base, own_len, level, is_last, rank=None, world=
         bit_off = 32 + sum(int(b.item()) for b in allbits[:rank])
     seg = engine.shard_emit(info, bit_off & 7, to_host=to_host)
     return seg, info, bit_off
+
+
+compress_shard.guesses = {True: 0, False: 0}   # speculative starts that held / had to be recut (this process)
 
 
 def gather_and_stitch(engine, seg, info, level, group=None):
