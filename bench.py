@@ -231,6 +231,8 @@ def main():
             stage[k] += st.ms_stage[k]
     barrier()
     t1 = time.time()
+    if world > 1:
+        print(f"[bench] rank {rank}: speculated shard starts held / recut = {compress_shard.guesses[True]} / {compress_shard.guesses[False]}", file=sys.stderr, flush=True)
     wall_ms = (t1 - t0) * 1e3
     clocks = sampler.stop(t0, t1) if rank == 0 else None
     st_last = eng.stats()

@@ -74,7 +74,8 @@ class Library:
         L.bz2b200_shard_cut.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(ShardInfo)]
         L.bz2b200_shard_compress.argtypes = [vp, C.POINTER(ShardInfo)]
         L.bz2b200_shard_gtotal.argtypes = [vp, C.c_uint64, C.POINTER(C.c_uint64)]
-        L.bz2b200_shard_cut_g.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(ShardInfo), C.POINTER(C.c_uint64)]
+        L.bz2b200_shard_cut_g.argtypes = [vp, C.c_uint64, C.c_uint64]
+        L.bz2b200_shard_cut_pick.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(ShardInfo), C.POINTER(C.c_int)]
         L.bz2b200_shard_emit.argtypes = [vp, C.c_int, C.POINTER(ShardInfo), u8pp, szp]
         L.bz2b200_stitch_shards.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_char_p), C.POINTER(ShardInfo), u8pp, szp]
         self.L = L

@@ -217,13 +217,19 @@ class Bzip2Engine:
             self._raise(rc)
         return g.value
 
-    def shard_cut_g(self, g_before, own_len, is_last):
-        """Speculative cut walk (g_before = G of the earlier shards); returns (info, first_start or None)."""
-        info, first = _native.ShardInfo(), C.c_uint64()
-        rc = self._L.bz2b200_shard_cut_g(self._ctx, g_before, own_len, int(is_last), C.byref(info), C.byref(first))
+    def shard_cut_g(self, g_before, own_len):
+        """Speculative cut walks (g_before = G of the earlier shards); shard_cut_pick chooses among them."""
+        rc = self._L.bz2b200_shard_cut_g(self._ctx, g_before, own_len)
         if rc:
             self._raise(rc)
-        return info, (None if first.value == 0xFFFFFFFFFFFFFFFF else first.value)
+
+    def shard_cut_pick(self, s_start, own_len, is_last):
+        """The speculated walk that started at s_start, or None (then call shard_cut)."""
+        info, found = _native.ShardInfo(), C.c_int()
+        rc = self._L.bz2b200_shard_cut_pick(self._ctx, s_start, own_len, int(is_last), C.byref(info), C.byref(found))
+        if rc:
+            self._raise(rc)
+        return info if found.value else None
 
     def shard_compress(self, info):
         rc = self._L.bz2b200_shard_compress(self._ctx, C.byref(info))

@@ -87,7 +87,7 @@ struct Ctx {
   DevBuf seg_cnt, seg_tile0, tile_blk, tile_i0, tile_i1, totals;
   DevBuf Lcol, ranks, lastocc, A, freq, meta, W, bit_off, scrc, out, out_len, used_bits;
   DevBuf key2, big_cnt, big_old, big_rank, big_tile0, big_tblk, totals2;
-  DevBuf out2, recs_all, blksort, r2_status, hfreq, hlens, hplen, hcodes, hsel, hcost, hgoff, hblk;
+  DevBuf recs_cand, cand_first, out2, recs_all, blksort, r2_status, hfreq, hlens, hplen, hcodes, hsel, hcost, hgoff, hblk;
   // decode-side buffers
   DevBuf d_in, cand, ncand, dmeta, dsyms, dL, dtt, dwalk, dblk, dout, dmisc, dsel, doff, dperm, dmap;
   // host staging (pinned)
@@ -111,6 +111,8 @@ struct Ctx {
   u32 cap_override = 0;    // tests only
   u32 batch_override = 0;  // tests only: blocks per batch
   u64 shard_bits = 0;      // bit length of the last shard segment (phase 0 in `out`)
+  int cand_n = 0, cand_max_blocks = 0, cand_nb[64];  // speculated cut walks of the last shard_cut_g
+  i64 cand_s[64];
   bool recs_batched = false;  // the last call ran in batches: the full block table is in recs_all
   int last_nb = 0;
   i64 last_bs = 0, last_as = 0;
@@ -124,7 +126,7 @@ struct Ctx {
                      &seg_cnt, &seg_tile0, &tile_blk, &tile_i0, &tile_i1, &totals,
                      &Lcol, &ranks, &lastocc, &A, &freq, &meta, &W, &bit_off, &scrc, &out, &out_len, &used_bits,
                      &key2, &big_cnt, &big_old, &big_rank, &big_tile0, &big_tblk, &totals2,
-                     &out2, &recs_all, &blksort, &r2_status, &hfreq, &hlens, &hplen, &hcodes, &hsel, &hcost, &hgoff, &hblk,
+                     &recs_cand, &cand_first, &out2, &recs_all, &blksort, &r2_status, &hfreq, &hlens, &hplen, &hcodes, &hsel, &hcost, &hgoff, &hblk,
                      &d_in, &cand, &ncand, &dmeta, &dsyms, &dL, &dtt, &dwalk, &dblk, &dout, &dmisc, &dsel, &doff, &dperm, &dmap};
     for (DevBuf *b : all) pool.push_back(b);
   }
@@ -276,18 +278,32 @@ int pipe_begin(Ctx *c, const u8 *d_in, size_t n_, int level) {
   return BZ2B200_OK;
 }
 
+#define CUT_CANDIDATES 64  // speculative shard starts tried at once (phases g_start - 32 .. g_start + 31)
 int pipe_cut(Ctx *c, i64 s_start, i64 own_end, i64 g_start = -1) {
   Ctx::Pipe &P_ = c->pipe;
   const i64 N = P_.N, T = P_.T;
   const u32 B = P_.B;
   const int max_blocks = (int)(N / ((i64)B * 4 / 5) + 2);
+  const int ncand = g_start >= 0 ? CUT_CANDIDATES : 1;
   ENS(c->recs, sizeof(BlockRec) * (size_t)max_blocks);
-  ENS(c->nblk, 64);
+  ENS(c->nblk, 64 + 4 * CUT_CANDIDATES);
   int nb = 0;
   P_.hrecs.clear();
-  if (N > 0 && (g_start >= 0 || (s_start < N && s_start < own_end))) {
+  c->cand_n = 0;
+  if (N > 0 && g_start >= 0) {
+    // all candidates walk at once; the tables stay on the device until pipe_pick installs the right one
+    ENS(c->recs_cand, sizeof(BlockRec) * (size_t)max_blocks * ncand);
+    LAUNCH(k_rle_cut, ncand, CUT_THREADS, 0, P_.d_in, N, B, P<u32>(c->g_sub), P<i64>(c->h_sub), P<i64>(c->tile_first), P<u64>(c->g_tile), T,
+           P<BlockRec>(c->recs_cand), max_blocks, P<int>(c->nblk) + 16, s_start, own_end, g_start);
+    LAUNCH(k_cand_firsts, 1, CUT_CANDIDATES, 0, P<BlockRec>(c->recs_cand), max_blocks, P<int>(c->nblk) + 16, P<i64>(c->cand_first));
+    RC(rb_add(c, c->cand_nb, P<int>(c->nblk) + 16, 4 * CUT_CANDIDATES));
+    RC(rb_add(c, c->cand_s, c->cand_first.p, 8 * CUT_CANDIDATES));
+    RC(rb_sync(c));
+    c->cand_n = ncand;
+    c->cand_max_blocks = max_blocks;
+  } else if (N > 0 && s_start < N && s_start < own_end) {
     LAUNCH(k_rle_cut, 1, CUT_THREADS, 0, P_.d_in, N, B, P<u32>(c->g_sub), P<i64>(c->h_sub), P<i64>(c->tile_first), P<u64>(c->g_tile), T,
-           P<BlockRec>(c->recs), max_blocks, P<int>(c->nblk), s_start, own_end, g_start);
+           P<BlockRec>(c->recs), max_blocks, P<int>(c->nblk), s_start, own_end, (i64)-1);
     RC(rb_add(c, &nb, c->nblk.p, sizeof(int)));
     RC(rb_sync(c));
     if (nb < 0) { c->err = "internal: block table overflow"; return BZ2B200_E_CUDA; }
@@ -297,6 +313,30 @@ int pipe_cut(Ctx *c, i64 s_start, i64 own_end, i64 g_start = -1) {
   P_.nb = nb;
   c->st.n_blocks = (u32)nb;
   return BZ2B200_OK;
+}
+// install the speculated block table whose walk started at s_local (or the empty one when no block starts before
+// own_end); false if no candidate matches
+bool pipe_pick(Ctx *c, i64 s_local, i64 own_end, int &rc) {
+  Ctx::Pipe &P_ = c->pipe;
+  rc = BZ2B200_OK;
+  if (!(s_local < P_.N && s_local < own_end)) {  // this shard owns no block whatever was speculated
+    P_.hrecs.clear();
+    P_.nb = 0;
+    c->st.n_blocks = 0;
+    return true;
+  }
+  for (int j = 0; j < c->cand_n; j++) {
+    const int nbj = c->cand_nb[j];
+    if (nbj <= 0 || c->cand_s[j] != s_local) continue;
+    P_.hrecs.resize((size_t)nbj);
+    const BlockRec *src = P<BlockRec>(c->recs_cand) + (size_t)j * c->cand_max_blocks;
+    if (cudaMemcpyAsync(c->recs.p, src, sizeof(BlockRec) * (size_t)nbj, cudaMemcpyDeviceToDevice, c->stream) != cudaSuccess ||
+        cudaMemcpy(P_.hrecs.data(), src, sizeof(BlockRec) * (size_t)nbj, cudaMemcpyDeviceToHost) != cudaSuccess) { rc = BZ2B200_E_CUDA; return false; }
+    P_.nb = nbj;
+    c->st.n_blocks = (u32)nbj;
+    return true;
+  }
+  return false;
 }
 
 int pipe_stages(Ctx *c) {
@@ -796,25 +836,24 @@ int bz2b200_shard_begin(bz2b200_ctx *ctx, const void *in, size_t n_avail, int on
   return pipe_begin(c, d_in, n_avail, level);
 }
 
-static int shard_cut_common(Ctx *c, i64 s_start, i64 g_start, uint64_t own_len, int is_last, bz2b200_shard_info *info, uint64_t *first_start) {
-  if ((i64)own_len > c->pipe.N) own_len = (uint64_t)c->pipe.N;
-  int rc = pipe_cut(c, s_start, (i64)own_len, g_start);
-  if (rc) return rc;
+static void shard_fill_info(Ctx *c, i64 s_start, int is_last, bz2b200_shard_info *info) {
   *info = bz2b200_shard_info{};
   const auto &h = c->pipe.hrecs;
   info->n_blocks = (uint32_t)h.size();
   info->next_start = h.empty() ? (uint64_t)(s_start < 0 ? 0 : s_start) : (uint64_t)h.back().p;
   info->complete = 1;
   if (!is_last && !h.empty() && h.back().p == c->pipe.N && h.back().n < c->pipe.B) info->complete = 0;  // halo too short
-  if (first_start) *first_start = h.empty() ? ~0ull : (uint64_t)h.front().s;
-  return BZ2B200_OK;
 }
 
 int bz2b200_shard_cut(bz2b200_ctx *ctx, uint64_t s_start, uint64_t own_len, int is_last, bz2b200_shard_info *info) {
   Ctx *c = reinterpret_cast<Ctx *>(ctx);
   if (!c || !info) return BZ2B200_E_ARG;
   CK(cudaSetDevice(c->device));
-  return shard_cut_common(c, (i64)s_start, -1, own_len, is_last, info, nullptr);
+  if ((i64)own_len > c->pipe.N) own_len = (uint64_t)c->pipe.N;
+  int rc = pipe_cut(c, (i64)s_start, (i64)own_len);
+  if (rc) return rc;
+  shard_fill_info(c, (i64)s_start, is_last, info);
+  return BZ2B200_OK;
 }
 
 int bz2b200_shard_gtotal(bz2b200_ctx *ctx, uint64_t pos, uint64_t *g) {
@@ -824,7 +863,7 @@ int bz2b200_shard_gtotal(bz2b200_ctx *ctx, uint64_t pos, uint64_t *g) {
   const i64 N = c->pipe.N;
   *g = 0;
   if (N == 0) return BZ2B200_OK;
-  ENS(c->nblk, 64);
+  ENS(c->nblk, 64 + 4 * CUT_CANDIDATES);
   LAUNCH(k_rle_gquery, 1, 32, 0, c->pipe.d_in, N, P<u32>(c->g_sub), P<i64>(c->h_sub), P<u64>(c->g_tile), c->pipe.T, (i64)(pos > (uint64_t)N ? (uint64_t)N : pos),
          P<u64>(c->nblk) + 1);
   u64 v = 0;
@@ -834,13 +873,28 @@ int bz2b200_shard_gtotal(bz2b200_ctx *ctx, uint64_t pos, uint64_t *g) {
   return BZ2B200_OK;
 }
 
-int bz2b200_shard_cut_g(bz2b200_ctx *ctx, uint64_t g_before, uint64_t own_len, int is_last, bz2b200_shard_info *info, uint64_t *first_start) {
+int bz2b200_shard_cut_g(bz2b200_ctx *ctx, uint64_t g_before, uint64_t own_len) {
   Ctx *c = reinterpret_cast<Ctx *>(ctx);
-  if (!c || !info || !first_start) return BZ2B200_E_ARG;
+  if (!c) return BZ2B200_E_ARG;
   CK(cudaSetDevice(c->device));
-  if (c->pipe.N == 0) { *info = bz2b200_shard_info{}; info->complete = 1; *first_start = ~0ull; c->pipe.nb = 0; c->pipe.hrecs.clear(); return BZ2B200_OK; }
+  c->cand_n = 0;
+  if (c->pipe.N == 0) return BZ2B200_OK;
+  if ((i64)own_len > c->pipe.N) own_len = (uint64_t)c->pipe.N;
   const u64 B = c->pipe.B, g_start = (B - g_before % B) % B;  // G still missing to the next multiple of B
-  return shard_cut_common(c, 0, (i64)g_start, own_len, is_last, info, first_start);
+  ENS(c->cand_first, 8 * CUT_CANDIDATES);
+  return pipe_cut(c, 0, (i64)own_len, (i64)g_start);
+}
+
+int bz2b200_shard_cut_pick(bz2b200_ctx *ctx, uint64_t s_start, uint64_t own_len, int is_last, bz2b200_shard_info *info, int *found) {
+  Ctx *c = reinterpret_cast<Ctx *>(ctx);
+  if (!c || !info || !found) return BZ2B200_E_ARG;
+  CK(cudaSetDevice(c->device));
+  if ((i64)own_len > c->pipe.N) own_len = (uint64_t)c->pipe.N;
+  int rc = BZ2B200_OK;
+  *found = pipe_pick(c, (i64)s_start, (i64)own_len, rc) ? 1 : 0;
+  if (rc) return rc;
+  if (*found) shard_fill_info(c, (i64)s_start, is_last, info);
+  return BZ2B200_OK;
 }
 
 int bz2b200_shard_compress(bz2b200_ctx *ctx, bz2b200_shard_info *info) {

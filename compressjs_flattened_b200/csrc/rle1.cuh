@@ -313,7 +313,17 @@ __global__ void __launch_bounds__(CUT_THREADS) k_rle_cut(const u8 *__restrict__ 
   const int lane = lane_id(), w = warp_id();
   const u64 Gtot = g_tile[T];
   i64 s = s_start;  // shards: the walk starts at a known cut point and owns the blocks that start before own_end
-  if (g_start >= 0) {  // speculative shard start: the first position whose G reaches g_start (every warp computes it)
+  if (g_start >= 0) {
+    // Speculative shard start: the first position whose G reaches g_start (every warp computes it).  With a grid of
+    // J CTAs, CTA j tries g_start + j - J/2 and fills its own block table: every cut inside a run upstream shifts the
+    // phase of all later block starts by a few units of G, and the caller picks the table whose start is the true one.
+    g_start += (i64)blockIdx.x - (i64)(gridDim.x / 2);
+    recs += (i64)blockIdx.x * max_blocks;
+    n_blocks += blockIdx.x;
+    if (g_start < 0) {  // not a candidate
+      if (threadIdx.x == 0) *n_blocks = -2;
+      return;
+    }
     s = 0;
     if (g_start > 0) {
       if ((u64)g_start > Gtot) s = N;
@@ -361,6 +371,11 @@ __global__ void __launch_bounds__(CUT_THREADS) k_rle_cut(const u8 *__restrict__ 
   if (threadIdx.x == 0) *n_blocks = (s < N && s < own_end) ? -1 : k;  // -1: max_blocks too small (cannot happen with the host's bound)
 }
 
+// first block start of every speculated cut walk (-1: the walk owns no block or was not a candidate)
+__global__ void k_cand_firsts(const BlockRec *__restrict__ recs, int max_blocks, const int *__restrict__ n_blocks, i64 *__restrict__ first) {
+  int j = threadIdx.x;
+  first[j] = n_blocks[j] > 0 ? recs[(i64)j * max_blocks].s : (i64)-1;
+}
 // G(pos): bytes emitted before input position pos (global-fresh coordinates of this buffer); one warp
 __global__ void __launch_bounds__(32) k_rle_gquery(const u8 *__restrict__ in, i64 N, const u32 *__restrict__ g_sub, const i64 *__restrict__ h_sub,
                                                    const u64 *__restrict__ g_tile, i64 T, i64 pos, u64 *__restrict__ out) {

@@ -79,18 +79,19 @@ def compress_shard(engine, buf, base, own_len, level, is_last, rank=None, world=
     dev = device or torch.device("cpu")
     engine.shard_begin(buf, level, device_ptr=device_ptr, nbytes=nbytes)   # summaries: no dependency on other ranks
     if mailbox is not None:
-        # All ranks cut AT ONCE from a speculated start (blocks begin where G reaches a multiple of B when no cut falls
-        # inside a run); the chain of true first-block offsets then only has to be compared, one scalar hop per rank.
+        # All ranks cut AT ONCE from speculated starts (blocks begin where G reaches a multiple of B, give or take a few
+        # units for every cut that fell inside a run upstream); the chain of true first-block offsets then only has to
+        # be compared, one scalar hop per rank.
         mailbox.next_round()
         mailbox.put(2, engine.shard_gtotal(own_len))                        # (0) what this shard adds to G
         g_before = sum(mailbox.get(r, 2) for r in range(rank))
-        info, first = engine.shard_cut_g(g_before, own_len, is_last)
+        engine.shard_cut_g(g_before, own_len)                               # 64 phases around the expected one, at once
         start_v = mailbox.get(rank - 1, 0) if rank > 0 else 0               # (1) first-block offset, global coordinates
         s_local = max(start_v - base, 0)
-        guess_ok = (first is not None and first == s_local and s_local < own_len) or (first is None and s_local >= own_len)
-        compress_shard.guesses[guess_ok] += 1
-        if not guess_ok:
-            info = engine.shard_cut(s_local, own_len, is_last)              # the guess was wrong: cut from the true start
+        info = engine.shard_cut_pick(s_local, own_len, is_last)
+        compress_shard.guesses[info is not None] += 1
+        if info is None:
+            info = engine.shard_cut(s_local, own_len, is_last)              # no speculated walk started there: cut now
     else:
         start = torch.zeros(1, dtype=torch.int64, device=dev)
         if rank > 0:

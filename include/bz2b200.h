@@ -102,13 +102,15 @@ typedef struct {
 int bz2b200_shard_begin(bz2b200_ctx *ctx, const void *in, size_t n_avail, int on_device, int level);
 int bz2b200_shard_cut(bz2b200_ctx *ctx, uint64_t s_start, uint64_t own_len, int is_last, bz2b200_shard_info *info);
 /* Speculative start, so that the shards need not cut one after the other: when no cut falls inside a run, blocks
- * start where the run-length-coded byte count G reaches a multiple of B.  shard_gtotal returns G(pos) of this buffer
- * (pos = own_len: what this shard adds to G); with g_before = sum over the earlier shards, shard_cut_g walks from the
- * first position whose G reaches ceil(g_before / B) * B - g_before and reports that position in *first_start
- * (~0 if the shard owns no block).  The caller must check it against the previous shard's next_start
- * and fall back to shard_cut when they differ. */
+ * start where the run-length-coded byte count G reaches a multiple of B, and every cut inside a run upstream shifts
+ * that phase by a few units.  shard_gtotal returns G(pos) of this buffer (pos = own_len: what this shard adds to G);
+ * with g_before = sum over the earlier shards, shard_cut_g runs 64 cut walks at once, from the first positions whose
+ * G reaches ceil(g_before / B) * B - g_before + d, d = -32..31.  Once the true offset of the shard's first block is
+ * known (the previous shard's next_start), shard_cut_pick installs the walk that started there (*found = 1, info
+ * filled) -- or reports *found = 0, and the caller falls back to shard_cut. */
 int bz2b200_shard_gtotal(bz2b200_ctx *ctx, uint64_t pos, uint64_t *g);
-int bz2b200_shard_cut_g(bz2b200_ctx *ctx, uint64_t g_before, uint64_t own_len, int is_last, bz2b200_shard_info *info, uint64_t *first_start);
+int bz2b200_shard_cut_g(bz2b200_ctx *ctx, uint64_t g_before, uint64_t own_len);
+int bz2b200_shard_cut_pick(bz2b200_ctx *ctx, uint64_t s_start, uint64_t own_len, int is_last, bz2b200_shard_info *info, int *found);
 int bz2b200_shard_compress(bz2b200_ctx *ctx, bz2b200_shard_info *info);
 int bz2b200_shard_emit(bz2b200_ctx *ctx, int bit_phase, bz2b200_shard_info *info, uint8_t **seg, size_t *seg_bytes);
 int bz2b200_stitch_shards(int level, int n_shards, const uint8_t *const *segs, const bz2b200_shard_info *infos, uint8_t **out, size_t *out_len);
