@@ -97,6 +97,12 @@ class ClockSampler:
         return out
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_rs_scatter<9> launch over 100 M keys (first pass of a bench step),
+# `ncu --set full`, profiles/r01_ncu_notes.md; the algorithmic figure for that launch is 1.6e9 bytes
+NCU_TRAFFIC_PER_LAUNCH = 1602111488
+NCU_TRAFFIC_NOTE = "ncu --set full, first scatter pass of a step (100 M keys, 1.6e9 algorithmic bytes): 850.6 MB read + 751.5 MB written"
+
+
 def peaks():
     try:
         p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -309,8 +315,8 @@ def main():
             "e2e": {"value": round(total_mb / (e2e_ms_max / 1e3), 2), "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": int(e2e_out),
                     "ms_per_step": round(e2e_ms_max / args.steps, 3), "api": "bz2b200_compress (N=1) / bz2b200_shard_begin..emit (N>1): pinned host input, page-locked host output from the library's result pool"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_rs_scatter (BWT radix-sort scatter pass)", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                         "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+            "roofline": {"bound": "hbm", "kernel": "k_rs_scatter<9>/<8> (BWT radix-sort scatter passes)", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                         "frac": round(achieved / peak, 4), "traffic": NCU_TRAFFIC_PER_LAUNCH, "traffic_note": NCU_TRAFFIC_NOTE, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(dom_bytes / max(dom_launches, 1)), "launches_per_step": dom_launches // args.steps,
                          "avg_launch_ms": round(dom_ms / max(dom_launches, 1), 4), "share_of_step": round(dom_ms / dev_ms, 3) if dev_ms else None,
                          "pipeline_algorithmic_GBps": round((1 + 12 * st_last.rle1_bytes / nbytes + 22 * st_last.mtf_syms / nbytes + 3 * out_len / nbytes)
