@@ -42,7 +42,7 @@ def workload_desc(level, mb, n_gpus):
     return {"workload": f"bzip2 level {level} ({level * 100} KB blocks) on {mb} MB synthetic enwik8-like text per GPU "
                         f"(compressjs_flattened_b200.corpus.gen_text, seed 8; BASELINE.json configs[1])",
             "level": level, "bytes_per_gpu": mb * 1_000_000, "parallelism": f"block-range shards x{n_gpus} of one {mb * n_gpus} MB stream; cross-rank: first-block offset chain + bit-length exscan (scalars), no data-path collective",
-            "l2": "two distinct 100 MB input buffers alternate between steps (200 MB > 126 MB L2); sort state is 4.4 GB"}
+            "l2": "two distinct 100 MB input buffers alternate between steps (200 MB > 126 MB L2); per-call device state is 5.3 GB"}
 
 
 class ClockSampler:
