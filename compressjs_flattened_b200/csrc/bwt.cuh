@@ -70,33 +70,23 @@ struct BlkSort {
 // grid (32, nb): used-byte bitmap of every block
 __global__ void __launch_bounds__(256) k_sym_used(const u8 *__restrict__ blk, i64 blk_stride, const BlockRec *__restrict__ recs,
                                                   BlkSort *__restrict__ bs) {
-  __shared__ u32 bm[8];
+  __shared__ u8 flag[256];  // flag[c] = 1: plain stores, every writer writes the same value
   const u32 p = blockIdx.y, n = recs[p].n;
   const u8 *T = blk + (i64)p * blk_stride;
-  if (threadIdx.x < 8) bm[threadIdx.x] = 0;
+  flag[threadIdx.x] = 0;
   __syncthreads();
-  u32 loc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  const u32 nw = (n + 3) / 4;  // padded stride: whole words; bytes past n are masked
-  for (u32 x = blockIdx.x * 256 + threadIdx.x; x < nw; x += gridDim.x * 256) {
-    u32 wv = reinterpret_cast<const u32 *>(T)[x];
+  const u32 nv = n / 16;  // whole 16-byte vectors, then the tail byte by byte
+  for (u32 x = blockIdx.x * 256 + threadIdx.x; x < nv; x += gridDim.x * 256) {
+    uint4 v4 = reinterpret_cast<const uint4 *>(T)[x];
+    u32 wv4[4] = {v4.x, v4.y, v4.z, v4.w};
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-      u32 c = (wv >> (8 * k)) & 0xffu;
-      if (4 * x + k < n) {
-#pragma unroll
-        for (int q = 0; q < 8; q++) if ((c >> 5) == (u32)q) loc[q] |= 1u << (c & 31);
-      }
-    }
+    for (int k = 0; k < 16; k++) flag[(wv4[k >> 2] >> (8 * (k & 3))) & 0xffu] = 1;
   }
-#pragma unroll
-  for (int q = 0; q < 8; q++) {
-    u32 v = loc[q];
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) v |= __shfl_xor_sync(FULL_MASK, v, d);
-    if (lane_id() == 0 && v) atomicOr(&bm[q], v);
-  }
+  if (blockIdx.x == 0)
+    for (u32 i = nv * 16 + threadIdx.x; i < n; i += 256) flag[T[i]] = 1;
   __syncthreads();
-  if (threadIdx.x < 8 && bm[threadIdx.x]) atomicOr(&bs[p].used[threadIdx.x], bm[threadIdx.x]);
+  u32 b = __ballot_sync(FULL_MASK, flag[threadIdx.x] != 0);  // warp w covers bytes 32w .. 32w+31
+  if (lane_id() == 0 && b) atomicOr(&bs[p].used[warp_id()], b);
 }
 // nb CTAs of 256 threads: dense codes, b and L
 __global__ void __launch_bounds__(256) k_sym_tab(BlkSort *__restrict__ bs) {
