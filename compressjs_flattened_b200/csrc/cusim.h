@@ -216,6 +216,15 @@ template <typename T> static inline unsigned __match_any_sync(unsigned mask, T v
   (void)mask; uint64_t o[32], x = 0; memcpy(&x, &v, sizeof(T)); cusim::exchange(x, o); unsigned r = 0;
   for (unsigned l = 0; l < cusim::lanes_in_warp(); l++) if (o[l] == x) r |= 1u << l; return r;
 }
+static inline unsigned __reduce_or_sync(unsigned mask, unsigned v) {
+  (void)mask; uint64_t o[32]; cusim::exchange(v, o); unsigned r = 0;
+  for (unsigned l = 0; l < cusim::lanes_in_warp(); l++) r |= (unsigned)o[l]; return r;
+}
+// position of the offset-th (1-based) set bit of mask at or above bit base; 0xffffffff if there is none (offset > 0 only)
+static inline unsigned __fns(unsigned mask, unsigned base, int offset) {
+  for (unsigned b = base; b < 32; b++) if ((mask >> b) & 1u) { if (--offset == 0) return b; }
+  return 0xffffffffu;
+}
 static inline unsigned __activemask() { unsigned n = cusim::lanes_in_warp(); return n == 32 ? 0xffffffffu : ((1u << n) - 1); }
 
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }

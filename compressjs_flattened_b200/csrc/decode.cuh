@@ -294,30 +294,57 @@ __global__ void __launch_bounds__(32) k_huff_parse(const u8 *__restrict__ in, u6
       }
       const u32 bp = P + (u32)lane;
       const u32 win = __funnelshift_l(ring32[(bp >> 5) + 1], ring32[bp >> 5], bp & 31u);  // 32 bits from bit P+lane
-      const u32 e = sm.lut[gi][win >> (32 - DEC_LUT_BITS)];  // (symbol << 5) | length, 0 = longer than the LUT
-      u32 p = 0, cnt = 0, mysym = 0;
-      while (p < 32 && cnt < left) {
-        u32 ee = __shfl_sync(FULL_MASK, e, (int)p);
-        if (ee == 0) {  // long code: the reference's limit/base/permute walk (BJ:1605-1616) on that lane's window
-          u32 wn = __shfl_sync(FULL_MASK, win, (int)p);
-          int L = sm.minl[gi];
-          int j = (int)(wn >> (32 - L));
-          for (;; L++) {
-            if (L > sm.maxl[gi]) { err = BZ2B200_E_DATA_ERROR; break; }
-            if (j <= sm.limit[gi][L]) break;
-            j = (j << 1) | (int)((wn >> (31 - L)) & 1u);
-          }
-          if (err) break;
-          j -= sm.base[gi][L];
-          if (j < 0 || j >= BZ_MAX_SYMS) { err = BZ2B200_E_DATA_ERROR; break; }
-          ee = ((u32)sm.permute[gi][j] << 5) | (u32)L;
+      u32 e = sm.lut[gi][win >> (32 - DEC_LUT_BITS)];  // (symbol << 5) | length, 0 = longer than the LUT
+      bool bad = false;
+      if (e == 0) {  // long code: the reference's limit/base/permute walk (BJ:1605-1616) on this lane's window
+        int L = sm.minl[gi];
+        int j = (int)(win >> (32 - L));
+        for (;; L++) {
+          if (L > sm.maxl[gi]) { bad = true; break; }
+          if (j <= sm.limit[gi][L]) break;
+          j = (j << 1) | (int)((win >> (31 - L)) & 1u);
         }
-        if (lane == (int)cnt) mysym = ee >> 5;
-        cnt++;
-        p += ee & 31u;
-        if ((ee >> 5) == eob) { done = 1; break; }
+        if (!bad) {
+          j -= sm.base[gi][L];
+          if (j < 0 || j >= BZ_MAX_SYMS) bad = true; else e = ((u32)sm.permute[gi][j] << 5) | (u32)L;
+        }
+        if (bad) e = 1;  // keeps the chain moving; an error only counts if this lane is ON the chain
       }
-      if (lane < (int)cnt) sm.stage[staged + lane] = (u16)mysym;
+      // the codes that really start in this window are the chain 0 -> 0+len[0] -> ...: found by pointer doubling
+      // (5 shuffles + 5 warp ORs) instead of one dependent shuffle per symbol
+      u32 jmp[5];
+      jmp[0] = (u32)lane + (e & 31u);
+#pragma unroll
+      for (int q = 1; q < 5; q++) {
+        u32 t = __shfl_sync(FULL_MASK, jmp[q - 1], (int)(jmp[q - 1] & 31u));
+        jmp[q] = jmp[q - 1] < 32 ? t : 64u;
+      }
+      u32 R = 1u;
+#pragma unroll
+      for (int q = 4; q >= 0; q--) {
+        u32 contrib = (((R >> lane) & 1u) && jmp[q] < 32) ? (1u << jmp[q]) : 0u;
+        R |= __reduce_or_sync(FULL_MASK, contrib);
+      }
+      const u32 sym = e >> 5;
+      const u32 eobm = __ballot_sync(FULL_MASK, sym == eob) & R;
+      u32 p, cnt;
+      bool fin = false;
+      if (eobm) {
+        const u32 f = (u32)__ffs((int)eobm) - 1, R1 = R & (f == 31 ? 0xffffffffu : ((2u << f) - 1));
+        if ((u32)__popc(R1) <= left) { R = R1; fin = true; }
+      }
+      cnt = (u32)__popc(R);
+      if (cnt > left) {  // the group ends inside the window: stop before its (left+1)-th code
+        const u32 nx = __fns(R, 0, (int)left + 1);
+        R &= (1u << nx) - 1;
+        cnt = left;
+        p = nx;
+      } else {
+        p = __shfl_sync(FULL_MASK, jmp[0], 31 - __clz((int)R));  // the bit after the last code taken
+      }
+      if (__ballot_sync(FULL_MASK, bad) & R) { err = BZ2B200_E_DATA_ERROR; break; }
+      if ((R >> lane) & 1u) sm.stage[staged + __popc(R & ((1u << lane) - 1))] = (u16)sym;
+      if (fin) done = 1;
       staged += cnt;
       left -= cnt;
       P += p;
