@@ -95,11 +95,15 @@ __device__ __forceinline__ u32 br_peek(BitRd &r, u32 nb) {
 }
 __device__ __forceinline__ u64 br_tell(const BitRd &r) { return r.pos * 8 - r.avail; }
 
-#define DEC_RING 1024       // bytes of compressed input staged in shared memory per pass
+#define DEC_RING 4096       // bytes of compressed input staged in shared memory per pass
+// threads of k_huff_parse = bit offsets looked at per step: 512 when few blocks are in flight (one step usually covers a
+// group), 128 when there are more blocks than the GPU holds CTAs of 512
+#define DEC_LEVELS 6        // pointer-doubling levels: 2^6 > 50 codes of a group
 #define DEC_SYM_STAGE 1024  // symbols staged per pass
 #define DEC_SYM_STRIDE 900096  // u16 symbols per candidate (dbuf + end-of-block + slack)
 #define IMTF_SEG 4096       // symbols per inverse-MTF segment
 
+template <int PT>
 struct DecSmem {
   int limit[BZ_MAX_GROUPS][BZ_MAX_CODE + 2];
   int base[BZ_MAX_GROUPS][BZ_MAX_CODE + 2];
@@ -113,18 +117,26 @@ struct DecSmem {
   u16 stage[DEC_SYM_STAGE];
   int hdr[8];  // err, ng, nsel, sym_total, staged, finished
   u64 bitpos_after_header;
+  u16 J[DEC_LEVELS][PT];  // J[k][b]: bit offset reached from offset b after 2^k codes (>= DEC_PT: outside the step)
+  u16 SY[PT];             // symbol decoded at offset b | 0x8000 if the code there is invalid
+  u8 F[PT];               // offset b starts a code of the chain from offset 0
+  u8 selbuf[256];             // selectors of the pass
+  u32 ws[34];
+  u32 first_eob, first_bad, adv;
 };
 
-// ---- K-U2/3a: header + Huffman parse (bits -> symbols).  One warp per candidate block. -------------
-// Only this part of the decoder is inherently serial (the coding table changes every 50 SYMBOLS, so the
-// position of a group in the bit stream is unknown until everything before it is parsed).  Lane 0 parses;
-// the whole warp prefetches the compressed bytes into a shared-memory ring and flushes the symbols.
-__global__ void __launch_bounds__(32) k_huff_parse(const u8 *__restrict__ in, u64 n, const u64 *__restrict__ cand, u32 ncand, u32 dbuf_cap, int verify,
+// ---- K-U2/3a: header + Huffman parse (bits -> symbols).  One CTA of DEC_PT threads per candidate block. -------
+// Only this part of the decoder is serial across GROUPS (the coding table changes every 50 symbols, so the position
+// of a group in the bit stream is unknown until everything before it is parsed); inside a group it is parallel:
+// thread b decodes the code that WOULD start at bit P+b, pointer doubling over those "next code" links finds the
+// codes that really start there (the chain from offset 0), a scan ranks them, the first `left` are the group.
+template <int PT>
+__global__ void __launch_bounds__(PT) k_huff_parse(const u8 *__restrict__ in, u64 n, const u64 *__restrict__ cand, u32 ncand, u32 dbuf_cap, int verify,
                                                    DecBlk *__restrict__ out, u16 *__restrict__ dsym, u8 *__restrict__ dsel, u8 *__restrict__ dmap) {
-  __shared__ DecSmem sm;
+  __shared__ DecSmem<PT> sm;
   const u32 k = blockIdx.x;
   if (k >= ncand) return;
-  const int lane = threadIdx.x;
+  const int lane = threadIdx.x;  // thread index in the CTA (the header code below predates the CTA-wide parse)
   const u64 bitpos = cand[k] >> 1;
   u32 kind = (u32)(cand[k] & 1);
   if (verify) {  // candidate given by the caller (decompressBlock): read the 48-bit signature here (BJ:1434-1439)
@@ -199,7 +211,7 @@ __global__ void __launch_bounds__(32) k_huff_parse(const u8 *__restrict__ in, u6
     sm.hdr[0] = err; sm.hdr[1] = ng; sm.hdr[2] = nsel; sm.hdr[3] = sym_total;
     sm.bitpos_after_header = br_tell(r);
   }
-  __syncwarp();
+  __syncthreads();
   const int err0 = sm.hdr[0], ng = sm.hdr[1], nsel = sm.hdr[2], sym_total = sm.hdr[3];
   const int S = sym_total + 2;
   if (kind != 0 || err0) {
@@ -210,7 +222,7 @@ __global__ void __launch_bounds__(32) k_huff_parse(const u8 *__restrict__ in, u6
     }
     return;
   }
-  for (int i = lane; i < 256; i += 32) dmap[(u64)k * 256 + i] = i < sym_total ? sm.sym2byte[i] : (u8)i;
+  for (int i = lane; i < 256; i += PT) dmap[(u64)k * 256 + i] = i < sym_total ? sm.sym2byte[i] : (u8)i;
   // ---- limit / base / permute per table (BJ:1521-1581), one lane per table ----
   if (lane < ng) {
     const int t = lane;
@@ -240,9 +252,9 @@ __global__ void __launch_bounds__(32) k_huff_parse(const u8 *__restrict__ in, u6
     sm.minl[t] = minl;
     sm.maxl[t] = maxl;
   }
-  __syncwarp();
+  __syncthreads();
   // ---- LUT: replay the reference's decode walk on every 10-bit prefix ----
-  for (int x = lane; x < ng * (1 << DEC_LUT_BITS); x += 32) {
+  for (int x = lane; x < ng * (1 << DEC_LUT_BITS); x += PT) {
     int t = x >> DEC_LUT_BITS, prefix = x & ((1 << DEC_LUT_BITS) - 1);
     u16 e = 0;
     for (int L = sm.minl[t]; L <= DEC_LUT_BITS && L <= sm.maxl[t]; L++) {
@@ -255,14 +267,12 @@ __global__ void __launch_bounds__(32) k_huff_parse(const u8 *__restrict__ in, u6
     }
     sm.lut[t][prefix] = e;
   }
-  __syncwarp();
+  __syncthreads();
   // ---- symbols (BJ:1597-1616): parse passes ----
-  // The warp stages DEC_RING bytes of the stream (byte-swapped words) per pass.  Inside a pass, all lanes run in
-  // lock step: lane l looks up the code that would start at bit P+l (same table: a group is 50 symbols), then the
-  // warp hops through the 32-bit window -- one shuffle per symbol -- and stores the window's symbols with one
-  // coalesced write.  A window never crosses a 50-symbol group (the table changes there).
+  // A pass stages DEC_RING bytes of the stream (byte-swapped words) and the selectors it can need.  A step looks at the
+  // PT bit offsets from P: thread b decodes the code that would start at P+b with the group's table.
   const u32 eob = (u32)sym_total + 1;
-  u64 cur_bit = sm.bitpos_after_header;  // absolute bit position (uniform across the warp)
+  u64 cur_bit = sm.bitpos_after_header;  // absolute bit position (uniform across the CTA)
   u32 flushed = 0;
   int err = 0, done = 0, selector = 0;
   u32 left = 0;  // symbols left in the current group
@@ -271,7 +281,7 @@ __global__ void __launch_bounds__(32) k_huff_parse(const u8 *__restrict__ in, u6
   const u32 RBITS = DEC_RING * 8;
   for (;;) {
     const u64 ring_base_w = (cur_bit >> 5) & ~(u64)3;  // 16-byte aligned word index
-    for (u32 q = lane; q < DEC_RING / 16; q += 32) {
+    for (u32 q = lane; q < DEC_RING / 16; q += PT) {
       u64 src = (ring_base_w + (u64)q * 4) * 4;
       u32 w[4] = {0, 0, 0, 0};
       if (src + 16 <= n) {
@@ -282,21 +292,24 @@ __global__ void __launch_bounds__(32) k_huff_parse(const u8 *__restrict__ in, u6
       }
       for (int z = 0; z < 4; z++) ring32[q * 4 + z] = __byte_perm(w[z], 0, 0x0123);
     }
-    __syncwarp();
+    const int sel0 = selector;  // selectors sel0 .. sel0+255 are staged (a pass of 32768 bits holds fewer groups than that)
+    for (int q = lane; q < 256; q += PT) sm.selbuf[q] = sel0 + q < nsel ? sel[sel0 + q] : 0;
+    __syncthreads();
     u32 P = (u32)(cur_bit - ring_base_w * 32);  // bit offset inside the ring
     u32 staged = 0;
-    while (!done && !err && staged + 32 <= DEC_SYM_STAGE && P + 96 <= RBITS) {
+    while (!done && !err && staged + BZ_GROUP <= DEC_SYM_STAGE && P + PT + 64 <= RBITS && selector - sel0 < 255) {
       if (left == 0) {
         if (selector >= nsel) { err = BZ2B200_E_DATA_ERROR; break; }  // BJ:1601
         if (flushed + staged + BZ_GROUP >= DEC_SYM_STRIDE) { err = BZ2B200_E_DATA_ERROR; break; }  // more symbols than any valid block
-        gi = sel[selector++];
+        gi = sm.selbuf[selector - sel0];
+        selector++;
         left = BZ_GROUP;
       }
       const u32 bp = P + (u32)lane;
       const u32 win = __funnelshift_l(ring32[(bp >> 5) + 1], ring32[bp >> 5], bp & 31u);  // 32 bits from bit P+lane
       u32 e = sm.lut[gi][win >> (32 - DEC_LUT_BITS)];  // (symbol << 5) | length, 0 = longer than the LUT
       bool bad = false;
-      if (e == 0) {  // long code: the reference's limit/base/permute walk (BJ:1605-1616) on this lane's window
+      if (e == 0) {  // long code: the reference's limit/base/permute walk (BJ:1605-1616) on this thread's window
         int L = sm.minl[gi];
         int j = (int)(win >> (32 - L));
         for (;; L++) {
@@ -308,53 +321,55 @@ __global__ void __launch_bounds__(32) k_huff_parse(const u8 *__restrict__ in, u6
           j -= sm.base[gi][L];
           if (j < 0 || j >= BZ_MAX_SYMS) bad = true; else e = ((u32)sm.permute[gi][j] << 5) | (u32)L;
         }
-        if (bad) e = 1;  // keeps the chain moving; an error only counts if this lane is ON the chain
+        if (bad) e = 1;  // keeps the chain moving; an invalid code only counts if it is ON the chain
       }
-      // the codes that really start in this window are the chain 0 -> 0+len[0] -> ...: found by pointer doubling
-      // (5 shuffles + 5 warp ORs) instead of one dependent shuffle per symbol
-      u32 jmp[5];
-      jmp[0] = (u32)lane + (e & 31u);
+      const u32 sym = e >> 5, nxt = (u32)lane + (e & 31u);
+      sm.J[0][lane] = (u16)nxt;
+      sm.SY[lane] = (u16)(sym | (bad ? 0x8000u : 0u));
+      sm.F[lane] = lane == 0;
+      if (lane == 0) { sm.first_eob = 0xffffffffu; sm.first_bad = 0xffffffffu; sm.adv = 0; }
+      __syncthreads();
 #pragma unroll
-      for (int q = 1; q < 5; q++) {
-        u32 t = __shfl_sync(FULL_MASK, jmp[q - 1], (int)(jmp[q - 1] & 31u));
-        jmp[q] = jmp[q - 1] < 32 ? t : 64u;
+      for (int q = 1; q < DEC_LEVELS; q++) {  // J[q] = J[q-1] o J[q-1]
+        u32 v = sm.J[q - 1][lane];
+        sm.J[q][lane] = v < PT ? sm.J[q - 1][v] : (u16)0xffff;
+        __syncthreads();
       }
-      u32 R = 1u;
 #pragma unroll
-      for (int q = 4; q >= 0; q--) {
-        u32 contrib = (((R >> lane) & 1u) && jmp[q] < 32) ? (1u << jmp[q]) : 0u;
-        R |= __reduce_or_sync(FULL_MASK, contrib);
+      for (int q = DEC_LEVELS - 1; q >= 0; q--) {  // chain members: every count of codes is a sum of powers of two
+        if (sm.F[lane]) {
+          u32 v = sm.J[q][lane];
+          if (v < PT) sm.F[v] = 1;  // a thread flagged during this sweep may propagate too: still on the chain
+        }
+        __syncthreads();
       }
-      const u32 sym = e >> 5;
-      const u32 eobm = __ballot_sync(FULL_MASK, sym == eob) & R;
-      u32 p, cnt;
+      const u32 mine = sm.F[lane];
+      u32 total;
+      const u32 rank = block_excl_sum<u32>(mine, total, sm.ws);  // position of my code among the codes of the step
+      if (mine && sym == eob) atomicMin(&sm.first_eob, rank);
+      if (mine && bad) atomicMin(&sm.first_bad, rank);
+      __syncthreads();
+      u32 take = left < total ? left : total;
       bool fin = false;
-      if (eobm) {
-        const u32 f = (u32)__ffs((int)eobm) - 1, R1 = R & (f == 31 ? 0xffffffffu : ((2u << f) - 1));
-        if ((u32)__popc(R1) <= left) { R = R1; fin = true; }
+      if (sm.first_eob < take) { take = sm.first_eob + 1; fin = true; }
+      if (sm.first_bad < take) { err = BZ2B200_E_DATA_ERROR; break; }
+      if (mine && rank < take) {
+        sm.stage[staged + rank] = (u16)sym;
+        if (rank == take - 1) sm.adv = nxt;  // the bit after the last code taken (= where the next code starts)
       }
-      cnt = (u32)__popc(R);
-      if (cnt > left) {  // the group ends inside the window: stop before its (left+1)-th code
-        const u32 nx = __fns(R, 0, (int)left + 1);
-        R &= (1u << nx) - 1;
-        cnt = left;
-        p = nx;
-      } else {
-        p = __shfl_sync(FULL_MASK, jmp[0], 31 - __clz((int)R));  // the bit after the last code taken
-      }
-      if (__ballot_sync(FULL_MASK, bad) & R) { err = BZ2B200_E_DATA_ERROR; break; }
-      if ((R >> lane) & 1u) sm.stage[staged + __popc(R & ((1u << lane) - 1))] = (u16)sym;
+      __syncthreads();
+      staged += take;
+      left -= take;
+      P += sm.adv;
       if (fin) done = 1;
-      staged += cnt;
-      left -= cnt;
-      P += p;
+      __syncthreads();  // adv / first_* are rewritten at the top of the next step
     }
     cur_bit = ring_base_w * 32 + P;
     if (!err && cur_bit > n * 8) err = BZ2B200_E_UNEXPECTED_INPUT_EOF;  // reference: spins on zero bits (D3)
-    __syncwarp();
-    for (u32 q = lane; q < staged; q += 32) Sk[flushed + q] = sm.stage[q];
+    __syncthreads();
+    for (u32 q = lane; q < staged; q += PT) Sk[flushed + q] = sm.stage[q];
     flushed += staged;
-    __syncwarp();
+    __syncthreads();
     if (err || done) break;
   }
   if (lane == 0) {

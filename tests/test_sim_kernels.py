@@ -145,6 +145,18 @@ def test_decode_fixtures_and_random_access(sim_engine):
     assert sim_engine.decompressBlock(s2, 544888) == fixture_bytes("sample2.544888")
 
 
+def test_decode_many_blocks_narrow_parse(sim_engine, oracle):
+    """More than 300 blocks in flight: the parse kernel runs with 128 threads per block (several steps per group)."""
+    rng = np.random.default_rng(4)
+    data = bytes(rng.integers(97, 123, 60_000, dtype=np.uint8)) + fixture_bytes("sample1.ref")[:30_000]
+    try:
+        oracle.set_block_cap(250)
+        comp = oracle.compress(data, 9)
+    finally:
+        oracle.set_block_cap(0)
+    assert sim_engine.decompressFile(comp) == data
+
+
 def test_decode_periodic_and_runs(sim_engine, oracle):
     rng = np.random.default_rng(2)
     cases = [b"abab" * 10, b"aaaab" * 50, bytes(5000), b"abc" * 700,
