@@ -23,8 +23,10 @@
 #include "rle1.cuh"
 
 #define SORT_TILE 4096
+#ifndef SORT_THREADS
 #define SORT_THREADS 512  // x 8 keys, warp-striped
 #define SORT_E 8
+#endif
 #define SEG_THREADS 256   // x 16 slots, blocked
 #define SEG_E 16
 #define KEEP_BIT 0x80000000u

@@ -259,6 +259,7 @@ static int decode_device(Ctx *c, const u8 *d_in, size_t n, int multistream, int 
     for (int i = 0; i < 5; i++) CK(cudaEventElapsedTime(&c->st.ms_stage[i], c->ev[i], c->ev[i + 1]));
     CK(cudaEventElapsedTime(&c->st.ms_total, c->ev[0], c->ev[5]));
   }
+  trace_report(c);
   return BZ2B200_OK;
 }
 
