@@ -72,8 +72,7 @@ struct RfSmem {
   u32 SC[RF_CAP];   // the same words, every group sorted
   u32 I[RF_CAP];    // gidx
   u32 RK[RF_CAP];   // rank
-  u16 gs[RF_CAP];   // first slot of the slot's group
-  u16 ge[RF_CAP];   // at a group's first slot: one past its last slot
+  u16 gx[RF_CAP];   // at a group's first slot t: one past its last slot (> t); elsewhere: the group's first slot (< t)
   u32 wc[RF_WARPS][128];       // warp-private digit counters
   u16 med_a[RF_MAXMED + 1];    // first slot of every medium group (<= RF_COOP slots)
   u16 lrg_a[RF_CAP / RF_COOP + 1];  // first slot of every large group
@@ -274,13 +273,13 @@ __global__ void __launch_bounds__(RF_THREADS) k_sort_groups(const u32 *__restric
     for (int e = 0; e < RF_E; e++) {
       if (t0 + e < m) {
         if ((flags >> e) & 1u) {
-          if (t0 + e > 0) sm.ge[cur] = (u16)(t0 + e);  // closes the previous group
+          if (t0 + e > 0) sm.gx[cur] = (u16)(t0 + e);  // closes the previous group
           cur = (int)(t0 + e);
         }
-        sm.gs[t0 + e] = (u16)cur;
+        if (!((flags >> e) & 1u)) sm.gx[t0 + e] = (u16)cur;
       }
     }
-    if (threadIdx.x == 0) sm.ge[tot_h] = (u16)m;  // the last group ends with the tile
+    if (threadIdx.x == 0) sm.gx[tot_h] = (u16)m;  // the last group ends with the tile
   }
   __syncthreads();
   // ---- small groups: position = group start + number of slots that precede in (key2, slot) order ----
@@ -288,7 +287,7 @@ __global__ void __launch_bounds__(RF_THREADS) k_sort_groups(const u32 *__restric
   for (int e = 0; e < RF_E; e++) {
     u32 t = e * RF_THREADS + threadIdx.x;
     if (t < m) {
-      const u32 a = sm.gs[t], b = sm.ge[a];
+      const u32 gv = sm.gx[t], a = gv > t ? t : gv, b = gv > t ? gv : (u32)sm.gx[a];
       if (b - a <= RF_SMALL) {
         const u32 cj = sm.C[t];
         u32 before = 0;
@@ -306,7 +305,7 @@ __global__ void __launch_bounds__(RF_THREADS) k_sort_groups(const u32 *__restric
     const u32 n_lrg = sm.bc[3];
     for (u32 g = 0; g < n_lrg; g++) {
       const u32 a = sm.lrg_a[g];
-      cta_radix_group(sm, a, (u32)sm.ge[a] - a);
+      cta_radix_group(sm, a, (u32)sm.gx[a] - a);
     }
   }
   // ---- medium groups: one warp per group, handed out dynamically ----
@@ -318,7 +317,7 @@ __global__ void __launch_bounds__(RF_THREADS) k_sort_groups(const u32 *__restric
       g = __shfl_sync(FULL_MASK, g, 0);
       if (g >= n_med) break;
       const u32 a = sm.med_a[g];
-      warp_radix_group(sm, a, (u32)sm.ge[a] - a);
+      warp_radix_group(sm, a, (u32)sm.gx[a] - a);
     }
   }
   __syncthreads();
@@ -331,7 +330,7 @@ __global__ void __launch_bounds__(RF_THREADS) k_sort_groups(const u32 *__restric
 #pragma unroll
     for (int e = 0; e <= RF_E; e++) {
       sc[e + 1] = t0 + e < m ? sm.SC[t0 + e] : 0;
-      g[e] = t0 + e < m ? sm.gs[t0 + e] : (u16)0xffff;
+      g[e] = t0 + e < m ? (sm.gx[t0 + e] > t0 + e ? (u16)(t0 + e) : sm.gx[t0 + e]) : (u16)0xffff;
     }
     u32 flags = 0;
     int my_last = -1;
