@@ -71,7 +71,6 @@ struct RfSmem {
   u32 C[RF_CAP];    // (key2 << RF_SBITS) | slot
   u32 SC[RF_CAP];   // the same words, every group sorted
   u32 I[RF_CAP];    // gidx
-  u32 RK[RF_CAP];   // rank
   u16 gx[RF_CAP];   // at a group's first slot t: one past its last slot (> t); elsewhere: the group's first slot (< t)
   u32 wc[RF_WARPS][128];       // warp-private digit counters
   u16 med_a[RF_MAXMED + 1];    // first slot of every medium group (<= RF_COOP slots)
@@ -201,7 +200,7 @@ __device__ __forceinline__ void cta_radix_group(RfSmem &sm, u32 a, u32 s) {
   }
 }
 
-__global__ void __launch_bounds__(RF_THREADS) k_sort_groups(const u32 *__restrict__ key2, const u32 *__restrict__ a_idx, const u32 *__restrict__ a_rank,
+__global__ void __launch_bounds__(RF_THREADS, 6) k_sort_groups(const u32 *__restrict__ key2, const u32 *__restrict__ a_idx, const u32 *__restrict__ a_rank,
                                                             u32 n_act, u32 *__restrict__ isa, u32 stride, u64 magic, u32 *__restrict__ s_idx,
                                                             u32 *__restrict__ s_rank, u32 *__restrict__ big_cnt, u32 *__restrict__ big_base,
                                                             u32 *__restrict__ big_rank, u32 *__restrict__ n_big, u32 big_cap,
@@ -213,12 +212,12 @@ __global__ void __launch_bounds__(RF_THREADS) k_sort_groups(const u32 *__restric
   const u32 j0 = tile * RF_T0, j1 = j0 + RF_T0 < n_act ? j0 + RF_T0 : n_act;
   const u32 *R = a_rank;
   // the nominal slots [j0, j1) are fetched first so that their latency overlaps the search for the bounds
-  u32 pk[RF_T0 / RF_THREADS], pi[RF_T0 / RF_THREADS], pr[RF_T0 / RF_THREADS];
+  u32 pk[RF_T0 / RF_THREADS], pi[RF_T0 / RF_THREADS];
 #pragma unroll
   for (int e = 0; e < RF_T0 / RF_THREADS; e++) {
     u32 j = j0 + e * RF_THREADS + threadIdx.x;
-    pk[e] = pi[e] = pr[e] = 0;
-    if (j < j1) { pk[e] = key2[j]; pi[e] = a_idx[j]; pr[e] = R[j]; }
+    pk[e] = pi[e] = 0;
+    if (j < j1) { pk[e] = key2[j]; pi[e] = a_idx[j]; }
   }
   // ---- tile bounds [lo, hi): whole groups only ----
   if (w < 2) {
@@ -248,23 +247,23 @@ __global__ void __launch_bounds__(RF_THREADS) k_sort_groups(const u32 *__restric
 #pragma unroll
   for (int e = 0; e < RF_T0 / RF_THREADS; e++) {
     u32 j = j0 + e * RF_THREADS + threadIdx.x;
-    if (j >= lo && j < hi) { u32 t = j - lo; sm.C[t] = (pk[e] << RF_SBITS) | t; sm.I[t] = pi[e]; sm.RK[t] = pr[e]; }
+    if (j >= lo && j < hi) { u32 t = j - lo; sm.C[t] = (pk[e] << RF_SBITS) | t; sm.I[t] = pi[e]; }
   }
   if (lo < j0) {
     const u32 pre = j0 - lo < m ? j0 - lo : m;
-    for (u32 t = threadIdx.x; t < pre; t += RF_THREADS) { sm.C[t] = (key2[lo + t] << RF_SBITS) | t; sm.I[t] = a_idx[lo + t]; sm.RK[t] = R[lo + t]; }
+    for (u32 t = threadIdx.x; t < pre; t += RF_THREADS) { sm.C[t] = (key2[lo + t] << RF_SBITS) | t; sm.I[t] = a_idx[lo + t]; }
   }
   __syncthreads();
   // ---- group structure (blocked: thread owns slots t0 .. t0+RF_E-1) ----
   {
     const u32 t0 = threadIdx.x * RF_E;
     u32 rk[RF_E + 1];
-    rk[0] = (t0 > 0 && t0 < m) ? sm.RK[t0 - 1] : 0;
+    rk[0] = (t0 > 0 && t0 < m) ? R[lo + t0 - 1] : 0;  // ranks straight from the list (L1/L2: this tile just read them)
     u32 flags = 0;
     int my_last = -1;
 #pragma unroll
     for (int e = 0; e < RF_E; e++) {
-      rk[e + 1] = t0 + e < m ? sm.RK[t0 + e] : 0;
+      rk[e + 1] = t0 + e < m ? R[lo + t0 + e] : 0;
       if (t0 + e < m && (t0 + e == 0 || rk[e + 1] != rk[e])) { flags |= 1u << e; my_last = (int)(t0 + e); }
     }
     int tot_h;
@@ -349,7 +348,7 @@ __global__ void __launch_bounds__(RF_THREADS) k_sort_groups(const u32 *__restric
         if (head) cur = (int)d;
         const bool next_head = d + 1 >= m || g[e + 1] != g[e] || (sc[e + 2] >> RF_SBITS) != (sc[e + 1] >> RF_SBITS);
         const u32 gi = sm.I[sc[e + 1] & (RF_CAP - 1)];
-        const u32 off = (u32)cur - g[e], nr = sm.RK[g[e]] + off;
+        const u32 off = (u32)cur - g[e], nr = R[lo + g[e]] + off;
         const bool single = head && next_head;
         if (off || single) {
           const u32 p = blk_of(gi, magic), pb = p * stride;
