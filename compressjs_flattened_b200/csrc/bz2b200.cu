@@ -90,9 +90,6 @@ struct Ctx {
   DevBuf recs_cand, cand_first, out2, recs_all, blksort, r2_status, hfreq, hlens, hplen, hcodes, hsel, hcost, hgoff, hblk;
   // decode-side buffers
   DevBuf d_in, cand, ncand, dmeta, dsyms, dL, dtt, dwalk, dblk, dout, dmisc, dsel, doff, dperm, dmap;
-  // host staging (pinned)
-  void *h_pin = nullptr;
-  size_t h_pin_cap = 0;
   // last compress, for debug_fetch
   struct Pipe {
     const u8 *d_in = nullptr;
@@ -213,15 +210,6 @@ int ensure(Ctx *c, DevBuf &b, size_t bytes) {
   size_t want = bytes + bytes / 8 + 4096;
   CK(cudaMalloc(&b.p, want));
   b.cap = want;
-  return 0;
-}
-int ensure_pinned(Ctx *c, size_t bytes) {
-  if (bytes <= c->h_pin_cap) return 0;
-  if (c->h_pin) CK(cudaFreeHost(c->h_pin));
-  c->h_pin = nullptr;
-  c->h_pin_cap = 0;
-  CK(cudaMallocHost(&c->h_pin, bytes + 4096));
-  c->h_pin_cap = bytes + 4096;
   return 0;
 }
 #define ENS(buf, bytes)                         \
@@ -701,7 +689,6 @@ int pipe_run(Ctx *c, u64 base_bits, bool whole, u32 *d_out, size_t out_cap, bool
   u64 running = base_bits, mtf_syms = 0;
   u32 fold = 0, d1 = 0;
   float ms_stage[5] = {0, 0, 0, 0, 0}, ms_total = 0, dom_ms = 0;
-  bz2b200_stats keep = c->st;
   for (int b0 = 0; b0 < nb_total; b0 += maxb) {
     const int bn = nb_total - b0 < maxb ? nb_total - b0 : maxb;
     CK(cudaMemcpyAsync(c->recs.p, P<BlockRec>(c->recs_all) + b0, sizeof(BlockRec) * (size_t)bn, cudaMemcpyDeviceToDevice, c->stream));
@@ -730,7 +717,6 @@ int pipe_run(Ctx *c, u64 base_bits, bool whole, u32 *d_out, size_t out_cap, bool
   P_.nb = nb_total;
   c->recs_batched = true;
   c->st.n_blocks = (u32)nb_total;
-  (void)keep;
   if (bits_out) *bits_out = running - base_bits;
   if (crc_fold) *crc_fold = fold;
   u64 olen = (running + 7) / 8;
@@ -789,7 +775,6 @@ void bz2b200_destroy(bz2b200_ctx *ctx) {
   if (!c) return;
   cudaSetDevice(c->device);
   for (DevBuf *b : c->pool) if (b->p) cudaFree(b->p);
-  if (c->h_pin) cudaFreeHost(c->h_pin);
   if (c->rb_pin) cudaFreeHost(c->rb_pin);
   if (c->ev_ok) for (auto &e : c->ev) cudaEventDestroy(e);
   for (auto &e : c->dom_ev) cudaEventDestroy(e);

@@ -406,12 +406,10 @@ __global__ void __launch_bounds__(RLE_THREADS) k_rle_emit(const u8 *__restrict__
   int k = lo;
   BlockRec r = recs[k];
   u8 *out = blk + (i64)k * blk_stride;
-  i64 cur = v.head_before;
   u64 g = g_tile[tile] + v.gpre;
   const i64 first = recs[0].s, last = recs[nblocks - 1].p;  // shards own only [first, last)
   for (int j = 0; j < v.nvalid; j++) {
     i64 i = v.p0 + j;
-    if (v.flags & (1u << j)) cur = i;
     u32 e = (v.em >> (2 * j)) & 3u;
     if (i < first || i >= last) { g += e; continue; }
     while (i >= r.p) { k++; r = recs[k]; out = blk + (i64)k * blk_stride; }
