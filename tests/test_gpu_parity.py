@@ -202,3 +202,16 @@ def test_shards_in_process_equal_whole_stream(gpu_engine):
         infos.append(info)
         bitpos += info.bits
     assert gpu_engine.stitch_shards(9, segs, infos) == whole
+
+
+def test_compress_stream_equals_whole(gpu_engine):
+    """Stream flavour on the GPU: 10 MB of text in 3 MB chunks == compressFile of the whole, and decodes back."""
+    import io
+    from compressjs_flattened_b200.corpus import gen_text
+    data = gen_text(10_000_000, 8).tobytes()
+    g = GOLD["text:10000000:8:L9"]
+    out = gpu_engine.compressStream(io.BytesIO(data), None, 9, chunk_bytes=3_000_000)
+    assert hashlib.sha256(out).hexdigest() == g["out_sha256"]
+    sink = io.BytesIO()
+    gpu_engine.compressStream(io.BytesIO(data), sink, 1, chunk_bytes=1_000_000)
+    assert sink.getvalue() == gpu_engine.compressFile(data, None, 1)

@@ -135,6 +135,50 @@ def test_batched_blocks_same_stream(sim_engine, oracle):
         sim_engine.debug_set_batch_blocks(0)
 
 
+def test_compress_stream_equals_whole(sim_engine, oracle):
+    """Stream flavour: chunks of every size, sources with read() / readByte, sinks with write() /
+    writeByte / none -- always the bytes compressFile gives for the whole input."""
+    import io
+    rng = np.random.default_rng(3)
+    data = (bytes(rng.integers(97, 123, 40000, dtype=np.uint8)) + bytes(3000) + b"ab" * 2000 +
+            bytes(np.repeat(rng.integers(0, 4, 2000, dtype=np.uint8), rng.choice([1, 2, 5, 300], 2000))))
+
+    class ByteSrc:
+        def __init__(self, b):
+            self.b, self.i = b, 0
+
+        def readByte(self):
+            self.i += 1
+            return self.b[self.i - 1] if self.i <= len(self.b) else -1
+
+    class ByteSink:
+        def __init__(self):
+            self.out = bytearray()
+
+        def writeByte(self, b):
+            self.out.append(b)
+
+    try:
+        for cap in (300, 4000):
+            oracle.set_block_cap(cap)
+            sim_engine.debug_set_block_cap(cap)
+            exp = oracle.compress(data, 9)
+            for chunk in (1000, 7777, 10 ** 7):
+                assert sim_engine.compressStream(io.BytesIO(data), None, 9, chunk_bytes=chunk) == exp, (cap, chunk)
+            sink = io.BytesIO()
+            assert sim_engine.compressStream(ByteSrc(data), sink, 9, chunk_bytes=20000) is sink and sink.getvalue() == exp
+            bs = ByteSink()
+            sim_engine.compressStream(data, bs, 9, chunk_bytes=30000)
+            assert bytes(bs.out) == exp
+    finally:
+        oracle.set_block_cap(0)
+        sim_engine.debug_set_block_cap(0)
+    for d in (b"", b"Q", b"aaaa", b"This is a test\n"):
+        assert sim_engine.compressStream(io.BytesIO(d), None, 1, chunk_bytes=5) == oracle.compress(d, 1)
+    with pytest.raises(ValueError, match="Invalid block size multiplier"):
+        sim_engine.compressStream(io.BytesIO(b"x"), None, 10)
+
+
 def test_decode_fixtures_and_random_access(sim_engine):
     for n in (0, 3):
         assert sim_engine.decompressFile(fixture_bytes(f"sample{n}.bz2")) == fixture_bytes(f"sample{n}.ref")
