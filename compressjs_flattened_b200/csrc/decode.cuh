@@ -571,8 +571,8 @@ __device__ __forceinline__ u32 ibwt_spl_index(u32 j, u32 pos0, u32 W) { return j
 
 __global__ void __launch_bounds__(256) k_ibwt_walk1(const u32 *__restrict__ tt, const DecBlk *__restrict__ blks, const u32 *__restrict__ order,
                                                     const u32 *__restrict__ seg_tile0, const u32 *__restrict__ spl0, int nb,
-                                                    u32 *__restrict__ spl_next, u32 *__restrict__ spl_len) {
-  u32 p = blockIdx.y;
+                                                    u32 *__restrict__ spl_next, u32 *__restrict__ spl_len, u32 p0) {
+  u32 p = p0 + blockIdx.y;  // launched in batches of blocks whose T-vectors fit the L2 together
   const DecBlk &b = blks[order[p]];
   u32 n = b.count;
   if (n == 0) return;
@@ -593,30 +593,38 @@ __global__ void __launch_bounds__(256) k_ibwt_walk1(const u32 *__restrict__ tt, 
   }
 }
 // one thread per block: offsets of the splitters along the walk from pos0; period if the walk closes
-__global__ void k_ibwt_rank(const DecBlk *__restrict__ blks, const u32 *__restrict__ order, const u32 *__restrict__ spl0, int nb,
-                            const u32 *__restrict__ spl_next, const u32 *__restrict__ spl_len, u32 *__restrict__ spl_off,
-                            u32 *__restrict__ period) {
-  int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= nb) return;
-  u32 n = blks[order[p]].count;
-  if (n == 0) { period[p] = 0; return; }
-  u32 W = (n + IBWT_S - 1) / IBWT_S + 1, base = spl0[p];
-  for (u32 s = 0; s < W; s++) spl_off[base + s] = 0xffffffffu;
-  u32 cur = W - 1, off = 0, per = 0;
-  while (off < n) {
-    if (spl_off[base + cur] != 0xffffffffu) { per = off - spl_off[base + cur]; break; }  // closed a cycle (periodic block)
-    spl_off[base + cur] = off;
-    off += spl_len[base + cur];
-    cur = spl_next[base + cur];
+// one CTA per block: the splitter links are staged in shared memory, one thread chases them there (a few dozen cycles
+// per hop instead of a DRAM round trip), all threads write the offsets back.  Dynamic shared memory: 3 * W words.
+__global__ void __launch_bounds__(256) k_ibwt_rank(const DecBlk *__restrict__ blks, const u32 *__restrict__ order, const u32 *__restrict__ spl0, int nb,
+                                                   const u32 *__restrict__ spl_next, const u32 *__restrict__ spl_len, u32 *__restrict__ spl_off,
+                                                   u32 *__restrict__ period) {
+  DYN_SMEM(u32, sm);
+  const int p = blockIdx.x;
+  const u32 n = blks[order[p]].count;
+  if (n == 0) { if (threadIdx.x == 0) period[p] = 0; return; }
+  const u32 W = (n + IBWT_S - 1) / IBWT_S + 1, base = spl0[p];
+  u32 *nx = sm, *ln = sm + W, *of = sm + 2 * W;
+  for (u32 s = threadIdx.x; s < W; s += blockDim.x) { nx[s] = spl_next[base + s]; ln[s] = spl_len[base + s]; of[s] = 0xffffffffu; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    u32 cur = W - 1, off = 0, per = 0;
+    while (off < n) {
+      if (of[cur] != 0xffffffffu) { per = off - of[cur]; break; }  // closed a cycle (periodic block)
+      of[cur] = off;
+      off += ln[cur];
+      cur = nx[cur];
+    }
+    period[p] = per;
   }
-  period[p] = per;
+  __syncthreads();
+  for (u32 s = threadIdx.x; s < W; s += blockDim.x) spl_off[base + s] = of[s];
 }
 __global__ void __launch_bounds__(256) k_ibwt_walk2(const u32 *__restrict__ tt, const u8 *__restrict__ dL, i64 l_stride,
                                                     const DecBlk *__restrict__ blks, const u32 *__restrict__ order,
                                                     const u32 *__restrict__ seg_tile0, const u32 *__restrict__ spl0, int nb,
                                                     const u32 *__restrict__ spl_len, const u32 *__restrict__ spl_off,
-                                                    const u32 *__restrict__ period, u8 *__restrict__ blk_out, i64 b_stride) {
-  u32 p = blockIdx.y;
+                                                    const u32 *__restrict__ period, u8 *__restrict__ blk_out, i64 b_stride, u32 p0) {
+  u32 p = p0 + blockIdx.y;
   const DecBlk &b = blks[order[p]];
   u32 n = b.count;
   if (n == 0) return;

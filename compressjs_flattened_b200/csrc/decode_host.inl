@@ -195,10 +195,13 @@ static int decode_device(Ctx *c, const u8 *d_in, size_t n, int multistream, int 
   ENS(c->dblk, (size_t)nb * BS);
   unsigned gx = (unsigned)(((max_cnt + IBWT_S - 1) / IBWT_S + 1 + 255) / 256);
   if (max_cnt) {
-    LAUNCH(k_ibwt_walk1, dim3(gx, (unsigned)nb), 256, 0, P<u32>(c->valsB), P<DecBlk>(c->dmeta), d_order, P<u32>(c->seg_tile0), d_spl0, nb, spl_next, spl_len);
-    LAUNCH(k_ibwt_rank, (unsigned)((nb + 63) / 64), 64, 0, P<DecBlk>(c->dmeta), d_order, d_spl0, nb, spl_next, spl_len, spl_off, period);
+    // (launching the walks for L2-sized batches of blocks was tried: slower -- a batch waits for its longest chain, ~11x
+    // the mean of 256 steps, and too few threads are left to hide the latency)
+    LAUNCH(k_ibwt_walk1, dim3(gx, (unsigned)nb), 256, 0, P<u32>(c->valsB), P<DecBlk>(c->dmeta), d_order, P<u32>(c->seg_tile0), d_spl0, nb, spl_next, spl_len, 0u);
+    LAUNCH(k_ibwt_rank, (unsigned)nb, 256, 12 * (size_t)((DEC_DBUF_MAX + IBWT_S - 1) / IBWT_S + 2), P<DecBlk>(c->dmeta), d_order, d_spl0, nb, spl_next, spl_len,
+           spl_off, period);
     LAUNCH(k_ibwt_walk2, dim3(gx, (unsigned)nb), 256, 0, P<u32>(c->valsB), P<u8>(c->dL), LS, P<DecBlk>(c->dmeta), d_order, P<u32>(c->seg_tile0), d_spl0, nb,
-           spl_len, spl_off, period, P<u8>(c->dblk), BS);
+           spl_len, spl_off, period, P<u8>(c->dblk), BS, 0u);
   }
   if ((rc = mark(c, 3))) return rc;
 
