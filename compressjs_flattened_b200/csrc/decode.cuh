@@ -119,7 +119,7 @@ struct DecSmem {
   u64 bitpos_after_header;
   u16 J[DEC_LEVELS][PT];  // J[k][b]: bit offset reached from offset b after 2^k codes (>= DEC_PT: outside the step)
   u16 SY[PT];             // symbol decoded at offset b | 0x8000 if the code there is invalid
-  u8 F[PT];               // offset b starts a code of the chain from offset 0
+  u16 csym[64], cend[64];     // symbol and end offset of the r-th code of the chain
   u8 selbuf[256];             // selectors of the pass
   u32 ws[34];
   u32 first_eob, first_bad, adv;
@@ -326,7 +326,6 @@ __global__ void __launch_bounds__(PT) k_huff_parse(const u8 *__restrict__ in, u6
       const u32 sym = e >> 5, nxt = (u32)lane + (e & 31u);
       sm.J[0][lane] = (u16)nxt;
       sm.SY[lane] = (u16)(sym | (bad ? 0x8000u : 0u));
-      sm.F[lane] = lane == 0;
       if (lane == 0) { sm.first_eob = 0xffffffffu; sm.first_bad = 0xffffffffu; sm.adv = 0; }
       __syncthreads();
 #pragma unroll
@@ -335,34 +334,38 @@ __global__ void __launch_bounds__(PT) k_huff_parse(const u8 *__restrict__ in, u6
         sm.J[q][lane] = v < PT ? sm.J[q - 1][v] : (u16)0xffff;
         __syncthreads();
       }
+      // thread r < 64 finds the offset of the r-th code of the chain by composing the jumps of r's binary digits
+      // (six dependent shared-memory reads, no barrier): it IS rank r
+      if (lane < 64) {
+        u32 pos = 0;
 #pragma unroll
-      for (int q = DEC_LEVELS - 1; q >= 0; q--) {  // chain members: every count of codes is a sum of powers of two
-        if (sm.F[lane]) {
-          u32 v = sm.J[q][lane];
-          if (v < PT) sm.F[v] = 1;  // a thread flagged during this sweep may propagate too: still on the chain
+        for (int q = 0; q < DEC_LEVELS; q++)
+          if (((u32)lane >> q) & 1u) pos = pos < PT ? sm.J[q][pos] : 0xffffu;
+        const bool have = pos < PT;                       // the r-th code starts inside the step
+        const u32 sy = have ? sm.SY[pos] : 0u;
+        sm.csym[lane] = (u16)sy;
+        sm.cend[lane] = have ? sm.J[0][pos] : (u16)0xffff;  // the bit after code r = where code r+1 starts
+        const u32 hb = __ballot_sync(FULL_MASK, have), eb = __ballot_sync(FULL_MASK, have && (sy & 0x7fffu) == eob),
+                  bb = __ballot_sync(FULL_MASK, have && (sy & 0x8000u));
+        if ((lane & 31) == 0) {  // `have` is monotone in r: the counts of the two warps add up
+          atomicAdd(&sm.adv, (u32)__popc(hb));
+          if (eb) atomicMin(&sm.first_eob, (u32)(lane + __ffs((int)eb) - 1));
+          if (bb) atomicMin(&sm.first_bad, (u32)(lane + __ffs((int)bb) - 1));
         }
-        __syncthreads();
       }
-      const u32 mine = sm.F[lane];
-      u32 total;
-      const u32 rank = block_excl_sum<u32>(mine, total, sm.ws);  // position of my code among the codes of the step
-      if (mine && sym == eob) atomicMin(&sm.first_eob, rank);
-      if (mine && bad) atomicMin(&sm.first_bad, rank);
       __syncthreads();
+      const u32 total = sm.adv;  // codes of the chain that start inside the step (at most 64 are looked at)
       u32 take = left < total ? left : total;
       bool fin = false;
       if (sm.first_eob < take) { take = sm.first_eob + 1; fin = true; }
       if (sm.first_bad < take) { err = BZ2B200_E_DATA_ERROR; break; }
-      if (mine && rank < take) {
-        sm.stage[staged + rank] = (u16)sym;
-        if (rank == take - 1) sm.adv = nxt;  // the bit after the last code taken (= where the next code starts)
-      }
-      __syncthreads();
+      if ((u32)lane < take) sm.stage[staged + lane] = (u16)(sm.csym[lane] & 0x7fffu);
+      const u32 advance = sm.cend[take - 1];
+      __syncthreads();  // csym / cend / adv / first_* are rewritten in the next step
       staged += take;
       left -= take;
-      P += sm.adv;
+      P += advance;
       if (fin) done = 1;
-      __syncthreads();  // adv / first_* are rewritten at the top of the next step
     }
     cur_bit = ring_base_w * 32 + P;
     if (!err && cur_bit > n * 8) err = BZ2B200_E_UNEXPECTED_INPUT_EOF;  // reference: spins on zero bits (D3)
