@@ -99,6 +99,8 @@ struct Ctx {
     std::vector<BlockRec> hrecs;
   } pipe;
   bool trace = false;      // BZ2B200_TRACE
+  int sms = 148;           // multiprocessors of the device
+  int parse_mode = 0;      // BZ2B200_PARSE: 0 = by block count, 1 = k_huff_parse, 2 = k_huff_parse_win (development aid)
   std::vector<cudaEvent_t> trace_ev, trace_pool;
   std::vector<const char *> trace_names;
   void *rb_pin = nullptr;  // page-locked scratch of rb_add / rb_sync
@@ -765,6 +767,8 @@ int bz2b200_create(int device, bz2b200_ctx **ctx) {
   if (cudaStreamCreate(&c->stream) != cudaSuccess) { delete c; return BZ2B200_E_CUDA; }
   c->ev_ok = true;
   { const char *t = getenv("BZ2B200_TRACE"); c->trace = t && *t && *t != '0'; }
+  { const char *t = getenv("BZ2B200_PARSE"); c->parse_mode = t ? atoi(t) : 0; }
+  { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) c->sms = v; }
   for (auto &e : c->ev) if (cudaEventCreate(&e) != cudaSuccess) c->ev_ok = false;
   *ctx = reinterpret_cast<bz2b200_ctx *>(c);
   return BZ2B200_OK;

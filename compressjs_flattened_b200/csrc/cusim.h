@@ -33,6 +33,7 @@ static inline uint2 make_uint2(unsigned a, unsigned b) { return uint2{a, b}; }
 #define __device__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__
 #define __restrict__
 #define __shared__ static
 #define __launch_bounds__(...)
@@ -282,6 +283,8 @@ static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = 0) { retur
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
 static inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t, cudaEvent_t) { *ms = 0; return 0; }
 #define cudaFuncSetAttribute(...) 0
+#define cudaDevAttrMultiProcessorCount 16
+static inline int cudaDeviceGetAttribute(int *v, int, int) { *v = 148; return 0; }
 #define cudaFuncAttributeMaxDynamicSharedMemorySize 0
 
 // kernel launch: KLAUNCH(kernel, grid, block, smem_bytes, stream, args...)

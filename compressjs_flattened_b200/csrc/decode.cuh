@@ -115,7 +115,9 @@ struct DecSmem {
   u8 sym2byte[256];
   __align__(16) u8 ring[DEC_RING + 16];
   u16 stage[DEC_SYM_STAGE];
-  int hdr[8];  // err, ng, nsel, sym_total, staged, finished
+  int hdr[8];  // err, ng, nsel, sym_total, overrun so far
+  u32 scr[72];  // CTA scans of the header
+  u64 sel_end;  // first bit after the selectors
   u64 bitpos_after_header;
   u16 J[DEC_LEVELS][PT];  // J[k][b]: bit offset reached from offset b after 2^k codes (>= DEC_PT: outside the step)
   u16 SY[PT];             // symbol decoded at offset b | 0x8000 if the code there is invalid
@@ -125,18 +127,35 @@ struct DecSmem {
   u32 first_eob, first_bad, adv;
 };
 
-// ---- K-U2/3a: header + Huffman parse (bits -> symbols).  One CTA of DEC_PT threads per candidate block. -------
-// Only this part of the decoder is serial across GROUPS (the coding table changes every 50 symbols, so the position
-// of a group in the bit stream is unknown until everything before it is parsed); inside a group it is parallel:
-// thread b decodes the code that WOULD start at bit P+b, pointer doubling over those "next code" links finds the
-// codes that really start there (the chain from offset 0), a scan ranks them, the first `left` are the group.
-template <int PT>
-__global__ void __launch_bounds__(PT) k_huff_parse(const u8 *__restrict__ in, u64 n, const u64 *__restrict__ cand, u32 ncand, u32 dbuf_cap, int verify,
-                                                   DecBlk *__restrict__ out, u16 *__restrict__ dsym, u8 *__restrict__ dsel, u8 *__restrict__ dmap) {
-  __shared__ DecSmem<PT> sm;
-  const u32 k = blockIdx.x;
-  if (k >= ncand) return;
-  const int lane = threadIdx.x;  // thread index in the CTA (the header code below predates the CTA-wide parse)
+// 32 bits of the stream from bit position bp, first bit in bit 31; bits past EOF read as 0 (BJ:149-150)
+__device__ __forceinline__ u32 dec_load32(const u8 *__restrict__ in, u64 n, u64 bp) {
+  const u64 by = bp >> 3;
+  u64 v = 0;
+#pragma unroll
+  for (int z = 0; z < 5; z++) v = (v << 8) | (by + z < n ? (u64)in[by + z] : 0ull);
+  return (u32)(v >> (8 - (u32)(bp & 7)));
+}
+// selector MTF (BJ:1481-1496) as maps over the 7 list positions a selector can name (3 bits each): after the moves
+// of map a, then those of map b, position q holds what position a[b[q]] held before
+#define DEC_PERM_ID 06543210u
+__device__ __forceinline__ u32 dec_perm_front(u32 p, u32 j) {  // move position j to the front
+  const u32 v = (p >> (3 * j)) & 7u, lowmask = (1u << (3 * j)) - 1u;
+  return (p & ~((lowmask << 3) | 7u)) | ((p & lowmask) << 3) | v;
+}
+__device__ __forceinline__ u32 dec_perm_compose(u32 a, u32 b) {
+  u32 c = 0;
+#pragma unroll
+  for (int q = 0; q < 7; q++) c |= ((a >> (3 * ((b >> (3 * q)) & 7u))) & 7u) << (3 * q);
+  return c;
+}
+
+// header (BJ:1434-1520), limit/base/permute (BJ:1521-1581) and the 10-bit LUT of one candidate block, shared by the two
+// parse kernels.  Returns false when the candidate is not a block to parse (end-of-stream magic, header error): `out[k]`
+// is written then.
+template <int PT, typename SM>
+__device__ __forceinline__ bool dec_header(SM &sm, const u8 *__restrict__ in, u64 n, const u64 *__restrict__ cand, u32 k, u32 dbuf_cap, int verify,
+                                           DecBlk *__restrict__ out, u8 *__restrict__ sel, u8 *__restrict__ dmap, DecBlk &res) {
+  const int lane = threadIdx.x;
   const u64 bitpos = cand[k] >> 1;
   u32 kind = (u32)(cand[k] & 1);
   if (verify) {  // candidate given by the caller (decompressBlock): read the 48-bit signature here (BJ:1434-1439)
@@ -145,9 +164,6 @@ __global__ void __launch_bounds__(PT) k_huff_parse(const u8 *__restrict__ in, u6
     u64 h = ((u64)br_get(r0, 24) << 24) | br_get(r0, 24);
     kind = h == BZ_MAGIC_END ? 1u : h == BZ_MAGIC_BLOCK ? 0u : 2u;
   }
-  u16 *Sk = dsym + (u64)k * DEC_SYM_STRIDE;
-  u8 *sel = dsel + (u64)k * DEC_MAX_SEL;
-  DecBlk res;
   res.bitpos = bitpos; res.endbit = 0; res.target_crc = 0; res.orig_ptr = 0; res.count = 0; res.err = 0; res.kind = kind; res.nsym = 0;
   // ---- header (lane 0), BJ:1434-1520 ----
   if (lane == 0) {
@@ -176,22 +192,104 @@ __global__ void __launch_bounds__(PT) k_huff_parse(const u8 *__restrict__ in, u6
         nsel = (int)br_get(r, 15);
         if (nsel == 0) err = BZ2B200_E_DATA_ERROR;
       }
-      if (!err) {
-        for (int i = 0; i < 256; i++) sm.mtf[i] = 0;  // Uint8Array(256), BJ:1481
-        for (int i = 0; i < ng; i++) sm.mtf[i] = (u8)i;
-        for (int i = 0; i < nsel && !err; i++) {
-          int j = 0;
-          while (br_get(r, 1)) {  // BJ:1488-1490: the bound is tested on each 1 bit, so j == ng passes
-            if (j >= ng) { err = BZ2B200_E_DATA_ERROR; break; }
-            j++;
-          }
-          if (err) break;
-          u8 v = sm.mtf[j];
-          for (int q = j; q > 0; q--) sm.mtf[q] = sm.mtf[q - 1];
-          sm.mtf[0] = v;
-          sel[i] = v;
-        }
+    }
+    sm.hdr[0] = err; sm.hdr[1] = ng; sm.hdr[2] = nsel; sm.hdr[3] = sym_total; sm.hdr[4] = (int)r.overrun;
+    sm.sel_end = br_tell(r);
+  }
+  __syncthreads();
+  // ---- selectors (BJ:1481-1496), all threads: selector i is the run of 1 bits before the i-th 0 bit, then an MTF move.
+  // Every thread takes a 32-bit word of the stream: zeros are counted and ranked by a CTA scan, the run length of a
+  // zero is its distance to the zero before it; the moves are composed by a scan of position maps.
+  if (kind == 0 && sm.hdr[0] == 0) {
+    const int ng = sm.hdr[1];
+    const u32 nsel = (u32)sm.hdr[2];
+    const u32 wid = (u32)lane >> 5, wl = (u32)lane & 31u, nw = PT / 32;
+    u64 cur = sm.sel_end;
+    u64 lastz = cur - 1;  // position of the zero before the run being measured
+    u32 donez = 0;
+    int perr = 0;
+    __syncthreads();
+    while (donez < nsel && !perr) {
+      const u64 bp = cur + 32ull * (u32)lane;
+      const u32 zm = ~dec_load32(in, n, bp);  // bit 31-k set: the k-th bit of the word is 0
+      const u32 z = (u32)__popc(zm);
+      const u32 lz = z ? 32u * (u32)lane + (32u - (u32)__ffs((int)zm)) + 1u : 0u;  // offset of the word's last zero, +1 (0: none)
+      u32 zin = z, lin = lz;  // inclusive sum / max scans over the CTA
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const u32 a = __shfl_up_sync(FULL_MASK, zin, d), b = __shfl_up_sync(FULL_MASK, lin, d);
+        if (wl >= (u32)d) { zin += a; lin = lin > b ? lin : b; }
       }
+      if (wl == 31) { sm.scr[wid] = zin; sm.scr[32 + wid] = lin; }
+      if (lane == 0) sm.scr[64] = 0;
+      __syncthreads();
+      u32 zbase = 0, lbase = 0, ztot = 0, lmax = 0;
+      for (u32 w2 = 0; w2 < nw; w2++) {
+        const u32 a = sm.scr[w2], b = sm.scr[32 + w2];
+        if (w2 < wid) { zbase += a; lbase = lbase > b ? lbase : b; }
+        ztot += a; lmax = lmax > b ? lmax : b;
+      }
+      u32 idx = donez + zbase + zin - z;
+      u32 lprev = __shfl_up_sync(FULL_MASK, lin, 1);
+      if (wl == 0) lprev = 0;
+      lprev = lprev > lbase ? lprev : lbase;
+      u64 prevpos = lprev ? cur + lprev - 1 : lastz;
+      u32 m = zm;
+      while (m && idx < nsel) {
+        const u32 k2 = (u32)__clz((int)m);
+        const u64 pos = bp + k2;
+        const u64 j = pos - prevpos - 1;
+        if (j > (u64)ng) perr = 1; else sel[idx] = (u8)j;  // BJ:1488-1490: the bound is tested on each 1 bit, so j == ng passes
+        if (idx == nsel - 1) sm.sel_end = pos + 1;
+        prevpos = pos;
+        idx++;
+        m &= ~(0x80000000u >> k2);
+      }
+      if (ztot == 0) perr = 1;  // a run of 1 bits longer than the whole chunk
+      if (perr) sm.scr[64] = 1;
+      __syncthreads();
+      perr = (int)sm.scr[64];
+      donez += ztot;
+      if (lmax) lastz = cur + lmax - 1;
+      cur += 32ull * PT;
+      __syncthreads();
+    }
+    if (perr) {
+      if (lane == 0) sm.hdr[0] = BZ2B200_E_DATA_ERROR;
+    } else {
+      // MTF: thread t owns selectors [t*C, (t+1)*C)
+      const u32 C = (nsel + PT - 1) / PT, i0 = (u32)lane * C, i1 = i0 + C < nsel ? i0 + C : nsel;
+      u32 p = DEC_PERM_ID;
+      for (u32 i = i0; i < i1; i++) p = dec_perm_front(p, sel[i]);
+      u32 pin = p;  // inclusive scan of the maps (earlier moves first)
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const u32 a = __shfl_up_sync(FULL_MASK, pin, d);
+        if (wl >= (u32)d) pin = dec_perm_compose(a, pin);
+      }
+      if (wl == 31) sm.scr[wid] = pin;
+      __syncthreads();
+      u32 pre = DEC_PERM_ID;
+      for (u32 w2 = 0; w2 < wid; w2++) pre = dec_perm_compose(pre, sm.scr[w2]);
+      u32 pex = __shfl_up_sync(FULL_MASK, pin, 1);
+      if (wl == 0) pex = DEC_PERM_ID;
+      p = dec_perm_compose(pre, pex);
+      for (u32 i = i0; i < i1; i++) {
+        const u32 j = sel[i], v = (p >> (3 * j)) & 7u;
+        sel[i] = (u8)(v < (u32)ng ? v : 0u);  // the list is a zeroed Uint8Array(256) with 0..ng-1 in front (BJ:1481-1483)
+        p = dec_perm_front(p, j);
+      }
+    }
+  }
+  __syncthreads();
+  // ---- code lengths (lane 0), BJ:1497-1520 ----
+  if (lane == 0) {
+    int err = sm.hdr[0];
+    const int ng = sm.hdr[1], sym_total = sm.hdr[3];
+    BitRd r;
+    br_init(r, in, n, sm.sel_end);
+    if (sm.hdr[4] || sm.sel_end > n * 8) r.overrun = 1;
+    if (kind == 0) {
       if (!err) {
         int S = sym_total + 2;
         for (int t = 0; t < ng && !err; t++) {
@@ -208,7 +306,7 @@ __global__ void __launch_bounds__(PT) k_huff_parse(const u8 *__restrict__ in, u6
       }
       if (!err && r.overrun) err = BZ2B200_E_UNEXPECTED_INPUT_EOF;
     }
-    sm.hdr[0] = err; sm.hdr[1] = ng; sm.hdr[2] = nsel; sm.hdr[3] = sym_total;
+    sm.hdr[0] = err;
     sm.bitpos_after_header = br_tell(r);
   }
   __syncthreads();
@@ -220,7 +318,7 @@ __global__ void __launch_bounds__(PT) k_huff_parse(const u8 *__restrict__ in, u6
       res.endbit = sm.bitpos_after_header;
       out[k] = res;
     }
-    return;
+    return false;
   }
   for (int i = lane; i < 256; i += PT) dmap[(u64)k * 256 + i] = i < sym_total ? sm.sym2byte[i] : (u8)i;
   // ---- limit / base / permute per table (BJ:1521-1581), one lane per table ----
@@ -268,6 +366,26 @@ __global__ void __launch_bounds__(PT) k_huff_parse(const u8 *__restrict__ in, u6
     sm.lut[t][prefix] = e;
   }
   __syncthreads();
+  return true;
+}
+
+// ---- K-U2/3a: header + Huffman parse (bits -> symbols).  One CTA of DEC_PT threads per candidate block. -------
+// Only this part of the decoder is serial across GROUPS (the coding table changes every 50 symbols, so the position
+// of a group in the bit stream is unknown until everything before it is parsed); inside a group it is parallel:
+// thread b decodes the code that WOULD start at bit P+b, pointer doubling over those "next code" links finds the
+// codes that really start there (the chain from offset 0), a scan ranks them, the first `left` are the group.
+template <int PT>
+__global__ void __launch_bounds__(PT) k_huff_parse(const u8 *__restrict__ in, u64 n, const u64 *__restrict__ cand, u32 ncand, u32 dbuf_cap, int verify,
+                                                   DecBlk *__restrict__ out, u16 *__restrict__ dsym, u8 *__restrict__ dsel, u8 *__restrict__ dmap) {
+  __shared__ DecSmem<PT> sm;
+  const u32 k = blockIdx.x;
+  if (k >= ncand) return;
+  const int lane = threadIdx.x;  // thread index in the CTA (the header code below predates the CTA-wide parse)
+  u16 *Sk = dsym + (u64)k * DEC_SYM_STRIDE;
+  u8 *sel = dsel + (u64)k * DEC_MAX_SEL;
+  DecBlk res;
+  if (!dec_header<PT>(sm, in, n, cand, k, dbuf_cap, verify, out, sel, dmap, res)) return;
+  const int nsel = sm.hdr[2], sym_total = sm.hdr[3];
   // ---- symbols (BJ:1597-1616): parse passes ----
   // A pass stages DEC_RING bytes of the stream (byte-swapped words) and the selectors it can need.  A step looks at the
   // PT bit offsets from P: thread b decodes the code that would start at P+b with the group's table.
@@ -372,6 +490,249 @@ __global__ void __launch_bounds__(PT) k_huff_parse(const u8 *__restrict__ in, u6
     __syncthreads();
     for (u32 q = lane; q < staged; q += PT) Sk[flushed + q] = sm.stage[q];
     flushed += staged;
+    __syncthreads();
+    if (err || done) break;
+  }
+  if (lane == 0) {
+    res.err = err;
+    res.count = 0;  // filled by k_sym_offsets
+    res.nsym = err ? 0 : flushed;
+    res.endbit = cur_bit;
+    out[k] = res;
+  }
+}
+
+// ---- K-U2/3a, few blocks: the same parse with the serial part cut to three dependent reads per group -----------
+// k_huff_parse above spends ~9 CTA barriers per group of 50 symbols; with fewer blocks than SMs that latency is the
+// whole decode.  Here a window of W bit offsets is decoded speculatively under EVERY table the next groups use (the
+// selectors are known up front): J_t[0][b] = b + length of the code that would start at b under table t, five
+// pointer-doubling levels give J_t[k][b] = offset after 2^k codes, and then
+//   * one thread walks the groups: the next group starts at J_t[1][J_t[4][J_t[5][start]]] (50 = 32 + 16 + 2);
+//   * thread (q, r) composes the jumps of r's binary digits from group q's start and IS the r-th symbol of it.
+// A window starts at a group start; a group is at most 50 * 20 = 1000 bits, so every window makes progress.  The price
+// is work (up to 6 tables over every offset), so the host picks this kernel only when the blocks cannot fill the GPU.
+#define DECW_PT 1024         // threads
+#define DECW_WIN 2048        // widest window
+#define DECW_ITEMS 6         // (table, offset) items per thread: 3 tables x 2048 offsets or 6 tables x 1024 offsets
+#define DECW_JCAP (DECW_ITEMS * DECW_PT * DEC_LEVELS)
+#define DECW_KMAX 16         // groups taken per window at most (16 * 50 symbols <= DECW_PT extraction threads)
+
+struct DecWinSmem {
+  int limit[BZ_MAX_GROUPS][BZ_MAX_CODE + 2];
+  int base[BZ_MAX_GROUPS][BZ_MAX_CODE + 2];
+  u16 permute[BZ_MAX_GROUPS][BZ_MAX_SYMS + 2];
+  u16 lut[BZ_MAX_GROUPS][1 << DEC_LUT_BITS];
+  u8 lens[BZ_MAX_GROUPS][BZ_MAX_SYMS + 2];
+  int minl[BZ_MAX_GROUPS], maxl[BZ_MAX_GROUPS];
+  u8 mtf[256];
+  u8 sym2byte[256];
+  __align__(16) u8 ring[DEC_RING + 16];
+  int hdr[8];  // err, ng, nsel, sym_total, overrun so far
+  u32 scr[72];  // CTA scans of the header
+  u64 sel_end;  // first bit after the selectors
+  u64 bitpos_after_header;
+  // J[(s * 6 + k) * W + b]: offset reached from b after 2^k codes of table slot s; 0xffff when one of those codes would
+  // start outside the window (a value in [W, W+20) is a valid end that cannot be continued)
+  u16 J[DECW_JCAP];
+  u8 selbuf[256];  // selectors of the pass
+  // plan of the window (written by thread 0 one barrier ahead)
+  u32 win_w, ntabs, kq, slot_of;  // slot_of: nibble t = slot of table t (0xF: not in this window)
+  u8 tabs[8];
+  u16 starts[DECW_KMAX];  // offset inside the window where the q-th group of the window starts
+  u32 ngd, wend;          // groups that end inside the window, offset where the next one starts
+  u32 first_eob, first_bad, eob_end;
+};
+
+// long code (not in the LUT): the reference's limit/base/permute walk (BJ:1605-1616) on a 32-bit window; an invalid
+// code comes back as length 1 with bit 20 set (it only counts when it is ON the chain)
+template <typename SM>
+__device__ __noinline__ u32 dec_long_code(const SM &sm, int gi, u32 win) {
+  int L = sm.minl[gi];
+  int j = (int)(win >> (32 - L));
+  for (;; L++) {
+    if (L > sm.maxl[gi]) return (0x8000u << 5) | 1u;
+    if (j <= sm.limit[gi][L]) break;
+    j = (j << 1) | (int)((win >> (31 - L)) & 1u);
+  }
+  j -= sm.base[gi][L];
+  if (j < 0 || j >= BZ_MAX_SYMS) return (0x8000u << 5) | 1u;
+  return ((u32)sm.permute[gi][j] << 5) | (u32)L;
+}
+
+// thread 0: which tables the window that starts at group `selector` looks at, how wide it is, how many groups the
+// walk may take.  Up to 3 distinct tables -> 2048 offsets; a 4th table close by -> 1024 offsets and up to 6 tables.
+__device__ __forceinline__ void decw_plan(DecWinSmem &sm, int selector, int sel0, int nsel) {
+  u32 slot_of = 0xffffffu, ntabs = 0, kq = 0;
+  for (; kq < DECW_KMAX && selector + (int)kq < nsel; kq++) {
+    const u32 t = sm.selbuf[selector - sel0 + (int)kq];
+    if (((slot_of >> (4 * t)) & 15u) == 15u) {
+      if (ntabs == 3) break;
+      sm.tabs[ntabs] = (u8)t;
+      slot_of = (slot_of & ~(15u << (4 * t))) | (ntabs << (4 * t));
+      ntabs++;
+    }
+  }
+  u32 w = DECW_WIN;
+  if (kq < 6 && selector + (int)kq < nsel) {
+    w = DECW_WIN / 2;
+    for (; kq < 8 && selector + (int)kq < nsel; kq++) {
+      const u32 t = sm.selbuf[selector - sel0 + (int)kq];
+      if (((slot_of >> (4 * t)) & 15u) == 15u) {
+        sm.tabs[ntabs] = (u8)t;
+        slot_of = (slot_of & ~(15u << (4 * t))) | (ntabs << (4 * t));
+        ntabs++;
+      }
+    }
+  }
+  sm.win_w = w; sm.ntabs = ntabs; sm.kq = kq; sm.slot_of = slot_of;
+}
+
+__global__ void __launch_bounds__(DECW_PT) k_huff_parse_win(const u8 *__restrict__ in, u64 n, const u64 *__restrict__ cand, u32 ncand, u32 dbuf_cap,
+                                                            int verify, DecBlk *__restrict__ out, u16 *__restrict__ dsym, u8 *__restrict__ dsel,
+                                                            u8 *__restrict__ dmap) {
+  DYN_SMEM(DecWinSmem, smp);
+  DecWinSmem &sm = *smp;
+  const int PT = DECW_PT;
+  const u32 k = blockIdx.x;
+  if (k >= ncand) return;
+  const int lane = threadIdx.x;
+  u16 *Sk = dsym + (u64)k * DEC_SYM_STRIDE;
+  u8 *sel = dsel + (u64)k * DEC_MAX_SEL;
+  DecBlk res;
+  if (!dec_header<PT>(sm, in, n, cand, k, dbuf_cap, verify, out, sel, dmap, res)) return;
+  const int nsel = sm.hdr[2], sym_total = sm.hdr[3];
+  const u32 eob = (u32)sym_total + 1;
+  u64 cur_bit = sm.bitpos_after_header;  // absolute bit position (uniform across the CTA)
+  u32 flushed = 0;
+  int err = 0, done = 0, selector = 0;
+  u32 *ring32 = reinterpret_cast<u32 *>(sm.ring);
+  const u32 RBITS = DEC_RING * 8;
+  for (;;) {
+    const u64 ring_base_w = (cur_bit >> 5) & ~(u64)3;  // 16-byte aligned word index
+    for (u32 q = lane; q < DEC_RING / 16; q += PT) {
+      u64 src = (ring_base_w + (u64)q * 4) * 4;
+      u32 w[4] = {0, 0, 0, 0};
+      if (src + 16 <= n) {
+        uint4 v = *reinterpret_cast<const uint4 *>(in + src);
+        w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+      } else {
+        for (int z = 0; z < 16; z++) if (src + z < n) w[z >> 2] |= (u32)in[src + z] << (8 * (z & 3));  // bits past EOF read as 0
+      }
+      for (int z = 0; z < 4; z++) ring32[q * 4 + z] = __byte_perm(w[z], 0, 0x0123);
+    }
+    const int sel0 = selector;  // selectors sel0 .. sel0+255 are staged
+    for (int q = lane; q < 256; q += PT) sm.selbuf[q] = sel0 + q < nsel ? sel[sel0 + q] : 0;
+    __syncthreads();
+    if (lane == 0) decw_plan(sm, selector, sel0, nsel);
+    __syncthreads();
+    u32 P = (u32)(cur_bit - ring_base_w * 32);  // bit offset inside the ring
+    while (P + DECW_WIN + 64 <= RBITS && selector - sel0 + DECW_KMAX <= 256) {
+      if (selector >= nsel) { err = BZ2B200_E_DATA_ERROR; break; }  // BJ:1601
+      if (flushed + BZ_GROUP >= DEC_SYM_STRIDE) { err = BZ2B200_E_DATA_ERROR; break; }  // more symbols than any valid block
+      const u32 W = sm.win_w, ntabs = sm.ntabs;
+      const u32 opl = W / DECW_PT, nitems = ntabs * opl;  // (table slot, offset) items of this thread, all in flight together
+      // level 0: the code that would start at every offset, under every table of the window
+      u32 nx[DECW_ITEMS], sb[DECW_ITEMS], bo[DECW_ITEMS];  // sb: index of J[slot][0][0], bo: the item's offset
+      {
+        u32 wn[DECW_ITEMS], e[DECW_ITEMS];
+        int tb[DECW_ITEMS];
+#pragma unroll
+        for (int i = 0; i < DECW_ITEMS; i++) {
+          const u32 s2 = opl == 2 ? (u32)i >> 1 : (u32)i;
+          bo[i] = (u32)lane + (opl == 2 ? ((u32)i & 1u) * DECW_PT : 0u);
+          sb[i] = s2 * DEC_LEVELS * W;
+          tb[i] = sm.tabs[s2 < ntabs ? s2 : 0];
+          const u32 bp = P + bo[i];
+          wn[i] = __funnelshift_l(ring32[(bp >> 5) + 1], ring32[bp >> 5], bp & 31u);  // 32 bits from bit P+b
+        }
+        bool any_long = false;
+#pragma unroll
+        for (int i = 0; i < DECW_ITEMS; i++) {
+          e[i] = sm.lut[tb[i]][wn[i] >> (32 - DEC_LUT_BITS)];  // (symbol << 5) | length, 0 = longer than the LUT
+          any_long |= e[i] == 0 && (u32)i < nitems;
+        }
+        if (any_long) {
+#pragma unroll
+          for (int i = 0; i < DECW_ITEMS; i++)
+            if (e[i] == 0 && (u32)i < nitems) e[i] = dec_long_code(sm, tb[i], wn[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < DECW_ITEMS; i++) {
+          nx[i] = bo[i] + (e[i] & 31u);
+          if ((u32)i < nitems) sm.J[sb[i] + bo[i]] = (u16)nx[i];
+        }
+      }
+      __syncthreads();
+      for (u32 q = 1; q < DEC_LEVELS; q++) {  // J[q] = J[q-1] o J[q-1]; a thread's own J[q-1] values stay in registers
+#pragma unroll
+        for (int i = 0; i < DECW_ITEMS; i++) nx[i] = ((u32)i < nitems && nx[i] < W) ? sm.J[sb[i] + (q - 1) * W + nx[i]] : 0xffffu;
+#pragma unroll
+        for (int i = 0; i < DECW_ITEMS; i++)
+          if ((u32)i < nitems) sm.J[sb[i] + q * W + bo[i]] = (u16)nx[i];
+        __syncthreads();
+      }
+      // the walk over the groups of the window (one thread)
+      if (lane == 0) {
+        const u32 kq = sm.kq, slot_of = sm.slot_of;
+        u32 pos = 0, g = 0;
+        while (g < kq && pos < W && flushed + (g + 1) * BZ_GROUP < DEC_SYM_STRIDE) {
+          const u32 s2 = (slot_of >> (4 * sm.selbuf[selector - sel0 + (int)g])) & 15u;
+          const u16 *Jb = sm.J + (s2 * DEC_LEVELS) * W;
+          const u32 a = Jb[5 * W + pos];
+          if (a >= W) break;
+          const u32 b2 = Jb[4 * W + a];
+          if (b2 >= W) break;
+          const u32 c2 = Jb[1 * W + b2];
+          if (c2 == 0xffffu) break;
+          sm.starts[g] = (u16)pos;
+          pos = c2;
+          g++;
+        }
+        sm.ngd = g; sm.wend = pos;
+        sm.first_eob = 0xffffffffu; sm.first_bad = 0xffffffffu;
+      }
+      __syncthreads();
+      const u32 ngd = sm.ngd, total = ngd * BZ_GROUP;
+      u32 my_end = 0;
+      if ((u32)lane < total) {  // thread (q, r): the r-th code of the q-th group
+        const u32 q = (u32)lane / BZ_GROUP, r = (u32)lane % BZ_GROUP;
+        const int t = sm.selbuf[selector - sel0 + (int)q];
+        const u32 s2 = (sm.slot_of >> (4 * t)) & 15u;
+        const u16 *Jb = sm.J + (s2 * DEC_LEVELS) * W;
+        u32 pos = sm.starts[q];
+#pragma unroll
+        for (int z = 0; z < DEC_LEVELS; z++)
+          if ((r >> z) & 1u) pos = Jb[z * W + pos];
+        const u32 bp = P + pos;
+        const u32 wn = __funnelshift_l(ring32[(bp >> 5) + 1], ring32[bp >> 5], bp & 31u);
+        u32 e = sm.lut[t][wn >> (32 - DEC_LUT_BITS)];
+        if (e == 0) e = dec_long_code(sm, t, wn);
+        const u32 sy = e >> 5;
+        my_end = pos + (e & 31u);
+        Sk[flushed + lane] = (u16)(sy & 0x7fffu);
+        if (sy & 0x8000u) atomicMin(&sm.first_bad, (u32)lane);
+        else if (sy == eob) atomicMin(&sm.first_eob, (u32)lane);
+      }
+      __syncthreads();
+      u32 take = total, advance = sm.wend;
+      const u32 fe = sm.first_eob, fb = sm.first_bad;
+      if (fe < take) {  // the block ends here: the bit after the end-of-block code
+        take = fe + 1;
+        if ((u32)lane == fe) sm.eob_end = my_end;
+        __syncthreads();
+        advance = sm.eob_end;
+        done = 1;
+      }
+      if (fb < take) { err = BZ2B200_E_DATA_ERROR; break; }
+      flushed += take;
+      P += advance;
+      selector += (int)ngd;
+      if (done || selector - sel0 + DECW_KMAX > 256) break;  // (the next pass plans its first window itself)
+      if (lane == 0) decw_plan(sm, selector, sel0, nsel);  // reads selbuf only; published by the next barrier
+      __syncthreads();
+    }
+    cur_bit = ring_base_w * 32 + P;
+    if (!err && cur_bit > n * 8) err = BZ2B200_E_UNEXPECTED_INPUT_EOF;  // reference: spins on zero bits (D3)
     __syncthreads();
     if (err || done) break;
   }

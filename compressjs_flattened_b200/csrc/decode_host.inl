@@ -73,8 +73,20 @@ static int decode_device(Ctx *c, const u8 *d_in, size_t n, int multistream, int 
     ENS(c->doff, 4 * (size_t)ncand * DEC_SYM_STRIDE);
     ENS(c->dperm, (size_t)ncand * nsegs * 256);
     ENS(c->dmap, (size_t)ncand * 256);
-    LAUNCH(k_huff_parse<256>, ncand, 256, 0, d_in, (u64)n, P<u64>(c->cand), ncand, (u32)DEC_DBUF_MAX, mode == DEC_BLOCK ? 1 : 0,
-           P<DecBlk>(c->dmeta), P<u16>(c->dsyms), P<u8>(c->dsel), P<u8>(c->dmap));
+    // few blocks (every CTA resident at once): the parse is pure latency, the window kernel trades work for it
+    const bool win = c->parse_mode ? c->parse_mode == 2 : ncand <= 2u * (u32)c->sms;
+    if (win) {
+      static bool dec_attr_set = false;
+      if (!dec_attr_set) {
+        CK(cudaFuncSetAttribute(k_huff_parse_win, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecWinSmem)));
+        dec_attr_set = true;
+      }
+      LAUNCH(k_huff_parse_win, ncand, DECW_PT, sizeof(DecWinSmem), d_in, (u64)n, P<u64>(c->cand), ncand, (u32)DEC_DBUF_MAX, mode == DEC_BLOCK ? 1 : 0,
+             P<DecBlk>(c->dmeta), P<u16>(c->dsyms), P<u8>(c->dsel), P<u8>(c->dmap));
+    } else {
+      LAUNCH(k_huff_parse<256>, ncand, 256, 0, d_in, (u64)n, P<u64>(c->cand), ncand, (u32)DEC_DBUF_MAX, mode == DEC_BLOCK ? 1 : 0,
+             P<DecBlk>(c->dmeta), P<u16>(c->dsyms), P<u8>(c->dsel), P<u8>(c->dmap));
+    }
     LAUNCH(k_sym_offsets, ncand, 1024, 0, P<DecBlk>(c->dmeta), P<u16>(c->dsyms), P<u32>(c->doff), (u32)DEC_DBUF_MAX);
     CK(cudaMemcpyAsync(blks.data(), c->dmeta.p, sizeof(DecBlk) * (size_t)ncand, cudaMemcpyDeviceToHost, c->stream));
     LAUNCH(k_imtf_perm, dim3((unsigned)((nsegs + 7) / 8), ncand), 256, 0, P<DecBlk>(c->dmeta), P<u16>(c->dsyms), P<u8>(c->dperm));
