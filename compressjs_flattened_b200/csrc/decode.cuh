@@ -24,6 +24,7 @@
 #include "bwt.cuh"
 
 #define DEC_LUT_BITS 10
+#define DEC_LUT_BAD 0xffffu  // LUT entry of a prefix the reference's walk rejects; 0 = code longer than the LUT
 #define DEC_MAX_SEL 32768
 #define DEC_DBUF_MAX 900000
 #define IBWT_S 256
@@ -126,6 +127,24 @@ struct DecSmem {
   u32 ws[34];
   u32 first_eob, first_bad, adv;
 };
+
+// a code the LUT does not hold: entry 0 = longer than DEC_LUT_BITS -> the reference's limit/base/permute walk
+// (BJ:1605-1616) continued from there on a 32-bit window; DEC_LUT_BAD or a failed walk = invalid code, which comes back
+// as length 1 with bit 20 set (it keeps the chain moving and only counts when it is ON the chain)
+template <typename SM>
+__device__ __noinline__ u32 dec_long_code(const SM &sm, int gi, u32 win, u32 entry) {
+  if (entry == DEC_LUT_BAD) return (0x8000u << 5) | 1u;
+  int L = sm.minl[gi] > DEC_LUT_BITS + 1 ? sm.minl[gi] : DEC_LUT_BITS + 1;
+  int j = (int)(win >> (32 - L));
+  for (;; L++) {
+    if (L > sm.maxl[gi]) return (0x8000u << 5) | 1u;
+    if (j <= sm.limit[gi][L]) break;
+    j = (j << 1) | (int)((win >> (31 - L)) & 1u);
+  }
+  j -= sm.base[gi][L];
+  if (j < 0 || j >= BZ_MAX_SYMS) return (0x8000u << 5) | 1u;
+  return ((u32)sm.permute[gi][j] << 5) | (u32)L;
+}
 
 // 32 bits of the stream from bit position bp, first bit in bit 31; bits past EOF read as 0 (BJ:149-150)
 __device__ __forceinline__ u32 dec_load32(const u8 *__restrict__ in, u64 n, u64 bp) {
@@ -359,8 +378,8 @@ __device__ __forceinline__ bool dec_header(SM &sm, const u8 *__restrict__ in, u6
       int j = prefix >> (DEC_LUT_BITS - L);
       if (j <= sm.limit[t][L]) {
         int idx = j - sm.base[t][L];
-        if (idx >= 0 && idx < BZ_MAX_SYMS) e = (u16)((sm.permute[t][idx] << 5) | L);
-        break;  // an out-of-range index is an error: leave it to the slow path
+        e = idx >= 0 && idx < BZ_MAX_SYMS ? (u16)((sm.permute[t][idx] << 5) | L) : (u16)DEC_LUT_BAD;  // out-of-range index: an error
+        break;
       }
     }
     sm.lut[t][prefix] = e;
@@ -426,24 +445,10 @@ __global__ void __launch_bounds__(PT) k_huff_parse(const u8 *__restrict__ in, u6
       const u32 bp = P + (u32)lane;
       const u32 win = __funnelshift_l(ring32[(bp >> 5) + 1], ring32[bp >> 5], bp & 31u);  // 32 bits from bit P+lane
       u32 e = sm.lut[gi][win >> (32 - DEC_LUT_BITS)];  // (symbol << 5) | length, 0 = longer than the LUT
-      bool bad = false;
-      if (e == 0) {  // long code: the reference's limit/base/permute walk (BJ:1605-1616) on this thread's window
-        int L = sm.minl[gi];
-        int j = (int)(win >> (32 - L));
-        for (;; L++) {
-          if (L > sm.maxl[gi]) { bad = true; break; }
-          if (j <= sm.limit[gi][L]) break;
-          j = (j << 1) | (int)((win >> (31 - L)) & 1u);
-        }
-        if (!bad) {
-          j -= sm.base[gi][L];
-          if (j < 0 || j >= BZ_MAX_SYMS) bad = true; else e = ((u32)sm.permute[gi][j] << 5) | (u32)L;
-        }
-        if (bad) e = 1;  // keeps the chain moving; an invalid code only counts if it is ON the chain
-      }
+      if (e == 0 || e == DEC_LUT_BAD) e = dec_long_code(sm, gi, win, e);  // sym 0x8000 = invalid code
       const u32 sym = e >> 5, nxt = (u32)lane + (e & 31u);
       sm.J[0][lane] = (u16)nxt;
-      sm.SY[lane] = (u16)(sym | (bad ? 0x8000u : 0u));
+      sm.SY[lane] = (u16)sym;
       if (lane == 0) { sm.first_eob = 0xffffffffu; sm.first_bad = 0xffffffffu; sm.adv = 0; }
       __syncthreads();
 #pragma unroll
@@ -505,16 +510,17 @@ __global__ void __launch_bounds__(PT) k_huff_parse(const u8 *__restrict__ in, u6
 // ---- K-U2/3a, few blocks: the same parse with the serial part cut to three dependent reads per group -----------
 // k_huff_parse above spends ~9 CTA barriers per group of 50 symbols; with fewer blocks than SMs that latency is the
 // whole decode.  Here a window of W bit offsets is decoded speculatively under EVERY table the next groups use (the
-// selectors are known up front): J_t[0][b] = b + length of the code that would start at b under table t, five
+// selectors are known up front): J_t[0][b] = b + length of the code that would start at b under table t, four
 // pointer-doubling levels give J_t[k][b] = offset after 2^k codes, and then
-//   * one thread walks the groups: the next group starts at J_t[1][J_t[4][J_t[5][start]]] (50 = 32 + 16 + 2);
+//   * one thread walks the groups: the next group starts 16 + 16 + 16 + 2 codes on (four dependent reads);
 //   * thread (q, r) composes the jumps of r's binary digits from group q's start and IS the r-th symbol of it.
 // A window starts at a group start; a group is at most 50 * 20 = 1000 bits, so every window makes progress.  The price
 // is work (up to 6 tables over every offset), so the host picks this kernel only when the blocks cannot fill the GPU.
 #define DECW_PT 1024         // threads
 #define DECW_WIN 2048        // widest window
 #define DECW_ITEMS 6         // (table, offset) items per thread: 3 tables x 2048 offsets or 6 tables x 1024 offsets
-#define DECW_JCAP (DECW_ITEMS * DECW_PT * DEC_LEVELS)
+#define DECW_LEVELS 5        // J1, J2, J4, J8, J16
+#define DECW_JCAP (DECW_ITEMS * DECW_PT * DECW_LEVELS)
 #define DECW_KMAX 16         // groups taken per window at most (16 * 50 symbols <= DECW_PT extraction threads)
 
 struct DecWinSmem {
@@ -531,60 +537,36 @@ struct DecWinSmem {
   u32 scr[72];  // CTA scans of the header
   u64 sel_end;  // first bit after the selectors
   u64 bitpos_after_header;
-  // J[(s * 6 + k) * W + b]: offset reached from b after 2^k codes of table slot s; 0xffff when one of those codes would
+  // J[(s * 5 + k) * W + b]: offset reached from b after 2^k codes of table slot s; 0xffff when one of those codes would
   // start outside the window (a value in [W, W+20) is a valid end that cannot be continued)
   u16 J[DECW_JCAP];
   u8 selbuf[256];  // selectors of the pass
-  // plan of the window (written by thread 0 one barrier ahead)
-  u32 win_w, ntabs, kq, slot_of;  // slot_of: nibble t = slot of table t (0xF: not in this window)
-  u8 tabs[8];
   u16 starts[DECW_KMAX];  // offset inside the window where the q-th group of the window starts
   u32 ngd, wend;          // groups that end inside the window, offset where the next one starts
   u32 first_eob, first_bad, eob_end;
 };
 
-// long code (not in the LUT): the reference's limit/base/permute walk (BJ:1605-1616) on a 32-bit window; an invalid
-// code comes back as length 1 with bit 20 set (it only counts when it is ON the chain)
-template <typename SM>
-__device__ __noinline__ u32 dec_long_code(const SM &sm, int gi, u32 win) {
-  int L = sm.minl[gi];
-  int j = (int)(win >> (32 - L));
-  for (;; L++) {
-    if (L > sm.maxl[gi]) return (0x8000u << 5) | 1u;
-    if (j <= sm.limit[gi][L]) break;
-    j = (j << 1) | (int)((win >> (31 - L)) & 1u);
+// plan of the window that starts at group `selector`, computed by every warp for itself (lane q looks at selector q):
+// up to 3 distinct tables among the next groups -> 2048 offsets and as many groups as keep to those tables (<= 16);
+// a 4th table within the next 6 groups -> 1024 offsets and all tables of the next 8 groups.  Table t sits in slot
+// popc(mask below bit t).  Returns the table mask; kq = groups the walk may take.
+__device__ __forceinline__ u32 decw_plan(const DecWinSmem &sm, int selector, int sel0, int nsel, u32 &W, u32 &kq) {
+  const u32 wl = threadIdx.x & 31u;
+  const bool valid = wl < DECW_KMAX && selector + (int)wl < nsel;
+  u32 m = valid ? 1u << sm.selbuf[selector - sel0 + (int)(wl < DECW_KMAX ? wl : 0u)] : 0u;
+#pragma unroll
+  for (int d = 1; d < DECW_KMAX; d <<= 1) {
+    const u32 o = __shfl_up_sync(FULL_MASK, m, d);
+    if (wl >= (u32)d) m |= o;
   }
-  j -= sm.base[gi][L];
-  if (j < 0 || j >= BZ_MAX_SYMS) return (0x8000u << 5) | 1u;
-  return ((u32)sm.permute[gi][j] << 5) | (u32)L;
-}
-
-// thread 0: which tables the window that starts at group `selector` looks at, how wide it is, how many groups the
-// walk may take.  Up to 3 distinct tables -> 2048 offsets; a 4th table close by -> 1024 offsets and up to 6 tables.
-__device__ __forceinline__ void decw_plan(DecWinSmem &sm, int selector, int sel0, int nsel) {
-  u32 slot_of = 0xffffffu, ntabs = 0, kq = 0;
-  for (; kq < DECW_KMAX && selector + (int)kq < nsel; kq++) {
-    const u32 t = sm.selbuf[selector - sel0 + (int)kq];
-    if (((slot_of >> (4 * t)) & 15u) == 15u) {
-      if (ntabs == 3) break;
-      sm.tabs[ntabs] = (u8)t;
-      slot_of = (slot_of & ~(15u << (4 * t))) | (ntabs << (4 * t));
-      ntabs++;
-    }
+  const u32 nvalid = (u32)__popc(__ballot_sync(FULL_MASK, valid));
+  kq = (u32)__popc(__ballot_sync(FULL_MASK, valid && __popc(m) <= 3));  // the count of tables grows with q
+  W = DECW_WIN;
+  if (kq < 6 && kq < nvalid) {
+    W = DECW_WIN / 2;
+    kq = nvalid < 8 ? nvalid : 8;
   }
-  u32 w = DECW_WIN;
-  if (kq < 6 && selector + (int)kq < nsel) {
-    w = DECW_WIN / 2;
-    for (; kq < 8 && selector + (int)kq < nsel; kq++) {
-      const u32 t = sm.selbuf[selector - sel0 + (int)kq];
-      if (((slot_of >> (4 * t)) & 15u) == 15u) {
-        sm.tabs[ntabs] = (u8)t;
-        slot_of = (slot_of & ~(15u << (4 * t))) | (ntabs << (4 * t));
-        ntabs++;
-      }
-    }
-  }
-  sm.win_w = w; sm.ntabs = ntabs; sm.kq = kq; sm.slot_of = slot_of;
+  return __shfl_sync(FULL_MASK, m, (int)(kq ? kq - 1 : 0));
 }
 
 __global__ void __launch_bounds__(DECW_PT) k_huff_parse_win(const u8 *__restrict__ in, u64 n, const u64 *__restrict__ cand, u32 ncand, u32 dbuf_cap,
@@ -623,69 +605,84 @@ __global__ void __launch_bounds__(DECW_PT) k_huff_parse_win(const u8 *__restrict
     const int sel0 = selector;  // selectors sel0 .. sel0+255 are staged
     for (int q = lane; q < 256; q += PT) sm.selbuf[q] = sel0 + q < nsel ? sel[sel0 + q] : 0;
     __syncthreads();
-    if (lane == 0) decw_plan(sm, selector, sel0, nsel);
-    __syncthreads();
     u32 P = (u32)(cur_bit - ring_base_w * 32);  // bit offset inside the ring
     while (P + DECW_WIN + 64 <= RBITS && selector - sel0 + DECW_KMAX <= 256) {
       if (selector >= nsel) { err = BZ2B200_E_DATA_ERROR; break; }  // BJ:1601
       if (flushed + BZ_GROUP >= DEC_SYM_STRIDE) { err = BZ2B200_E_DATA_ERROR; break; }  // more symbols than any valid block
-      const u32 W = sm.win_w, ntabs = sm.ntabs;
+      u32 W, kq;
+      const u32 tmask = decw_plan(sm, selector, sel0, nsel, W, kq);
+      const u32 ntabs = (u32)__popc(tmask);
+      u32 tabs = 0;  // nibble s: the table in slot s
+      for (u32 t = 0, c = 0; t < BZ_MAX_GROUPS; t++)
+        if ((tmask >> t) & 1u) { tabs |= t << (4 * c); c++; }
       const u32 opl = W / DECW_PT, nitems = ntabs * opl;  // (table slot, offset) items of this thread, all in flight together
       // level 0: the code that would start at every offset, under every table of the window
-      u32 nx[DECW_ITEMS], sb[DECW_ITEMS], bo[DECW_ITEMS];  // sb: index of J[slot][0][0], bo: the item's offset
+      u32 nx[DECW_ITEMS];
+      u16 *jr[DECW_ITEMS], *jw[DECW_ITEMS];  // J[slot][level][0] (gathers) and J[slot][level][own offset] (stores)
       {
         u32 wn[DECW_ITEMS], e[DECW_ITEMS];
         int tb[DECW_ITEMS];
 #pragma unroll
         for (int i = 0; i < DECW_ITEMS; i++) {
-          const u32 s2 = opl == 2 ? (u32)i >> 1 : (u32)i;
-          bo[i] = (u32)lane + (opl == 2 ? ((u32)i & 1u) * DECW_PT : 0u);
-          sb[i] = s2 * DEC_LEVELS * W;
-          tb[i] = sm.tabs[s2 < ntabs ? s2 : 0];
-          const u32 bp = P + bo[i];
+          if ((u32)i >= nitems) break;
+          const u32 s2 = (u32)i >> (opl - 1u), bo = (u32)lane + (((u32)i & (opl - 1u)) << 10);
+          jr[i] = sm.J + s2 * DECW_LEVELS * W;
+          jw[i] = jr[i] + bo;
+          nx[i] = bo;
+          tb[i] = (int)((tabs >> (4 * s2)) & 15u);
+          const u32 bp = P + bo;
           wn[i] = __funnelshift_l(ring32[(bp >> 5) + 1], ring32[bp >> 5], bp & 31u);  // 32 bits from bit P+b
         }
-        bool any_long = false;
 #pragma unroll
         for (int i = 0; i < DECW_ITEMS; i++) {
+          if ((u32)i >= nitems) break;
           e[i] = sm.lut[tb[i]][wn[i] >> (32 - DEC_LUT_BITS)];  // (symbol << 5) | length, 0 = longer than the LUT
-          any_long |= e[i] == 0 && (u32)i < nitems;
-        }
-        if (any_long) {
-#pragma unroll
-          for (int i = 0; i < DECW_ITEMS; i++)
-            if (e[i] == 0 && (u32)i < nitems) e[i] = dec_long_code(sm, tb[i], wn[i]);
         }
 #pragma unroll
         for (int i = 0; i < DECW_ITEMS; i++) {
-          nx[i] = bo[i] + (e[i] & 31u);
-          if ((u32)i < nitems) sm.J[sb[i] + bo[i]] = (u16)nx[i];
+          if ((u32)i >= nitems) break;
+          if (e[i] == 0 || e[i] == DEC_LUT_BAD) e[i] = dec_long_code(sm, tb[i], wn[i], e[i]);
+          nx[i] += e[i] & 31u;
+          *jw[i] = (u16)nx[i];
         }
       }
       __syncthreads();
-      for (u32 q = 1; q < DEC_LEVELS; q++) {  // J[q] = J[q-1] o J[q-1]; a thread's own J[q-1] values stay in registers
+      for (u32 q = 1; q < DECW_LEVELS; q++) {  // J[q] = J[q-1] o J[q-1]; a thread's own J[q-1] values stay in registers
 #pragma unroll
-        for (int i = 0; i < DECW_ITEMS; i++) nx[i] = ((u32)i < nitems && nx[i] < W) ? sm.J[sb[i] + (q - 1) * W + nx[i]] : 0xffffu;
+        for (int i = 0; i < DECW_ITEMS; i++) {
+          if ((u32)i >= nitems) break;
+          const u32 v = jr[i][nx[i] < W ? nx[i] : 0u];
+          nx[i] = nx[i] < W ? v : 0xffffu;
+        }
 #pragma unroll
-        for (int i = 0; i < DECW_ITEMS; i++)
-          if ((u32)i < nitems) sm.J[sb[i] + q * W + bo[i]] = (u16)nx[i];
+        for (int i = 0; i < DECW_ITEMS; i++) {
+          if ((u32)i >= nitems) break;
+          jr[i] += W;
+          jw[i] += W;
+          *jw[i] = (u16)nx[i];
+        }
         __syncthreads();
       }
-      // the walk over the groups of the window (one thread)
+      // the walk over the groups of the window (one thread): 50 = 16 + 16 + 16 + 2
       if (lane == 0) {
-        const u32 kq = sm.kq, slot_of = sm.slot_of;
         u32 pos = 0, g = 0;
-        while (g < kq && pos < W && flushed + (g + 1) * BZ_GROUP < DEC_SYM_STRIDE) {
-          const u32 s2 = (slot_of >> (4 * sm.selbuf[selector - sel0 + (int)g])) & 15u;
-          const u16 *Jb = sm.J + (s2 * DEC_LEVELS) * W;
-          const u32 a = Jb[5 * W + pos];
+        u32 lim = (DEC_SYM_STRIDE - 1 - flushed) / BZ_GROUP;  // groups g with flushed + (g + 1) * 50 < DEC_SYM_STRIDE
+        if (lim > kq) lim = kq;
+        const u16 *Jn = sm.J + (u32)__popc(tmask & ((1u << sm.selbuf[selector - sel0]) - 1u)) * DECW_LEVELS * W;
+        while (g < lim && pos < W) {
+          const u16 *Jb = Jn;
+          Jn = sm.J + (u32)__popc(tmask & ((1u << sm.selbuf[selector - sel0 + (int)(g + 1 < lim ? g + 1 : g)]) - 1u)) * DECW_LEVELS * W;  // next group's table, off the chain
+          const u16 *J16 = Jb + 4 * W;
+          const u32 a = J16[pos];
           if (a >= W) break;
-          const u32 b2 = Jb[4 * W + a];
+          const u32 b2 = J16[a];
           if (b2 >= W) break;
-          const u32 c2 = Jb[1 * W + b2];
-          if (c2 == 0xffffu) break;
+          const u32 c2 = J16[b2];
+          if (c2 >= W) break;
+          const u32 d2 = Jb[W + c2];
+          if (d2 == 0xffffu) break;
           sm.starts[g] = (u16)pos;
-          pos = c2;
+          pos = d2;
           g++;
         }
         sm.ngd = g; sm.wend = pos;
@@ -697,16 +694,17 @@ __global__ void __launch_bounds__(DECW_PT) k_huff_parse_win(const u8 *__restrict
       if ((u32)lane < total) {  // thread (q, r): the r-th code of the q-th group
         const u32 q = (u32)lane / BZ_GROUP, r = (u32)lane % BZ_GROUP;
         const int t = sm.selbuf[selector - sel0 + (int)q];
-        const u32 s2 = (sm.slot_of >> (4 * t)) & 15u;
-        const u16 *Jb = sm.J + (s2 * DEC_LEVELS) * W;
+        const u32 s2 = (u32)__popc(tmask & ((1u << t) - 1u));
+        const u16 *Jb = sm.J + (s2 * DECW_LEVELS) * W;
         u32 pos = sm.starts[q];
+        for (u32 z = r >> 4; z; z--) pos = Jb[4 * W + pos];
 #pragma unroll
-        for (int z = 0; z < DEC_LEVELS; z++)
+        for (int z = 0; z < 4; z++)
           if ((r >> z) & 1u) pos = Jb[z * W + pos];
         const u32 bp = P + pos;
         const u32 wn = __funnelshift_l(ring32[(bp >> 5) + 1], ring32[bp >> 5], bp & 31u);
         u32 e = sm.lut[t][wn >> (32 - DEC_LUT_BITS)];
-        if (e == 0) e = dec_long_code(sm, t, wn);
+        if (e == 0 || e == DEC_LUT_BAD) e = dec_long_code(sm, t, wn, e);
         const u32 sy = e >> 5;
         my_end = pos + (e & 31u);
         Sk[flushed + lane] = (u16)(sy & 0x7fffu);
@@ -727,9 +725,7 @@ __global__ void __launch_bounds__(DECW_PT) k_huff_parse_win(const u8 *__restrict
       flushed += take;
       P += advance;
       selector += (int)ngd;
-      if (done || selector - sel0 + DECW_KMAX > 256) break;  // (the next pass plans its first window itself)
-      if (lane == 0) decw_plan(sm, selector, sel0, nsel);  // reads selbuf only; published by the next barrier
-      __syncthreads();
+      if (done) break;
     }
     cur_bit = ring_base_w * 32 + P;
     if (!err && cur_bit > n * 8) err = BZ2B200_E_UNEXPECTED_INPUT_EOF;  // reference: spins on zero bits (D3)
