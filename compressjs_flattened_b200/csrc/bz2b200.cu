@@ -100,6 +100,7 @@ struct Ctx {
   } pipe;
   bool trace = false;      // BZ2B200_TRACE
   int sms = 148;           // multiprocessors of the device
+  unsigned ibwt_s = 64;    // splitter spacing of the inverse-BWT list ranking (BZ2B200_IBWT_S overrides: 64..1024)
   int parse_mode = 0;      // BZ2B200_PARSE: 0 = by block count, 1 = k_huff_parse, 2 = k_huff_parse_win (development aid)
   std::vector<cudaEvent_t> trace_ev, trace_pool;
   std::vector<const char *> trace_names;
@@ -768,6 +769,7 @@ int bz2b200_create(int device, bz2b200_ctx **ctx) {
   c->ev_ok = true;
   { const char *t = getenv("BZ2B200_TRACE"); c->trace = t && *t && *t != '0'; }
   { const char *t = getenv("BZ2B200_PARSE"); c->parse_mode = t ? atoi(t) : 0; }
+  { const char *t = getenv("BZ2B200_IBWT_S"); int v = t ? atoi(t) : 0; if (v == 64 || v == 128 || v == 256 || v == 512 || v == 1024) c->ibwt_s = (unsigned)v; }
   { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) c->sms = v; }
   for (auto &e : c->ev) if (cudaEventCreate(&e) != cudaSuccess) c->ev_ok = false;
   *ctx = reinterpret_cast<bz2b200_ctx *>(c);

@@ -27,7 +27,7 @@
 #define DEC_LUT_BAD 0xffffu  // LUT entry of a prefix the reference's walk rejects; 0 = code longer than the LUT
 #define DEC_MAX_SEL 32768
 #define DEC_DBUF_MAX 900000
-#define IBWT_S 256
+#define IBWT_S ibwt_s  // splitter spacing: a kernel parameter / host variable (power of two)
 
 struct DecBlk {
   u64 bitpos;      // position of the 48-bit magic
@@ -917,28 +917,37 @@ __global__ void __launch_bounds__(SEG_THREADS) k_dec_keys(const u8 *__restrict__
   }
 }
 
-// sorted keys -> T vector (position of the slot's byte in the L column)
-__global__ void k_dec_extract(const u64 *__restrict__ keys, u32 *__restrict__ tt, u64 nslots) {
-  u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g < nslots) tt[g] = (u32)(keys[g] & 0xFFFFFu);
+// sorted keys -> T vector, packed like the reference's dbuf (BJ:1686-1690): (position of the slot's byte in the L
+// column << 8) | the L byte AT this slot, so a hop of the walk is one random read instead of two
+__global__ void __launch_bounds__(SEG_THREADS) k_dec_extract(const u64 *__restrict__ keys, const u8 *__restrict__ dL, i64 l_stride,
+                                                             const u32 *__restrict__ order, const u32 *__restrict__ seg_cnt,
+                                                             const u32 *__restrict__ seg_tile0, const u32 *__restrict__ tile_blk, u32 *__restrict__ tt) {
+  u32 tile = blockIdx.x, p = tile_blk[tile];
+  u32 cnt = seg_cnt[p], l0 = (tile - seg_tile0[p]) * SORT_TILE;
+  const u8 *Lk = dL + (i64)order[p] * l_stride;
+  u64 g0 = (u64)tile * SORT_TILE;
+  for (int e = 0; e < SEG_E; e++) {
+    u32 lj = l0 + e * SEG_THREADS + threadIdx.x;
+    if (lj < cnt) tt[g0 + (lj - l0)] = ((u32)(keys[g0 + (lj - l0)] & 0xFFFFFu) << 8) | Lk[lj];
+  }
 }
 
 // ---- K-U4b: list ranking ----------------------------------------------------------------------
 // Splitters of block p: slots 0, S, 2S, ... plus one extra for the start slot pos0 = tt[origPtr].
 // spl arrays are laid out per block at offset spl0[p]; W_p = ceil(n/S) + 1.
-__device__ __forceinline__ bool ibwt_is_spl(u32 j, u32 pos0) { return (j % IBWT_S) == 0 || j == pos0; }
-__device__ __forceinline__ u32 ibwt_spl_index(u32 j, u32 pos0, u32 W) { return j == pos0 ? W - 1 : j / IBWT_S; }
+__device__ __forceinline__ bool ibwt_is_spl(u32 j, u32 pos0, u32 ibwt_s) { return (j & (IBWT_S - 1)) == 0 || j == pos0; }
+__device__ __forceinline__ u32 ibwt_spl_index(u32 j, u32 pos0, u32 W, u32 ibwt_s) { return j == pos0 ? W - 1 : j / IBWT_S; }
 
 __global__ void __launch_bounds__(256) k_ibwt_walk1(const u32 *__restrict__ tt, const DecBlk *__restrict__ blks, const u32 *__restrict__ order,
                                                     const u32 *__restrict__ seg_tile0, const u32 *__restrict__ spl0, int nb,
-                                                    u32 *__restrict__ spl_next, u32 *__restrict__ spl_len, u32 p0) {
+                                                    u32 *__restrict__ spl_next, u32 *__restrict__ spl_len, u32 p0, u32 ibwt_s) {
   u32 p = p0 + blockIdx.y;  // launched in batches of blocks whose T-vectors fit the L2 together
   const DecBlk &b = blks[order[p]];
   u32 n = b.count;
   if (n == 0) return;
   const u32 *T = tt + (u64)seg_tile0[p] * SORT_TILE;
   u32 W = (n + IBWT_S - 1) / IBWT_S + 1;
-  u32 pos0 = T[b.orig_ptr];
+  u32 pos0 = T[b.orig_ptr] >> 8;
   for (u32 s = blockIdx.x * blockDim.x + threadIdx.x; s < W; s += gridDim.x * blockDim.x) {
     u32 start = s == W - 1 ? pos0 : s * IBWT_S;
     if (s != W - 1 && start == pos0) {  // duplicate of the extra splitter: unused
@@ -947,32 +956,36 @@ __global__ void __launch_bounds__(256) k_ibwt_walk1(const u32 *__restrict__ tt, 
       continue;
     }
     u32 cur = start, len = 0;
-    do { cur = T[cur]; len++; } while (!ibwt_is_spl(cur, pos0) && len < n);
-    spl_next[spl0[p] + s] = ibwt_spl_index(cur, pos0, W);
+    do { cur = T[cur] >> 8; len++; } while (!ibwt_is_spl(cur, pos0, ibwt_s) && len < n);
+    spl_next[spl0[p] + s] = ibwt_spl_index(cur, pos0, W, ibwt_s);
     spl_len[spl0[p] + s] = len;
   }
 }
 // one thread per block: offsets of the splitters along the walk from pos0; period if the walk closes
 // one CTA per block: the splitter links are staged in shared memory, one thread chases them there (a few dozen cycles
 // per hop instead of a DRAM round trip), all threads write the offsets back.  Dynamic shared memory: 3 * W words.
+// The walks between splitters are tail-bound (the longest chain is ~11x the spacing), so the spacing is small (64:
+// walk1 + walk2 + rank = 0.64 + 1.29 + 0.85 ms per 100 MB; 128: 1.26 + 1.70 + 0.43; 256: 2.27 + 2.64 + 0.22).
 __global__ void __launch_bounds__(256) k_ibwt_rank(const DecBlk *__restrict__ blks, const u32 *__restrict__ order, const u32 *__restrict__ spl0, int nb,
                                                    const u32 *__restrict__ spl_next, const u32 *__restrict__ spl_len, u32 *__restrict__ spl_off,
-                                                   u32 *__restrict__ period) {
+                                                   u32 *__restrict__ period, u32 ibwt_s) {
   DYN_SMEM(u32, sm);
   const int p = blockIdx.x;
   const u32 n = blks[order[p]].count;
   if (n == 0) { if (threadIdx.x == 0) period[p] = 0; return; }
   const u32 W = (n + IBWT_S - 1) / IBWT_S + 1, base = spl0[p];
-  u32 *nx = sm, *ln = sm + W, *of = sm + 2 * W;
-  for (u32 s = threadIdx.x; s < W; s += blockDim.x) { nx[s] = spl_next[base + s]; ln[s] = spl_len[base + s]; of[s] = 0xffffffffu; }
+  u64 *lk = reinterpret_cast<u64 *>(sm);  // (length << 32) | next splitter: one dependent read per hop
+  u32 *of = sm + 2 * W;
+  for (u32 s = threadIdx.x; s < W; s += blockDim.x) { lk[s] = ((u64)spl_len[base + s] << 32) | spl_next[base + s]; of[s] = 0xffffffffu; }
   __syncthreads();
   if (threadIdx.x == 0) {
     u32 cur = W - 1, off = 0, per = 0;
     while (off < n) {
+      const u64 e = lk[cur];
       if (of[cur] != 0xffffffffu) { per = off - of[cur]; break; }  // closed a cycle (periodic block)
       of[cur] = off;
-      off += ln[cur];
-      cur = nx[cur];
+      off += (u32)(e >> 32);
+      cur = (u32)e;
     }
     period[p] = per;
   }
@@ -983,24 +996,24 @@ __global__ void __launch_bounds__(256) k_ibwt_walk2(const u32 *__restrict__ tt, 
                                                     const DecBlk *__restrict__ blks, const u32 *__restrict__ order,
                                                     const u32 *__restrict__ seg_tile0, const u32 *__restrict__ spl0, int nb,
                                                     const u32 *__restrict__ spl_len, const u32 *__restrict__ spl_off,
-                                                    const u32 *__restrict__ period, u8 *__restrict__ blk_out, i64 b_stride, u32 p0) {
+                                                    const u32 *__restrict__ period, u8 *__restrict__ blk_out, i64 b_stride, u32 p0, u32 ibwt_s) {
   u32 p = p0 + blockIdx.y;
   const DecBlk &b = blks[order[p]];
   u32 n = b.count;
   if (n == 0) return;
   const u32 *T = tt + (u64)seg_tile0[p] * SORT_TILE;
-  const u8 *Lk = dL + (i64)order[p] * l_stride;
   u8 *out = blk_out + (i64)p * b_stride;
   u32 W = (n + IBWT_S - 1) / IBWT_S + 1;
-  u32 pos0 = T[b.orig_ptr], per = period[p];
+  u32 pos0 = T[b.orig_ptr] >> 8, per = period[p];
   for (u32 s = blockIdx.x * blockDim.x + threadIdx.x; s < W; s += gridDim.x * blockDim.x) {
     u32 off = spl_off[spl0[p] + s], len = spl_len[spl0[p] + s];
     if (off == 0xffffffffu || len == 0) continue;
     u32 cur = s == W - 1 ? pos0 : s * IBWT_S;
     for (u32 t = 0; t < len; t++) {
-      u8 byte = Lk[cur];
+      const u32 en = T[cur];
+      const u8 byte = (u8)en;
       for (u64 o = (u64)off + t; o < n; o += per ? per : n) out[o] = byte;
-      cur = T[cur];
+      cur = en >> 8;
     }
   }
 }

@@ -165,6 +165,7 @@ static int decode_device(Ctx *c, const u8 *d_in, size_t n, int multistream, int 
   size_t slots = 0;
   u32 max_cnt = 0;
   std::vector<u32> spl0((size_t)nb + 1);
+  const u32 ibwt_s = c->ibwt_s;
   u32 spl_total = 0;
   for (int p = 0; p < nb; p++) {
     u32 cnt = blks[chain[p]].count;
@@ -196,7 +197,8 @@ static int decode_device(Ctx *c, const u8 *d_in, size_t n, int multistream, int 
     LAUNCH(k_rs_scan<8>, dim3((unsigned)nb, 256 / 32), RSS_WARPS * 32, 0, P<u32>(c->hist), P<u32>(c->seg_tile0), P<u32>(c->digit_base));
     LAUNCH(k_rs_scatter<8>, (unsigned)tiles, SORT_THREADS, 0, P<u64>(c->keysA), P<u64>(c->keysB), P<u32>(c->seg_cnt),
            P<u32>(c->seg_tile0), P<u32>(c->tile_blk), 20, P<u32>(c->hist), P<u32>(c->digit_base), (const u32 *)nullptr);
-    LAUNCH(k_dec_extract, (unsigned)((slots + 255) / 256), 256, 0, P<u64>(c->keysB), P<u32>(c->valsB), (u64)slots);
+    LAUNCH(k_dec_extract, (unsigned)tiles, SEG_THREADS, 0, P<u64>(c->keysB), P<u8>(c->dL), LS, d_order, P<u32>(c->seg_cnt), P<u32>(c->seg_tile0), P<u32>(c->tile_blk),
+           P<u32>(c->valsB));
   }
   // ---- K-U4b: list ranking ----
   const i64 BS = round_up((i64)max_cnt + 8, 256);
@@ -207,11 +209,17 @@ static int decode_device(Ctx *c, const u8 *d_in, size_t n, int multistream, int 
   if (max_cnt) {
     // (launching the walks for L2-sized batches of blocks was tried: slower -- a batch waits for its longest chain, ~11x
     // the mean of 256 steps, and too few threads are left to hide the latency)
-    LAUNCH(k_ibwt_walk1, dim3(gx, (unsigned)nb), 256, 0, P<u32>(c->valsB), P<DecBlk>(c->dmeta), d_order, P<u32>(c->seg_tile0), d_spl0, nb, spl_next, spl_len, 0u);
-    LAUNCH(k_ibwt_rank, (unsigned)nb, 256, 12 * (size_t)((DEC_DBUF_MAX + IBWT_S - 1) / IBWT_S + 2), P<DecBlk>(c->dmeta), d_order, d_spl0, nb, spl_next, spl_len,
-           spl_off, period);
+    LAUNCH(k_ibwt_walk1, dim3(gx, (unsigned)nb), 256, 0, P<u32>(c->valsB), P<DecBlk>(c->dmeta), d_order, P<u32>(c->seg_tile0), d_spl0, nb, spl_next, spl_len, 0u, ibwt_s);
+    const size_t rank_smem = 12 * (size_t)((DEC_DBUF_MAX + IBWT_S - 1) / IBWT_S + 2);
+    static size_t rank_attr = 0;
+    if (rank_smem > 48 * 1024 && rank_attr < rank_smem) {
+      CK(cudaFuncSetAttribute(k_ibwt_rank, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rank_smem));
+      rank_attr = rank_smem;
+    }
+    LAUNCH(k_ibwt_rank, (unsigned)nb, 256, rank_smem, P<DecBlk>(c->dmeta), d_order, d_spl0, nb, spl_next, spl_len,
+           spl_off, period, ibwt_s);
     LAUNCH(k_ibwt_walk2, dim3(gx, (unsigned)nb), 256, 0, P<u32>(c->valsB), P<u8>(c->dL), LS, P<DecBlk>(c->dmeta), d_order, P<u32>(c->seg_tile0), d_spl0, nb,
-           spl_len, spl_off, period, P<u8>(c->dblk), BS, 0u);
+           spl_len, spl_off, period, P<u8>(c->dblk), BS, 0u, ibwt_s);
   }
   if ((rc = mark(c, 3))) return rc;
 
