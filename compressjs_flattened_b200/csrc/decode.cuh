@@ -132,7 +132,7 @@ struct DecSmem {
 // (BJ:1605-1616) continued from there on a 32-bit window; DEC_LUT_BAD or a failed walk = invalid code, which comes back
 // as length 1 with bit 20 set (it keeps the chain moving and only counts when it is ON the chain)
 template <typename SM>
-__device__ __noinline__ u32 dec_long_code(const SM &sm, int gi, u32 win, u32 entry) {
+__device__ __forceinline__ u32 dec_long_code_inl(const SM &sm, int gi, u32 win, u32 entry) {
   if (entry == DEC_LUT_BAD) return (0x8000u << 5) | 1u;
   int L = sm.minl[gi] > DEC_LUT_BITS + 1 ? sm.minl[gi] : DEC_LUT_BITS + 1;
   int j = (int)(win >> (32 - L));
@@ -145,6 +145,8 @@ __device__ __noinline__ u32 dec_long_code(const SM &sm, int gi, u32 win, u32 ent
   if (j < 0 || j >= BZ_MAX_SYMS) return (0x8000u << 5) | 1u;
   return ((u32)sm.permute[gi][j] << 5) | (u32)L;
 }
+template <typename SM>
+__device__ __noinline__ u32 dec_long_code(const SM &sm, int gi, u32 win, u32 entry) { return dec_long_code_inl(sm, gi, win, entry); }
 
 // 32 bits of the stream from bit position bp, first bit in bit 31; bits past EOF read as 0 (BJ:149-150)
 __device__ __forceinline__ u32 dec_load32(const u8 *__restrict__ in, u64 n, u64 bp) {
@@ -445,7 +447,7 @@ __global__ void __launch_bounds__(PT) k_huff_parse(const u8 *__restrict__ in, u6
       const u32 bp = P + (u32)lane;
       const u32 win = __funnelshift_l(ring32[(bp >> 5) + 1], ring32[bp >> 5], bp & 31u);  // 32 bits from bit P+lane
       u32 e = sm.lut[gi][win >> (32 - DEC_LUT_BITS)];  // (symbol << 5) | length, 0 = longer than the LUT
-      if (e == 0 || e == DEC_LUT_BAD) e = dec_long_code(sm, gi, win, e);  // sym 0x8000 = invalid code
+      if (e == 0 || e == DEC_LUT_BAD) e = dec_long_code_inl(sm, gi, win, e);  // sym 0x8000 = invalid code
       const u32 sym = e >> 5, nxt = (u32)lane + (e & 31u);
       sm.J[0][lane] = (u16)nxt;
       sm.SY[lane] = (u16)sym;
@@ -961,7 +963,9 @@ __global__ void __launch_bounds__(256) k_ibwt_walk1(const u32 *__restrict__ tt, 
     spl_len[spl0[p] + s] = len;
   }
 }
-// one thread per block: offsets of the splitters along the walk from pos0; period if the walk closes
+#define IBWT_R 64      // sub-splitter spacing of the splitter chase
+#define IBWT_SUBS 256  // >= (900000 / 64 + 2) / IBWT_R + 2 sub-splitters
+// one CTA per block: offsets of the splitters along the walk from pos0; period if the walk closes
 // one CTA per block: the splitter links are staged in shared memory, one thread chases them there (a few dozen cycles
 // per hop instead of a DRAM round trip), all threads write the offsets back.  Dynamic shared memory: 3 * W words.
 // The walks between splitters are tail-bound (the longest chain is ~11x the spacing), so the spacing is small (64:
@@ -978,16 +982,47 @@ __global__ void __launch_bounds__(256) k_ibwt_rank(const DecBlk *__restrict__ bl
   u32 *of = sm + 2 * W;
   for (u32 s = threadIdx.x; s < W; s += blockDim.x) { lk[s] = ((u64)spl_len[base + s] << 32) | spl_next[base + s]; of[s] = 0xffffffffu; }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    u32 cur = W - 1, off = 0, per = 0;
-    while (off < n) {
+  // the chase over W links is itself list ranking: every 64th link (and the start) is a sub-splitter, all threads walk
+  // from theirs to the next one, one thread chases the few hundred sub-splitters, all threads walk again writing offsets
+  __shared__ u32 sub_next[IBWT_SUBS], sub_len[IBWT_SUBS], sub_off[IBWT_SUBS];
+  const u32 NS = (W + IBWT_R - 1) / IBWT_R + 1;  // the last one is the start link W-1
+  for (u32 q = threadIdx.x; q < NS; q += blockDim.x) {
+    const u32 s0 = q == NS - 1 ? W - 1 : q * IBWT_R;
+    sub_off[q] = 0xffffffffu;
+    sub_next[q] = q; sub_len[q] = 0;
+    if (q != NS - 1 && s0 >= W - 1) continue;  // past the end, or the start link itself (its own sub-splitter)
+    u32 cur = s0, acc = 0, hops = 0;
+    do {
       const u64 e = lk[cur];
-      if (of[cur] != 0xffffffffu) { per = off - of[cur]; break; }  // closed a cycle (periodic block)
+      acc += (u32)(e >> 32);
+      cur = (u32)e;
+      hops++;
+    } while (cur != W - 1 && (cur % IBWT_R) != 0 && hops < W);  // (a cycle without sub-splitters is not on the path)
+    sub_next[q] = cur == W - 1 ? NS - 1 : cur / IBWT_R;
+    sub_len[q] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    u32 q = NS - 1, off = 0, per = 0;
+    while (off < n) {
+      if (sub_off[q] != 0xffffffffu) { per = off - sub_off[q]; break; }  // closed a cycle (periodic block)
+      sub_off[q] = off;
+      off += sub_len[q];
+      q = sub_next[q];
+    }
+    period[p] = per;
+  }
+  __syncthreads();
+  for (u32 q = threadIdx.x; q < NS; q += blockDim.x) {
+    u32 off = sub_off[q];
+    if (off == 0xffffffffu) continue;
+    u32 cur = q == NS - 1 ? W - 1 : q * IBWT_R;
+    do {
+      const u64 e = lk[cur];
       of[cur] = off;
       off += (u32)(e >> 32);
       cur = (u32)e;
-    }
-    period[p] = per;
+    } while (cur != W - 1 && (cur % IBWT_R) != 0);
   }
   __syncthreads();
   for (u32 s = threadIdx.x; s < W; s += blockDim.x) spl_off[base + s] = of[s];
@@ -1052,6 +1087,8 @@ __device__ __forceinline__ u32 block_excl_fn(u32 f, u32 &total, u32 *ws) {
   __syncthreads();
   return res;
 }
+#define RLI_K 8  // bytes per thread and strip
+// threads: 1024 when every block has an SM to itself (latency), else 512 (62 registers: two CTAs per SM)
 // mode 0: out_len[p] = decoded size of block p.  mode 1: write the bytes at out + out_off[p].
 __global__ void __launch_bounds__(1024) k_rle1_inv(const u8 *__restrict__ blk, i64 b_stride, const DecBlk *__restrict__ blks,
                                                    const u32 *__restrict__ order, int mode, u64 *__restrict__ out_len,
@@ -1067,31 +1104,45 @@ __global__ void __launch_bounds__(1024) k_rle1_inv(const u8 *__restrict__ blk, i
   u32 carry_fn = 0;     // composed carry function so far, applied to 0: constant -> store as value 0/1 in both bits
   u64 carry_out = 0;
   carry_fn = 0u;        // const 0 (c of the first run is 0)
-  for (u32 base = 0; base < n; base += 1024 * 4) {
-    u32 i0 = base + threadIdx.x * 4;
-    u8 e[6];  // e[0] = byte before i0, e[1..4] = mine, e[5] = byte after
-    for (int k = 0; k < 6; k++) { i64 j = (i64)i0 - 1 + k; e[k] = (j >= 0 && j < (i64)n) ? E[j] : 0; }
-    // run heads and ends among my 4 positions
+  // a strip is RLI_K bytes per thread: the three CTA scans per strip are the cost (one CTA walks a block serially), so
+  // the strip is wide
+  for (u32 base = 0; base < n; base += blockDim.x * RLI_K) {
+    u32 i0 = base + threadIdx.x * RLI_K;
+    u8 e[RLI_K + 2];  // e[0] = byte before i0, e[1..RLI_K] = mine, e[RLI_K+1] = byte after
+    if (i0 + RLI_K <= n) {  // (block buffers are 256-byte aligned and i0 is a multiple of 8)
+      const uint2 v = *reinterpret_cast<const uint2 *>(E + i0);
+#pragma unroll
+      for (int k = 0; k < 4; k++) { e[1 + k] = (u8)(v.x >> (8 * k)); e[5 + k] = (u8)(v.y >> (8 * k)); }
+    } else {
+#pragma unroll
+      for (int k = 0; k < RLI_K; k++) e[1 + k] = i0 + k < n ? E[i0 + k] : 0;
+    }
+    e[0] = i0 > 0 && i0 - 1 < n ? E[i0 - 1] : 0;
+    e[RLI_K + 1] = i0 + RLI_K < n ? E[i0 + RLI_K] : 0;
+    // run heads and ends among my positions
     int my_head = -1;
-    bool head[4], endr[4];
-    for (int k = 0; k < 4; k++) {
+    u32 headm = 0, endm = 0;
+#pragma unroll
+    for (int k = 0; k < RLI_K; k++) {
       u32 i = i0 + k;
-      head[k] = i < n && (i == 0 || e[k + 1] != e[k]);
-      endr[k] = i < n && (i + 1 >= n || e[k + 2] != e[k + 1]);
-      if (head[k]) my_head = (int)i;
+      const bool hd = i < n && (i == 0 || e[k + 1] != e[k]);
+      const bool en = i < n && (i + 1 >= n || e[k + 2] != e[k + 1]);
+      headm |= (u32)hd << k;
+      endm |= (u32)en << k;
+      if (hd) my_head = (int)i;
     }
     int tot_h;
     int hb = block_excl_max<int>(my_head, -1, tot_h, wsi);
     if (carry_head > hb) hb = carry_head;
-    // carry function of my 4 positions: at a run end of length l, f(c) = ((l - c) mod 5 == 4)
+    // carry function of my positions: at a run end of length l, f(c) = ((l - c) mod 5 == 4)
     u32 f = FN_ID;
     {
       int cur = hb;
-      for (int k = 0; k < 4; k++) {
+#pragma unroll
+      for (int k = 0; k < RLI_K; k++) {
         u32 i = i0 + k;
-        if (i >= n) break;
-        if (head[k]) cur = (int)i;
-        if (endr[k]) {
+        if ((headm >> k) & 1u) cur = (int)i;
+        if ((endm >> k) & 1u) {
           u32 l = i - (u32)cur + 1;
           u32 g = ((l % 5) == 4 ? 1u : 0u) | ((((l + 4) % 5) == 4) ? 2u : 0u);  // (l-1) mod 5 == 4  <=>  (l+4) mod 5 == 4
           f = fn_compose(f, g);
@@ -1103,30 +1154,33 @@ __global__ void __launch_bounds__(1024) k_rle1_inv(const u8 *__restrict__ blk, i
     u32 c_in = (fn_compose(carry_fn, fe)) & 1u;  // carry_fn is constant: value in bit 0
     // counts
     u32 cnt = 0;
-    u32 emit[4] = {0u, 0u, 0u, 0u};
+    u32 emit[RLI_K];
     {
       int cur = hb;
       u32 c = c_in;
-      for (int k = 0; k < 4; k++) {
+#pragma unroll
+      for (int k = 0; k < RLI_K; k++) {
         u32 i = i0 + k;
         emit[k] = 0;
-        if (i >= n) break;
-        if (head[k]) cur = (int)i;
-        int kk = (int)(i - (u32)cur) - (int)c;  // index among the run's own literals/counts
-        if (kk < 0) emit[k] = 0x100u | e[k + 1];            // count byte of the previous run: e[k+1] copies of e[k]
-        else if (kk % 5 == 4) emit[k] = 0x200u | e[k + 1];  // count byte of this run
-        else emit[k] = 0x400u;                               // literal
-        cnt += (emit[k] & 0x400u) ? 1u : (emit[k] & 0xffu);
-        if (endr[k]) {
-          u32 l = i - (u32)cur + 1;
-          c = ((l - c) % 5 == 4) ? 1u : 0u;
+        if (i < n) {
+          if ((headm >> k) & 1u) cur = (int)i;
+          int kk = (int)(i - (u32)cur) - (int)c;  // index among the run's own literals/counts
+          if (kk < 0) emit[k] = 0x100u | e[k + 1];            // count byte of the previous run: e[k+1] copies of e[k]
+          else if (kk % 5 == 4) emit[k] = 0x200u | e[k + 1];  // count byte of this run
+          else emit[k] = 0x400u;                               // literal
+          cnt += (emit[k] & 0x400u) ? 1u : (emit[k] & 0xffu);
+          if ((endm >> k) & 1u) {
+            u32 l = i - (u32)cur + 1;
+            c = ((l - c) % 5 == 4) ? 1u : 0u;
+          }
         }
       }
     }
     u64 tot_o;
     u64 o = carry_out + block_excl_sum<u64>((u64)cnt, tot_o, ws64);
     if (mode) {
-      for (int k = 0; k < 4; k++) {
+#pragma unroll
+      for (int k = 0; k < RLI_K; k++) {
         if (!emit[k]) continue;
         if (emit[k] & 0x400u) O[o++] = e[k + 1];
         else {

@@ -226,7 +226,8 @@ static int decode_device(Ctx *c, const u8 *d_in, size_t n, int multistream, int 
   // ---- K-U4c: RLE1^-1 (sizes, then bytes) ----
   ENS(c->bit_off, 8 * 2 * ((size_t)nb + 2));
   u64 *d_len = P<u64>(c->bit_off), *d_off = d_len + nb + 1;
-  LAUNCH(k_rle1_inv, (unsigned)nb, 1024, 0, P<u8>(c->dblk), BS, P<DecBlk>(c->dmeta), d_order, 0, d_len, (const u64 *)nullptr, (u8 *)nullptr);
+  const unsigned rli_threads = nb <= c->sms ? 1024 : 512;
+  LAUNCH(k_rle1_inv, (unsigned)nb, rli_threads, 0, P<u8>(c->dblk), BS, P<DecBlk>(c->dmeta), d_order, 0, d_len, (const u64 *)nullptr, (u8 *)nullptr);
   std::vector<u64> lens((size_t)nb), offs((size_t)nb + 1);
   CK(cudaMemcpyAsync(lens.data(), d_len, 8 * (size_t)nb, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
@@ -242,7 +243,7 @@ static int decode_device(Ctx *c, const u8 *d_in, size_t n, int multistream, int 
     c->err = "output buffer too small";
     return BZ2B200_E_UNEXPECTED_OUTPUT_EOF;
   }
-  LAUNCH(k_rle1_inv, (unsigned)nb, 1024, 0, P<u8>(c->dblk), BS, P<DecBlk>(c->dmeta), d_order, 1, d_len, d_off, d_out);
+  LAUNCH(k_rle1_inv, (unsigned)nb, rli_threads, 0, P<u8>(c->dblk), BS, P<DecBlk>(c->dmeta), d_order, 1, d_len, d_off, d_out);
   // ---- block CRCs over the output (BJ:1756-1761) ----
   ENS(c->recs, sizeof(BlockRec) * (size_t)nb);
   LAUNCH(k_dec_crc_recs, (unsigned)((nb + 127) / 128), 128, 0, d_off, nb, P<BlockRec>(c->recs));
