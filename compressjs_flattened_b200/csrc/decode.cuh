@@ -125,24 +125,28 @@ struct DecSmem {
   u16 csym[64], cend[64];     // symbol and end offset of the r-th code of the chain
   u8 selbuf[256];             // selectors of the pass
   u32 ws[34];
-  u32 first_eob, first_bad, adv;
+  u32 first_eob, first_bad, first_eof, adv;
 };
 
 // a code the LUT does not hold: entry 0 = longer than DEC_LUT_BITS -> the reference's limit/base/permute walk
 // (BJ:1605-1616) continued from there on a 32-bit window; DEC_LUT_BAD or a failed walk = invalid code, which comes back
-// as length 1 with bit 20 set (it keeps the chain moving and only counts when it is ON the chain)
+// as length 1 with DEC_BAD set (it keeps the chain moving and only counts when it is ON the chain)
+#define DEC_BAD (1u << 20)  // bit 15 of the symbol field: invalid code
+#define DEC_BAD_CODE(bits_read) (DEC_BAD | ((u32)(bits_read) << 21) | 1u)
 template <typename SM>
 __device__ __forceinline__ u32 dec_long_code_inl(const SM &sm, int gi, u32 win, u32 entry) {
-  if (entry == DEC_LUT_BAD) return (0x8000u << 5) | 1u;
-  int L = sm.minl[gi] > DEC_LUT_BITS + 1 ? sm.minl[gi] : DEC_LUT_BITS + 1;
+  // (an invalid code also reports how many bits the reference's walk read before it gave up, bits 21+: whether those
+  // reach past the end of the input decides between "data error" and "unexpected EOF")
+  int L = sm.minl[gi];
+  if (entry != DEC_LUT_BAD && L < DEC_LUT_BITS + 1) L = DEC_LUT_BITS + 1;
   int j = (int)(win >> (32 - L));
   for (;; L++) {
-    if (L > sm.maxl[gi]) return (0x8000u << 5) | 1u;
+    if (L > sm.maxl[gi]) return DEC_BAD_CODE(sm.maxl[gi] + 1);
     if (j <= sm.limit[gi][L]) break;
     j = (j << 1) | (int)((win >> (31 - L)) & 1u);
   }
   j -= sm.base[gi][L];
-  if (j < 0 || j >= BZ_MAX_SYMS) return (0x8000u << 5) | 1u;
+  if (j < 0 || j >= BZ_MAX_SYMS) return DEC_BAD_CODE(L);
   return ((u32)sm.permute[gi][j] << 5) | (u32)L;
 }
 template <typename SM>
@@ -451,7 +455,7 @@ __global__ void __launch_bounds__(PT) k_huff_parse(const u8 *__restrict__ in, u6
       const u32 sym = e >> 5, nxt = (u32)lane + (e & 31u);
       sm.J[0][lane] = (u16)nxt;
       sm.SY[lane] = (u16)sym;
-      if (lane == 0) { sm.first_eob = 0xffffffffu; sm.first_bad = 0xffffffffu; sm.adv = 0; }
+      if (lane == 0) { sm.first_eob = 0xffffffffu; sm.first_bad = 0xffffffffu; sm.first_eof = 0xffffffffu; sm.adv = 0; }
       __syncthreads();
 #pragma unroll
       for (int q = 1; q < DEC_LEVELS; q++) {  // J[q] = J[q-1] o J[q-1]
@@ -470,12 +474,25 @@ __global__ void __launch_bounds__(PT) k_huff_parse(const u8 *__restrict__ in, u6
         const u32 sy = have ? sm.SY[pos] : 0u;
         sm.csym[lane] = (u16)sy;
         sm.cend[lane] = have ? sm.J[0][pos] : (u16)0xffff;  // the bit after code r = where code r+1 starts
-        const u32 hb = __ballot_sync(FULL_MASK, have), eb = __ballot_sync(FULL_MASK, have && (sy & 0x7fffu) == eob),
-                  bb = __ballot_sync(FULL_MASK, have && (sy & 0x8000u));
+        // the first code whose bits reach past the end of the input is "unexpected EOF" (the oracle checks per code;
+        // an invalid code read as many bits as the reference's walk did before giving up)
+        bool over = false;
+        if (have) {
+          u32 bits = sm.J[0][pos] - pos;
+          if (sy & 0x8000u) {
+            const u32 bp2 = P + pos;
+            const u32 w2 = __funnelshift_l(ring32[(bp2 >> 5) + 1], ring32[bp2 >> 5], bp2 & 31u);
+            bits = dec_long_code_inl(sm, gi, w2, sm.lut[gi][w2 >> (32 - DEC_LUT_BITS)]) >> 21;
+          }
+          over = ring_base_w * 32 + P + pos + bits > n * 8;
+        }
+        const u32 hb = __ballot_sync(FULL_MASK, have), ob = __ballot_sync(FULL_MASK, over),
+                  eb = __ballot_sync(FULL_MASK, have && !over && (sy & 0x7fffu) == eob), bb = __ballot_sync(FULL_MASK, have && !over && (sy & 0x8000u));
         if ((lane & 31) == 0) {  // `have` is monotone in r: the counts of the two warps add up
           atomicAdd(&sm.adv, (u32)__popc(hb));
           if (eb) atomicMin(&sm.first_eob, (u32)(lane + __ffs((int)eb) - 1));
           if (bb) atomicMin(&sm.first_bad, (u32)(lane + __ffs((int)bb) - 1));
+          if (ob) atomicMin(&sm.first_eof, (u32)(lane + __ffs((int)ob) - 1));
         }
       }
       __syncthreads();
@@ -483,7 +500,7 @@ __global__ void __launch_bounds__(PT) k_huff_parse(const u8 *__restrict__ in, u6
       u32 take = left < total ? left : total;
       bool fin = false;
       if (sm.first_eob < take) { take = sm.first_eob + 1; fin = true; }
-      if (sm.first_bad < take) { err = BZ2B200_E_DATA_ERROR; break; }
+      if (sm.first_bad < take || sm.first_eof < take) { err = sm.first_eof < sm.first_bad ? BZ2B200_E_UNEXPECTED_INPUT_EOF : BZ2B200_E_DATA_ERROR; break; }
       if ((u32)lane < take) sm.stage[staged + lane] = (u16)(sm.csym[lane] & 0x7fffu);
       const u32 advance = sm.cend[take - 1];
       __syncthreads();  // csym / cend / adv / first_* are rewritten in the next step
@@ -545,7 +562,7 @@ struct DecWinSmem {
   u8 selbuf[256];  // selectors of the pass
   u16 starts[DECW_KMAX];  // offset inside the window where the q-th group of the window starts
   u32 ngd, wend;          // groups that end inside the window, offset where the next one starts
-  u32 first_eob, first_bad, eob_end;
+  u32 first_eob, first_bad, first_eof, eob_end;
 };
 
 // plan of the window that starts at group `selector`, computed by every warp for itself (lane q looks at selector q):
@@ -688,7 +705,7 @@ __global__ void __launch_bounds__(DECW_PT) k_huff_parse_win(const u8 *__restrict
           g++;
         }
         sm.ngd = g; sm.wend = pos;
-        sm.first_eob = 0xffffffffu; sm.first_bad = 0xffffffffu;
+        sm.first_eob = 0xffffffffu; sm.first_bad = 0xffffffffu; sm.first_eof = 0xffffffffu;
       }
       __syncthreads();
       const u32 ngd = sm.ngd, total = ngd * BZ_GROUP;
@@ -710,12 +727,14 @@ __global__ void __launch_bounds__(DECW_PT) k_huff_parse_win(const u8 *__restrict
         const u32 sy = e >> 5;
         my_end = pos + (e & 31u);
         Sk[flushed + lane] = (u16)(sy & 0x7fffu);
-        if (sy & 0x8000u) atomicMin(&sm.first_bad, (u32)lane);
+        // the first code whose bits reach past the end of the input is "unexpected EOF" (the oracle checks per code)
+        if (ring_base_w * 32 + P + pos + ((sy & 0x8000u) ? e >> 21 : e & 31u) > n * 8) atomicMin(&sm.first_eof, (u32)lane);
+        else if (sy & 0x8000u) atomicMin(&sm.first_bad, (u32)lane);
         else if (sy == eob) atomicMin(&sm.first_eob, (u32)lane);
       }
       __syncthreads();
       u32 take = total, advance = sm.wend;
-      const u32 fe = sm.first_eob, fb = sm.first_bad;
+      const u32 fe = sm.first_eob, fb = sm.first_bad, fo = sm.first_eof;
       if (fe < take) {  // the block ends here: the bit after the end-of-block code
         take = fe + 1;
         if ((u32)lane == fe) sm.eob_end = my_end;
@@ -723,7 +742,7 @@ __global__ void __launch_bounds__(DECW_PT) k_huff_parse_win(const u8 *__restrict
         advance = sm.eob_end;
         done = 1;
       }
-      if (fb < take) { err = BZ2B200_E_DATA_ERROR; break; }
+      if (fb < take || fo < take) { err = fo < fb ? BZ2B200_E_UNEXPECTED_INPUT_EOF : BZ2B200_E_DATA_ERROR; break; }
       flushed += take;
       P += advance;
       selector += (int)ngd;

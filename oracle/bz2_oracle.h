@@ -78,6 +78,8 @@ size_t orc_cut_points(const uint8_t *in, size_t n, int level, uint64_t **starts,
                       uint32_t **lens, uint32_t **crcs);
 /* test hook: block capacity override for stress tests (0 restores level*100000-19) */
 void orc_debug_set_block_cap(size_t cap);
+/* test hook: skip the block CRC comparison of the decoder (damaged streams compared byte for byte) */
+void orc_debug_set_ignore_block_crc(int on);
 /* cyclic BWT with the reference's tie rule (BJ:928-971): returns origPtr */
 int orc_bwt(const uint8_t *T, size_t n, uint8_t *U);
 /* in-place length-limited allocator on an ascending-sorted array (BJ:1275-1298) */

@@ -70,6 +70,8 @@ def lib():
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_debug_set_block_cap.argtypes = [C.c_size_t]
         L.orc_debug_set_block_cap.restype = None
+        L.orc_debug_set_ignore_block_crc.argtypes = [C.c_int]
+        L.orc_debug_set_ignore_block_crc.restype = None
         _lib = L
     return _lib
 
@@ -134,6 +136,11 @@ def table(data, multistream=False):
 def set_block_cap(cap):
     """test hook: 0 restores the reference's capacity"""
     lib().orc_debug_set_block_cap(cap)
+
+
+def set_ignore_block_crc(on):
+    """test hook: decode damaged streams without the block CRC comparison"""
+    lib().orc_debug_set_ignore_block_crc(1 if on else 0)
 
 
 def crc32(data):

@@ -215,3 +215,44 @@ def test_compress_stream_equals_whole(gpu_engine):
     sink = io.BytesIO()
     gpu_engine.compressStream(io.BytesIO(data), sink, 1, chunk_bytes=1_000_000)
     assert sink.getvalue() == gpu_engine.compressFile(data, None, 1)
+
+
+@pytest.mark.parametrize("parse_mode", ["1", "2"])
+def test_decode_damaged_streams_match_oracle(oracle, parse_mode, monkeypatch):
+    """Both parse kernels (BZ2B200_PARSE: 1 = one CTA per block and group, 2 = speculative window) on a full level-9
+    block (~11 000 selectors) whose selector list, code lengths or symbol data are damaged: same error code as the
+    oracle, and -- with the block CRC comparison switched off on both sides -- the same decoded bytes."""
+    from compressjs_flattened_b200.bzip2 import Bzip2Engine, Bzip2Error
+    from compressjs_flattened_b200.corpus import gen_text
+    from test_sim_kernels import _decode_outcome, _selector_region
+    monkeypatch.setenv("BZ2B200_PARSE", parse_mode)
+    eng = Bzip2Engine(0)
+    rng = np.random.default_rng(13)
+    data = gen_text(880_000, 4).tobytes()
+    good = oracle.compress(data, 9)
+    assert eng.decompressFile(good) == data
+    s0 = _selector_region(good)
+    cases = []
+    for _ in range(10):
+        b = bytearray(good)
+        for pos in rng.integers(s0, s0 + 40_000, rng.integers(1, 3)):
+            b[pos >> 3] ^= 0x80 >> (pos & 7)
+        cases.append(bytes(b))
+    for _ in range(14):
+        b = bytearray(good)
+        pos = int(rng.integers(8 * len(good) // 4, 8 * len(good) - 200))
+        b[pos >> 3] ^= 0x80 >> (pos & 7)
+        cases.append(bytes(b))
+    for cut in (s0 // 8 + 1000, len(good) // 2, len(good) - 9):
+        cases.append(good[:cut])
+    for blob in cases:
+        assert _decode_outcome(eng, blob, Bzip2Error) == _decode_outcome(oracle, blob, oracle.OracleError)
+    monkeypatch.setenv("BZ2B200_DEBUG_IGNORE_CRC", "1")
+    oracle.set_ignore_block_crc(True)
+    try:
+        outcomes = [_decode_outcome(oracle, blob, oracle.OracleError) for blob in cases]
+        for blob, exp in zip(cases, outcomes):
+            assert _decode_outcome(eng, blob, Bzip2Error) == exp
+        assert sum(1 for o in outcomes if o[0] == "ok") >= 3 and sum(1 for o in outcomes if o[0] == "err") >= 3
+    finally:
+        oracle.set_ignore_block_crc(False)

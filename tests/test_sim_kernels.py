@@ -1,5 +1,6 @@
 """Kernel LOGIC on the CPU simulator (tests/sim): the same .cu sources compiled with -DBZ_SIM.
 Parity is checked against the oracle; the real-GPU parity tests are in test_gpu_parity.py."""
+import os
 import numpy as np
 import pytest
 
@@ -272,3 +273,83 @@ def test_api_mirror_coercions(sim_engine):
     for bad in (0, 10, -1, 2.5):
         with pytest.raises(ValueError, match="Invalid block size multiplier"):
             sim_engine.compressFile(data, None, bad)
+
+
+def _decode_outcome(engine_or_oracle, blob, err_type):
+    try:
+        if hasattr(engine_or_oracle, "decompressFile"):
+            return ("ok", engine_or_oracle.decompressFile(blob))
+        return ("ok", engine_or_oracle.decompress(blob))
+    except err_type as e:
+        return ("err", e.errorCode)
+
+
+def _selector_region(blob):
+    """Bit range [start, start + 8 * bits) of the selector list of the first block (SURVEY appendix A layout)."""
+    bits = int.from_bytes(blob[:64], "big")
+    total = 64 * 8
+    used_map = (bits >> (total - (32 + 48 + 32 + 1 + 24) - 16)) & 0xFFFF
+    k = bin(used_map).count("1")
+    return 32 + 48 + 32 + 1 + 24 + 16 + 16 * k + 3 + 15
+
+
+@pytest.mark.parametrize("parse_mode", ["1", "2"])
+def test_decode_header_mutations_match_oracle(oracle, parse_mode, monkeypatch):
+    """Both parse kernels against the oracle on streams whose selector list / code lengths / first symbols are damaged
+    (runs of 1 bits longer than nGroups, the j == nGroups quirk of BJ:1488-1490, shifted lists, truncation)."""
+    from compressjs_flattened_b200 import _native
+    from compressjs_flattened_b200.bzip2 import Bzip2Engine, Bzip2Error
+    from compressjs_flattened_b200.corpus import gen_text
+    monkeypatch.setenv("BZ2B200_PARSE", parse_mode)
+    eng = Bzip2Engine(0, _native.Library(os.path.join(os.path.dirname(__file__), "sim", "libbz2b200_sim.so")))
+    rng = np.random.default_rng(11)
+    good = oracle.compress(gen_text(40_000, 5).tobytes(), 9)
+    assert eng.decompressFile(good) == oracle.decompress(good)
+    s0 = _selector_region(good)
+    cases = []
+    for _ in range(24):  # single and double bit flips inside the selector list and the code lengths behind it
+        b = bytearray(good)
+        for pos in rng.integers(s0, s0 + 2500, rng.integers(1, 3)):
+            b[pos >> 3] ^= 0x80 >> (pos & 7)
+        cases.append(bytes(b))
+    for _ in range(12):  # flips in the symbol data: other symbols, invalid codes, an early end-of-block
+        b = bytearray(good)
+        pos = int(rng.integers(8 * len(good) // 3, 8 * len(good) - 200))
+        b[pos >> 3] ^= 0x80 >> (pos & 7)
+        cases.append(bytes(b))
+    for cut in (s0 // 8 + 3, s0 // 8 + 40, s0 // 8 + 200, len(good) - 9):
+        cases.append(good[:cut])
+    ones = bytearray(good)  # a run of 1 bits across a whole 32-bit word of the selector list
+    for pos in range(s0 + 64, s0 + 64 + 70):
+        ones[pos >> 3] |= 0x80 >> (pos & 7)
+    cases.append(bytes(ones))
+    for blob in cases:
+        assert _decode_outcome(eng, blob, Bzip2Error) == _decode_outcome(oracle, blob, oracle.OracleError)
+    # the same without the block CRC comparison on either side: what the damaged streams decode TO must agree as well
+    monkeypatch.setenv("BZ2B200_DEBUG_IGNORE_CRC", "1")
+    oracle.set_ignore_block_crc(True)
+    try:
+        outcomes = [_decode_outcome(oracle, blob, oracle.OracleError) for blob in cases]
+        for blob, exp in zip(cases, outcomes):
+            assert _decode_outcome(eng, blob, Bzip2Error) == exp
+        assert sum(1 for o in outcomes if o[0] == "ok") >= 3 and sum(1 for o in outcomes if o[0] == "err") >= 3
+    finally:
+        oracle.set_ignore_block_crc(False)
+
+
+def test_decode_many_selectors_multi_chunk(oracle, monkeypatch):
+    """A block with ~5 000 selectors: the selector scan of the CTA parse kernel (256 threads = 8 192 bits per chunk) takes
+    several chunks; both kernels must agree with the oracle, also when the list is damaged late."""
+    from compressjs_flattened_b200 import _native
+    from compressjs_flattened_b200.bzip2 import Bzip2Engine, Bzip2Error
+    from compressjs_flattened_b200.corpus import gen_text
+    data = gen_text(420_000, 6).tobytes()
+    good = oracle.compress(data, 9)
+    s0 = _selector_region(good)
+    late = bytearray(good)
+    late[(s0 + 9000) >> 3] ^= 0x10
+    for mode in ("1", "2"):
+        monkeypatch.setenv("BZ2B200_PARSE", mode)
+        eng = Bzip2Engine(0, _native.Library(os.path.join(os.path.dirname(__file__), "sim", "libbz2b200_sim.so")))
+        assert eng.decompressFile(good) == data
+        assert _decode_outcome(eng, bytes(late), Bzip2Error) == _decode_outcome(oracle, bytes(late), oracle.OracleError)
