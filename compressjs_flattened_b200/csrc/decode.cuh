@@ -810,13 +810,13 @@ __global__ void __launch_bounds__(1024) k_sym_offsets(DecBlk *__restrict__ blks,
 }
 
 // ---- K-U3c: MTF^-1 in parallel.  The list is striped over the warp like in k_mtf_ranks. ----------------
-__device__ __forceinline__ u32 imtf_step(u32 &hot, u64 &cold, u32 j, int lane) {  // returns list[j], moves it to the front
-  if (j < 32) {
-    u32 byte = __shfl_sync(FULL_MASK, hot, (int)j);
-    u32 up = __shfl_up_sync(FULL_MASK, hot, 1);
-    if (lane <= (int)j) hot = lane == 0 ? byte : up;
-    return byte;
-  }
+// rank j < 32: one shuffle with a per-lane source (lane 0 takes list[j], lanes 1..j their left neighbour)
+__device__ __forceinline__ void imtf_hot(u32 &hot, u32 j, int lane) {
+  const int src = lane == 0 ? (int)j : lane - (lane <= (int)j ? 1 : 0);
+  hot = __shfl_sync(FULL_MASK, hot, src);
+}
+// rank j >= 32 (rare): the target comes from a cold row, every row up to it shifts by one
+__device__ __noinline__ void imtf_cold(u32 &hot, u64 &cold, u32 j, int lane) {
   int row = (int)(j >> 5), l = (int)(j & 31);
   u32 target = __shfl_sync(FULL_MASK, (u32)(cold >> (8 * (row - 1))) & 0xffu, l);
   u32 carry = target;
@@ -834,7 +834,13 @@ __device__ __forceinline__ u32 imtf_step(u32 &hot, u64 &cold, u32 j, int lane) {
     if (r < row || lane <= l) cold = (cold & ~(0xffULL << (8 * (r - 1)))) | ((u64)nv << (8 * (r - 1)));
     carry = last;
   }
-  return target;
+}
+// one symbol: ranks 1..255 arrive as symbols 2..256 (0/1 = RUNA/RUNB, > 256 = end-of-block: no move)
+__device__ __forceinline__ void imtf_sym(u32 &hot, u64 &cold, u32 sy, int lane) {
+  const u32 j = sy - 1;
+  if (j - 1 < 255u) {
+    if (j < 32) imtf_hot(hot, j, lane); else imtf_cold(hot, cold, j, lane);
+  }
 }
 // pass P: permutation of list positions caused by each segment of IMTF_SEG symbols (grid (segs/8, ncand), one warp per segment)
 __global__ void __launch_bounds__(256) k_imtf_perm(const DecBlk *__restrict__ blks, const u16 *__restrict__ dsym, u8 *__restrict__ segperm) {
@@ -852,9 +858,11 @@ __global__ void __launch_bounds__(256) k_imtf_perm(const DecBlk *__restrict__ bl
   for (u32 c0 = 0; c0 < lim; c0 += 32) {
     u32 mysym = c0 + lane < lim ? Sk[c0 + lane] : 0u;
     u32 cnt = lim - c0 < 32 ? lim - c0 : 32;
-    for (u32 t = 0; t < cnt; t++) {
-      u32 sy = __shfl_sync(FULL_MASK, mysym, (int)t);
-      if (sy >= 2 && sy - 1 < 256) imtf_step(hot, cold, sy - 1, lane);  // end-of-block (> sym_total <= 257) is the last symbol: harmless
+    if (cnt == 32) {
+#pragma unroll
+      for (int t = 0; t < 32; t++) imtf_sym(hot, cold, __shfl_sync(FULL_MASK, mysym, t), lane);
+    } else {
+      for (u32 t = 0; t < cnt; t++) imtf_sym(hot, cold, __shfl_sync(FULL_MASK, mysym, (int)t), lane);  // (end-of-block is the last symbol)
     }
   }
   u8 *P = segperm + ((u64)k * (DEC_SYM_STRIDE / IMTF_SEG + 1) + seg) * 256;
@@ -904,18 +912,20 @@ __global__ void __launch_bounds__(256) k_imtf_decode(const DecBlk *__restrict__ 
     u32 mylen = c0 + lane < lim ? nxoff - myoff : 0u;
     u32 cnt = lim - c0 < 32 ? lim - c0 : 32;
     u32 out_byte = 0;
-    for (u32 t = 0; t < cnt; t++) {
-      u32 sy = __shfl_sync(FULL_MASK, mysym, (int)t);
-      u32 byte;
-      if (sy >= 2 && sy - 1 < 256) byte = imtf_step(hot, cold, sy - 1, lane);
-      else byte = __shfl_sync(FULL_MASK, hot, 0);
-      u32 len = __shfl_sync(FULL_MASK, mylen, (int)t);
-      if (len > 1) {  // a RUNA/RUNB digit: many copies of the front byte, written by the whole warp
-        u32 o = __shfl_sync(FULL_MASK, myoff, (int)t);
-        for (u32 q = lane; q < len; q += 32) Lk[o + q] = (u8)byte;
-      }
-      if (lane == (int)t) out_byte = byte;
+    const u32 runs = __ballot_sync(FULL_MASK, mylen > 1);  // RUNA/RUNB digits that stand for several bytes
+#define IMTF_DECODE_STEP(t)                                                                              \
+    {                                                                                                    \
+      imtf_sym(hot, cold, __shfl_sync(FULL_MASK, mysym, (int)(t)), lane);                                \
+      const u32 byte = __shfl_sync(FULL_MASK, hot, 0); /* the decoded byte is the front of the list */   \
+      if ((runs >> (t)) & 1u) { /* many copies of the front byte, written by the whole warp */           \
+        const u32 len = __shfl_sync(FULL_MASK, mylen, (int)(t)), o = __shfl_sync(FULL_MASK, myoff, (int)(t)); \
+        for (u32 q = lane; q < len; q += 32) Lk[o + q] = (u8)byte;                                       \
+      }                                                                                                  \
+      if (lane == (int)(t)) out_byte = byte;                                                             \
     }
+    // (not unrolled: 32 copies of the step with its run branch ran 60 % slower -- instruction cache)
+    for (u32 t = 0; t < cnt; t++) IMTF_DECODE_STEP(t)
+#undef IMTF_DECODE_STEP
     if (mylen == 1) Lk[myoff] = (u8)out_byte;
   }
 }
