@@ -9,8 +9,9 @@
 //                          serial part (table switch every 50 symbols); a 10-bit LUT built by replaying
 //                          the reference's limit/base/permute walk serves short codes.
 //   K-U3b k_sym_offsets  : RLE2^-1 as a scan: the k-th RUNA/RUNB of a run = (sym+1)<<k copies of the front
-//   K-U3c k_imtf_*       : MTF^-1 in parallel: per-segment list permutations, composed per block, then every
-//                          segment decodes from its start list (list striped over a warp)
+//   K-U3c k_imtf_*       : MTF^-1 in parallel: every segment runs the MTF once from the identity list (list striped
+//                          over a warp) and emits list positions + its permutation; permutations composed per
+//                          block; positions mapped to bytes through the list at the segment start
 //   K-U4a                : T-vector = one stable 8-bit radix pass (bwt.cuh kernels) of positions by byte
 //   K-U4b k_ibwt_*       : list ranking: splitters every IBWT_S slots walk to the next splitter,
 //                          one thread per block ranks the splitters, second walk writes bytes
@@ -842,33 +843,6 @@ __device__ __forceinline__ void imtf_sym(u32 &hot, u64 &cold, u32 sy, int lane) 
     if (j < 32) imtf_hot(hot, j, lane); else imtf_cold(hot, cold, j, lane);
   }
 }
-// pass P: permutation of list positions caused by each segment of IMTF_SEG symbols (grid (segs/8, ncand), one warp per segment)
-__global__ void __launch_bounds__(256) k_imtf_perm(const DecBlk *__restrict__ blks, const u16 *__restrict__ dsym, u8 *__restrict__ segperm) {
-  const u32 k = blockIdx.y;
-  const u32 m = blks[k].nsym;
-  const int lane = lane_id();
-  const u32 seg = blockIdx.x * 8 + warp_id();
-  const u32 b0 = seg * IMTF_SEG;
-  if (blks[k].kind != 0 || blks[k].err || b0 >= m) return;
-  const u16 *Sk = dsym + (u64)k * DEC_SYM_STRIDE + b0;
-  u32 hot = (u32)lane;
-  u64 cold = 0;
-  for (int r = 7; r >= 1; r--) cold = (cold << 8) | (u64)(32 * r + lane);
-  u32 lim = m - b0 < IMTF_SEG ? m - b0 : IMTF_SEG;
-  for (u32 c0 = 0; c0 < lim; c0 += 32) {
-    u32 mysym = c0 + lane < lim ? Sk[c0 + lane] : 0u;
-    u32 cnt = lim - c0 < 32 ? lim - c0 : 32;
-    if (cnt == 32) {
-#pragma unroll
-      for (int t = 0; t < 32; t++) imtf_sym(hot, cold, __shfl_sync(FULL_MASK, mysym, t), lane);
-    } else {
-      for (u32 t = 0; t < cnt; t++) imtf_sym(hot, cold, __shfl_sync(FULL_MASK, mysym, (int)t), lane);  // (end-of-block is the last symbol)
-    }
-  }
-  u8 *P = segperm + ((u64)k * (DEC_SYM_STRIDE / IMTF_SEG + 1) + seg) * 256;
-  P[lane] = (u8)hot;
-  for (int r = 1; r < 8; r++) P[32 * r + lane] = (u8)(cold >> (8 * (r - 1)));
-}
 // per candidate: the list at the start of every segment (in place over segperm)
 __global__ void __launch_bounds__(32) k_imtf_scan(const DecBlk *__restrict__ blks, const u8 *__restrict__ dmap, u8 *__restrict__ segperm) {
   __shared__ u8 cur[256];
@@ -888,9 +862,13 @@ __global__ void __launch_bounds__(32) k_imtf_scan(const DecBlk *__restrict__ blk
     __syncwarp();
   }
 }
-// pass D: decode every segment from its start list; writes the L column
-__global__ void __launch_bounds__(256) k_imtf_decode(const DecBlk *__restrict__ blks, const u16 *__restrict__ dsym, const u32 *__restrict__ doff,
-                                                     const u8 *__restrict__ segperm, u8 *__restrict__ dL, i64 l_stride) {
+// pass I (grid (segs/8, ncand), one warp per segment of IMTF_SEG symbols): the MTF of the segment run ONCE, from the
+// identity list: what it emits are list POSITIONS at the segment start (written where the L bytes will be), what is left
+// at the end is the permutation of positions the segment causes.  k_imtf_scan turns the permutations into the list at
+// every segment start, k_imtf_map turns positions into bytes (a 256-byte table per segment) -- instead of one MTF pass
+// for the permutations and a second one for the bytes.
+__global__ void __launch_bounds__(256) k_imtf_index(const DecBlk *__restrict__ blks, const u16 *__restrict__ dsym, const u32 *__restrict__ doff,
+                                                    u8 *__restrict__ segperm, u8 *__restrict__ dL, i64 l_stride) {
   const u32 k = blockIdx.y;
   const u32 m = blks[k].nsym;
   const int lane = lane_id();
@@ -900,10 +878,9 @@ __global__ void __launch_bounds__(256) k_imtf_decode(const DecBlk *__restrict__ 
   const u16 *Sk = dsym + (u64)k * DEC_SYM_STRIDE + b0;
   const u32 *Ok = doff + (u64)k * DEC_SYM_STRIDE + b0;
   u8 *Lk = dL + (i64)k * l_stride;
-  const u8 *P = segperm + ((u64)k * (DEC_SYM_STRIDE / IMTF_SEG + 1) + seg) * 256;
-  u32 hot = P[lane];
+  u32 hot = (u32)lane;
   u64 cold = 0;
-  for (int r = 7; r >= 1; r--) cold = (cold << 8) | P[32 * r + lane];
+  for (int r = 7; r >= 1; r--) cold = (cold << 8) | (u64)(32 * r + lane);
   u32 lim = m - b0 < IMTF_SEG ? m - b0 : IMTF_SEG;
   for (u32 c0 = 0; c0 < lim; c0 += 32) {
     u32 mysym = c0 + lane < lim ? Sk[c0 + lane] : 0u;
@@ -936,6 +913,23 @@ __global__ void __launch_bounds__(256) k_imtf_decode(const DecBlk *__restrict__ 
 #undef IMTF_DECODE_STEP
     if (mylen == 1) Lk[myoff] = (u8)out_byte;
   }
+  u8 *P = segperm + ((u64)k * (DEC_SYM_STRIDE / IMTF_SEG + 1) + seg) * 256;
+  P[lane] = (u8)hot;
+  for (int r = 1; r < 8; r++) P[32 * r + lane] = (u8)(cold >> (8 * (r - 1)));
+}
+// pass M (grid (segs, ncand)): list positions -> bytes through the list at the segment start
+__global__ void __launch_bounds__(256) k_imtf_map(const DecBlk *__restrict__ blks, const u32 *__restrict__ doff, const u8 *__restrict__ segperm,
+                                                  u8 *__restrict__ dL, i64 l_stride) {
+  __shared__ u8 list[256];
+  const u32 k = blockIdx.y, seg = blockIdx.x;
+  const u32 m = blks[k].nsym, b0 = seg * IMTF_SEG;
+  if (blks[k].kind != 0 || blks[k].err || b0 >= m) return;
+  list[threadIdx.x] = segperm[((u64)k * (DEC_SYM_STRIDE / IMTF_SEG + 1) + seg) * 256 + threadIdx.x];
+  __syncthreads();
+  const u32 *Ok = doff + (u64)k * DEC_SYM_STRIDE;
+  const u32 e = b0 + IMTF_SEG < m ? b0 + IMTF_SEG : m;
+  u8 *Lk = dL + (i64)k * l_stride;
+  for (u32 o = Ok[b0] + threadIdx.x, o1 = Ok[e]; o < o1; o += 256) Lk[o] = list[Lk[o]];
 }
 
 // ---- K-U4a helpers ----------------------------------------------------------------------------

@@ -89,10 +89,10 @@ static int decode_device(Ctx *c, const u8 *d_in, size_t n, int multistream, int 
     }
     LAUNCH(k_sym_offsets, ncand, 1024, 0, P<DecBlk>(c->dmeta), P<u16>(c->dsyms), P<u32>(c->doff), (u32)DEC_DBUF_MAX);
     CK(cudaMemcpyAsync(blks.data(), c->dmeta.p, sizeof(DecBlk) * (size_t)ncand, cudaMemcpyDeviceToHost, c->stream));
-    LAUNCH(k_imtf_perm, dim3((unsigned)((nsegs + 7) / 8), ncand), 256, 0, P<DecBlk>(c->dmeta), P<u16>(c->dsyms), P<u8>(c->dperm));
-    LAUNCH(k_imtf_scan, ncand, 32, 0, P<DecBlk>(c->dmeta), P<u8>(c->dmap), P<u8>(c->dperm));
-    LAUNCH(k_imtf_decode, dim3((unsigned)((nsegs + 7) / 8), ncand), 256, 0, P<DecBlk>(c->dmeta), P<u16>(c->dsyms), P<u32>(c->doff), P<u8>(c->dperm),
+    LAUNCH(k_imtf_index, dim3((unsigned)((nsegs + 7) / 8), ncand), 256, 0, P<DecBlk>(c->dmeta), P<u16>(c->dsyms), P<u32>(c->doff), P<u8>(c->dperm),
            P<u8>(c->dL), LS);
+    LAUNCH(k_imtf_scan, ncand, 32, 0, P<DecBlk>(c->dmeta), P<u8>(c->dmap), P<u8>(c->dperm));
+    LAUNCH(k_imtf_map, dim3((unsigned)nsegs, ncand), 256, 0, P<DecBlk>(c->dmeta), P<u32>(c->doff), P<u8>(c->dperm), P<u8>(c->dL), LS);
     CK(cudaStreamSynchronize(c->stream));
   }
   if ((rc = mark(c, 2))) return rc;
