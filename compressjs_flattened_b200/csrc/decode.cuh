@@ -4,17 +4,21 @@
 //   K-U1 k_magic_scan    : every bit offset is tested for the 48-bit block / end-of-stream magic
 //                          (the reference has no search: it walks the stream sequentially; the host
 //                          re-creates that walk over the candidates, so false hits are ignored)
-//   K-U2/3a k_huff_parse : one warp per candidate block: header, selectors, code lengths
-//                          (BJ:1434-1581), then bits -> symbols (BJ:1597-1616).  This is the only
-//                          serial part (table switch every 50 symbols); a 10-bit LUT built by replaying
-//                          the reference's limit/base/permute walk serves short codes.
+//   K-U2   dec_header     : header fields, selectors (parallel: zero-bit ranks by a CTA scan, MTF moves composed
+//                          as position maps), code lengths, limit/base/permute and a 10-bit LUT built by replaying
+//                          the reference's walk (BJ:1434-1581)
+//   K-U3a  k_huff_parse   : bits -> symbols (BJ:1597-1616), one CTA per candidate block; serial across the groups of
+//                          50 symbols (table switch), parallel inside a group (pointer doubling over "next code")
+//          k_huff_parse_win: the same for few blocks: a window of offsets decoded under every table of the next
+//                          groups, one dependent chain of reads per group
 //   K-U3b k_sym_offsets  : RLE2^-1 as a scan: the k-th RUNA/RUNB of a run = (sym+1)<<k copies of the front
 //   K-U3c k_imtf_*       : MTF^-1 in parallel: every segment runs the MTF once from the identity list (list striped
 //                          over a warp) and emits list positions + its permutation; permutations composed per
 //                          block; positions mapped to bytes through the list at the segment start
-//   K-U4a                : T-vector = one stable 8-bit radix pass (bwt.cuh kernels) of positions by byte
-//   K-U4b k_ibwt_*       : list ranking: splitters every IBWT_S slots walk to the next splitter,
-//                          one thread per block ranks the splitters, second walk writes bytes
+//   K-U4a                : T-vector = one stable 8-bit radix pass (bwt.cuh kernels) of positions by byte, packed
+//                          with the L byte like the reference's dbuf
+//   K-U4b k_ibwt_*       : list ranking: splitters every IBWT_S slots walk to the next splitter, one CTA per
+//                          block ranks the splitters (two levels, shared memory), second walk writes bytes
 //   K-U4c k_rle1_inv     : RLE1^-1 in parallel: inside a maximal run of equal bytes every 5th byte
 //                          is a count; whether a run's first byte is the previous run's count is a
 //                          1-bit state propagated by a scan of functions {0,1}->{0,1}
