@@ -355,6 +355,12 @@ class Bzip2Engine:
         if rc:
             self._raise(rc)
 
+    def debug_set_ignore_block_crc(self, on):
+        """tests only: decode without comparing block CRCs (what a damaged stream decodes TO)"""
+        rc = self._L.bz2b200_debug_set_ignore_block_crc(self._ctx, int(bool(on)))
+        if rc:
+            self._raise(rc)
+
     def block_table(self):
         nb = self.stats().n_blocks
         raw = self.debug_fetch(0, 0, C.sizeof(_native.BlockRec) * nb)

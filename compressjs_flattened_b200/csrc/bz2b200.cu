@@ -108,6 +108,7 @@ struct Ctx {
   void *rb_dst[8];
   size_t rb_off[8], rb_len[8], rb_used = 0;
   int rb_n = 0;
+  bool ignore_block_crc = false;  // tests only (bz2b200_debug_set_ignore_block_crc)
   u32 cap_override = 0;    // tests only
   u32 batch_override = 0;  // tests only: blocks per batch
   u64 shard_bits = 0;      // bit length of the last shard segment (phase 0 in `out`)
@@ -445,13 +446,6 @@ int pipe_stages(Ctx *c) {
     }
     // ---- rounds >= 1 (refine.cuh): list A (+ key2) -> sorted staging list B -> compacted list A ----
     u32 n_act = hv[1], round = 0;  // doubling round r compares h = L << r symbols further on (L per block)
-#ifndef BZ_SIM
-    static bool attr2 = false;
-    if (!attr2) {
-      CK(cudaFuncSetAttribute(k_sort_groups, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RfSmem)));
-      attr2 = true;
-    }
-#endif
     if (n_act) LAUNCH(k_keys2, (n_act + 255) / 256, 256, 0, actI[0], n_act, P<BlockRec>(c->recs), P<u32>(c->isa), (u32)BS, magic, P<BlkSort>(c->blksort), round,
                       P<u32>(c->key2));
     while (n_act) {
@@ -507,13 +501,6 @@ int pipe_stages(Ctx *c) {
     LAUNCH(k_mtf_lastocc, dim3((unsigned)((nseg_max + 7) / 8), (unsigned)nb), 256, 0, P<u8>(c->Lcol), BS, P<BlockRec>(c->recs), P<int>(c->lastocc),
            nseg_max * 256, P<u32>(c->used_bits));
     LAUNCH(k_mtf_scan, (unsigned)nb, 256, 0, P<BlockRec>(c->recs), P<int>(c->lastocc), nseg_max * 256, P<u32>(c->used_bits), P<BlockMeta>(c->meta));
-#ifndef BZ_SIM
-    static bool attr3 = false;
-    if (!attr3) {
-      CK(cudaFuncSetAttribute(k_mtf_ranks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MTR_WARPS * sizeof(MtrSmem))));
-      attr3 = true;
-    }
-#endif
     LAUNCH(k_mtf_ranks, dim3((unsigned)((nseg_max + MTR_WARPS - 1) / MTR_WARPS), (unsigned)nb), MTR_WARPS * 32, MTR_WARPS * sizeof(MtrSmem), P<u8>(c->Lcol),
            BS, P<BlockRec>(c->recs), P<int>(c->lastocc), nseg_max * 256, P<u8>(c->ranks));
     {
@@ -543,14 +530,6 @@ int pipe_stages(Ctx *c) {
     ENS(c->hblk, sizeof(HufBlk) * (size_t)nb);
     ha.freq = P<u32>(c->hfreq); ha.lens = P<u8>(c->hlens); ha.plen = P<u64>(c->hplen); ha.codes = P<u32>(c->hcodes);
     ha.sel = P<u8>(c->hsel); ha.cost = P<u16>(c->hcost); ha.goff = P<u32>(c->hgoff); ha.hb = P<HufBlk>(c->hblk);
-#ifndef BZ_SIM
-    static bool attr_set = false;
-    if (!attr_set) {
-      CK(cudaFuncSetAttribute(k_huf_init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HufBuildSmem)));
-      CK(cudaFuncSetAttribute(k_huf_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HufBuildSmem)));
-      attr_set = true;
-    }
-#endif
     const dim3 ggrid((max_nsel + HUF_GT - 1) / HUF_GT, (unsigned)nb);
     LAUNCH(k_huf_init, (unsigned)nb, HUF_BT, sizeof(HufBuildSmem), ha, P<u32>(c->freq), P<BlockMeta>(c->meta));
     for (int it = 0; it < BZ_MAX_GROUPS - 2; it++) {  // 2 -> 6 tables; blocks at their target skip
@@ -752,6 +731,22 @@ int compress_device(Ctx *c, const u8 *d_in, size_t n_, int level, u32 *d_out, si
 
 #include "decode_host.inl"
 
+// The opt-in for more than 48 KB of dynamic shared memory is a per-DEVICE function attribute: set for the current
+// device by every bz2b200_create (contexts on several GPUs in one process each set their own).
+cudaError_t set_kernel_attributes() {
+#ifndef BZ_SIM
+  cudaError_t e;
+  if ((e = cudaFuncSetAttribute(k_sort_groups, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RfSmem))) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_mtf_ranks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MTR_WARPS * sizeof(MtrSmem)))) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_huf_init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HufBuildSmem))) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_huf_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HufBuildSmem))) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_huff_parse_win, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecWinSmem))) != cudaSuccess) return e;
+  const size_t rank_smem = 12 * (size_t)((DEC_DBUF_MAX + 64 - 1) / 64 + 2);  // the smallest splitter spacing (64) needs the most
+  if ((e = cudaFuncSetAttribute(k_ibwt_rank, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rank_smem)) != cudaSuccess) return e;
+#endif
+  return cudaSuccess;
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------ C ABI
@@ -772,6 +767,7 @@ int bz2b200_create(int device, bz2b200_ctx **ctx) {
   { const char *t = getenv("BZ2B200_IBWT_S"); int v = t ? atoi(t) : 0; if (v == 64 || v == 128 || v == 256 || v == 512 || v == 1024) c->ibwt_s = (unsigned)v; }
   { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) c->sms = v; }
   for (auto &e : c->ev) if (cudaEventCreate(&e) != cudaSuccess) c->ev_ok = false;
+  if (set_kernel_attributes() != cudaSuccess) { bz2b200_destroy(reinterpret_cast<bz2b200_ctx *>(c)); return BZ2B200_E_CUDA; }
   *ctx = reinterpret_cast<bz2b200_ctx *>(c);
   return BZ2B200_OK;
 }
@@ -782,8 +778,9 @@ void bz2b200_destroy(bz2b200_ctx *ctx) {
   cudaSetDevice(c->device);
   for (DevBuf *b : c->pool) if (b->p) cudaFree(b->p);
   if (c->rb_pin) cudaFreeHost(c->rb_pin);
-  if (c->ev_ok) for (auto &e : c->ev) cudaEventDestroy(e);
+  for (auto &e : c->ev) if (e) cudaEventDestroy(e);
   for (auto &e : c->dom_ev) cudaEventDestroy(e);
+  for (auto &e : c->trace_pool) cudaEventDestroy(e);
   cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -1027,6 +1024,13 @@ int bz2b200_debug_set_batch_blocks(bz2b200_ctx *ctx, uint32_t blocks) {
   Ctx *c = reinterpret_cast<Ctx *>(ctx);
   if (!c) return BZ2B200_E_ARG;
   c->batch_override = blocks;
+  return BZ2B200_OK;
+}
+
+int bz2b200_debug_set_ignore_block_crc(bz2b200_ctx *ctx, int on) {
+  Ctx *c = reinterpret_cast<Ctx *>(ctx);
+  if (!c) return BZ2B200_E_ARG;
+  c->ignore_block_crc = on != 0;
   return BZ2B200_OK;
 }
 

@@ -779,6 +779,7 @@ __global__ void __launch_bounds__(1024) k_sym_offsets(DecBlk *__restrict__ blks,
   u32 *Ok = doff + (u64)k * DEC_SYM_STRIDE;
   int carry_lit = -1;  // last non-run symbol so far
   u32 carry = 0;
+  const u32 over = dbuf_cap + 1;
   for (u32 base = 0; base < m; base += 1024 * 4) {
     u32 i0 = base + threadIdx.x * 4;
     u32 sy[4];
@@ -795,7 +796,10 @@ __global__ void __launch_bounds__(1024) k_sym_offsets(DecBlk *__restrict__ blks,
         cp[q] = 0;
         if (i >= m) continue;
         if (sy[q] >= 2) { cur = (int)i; cp[q] = i + 1 == m ? 0u : 1u; }  // the last symbol is end-of-block
-        else { u32 kk = i - (u32)(cur + 1); cp[q] = kk < 21 ? (sy[q] + 1) << kk : 0x400000u; }  // > dbuf_cap: caught below
+        else {  // a run digit is clamped to dbuf_cap + 1 ("too large"), so no sum below can wrap: 4096 x 900 001 < 2^32
+          u32 kk = i - (u32)(cur + 1), v = kk < 21 ? (sy[q] + 1) << kk : over;
+          cp[q] = v < over ? v : over;
+        }
         mine += cp[q];
       }
     }
@@ -803,7 +807,7 @@ __global__ void __launch_bounds__(1024) k_sym_offsets(DecBlk *__restrict__ blks,
     u32 o = carry + block_excl_sum<u32>(mine, tot, ws);
     for (int q = 0; q < 4; q++) if (i0 + q < m) { Ok[i0 + q] = o; o += cp[q]; }
     carry += tot;
-    if (carry > 0x40000000u) carry = 0x40000000u;  // saturate: only "too large" matters
+    if (carry > over) carry = over;  // saturate at once (only "too large" matters): carry + a chunk's total stays below 2^32
     if (tot_l > carry_lit) carry_lit = tot_l;
   }
   if (threadIdx.x == 0) {

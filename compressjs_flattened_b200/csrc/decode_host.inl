@@ -77,11 +77,6 @@ static int decode_device(Ctx *c, const u8 *d_in, size_t n, int multistream, int 
     // (measured: 113 candidates 8.4 vs 11.2 ms for the CTA kernel; 224 candidates, two window CTAs per SM, 16.3 vs 13.4 ms)
     const bool win = c->parse_mode ? c->parse_mode == 2 : ncand <= (u32)c->sms;
     if (win) {
-      static bool dec_attr_set = false;
-      if (!dec_attr_set) {
-        CK(cudaFuncSetAttribute(k_huff_parse_win, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecWinSmem)));
-        dec_attr_set = true;
-      }
       LAUNCH(k_huff_parse_win, ncand, DECW_PT, sizeof(DecWinSmem), d_in, (u64)n, P<u64>(c->cand), ncand, (u32)DEC_DBUF_MAX, mode == DEC_BLOCK ? 1 : 0,
              P<DecBlk>(c->dmeta), P<u16>(c->dsyms), P<u8>(c->dsel), P<u8>(c->dmap));
     } else {
@@ -211,12 +206,7 @@ static int decode_device(Ctx *c, const u8 *d_in, size_t n, int multistream, int 
     // (launching the walks for L2-sized batches of blocks was tried: slower -- a batch waits for its longest chain, ~11x
     // the mean of 256 steps, and too few threads are left to hide the latency)
     LAUNCH(k_ibwt_walk1, dim3(gx, (unsigned)nb), 256, 0, P<u32>(c->valsB), P<DecBlk>(c->dmeta), d_order, P<u32>(c->seg_tile0), d_spl0, nb, spl_next, spl_len, 0u, ibwt_s);
-    const size_t rank_smem = 12 * (size_t)((DEC_DBUF_MAX + IBWT_S - 1) / IBWT_S + 2);
-    static size_t rank_attr = 0;
-    if (rank_smem > 48 * 1024 && rank_attr < rank_smem) {
-      CK(cudaFuncSetAttribute(k_ibwt_rank, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rank_smem));
-      rank_attr = rank_smem;
-    }
+    const size_t rank_smem = 12 * (size_t)((DEC_DBUF_MAX + IBWT_S - 1) / IBWT_S + 2);  // opt-in set per device in bz2b200_create
     LAUNCH(k_ibwt_rank, (unsigned)nb, 256, rank_smem, P<DecBlk>(c->dmeta), d_order, d_spl0, nb, spl_next, spl_len,
            spl_off, period, ibwt_s);
     LAUNCH(k_ibwt_walk2, dim3(gx, (unsigned)nb), 256, 0, P<u32>(c->valsB), P<u8>(c->dL), LS, P<DecBlk>(c->dmeta), d_order, P<u32>(c->seg_tile0), d_spl0, nb,
@@ -265,7 +255,7 @@ static int decode_device(Ctx *c, const u8 *d_in, size_t n, int multistream, int 
   if ((rc = mark(c, 5))) return rc;
   CK(cudaStreamSynchronize(c->stream));
   CK(cudaGetLastError());
-  const bool ignore_crc = getenv("BZ2B200_DEBUG_IGNORE_CRC") != nullptr;  // development aid only
+  const bool ignore_crc = c->ignore_block_crc;  // tests only (bz2b200_debug_set_ignore_block_crc)
   for (int p = 0; p < nb && !ignore_crc; p++)
     if (hrecs[p].crc != blks[chain[p]].target_crc) {  // earlier in stream order than struct_err
       char msg[128];

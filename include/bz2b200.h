@@ -53,7 +53,7 @@ typedef struct {
   float ms_total;            /* device time of the last call (CUDA events) */
   float ms_stage[8];         /* compress: rle1, bwt, mtf, huff, stitch; decompress: scan, huff, ibwt, out */
   /* dominant kernel of the last compress (k_rs_scatter, the radix-sort scatter pass), timed live with
-   * CUDA events on the launching stream; bytes = algorithmic bytes (24 B per sorted slot per pass) */
+   * CUDA events on the launching stream; bytes = algorithmic bytes (16 B per sorted key per pass: 8 read + 8 written) */
   float dom_ms;
   uint32_t dom_launches;
   uint64_t dom_bytes;
@@ -129,6 +129,9 @@ int bz2b200_debug_set_block_cap(bz2b200_ctx *ctx, uint32_t cap);
 /* tests/ only: run the per-block stages in batches of at most `blocks` blocks (0 = as many as fit the
  * 31-bit index space and 70 % of the free device memory).  Stage dumps then show the last batch. */
 int bz2b200_debug_set_batch_blocks(bz2b200_ctx *ctx, uint32_t blocks);
+/* tests/ only: skip the block-CRC comparison of the decoder (BJ:1756-1761), so that what a damaged stream decodes TO
+ * can be compared with the oracle.  Not reachable from the environment. */
+int bz2b200_debug_set_ignore_block_crc(bz2b200_ctx *ctx, int on);
 
 #ifdef __cplusplus
 }

@@ -247,7 +247,7 @@ def test_decode_damaged_streams_match_oracle(oracle, parse_mode, monkeypatch):
         cases.append(good[:cut])
     for blob in cases:
         assert _decode_outcome(eng, blob, Bzip2Error) == _decode_outcome(oracle, blob, oracle.OracleError)
-    monkeypatch.setenv("BZ2B200_DEBUG_IGNORE_CRC", "1")
+    eng.debug_set_ignore_block_crc(True)
     oracle.set_ignore_block_crc(True)
     try:
         outcomes = [_decode_outcome(oracle, blob, oracle.OracleError) for blob in cases]
@@ -256,3 +256,15 @@ def test_decode_damaged_streams_match_oracle(oracle, parse_mode, monkeypatch):
         assert sum(1 for o in outcomes if o[0] == "ok") >= 3 and sum(1 for o in outcomes if o[0] == "err") >= 3
     finally:
         oracle.set_ignore_block_crc(False)
+
+
+@pytest.mark.gpu
+def test_decode_run_length_sum_cannot_wrap(gpu_engine, oracle):
+    """run lengths that sum past 2^32 are a Data error (BJ:1647), never an out-of-bounds write."""
+    from compressjs_flattened_b200.bzip2 import Bzip2Error
+    from test_sim_kernels import crafted_run_overflow_stream
+    for deep, tail in ((1023, 1000), (1024, 5000), (2047, 10)):
+        blob, _ = crafted_run_overflow_stream(deep, tail)
+        assert _decode_outcome(gpu_engine, blob, Bzip2Error) == ("err", -5) == _decode_outcome(oracle, blob, oracle.OracleError)
+    good = oracle.compress(b"still alive after the crafted streams " * 100)
+    assert gpu_engine.decompressFile(good) == b"still alive after the crafted streams " * 100

@@ -326,7 +326,7 @@ def test_decode_header_mutations_match_oracle(oracle, parse_mode, monkeypatch):
     for blob in cases:
         assert _decode_outcome(eng, blob, Bzip2Error) == _decode_outcome(oracle, blob, oracle.OracleError)
     # the same without the block CRC comparison on either side: what the damaged streams decode TO must agree as well
-    monkeypatch.setenv("BZ2B200_DEBUG_IGNORE_CRC", "1")
+    eng.debug_set_ignore_block_crc(True)
     oracle.set_ignore_block_crc(True)
     try:
         outcomes = [_decode_outcome(oracle, blob, oracle.OracleError) for blob in cases]
@@ -353,3 +353,59 @@ def test_decode_many_selectors_multi_chunk(oracle, monkeypatch):
         eng = Bzip2Engine(0, _native.Library(os.path.join(os.path.dirname(__file__), "sim", "libbz2b200_sim.so")))
         assert eng.decompressFile(good) == data
         assert _decode_outcome(eng, bytes(late), Bzip2Error) == _decode_outcome(oracle, bytes(late), oracle.OracleError)
+
+
+class _BitW:
+    def __init__(self):
+        self.v, self.n = 0, 0
+
+    def put(self, nbits, val):
+        self.v = (self.v << nbits) | (val & ((1 << nbits) - 1))
+        self.n += nbits
+
+    def bytes(self):
+        pad = -self.n % 8
+        return ((self.v << pad).to_bytes((self.n + pad) // 8, "big"))
+
+
+def crafted_run_overflow_stream(deep_total=1023, tail_literals=1000):
+    """a hand-built block whose RUNA/RUNB run lengths sum past 2^32.  Two used bytes (alphabet RUNA, RUNB,
+    literal, end-of-block; two tables of 2-bit codes); two runs of 21 shallow RUNA digits followed by `deep` RUNB digits.
+    With u32 sums and 0x400000 per deep digit (the round-1 kernel) the total wrapped to a small count that passed the dbuf
+    check while per-symbol offsets ran to 4 GiB.  The reference rejects the first run at BJ:1647 (Data error)."""
+    syms = []
+    for deep in (deep_total // 2 + deep_total % 2, deep_total // 2):
+        syms += [0] * 21 + [1] * deep + [2]
+    syms += [2] * tail_literals + [3]
+    w = _BitW()
+    for ch in b"BZh9":
+        w.put(8, ch)
+    w.put(48, 0x314159265359)
+    w.put(32, 0)                 # block CRC (never reached)
+    w.put(1, 0)
+    w.put(24, 5)                 # origPtr
+    w.put(16, 0x8000)            # range 0 used
+    w.put(16, 0xC000)            # bytes 0 and 1 used
+    nsel = (len(syms) + 49) // 50
+    w.put(3, 2)
+    w.put(15, nsel)
+    for _ in range(nsel):
+        w.put(1, 0)              # selector MTF index 0
+    for _ in range(2):           # two tables: every symbol 2 bits
+        w.put(5, 2)
+        for _ in range(4):
+            w.put(1, 0)
+    for s in syms:
+        w.put(2, s)              # canonical codes of four 2-bit symbols: 00 01 10 11
+    w.put(48, 0x177245385090)
+    w.put(32, 0)
+    wrapped = (2 * ((1 << 21) - 1) + deep_total * 0x400000 + 2 + tail_literals) % (1 << 32)
+    return w.bytes(), wrapped
+
+
+def test_decode_run_length_sum_cannot_wrap(sim_engine, oracle):
+    from compressjs_flattened_b200.bzip2 import Bzip2Error
+    blob, wrapped = crafted_run_overflow_stream()
+    assert wrapped <= 900_000   # the old u32 sum would have passed the dbuf check
+    assert _decode_outcome(oracle, blob, oracle.OracleError) == ("err", -5)
+    assert _decode_outcome(sim_engine, blob, Bzip2Error) == ("err", -5)
