@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 DEFAULT_SO = os.path.join(_HERE, "libbz2b200.so")
 
-E_LEVEL, E_CUDA, E_ARG = -100, -101, -102
+E_LEVEL, E_CUDA, E_ARG, E_PEER = -100, -101, -102, -103
 
 
 class Stats(C.Structure):
@@ -34,6 +34,16 @@ class BlockMeta(C.Structure):
 class ShardInfo(C.Structure):
     _fields_ = [("next_start", C.c_uint64), ("bits", C.c_uint64), ("n_blocks", C.c_uint32), ("crc_fold", C.c_uint32),
                 ("complete", C.c_uint32), ("bit_phase", C.c_uint32)]
+
+
+class ShardJob(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("n_readable", C.c_size_t), ("own_len", C.c_size_t), ("base", C.c_uint64),
+                ("index", C.c_int32), ("on_device", C.c_int32)]
+
+
+class ShardResult(C.Structure):
+    _fields_ = [("seg", C.POINTER(C.c_uint8)), ("seg_bytes", C.c_size_t), ("info", ShardInfo), ("bit_offset", C.c_uint64),
+                ("end_bit", C.c_uint64), ("blocks_through", C.c_uint64), ("crc_fold_through", C.c_uint32), ("pad", C.c_uint32)]
 
 
 class Library:
@@ -79,6 +89,19 @@ class Library:
         L.bz2b200_shard_cut_pick.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(ShardInfo), C.POINTER(C.c_int)]
         L.bz2b200_shard_emit.argtypes = [vp, C.c_int, C.POINTER(ShardInfo), u8pp, szp]
         L.bz2b200_stitch_shards.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_char_p), C.POINTER(ShardInfo), u8pp, szp]
+        L.bz2b200_pool_create.argtypes = [C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(vp)]
+        L.bz2b200_pool_destroy.argtypes = [vp]
+        L.bz2b200_pool_destroy.restype = None
+        L.bz2b200_pool_compress.argtypes = [vp, vp, C.c_size_t, C.c_int, C.c_size_t, u8pp, szp]
+        L.bz2b200_pool_last_stats.argtypes = [vp, C.POINTER(Stats)]
+        L.bz2b200_pool_last_error.argtypes = [vp]
+        L.bz2b200_pool_last_error.restype = C.c_char_p
+        L.bz2b200_group_open.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+        L.bz2b200_group_close.argtypes = [vp]
+        L.bz2b200_group_close.restype = None
+        L.bz2b200_pool_compress_shards.argtypes = [vp, vp, C.POINTER(ShardJob), C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(ShardResult)]
+        L.bz2b200_pool_debug.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_size_t, C.c_int]
+        L.bz2b200_debug_set_pool.argtypes = [vp, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int]
         self.L = L
         self.path = path
 

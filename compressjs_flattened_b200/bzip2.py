@@ -361,6 +361,12 @@ class Bzip2Engine:
         if rc:
             self._raise(rc)
 
+    def debug_set_pool(self, min_bytes=32_000_000, shard_bytes=0, first_halo=0, force_staging=False):
+        """tests only: which inputs compressFile sends through the context's two-lane pool, and how they are cut"""
+        rc = self._L.bz2b200_debug_set_pool(self._ctx, min_bytes, shard_bytes, first_halo, int(bool(force_staging)))
+        if rc:
+            self._raise(rc)
+
     def block_table(self):
         nb = self.stats().n_blocks
         raw = self.debug_fetch(0, 0, C.sizeof(_native.BlockRec) * nb)

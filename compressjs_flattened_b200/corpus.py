@@ -198,18 +198,54 @@ def _html_chunk(seed, c):
     return _assemble(ids, T, CHUNK)
 
 
-def _gen(n, seed, fn, first_chunk=0):
-    out = np.empty(n, dtype=np.uint8)
-    for i, off in enumerate(range(0, n, CHUNK)):
+def _gen(n, seed, fn, first_chunk=0, workers=None, out=None):
+    """chunks are independent, so they are produced by a few threads (numpy releases the GIL in its array loops); the bytes
+    do not depend on the number of workers"""
+    import os
+    out = np.empty(n, dtype=np.uint8) if out is None else out
+    offs = list(range(0, n, CHUNK))
+    _table()
+
+    def one(i):
+        off = offs[i]
         m = min(CHUNK, n - off)
         out[off:off + m] = fn(seed, first_chunk + i)[:m]
+
+    if workers is None:
+        workers = min(8, os.cpu_count() or 1)
+    if workers <= 1 or len(offs) < 4:
+        for i in range(len(offs)):
+            one(i)
+    else:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(workers) as ex:
+            list(ex.map(one, range(len(offs))))
     return out
 
 
-def gen_text(n, seed=8, first_chunk=0):
+def gen_text(n, seed=8, first_chunk=0, workers=None, out=None):
     """n bytes of enwik8-like text as a uint8 array; chunk k of the corpus is bytes [k*1e6, (k+1)*1e6)."""
-    return _gen(int(n), int(seed), _text_chunk, first_chunk)
+    return _gen(int(n), int(seed), _text_chunk, first_chunk, workers, out)
 
 
-def gen_html(n, seed=5, first_chunk=0):
-    return _gen(int(n), int(seed), _html_chunk, first_chunk)
+def gen_html(n, seed=5, first_chunk=0, workers=None, out=None):
+    return _gen(int(n), int(seed), _html_chunk, first_chunk, workers, out)
+
+
+def gen_adversarial(name):
+    """SURVEY.md 8d C5b at full size: suffix-sort and cut-walk stress inputs."""
+    if name == "zeros1e8":
+        return np.zeros(100_000_000, dtype=np.uint8)
+    if name == "ab5e7":
+        return np.tile(np.frombuffer(b"ab", dtype=np.uint8), 50_000_000)
+    if name == "rand1e8":
+        with np.errstate(over="ignore"):
+            return (_mix(np.arange(12_500_000, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15) + np.uint64(99))).view(np.uint8)[:100_000_000].copy()
+    if name == "line97x1e6":
+        line = b"0123456789abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ-the quick brown fox jumps over a \n"
+        assert len(line) == 97
+        return np.tile(np.frombuffer(line, dtype=np.uint8), 1_000_000)
+    raise KeyError(name)
+
+
+ADVERSARIAL = ("zeros1e8", "ab5e7", "rand1e8", "line97x1e6")

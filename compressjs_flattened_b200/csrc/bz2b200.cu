@@ -13,7 +13,16 @@
 #include "decode.cuh"
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <future>
 #include <mutex>
+#include <thread>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <string>
 #include <utility>
 #include <vector>
@@ -75,7 +84,13 @@ struct DevBuf {
 };
 
 struct Ctx;
+struct Pool;
+void pool_delete(Pool *p);
 struct Ctx {
+  Pool *own_pool = nullptr;         // two lanes on this context's device: large host inputs of bz2b200_compress
+  size_t pool_min_bytes = 32000000; // inputs of this size or more go through own_pool
+  size_t pool_shard_bytes = 0, pool_halo0 = 0;
+  bool pool_force_staging = false;
   int device = 0;
   cudaStream_t stream = nullptr;
   std::string err;
@@ -730,6 +745,7 @@ int compress_device(Ctx *c, const u8 *d_in, size_t n_, int level, u32 *d_out, si
 }
 
 #include "decode_host.inl"
+#include "pool.inl"
 
 // The opt-in for more than 48 KB of dynamic shared memory is a per-DEVICE function attribute: set for the current
 // device by every bz2b200_create (contexts on several GPUs in one process each set their own).
@@ -747,14 +763,7 @@ cudaError_t set_kernel_attributes() {
   return cudaSuccess;
 }
 
-}  // namespace
-
-// ------------------------------------------------------------------------------------ C ABI
-extern "C" {
-
-int bz2b200_create(int device, bz2b200_ctx **ctx) {
-  if (!ctx) return BZ2B200_E_ARG;
-  *ctx = nullptr;
+int ctx_new(int device, Ctx **out) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return BZ2B200_E_CUDA;
   if (cudaSetDevice(device) != cudaSuccess) return BZ2B200_E_CUDA;
@@ -767,14 +776,14 @@ int bz2b200_create(int device, bz2b200_ctx **ctx) {
   { const char *t = getenv("BZ2B200_IBWT_S"); int v = t ? atoi(t) : 0; if (v == 64 || v == 128 || v == 256 || v == 512 || v == 1024) c->ibwt_s = (unsigned)v; }
   { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) c->sms = v; }
   for (auto &e : c->ev) if (cudaEventCreate(&e) != cudaSuccess) c->ev_ok = false;
-  if (set_kernel_attributes() != cudaSuccess) { bz2b200_destroy(reinterpret_cast<bz2b200_ctx *>(c)); return BZ2B200_E_CUDA; }
-  *ctx = reinterpret_cast<bz2b200_ctx *>(c);
+  if (set_kernel_attributes() != cudaSuccess) { ctx_delete(c); return BZ2B200_E_CUDA; }
+  *out = c;
   return BZ2B200_OK;
 }
 
-void bz2b200_destroy(bz2b200_ctx *ctx) {
-  Ctx *c = reinterpret_cast<Ctx *>(ctx);
+void ctx_delete(Ctx *c) {
   if (!c) return;
+  if (c->own_pool) pool_delete(c->own_pool);
   cudaSetDevice(c->device);
   for (DevBuf *b : c->pool) if (b->p) cudaFree(b->p);
   if (c->rb_pin) cudaFreeHost(c->rb_pin);
@@ -784,6 +793,23 @@ void bz2b200_destroy(bz2b200_ctx *ctx) {
   cudaStreamDestroy(c->stream);
   delete c;
 }
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------ C ABI
+extern "C" {
+
+int bz2b200_create(int device, bz2b200_ctx **ctx) {
+  if (!ctx) return BZ2B200_E_ARG;
+  *ctx = nullptr;
+  Ctx *c = nullptr;
+  int rc = ctx_new(device, &c);
+  if (rc) return rc;
+  *ctx = reinterpret_cast<bz2b200_ctx *>(c);
+  return BZ2B200_OK;
+}
+
+void bz2b200_destroy(bz2b200_ctx *ctx) { ctx_delete(reinterpret_cast<Ctx *>(ctx)); }
 
 int bz2b200_compress_device(bz2b200_ctx *ctx, const void *d_in, size_t n, int level, void *d_out, size_t out_cap, size_t *out_len) {
   Ctx *c = reinterpret_cast<Ctx *>(ctx);
@@ -797,6 +823,21 @@ int bz2b200_compress(bz2b200_ctx *ctx, const uint8_t *in, size_t n, int level, u
   if (!c || !out || !out_len || (n && !in)) return BZ2B200_E_ARG;
   if (level < 1 || level > 9) return BZ2B200_E_LEVEL;
   CK(cudaSetDevice(c->device));
+  if (n >= c->pool_min_bytes) {
+    // large input: shards over two lanes of this device, so that the copies in both directions hide under the kernels
+    if (!c->own_pool) {
+      const int dev = c->device;
+      int prc = pool_new(&dev, 1, 2, &c->own_pool);
+      if (prc) { c->err = "cannot create the lanes of the context's pool"; return prc; }
+    }
+    Pool *p = c->own_pool;
+    p->cap_override = c->cap_override; p->batch_override = c->batch_override;
+    p->halo0 = c->pool_halo0; p->force_staging = c->pool_force_staging;
+    int prc = pool_compress_whole(p, in, n, level, c->pool_shard_bytes, out, out_len);
+    c->st = p->st;
+    c->err = p->err;
+    return prc;
+  }
   ENS(c->in, n + 64);
   if (n) CK(cudaMemcpyAsync(c->in.p, in, n, cudaMemcpyHostToDevice, c->stream));
   size_t olen = 0;
@@ -981,6 +1022,7 @@ const char *bz2b200_strerror(int rc) {
     case BZ2B200_E_LEVEL: return "Invalid block size multiplier";
     case BZ2B200_E_CUDA: return "CUDA failure";
     case BZ2B200_E_ARG: return "bad argument";
+    case BZ2B200_E_PEER: return "a peer of the shard group failed or timed out";
     default: return "unknown error";
   }
 }
@@ -1042,5 +1084,6 @@ int bz2b200_debug_set_block_cap(bz2b200_ctx *ctx, uint32_t cap) {
 }
 
 #include "decode_abi.inl"
+#include "pool_abi.inl"
 
 }  // extern "C"

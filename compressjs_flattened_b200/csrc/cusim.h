@@ -18,6 +18,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <mutex>
 #include <vector>
 
 struct dim3 {
@@ -116,7 +117,9 @@ inline void set_tid(unsigned t) {
   s.threadIdx.y = (t / s.blockDim.x) % s.blockDim.y;
   s.threadIdx.z = t / (s.blockDim.x * s.blockDim.y);
 }
+inline std::mutex &launch_mutex() { static std::mutex m; return m; }
 inline void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> &body) {
+  std::lock_guard<std::mutex> one_kernel_at_a_time(launch_mutex());  // the shard scheduler launches from several host threads
   State &s = S();
   unsigned nt = block.x * block.y * block.z;
   assert(nt >= 1 && nt <= 1024);
@@ -271,6 +274,9 @@ static inline cudaError_t cudaMemset(void *d, int v, size_t n) { memset(d, v, n)
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
 static inline cudaError_t cudaDeviceSynchronize() { return 0; }
 static inline cudaError_t cudaStreamCreate(cudaStream_t *s) { *s = nullptr; return 0; }
+static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = nullptr; return 0; }
+static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return 0; }
+#define cudaStreamNonBlocking 1
 static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }
 static inline cudaError_t cudaGetLastError() { return 0; }
 static inline cudaError_t cudaSetDevice(int) { return 0; }

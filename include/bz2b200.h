@@ -36,7 +36,8 @@ enum {
   BZ2B200_E_END_OF_BLOCK = -8,
   BZ2B200_E_LEVEL = -100,   /* Error('Invalid block size multiplier') */
   BZ2B200_E_CUDA = -101,    /* CUDA runtime failure; see bz2b200_last_error */
-  BZ2B200_E_ARG = -102
+  BZ2B200_E_ARG = -102,
+  BZ2B200_E_PEER = -103     /* a peer of the shard group failed, or did not answer before the deadline */
 };
 
 typedef struct bz2b200_ctx bz2b200_ctx;
@@ -114,6 +115,55 @@ int bz2b200_shard_cut_pick(bz2b200_ctx *ctx, uint64_t s_start, uint64_t own_len,
 int bz2b200_shard_compress(bz2b200_ctx *ctx, bz2b200_shard_info *info);
 int bz2b200_shard_emit(bz2b200_ctx *ctx, int bit_phase, bz2b200_shard_info *info, uint8_t **seg, size_t *seg_bytes);
 int bz2b200_stitch_shards(int level, int n_shards, const uint8_t *const *segs, const bz2b200_shard_info *infos, uint8_t **out, size_t *out_len);
+
+/* ---- the shard scheduler: one stream over several lanes, devices and processes (csrc/pool.inl) ----
+ * A pool owns `lanes_per_device` contexts (each with its own stream) on every listed device.  A stream is cut into
+ * shards; shard i goes to lane i mod lanes, lanes work at the same time, and the host<->device copies of one shard
+ * run under the kernels of the others -- inside one blocking call.  bz2b200_compress() itself routes inputs of 32 MB
+ * or more through a two-lane pool on its context's device; pageable input is staged through page-locked memory by a
+ * helper thread (SURVEY.md 8b "may be pageable; the library stages through pinned memory").
+ *   pool_compress    Bzip2.compressFile (BJ:2199-2249) on every device of the pool: the multi-GPU form of the
+ *                    reference-facing call (SURVEY.md 8b `ngpus`).  shard_bytes = 0 picks a size.
+ *   pool_decompress  Bzip2.decompressFile (BJ:1769-1796) of ONE stream, block ranges over the lanes
+ * Ranks of one node (one process per GPU) join a GROUP: a page of POSIX shared memory that carries the per-shard
+ * scalars (first-block offset, end bit, CRC fold) between processes.  Calls with a group are collective: every rank
+ * makes the same sequence of calls; waits have a deadline (timeout_ms) and a failing rank wakes the others with
+ * BZ2B200_E_PEER.  `name` must be unique per job (e.g. master port + launcher pid). */
+typedef struct bz2b200_pool bz2b200_pool;
+typedef struct bz2b200_group bz2b200_group;
+int bz2b200_pool_create(const int *devices, int n_devices, int lanes_per_device, bz2b200_pool **pool);
+void bz2b200_pool_destroy(bz2b200_pool *pool);
+int bz2b200_pool_compress(bz2b200_pool *pool, const uint8_t *in, size_t n, int level, size_t shard_bytes, uint8_t **out, size_t *out_len);
+int bz2b200_pool_last_stats(bz2b200_pool *pool, bz2b200_stats *st);
+const char *bz2b200_pool_last_error(bz2b200_pool *pool);
+int bz2b200_group_open(const char *name, int rank, int world, int timeout_ms, bz2b200_group **grp);
+void bz2b200_group_close(bz2b200_group *grp);
+/* This process's shards of a stream that spans the group (grp == NULL: this process holds all of them).
+ * jobs[] in ascending `index`; shard `index` starts at input offset `base`, owns the blocks that start in
+ * [base, base + own_len) and may read n_readable >= own_len bytes at src (the rest is its halo: the library starts
+ * with 5/4 of a block and takes more when a run-heavy block needs it).  The last shard (index == total_shards - 1)
+ * ends the stream.  results[i]: the segment of jobs[i], already shifted to its bit phase (seg == NULL with
+ * keep_on_device), its bit offset in the stream and the running totals; bz2b200_stitch_shards assembles them. */
+typedef struct {
+  const void *src;
+  size_t n_readable, own_len;
+  uint64_t base;
+  int32_t index, on_device;
+} bz2b200_shard_job;
+typedef struct {
+  uint8_t *seg;               /* page-locked; release with bz2b200_free */
+  size_t seg_bytes;
+  bz2b200_shard_info info;    /* next_start in GLOBAL input coordinates here */
+  uint64_t bit_offset;        /* of the segment's first bit in the stream */
+  uint64_t end_bit, blocks_through;
+  uint32_t crc_fold_through, pad;
+} bz2b200_shard_result;
+int bz2b200_pool_compress_shards(bz2b200_pool *pool, bz2b200_group *grp, const bz2b200_shard_job *jobs, int n_jobs, int total_shards, int level,
+                                 int keep_on_device, bz2b200_shard_result *results);
+/* tests/ only: block capacity, blocks per batch, first halo (0 = defaults) and forced staging for every lane of a pool;
+ * and for a context: inputs of min_bytes or more go through its own two-lane pool in shards of shard_bytes (0 = auto). */
+int bz2b200_pool_debug(bz2b200_pool *pool, uint32_t block_cap, uint32_t batch_blocks, size_t first_halo, int force_staging);
+int bz2b200_debug_set_pool(bz2b200_ctx *ctx, size_t min_bytes, size_t shard_bytes, size_t first_halo, int force_staging);
 
 const char *bz2b200_strerror(int rc);
 const char *bz2b200_last_error(bz2b200_ctx *ctx);

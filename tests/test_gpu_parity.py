@@ -142,10 +142,17 @@ def test_full_size_configs(gpu_engine, key):
     data = (gen_text if kind == "text" else gen_html)(n, seed)
     g = GOLD[key]
     assert hashlib.sha256(data.tobytes()).hexdigest() == g["input_sha256"]
-    comp = gpu_engine.compressFile(data, None, level)
+    comp = gpu_engine.compressFile(data, None, level)   # >= 32 MB: shards over the context's two lanes (pool.inl)
     st = gpu_engine.stats()
     assert (len(comp), hashlib.sha256(comp).hexdigest()) == (g["out_bytes"], g["out_sha256"])
     assert (st.n_blocks, st.rle1_bytes, st.mtf_syms) == (g["n_blocks"], g["rle1_bytes"], g["mtf_syms"])
+    if n >= 32_000_000:   # the same through the single-launch path, whose block table the checks below read
+        gpu_engine.debug_set_pool(1 << 62)
+        try:
+            comp1 = gpu_engine.compressFile(data, None, level)
+        finally:
+            gpu_engine.debug_set_pool()
+        assert comp1 == comp
     recs = gpu_engine.block_table()
     sizes_enc = [r.p - r.s for r in recs]
     fold = 0
