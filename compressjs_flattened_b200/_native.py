@@ -46,6 +46,10 @@ class ShardResult(C.Structure):
                 ("end_bit", C.c_uint64), ("blocks_through", C.c_uint64), ("crc_fold_through", C.c_uint32), ("pad", C.c_uint32)]
 
 
+class RangeResult(C.Structure):
+    _fields_ = [("part", C.POINTER(C.c_uint8)), ("bytes", C.c_uint64), ("out_offset", C.c_uint64), ("rc", C.c_int32), ("n_blocks", C.c_uint32)]
+
+
 class Library:
     """Thin typed view of the C ABI."""
 
@@ -93,6 +97,8 @@ class Library:
         L.bz2b200_pool_destroy.argtypes = [vp]
         L.bz2b200_pool_destroy.restype = None
         L.bz2b200_pool_compress.argtypes = [vp, vp, C.c_size_t, C.c_int, C.c_size_t, u8pp, szp]
+        L.bz2b200_pool_set_plan.argtypes = [vp, C.c_size_t, C.c_double]
+        L.bz2b200_pool_plan.argtypes = [C.c_size_t, C.c_int, C.c_int, C.c_size_t, C.c_double, C.POINTER(C.c_size_t), C.c_int]
         L.bz2b200_pool_last_stats.argtypes = [vp, C.POINTER(Stats)]
         L.bz2b200_pool_last_error.argtypes = [vp]
         L.bz2b200_pool_last_error.restype = C.c_char_p
@@ -100,6 +106,10 @@ class Library:
         L.bz2b200_group_close.argtypes = [vp]
         L.bz2b200_group_close.restype = None
         L.bz2b200_pool_compress_shards.argtypes = [vp, vp, C.POINTER(ShardJob), C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(ShardResult)]
+        L.bz2b200_pool_decompress.argtypes = [vp, vp, C.c_size_t, C.c_int, C.c_size_t, C.c_size_t, u8pp, szp]
+        L.bz2b200_pool_decompress_shards.argtypes = [vp, vp, C.POINTER(ShardJob), C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int,
+                                                     C.POINTER(RangeResult)]
+        L.bz2b200_debug_set_decode_batch.argtypes = [vp, vp, C.c_uint32]
         L.bz2b200_pool_debug.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_size_t, C.c_int]
         L.bz2b200_debug_set_pool.argtypes = [vp, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int]
         self.L = L

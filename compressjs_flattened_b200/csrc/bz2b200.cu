@@ -126,6 +126,7 @@ struct Ctx {
   bool ignore_block_crc = false;  // tests only (bz2b200_debug_set_ignore_block_crc)
   u32 cap_override = 0;    // tests only
   u32 batch_override = 0;  // tests only: blocks per batch
+  u32 dec_batch = 0;       // tests only: candidates per decode batch (0 = DEC_BATCH)
   u64 shard_bits = 0;      // bit length of the last shard segment (phase 0 in `out`)
   int cand_n = 0, cand_max_blocks = 0, cand_nb[64];  // speculated cut walks of the last shard_cut_g
   i64 cand_s[64];
@@ -1003,8 +1004,11 @@ size_t bz2b200_compress_bound(size_t n, int level) {
   if (level < 1 || level > 9) level = 9;
   size_t B = (size_t)level * 100000 - 19;
   size_t nblocks = n / (B * 4 / 5) + 2;
-  // RLE1 expands by at most 5/4, Huffman codes are at most 20 bits per symbol
-  return (n + n / 4 + nblocks) * 20 / 8 + nblocks * (10 + 4 + 32 + 3 + 18001 + 6 * 1300) + 64;
+  // RLE1 expands by at most 5/4 (a run of exactly four bytes becomes five), a block adds its end-of-block symbol, and a
+  // table never costs more than 9 bits per symbol on the groups it was built from (a fixed 9-bit code is admissible for
+  // <= 258 symbols and the allocator's lengths are optimal under the 20-bit limit; the final selector pass only lowers the
+  // cost).  Per block: header 105 bits + maps 272 + 18 + selectors 18 002 x 6 bits + six tables of 5 + 258 x 39 bits.
+  return (n + n / 4 + nblocks) / 8 * 9 + nblocks * 22000 + 1024;
 }
 
 void bz2b200_free(void *p) { result_pool().put(p); }

@@ -46,9 +46,11 @@ struct DecBlk {
 };
 
 // ---- K-U1 -----------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_magic_scan(const u8 *__restrict__ in, u64 n, u64 *__restrict__ cand, u32 cap, u32 *__restrict__ ncand) {
-  u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+// bytes [b0, b1) of the buffer (n bytes readable): a range of a stream scans only its own bytes
+__global__ void __launch_bounds__(256) k_magic_scan(const u8 *__restrict__ in, u64 n, u64 b0, u64 b1, u64 *__restrict__ cand, u32 cap,
+                                                    u32 *__restrict__ ncand) {
+  u64 i = b0 + (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= b1 || i >= n) return;
   u64 w = 0;
   for (int k = 0; k < 8; k++) w = (w << 8) | (i + k < n ? in[i + k] : 0);
   for (int b = 0; b < 8; b++) {

@@ -18,8 +18,8 @@ struct ExTail { u64 end_bit = 32, blocks = 0; u32 fold = 0; u64 aux = 0; };
 
 struct Exchange {
   virtual ~Exchange() {}
-  virtual int put_cut(int j, u64 next_start) = 0;
-  virtual int get_cut(int j, u64 *next_start) = 0;
+  virtual int put_cut(int j, u64 next_start, u64 aux = 0) = 0;
+  virtual int get_cut(int j, u64 *next_start, u64 *aux = nullptr) = 0;
   virtual int put_tail(int j, const ExTail &t) = 0;
   virtual int get_tail(int j, ExTail *t) = 0;
   virtual void fail(int rc) = 0;
@@ -29,22 +29,23 @@ struct Exchange {
 struct LocalExchange : Exchange {
   std::mutex mu;
   std::condition_variable cv;
-  std::vector<u64> cut;
+  std::vector<u64> cut, cut_aux;
   std::vector<ExTail> tail;
   std::vector<u8> cut_ok, tail_ok;
   int err = 0;
   int timeout_ms = 600000;
-  explicit LocalExchange(int n) : cut((size_t)n), tail((size_t)n), cut_ok((size_t)n, 0), tail_ok((size_t)n, 0) {}
-  int put_cut(int j, u64 v) override {
-    { std::lock_guard<std::mutex> g(mu); cut[(size_t)j] = v; cut_ok[(size_t)j] = 1; }
+  explicit LocalExchange(int n) : cut((size_t)n), cut_aux((size_t)n), tail((size_t)n), cut_ok((size_t)n, 0), tail_ok((size_t)n, 0) {}
+  int put_cut(int j, u64 v, u64 aux = 0) override {
+    { std::lock_guard<std::mutex> g(mu); cut[(size_t)j] = v; cut_aux[(size_t)j] = aux; cut_ok[(size_t)j] = 1; }
     cv.notify_all();
     return 0;
   }
-  int get_cut(int j, u64 *v) override {
+  int get_cut(int j, u64 *v, u64 *aux = nullptr) override {
     std::unique_lock<std::mutex> l(mu);
     if (!cv.wait_for(l, std::chrono::milliseconds(timeout_ms), [&] { return err || cut_ok[(size_t)j]; })) return BZ2B200_E_PEER;
     if (err) return err;
     *v = cut[(size_t)j];
+    if (aux) *aux = cut_aux[(size_t)j];
     return 0;
   }
   int put_tail(int j, const ExTail &t) override {
@@ -73,7 +74,7 @@ struct LocalExchange : Exchange {
 #define GRP_SLOTS 4096
 struct GrpSlot {
   std::atomic<u64> cut_seq, tail_seq;
-  u64 next_start, end_bit, blocks, aux;
+  u64 next_start, cut_aux, end_bit, blocks, aux;
   u32 fold, pad;
 };
 struct GrpHeader {
@@ -108,16 +109,17 @@ struct GroupExchange : Exchange {
       }
     }
   }
-  int put_cut(int j, u64 v) override {
+  int put_cut(int j, u64 v, u64 aux = 0) override {
     if (j < 0 || j >= GRP_SLOTS) return BZ2B200_E_ARG;
     g->h->slot[j].next_start = v;
+    g->h->slot[j].cut_aux = aux;
     g->h->slot[j].cut_seq.store(g->epoch, std::memory_order_release);
     return 0;
   }
-  int get_cut(int j, u64 *v) override {
+  int get_cut(int j, u64 *v, u64 *aux = nullptr) override {
     if (j < 0 || j >= GRP_SLOTS) return BZ2B200_E_ARG;
     int rc = wait([&] { return g->h->slot[j].cut_seq.load(std::memory_order_acquire) == g->epoch; });
-    if (!rc) *v = g->h->slot[j].next_start;
+    if (!rc) { *v = g->h->slot[j].next_start; if (aux) *aux = g->h->slot[j].cut_aux; }
     return rc;
   }
   int put_tail(int j, const ExTail &t) override {
@@ -205,6 +207,7 @@ struct Lane {
   cudaStream_t copy = nullptr;
   cudaEvent_t in_ev[2] = {nullptr, nullptr};
   DevBuf in_slot[2];
+  DevBuf out_slot[2];                   // decode: the bytes of a range until their place in the output is known
   void *stage[2] = {nullptr, nullptr};  // page-locked staging of pageable input
   size_t stage_cap[2] = {0, 0};
   std::string err;
@@ -215,8 +218,10 @@ struct Pool {
   std::string err;
   bz2b200_stats st{};
   bool force_staging = false;   // tests only: treat the input as pageable
-  u32 cap_override = 0, batch_override = 0;
+  u32 cap_override = 0, batch_override = 0, dec_batch = 0;
   size_t halo0 = 0;             // tests only: first halo tried (0 = 5/4 of a block + 64 KiB)
+  size_t plan_first = 0;        // shard plan: first shard (0 = six blocks) and growth per wave (0 = 2.5)
+  double plan_growth = 0;
 };
 
 int ctx_new(int device, Ctx **out);   // bz2b200.cu
@@ -230,6 +235,7 @@ void pool_delete(Pool *p) {
       cudaSetDevice(L->c->device);
       for (int s = 0; s < 2; s++) {
         if (L->in_slot[s].p) cudaFree(L->in_slot[s].p);
+        if (L->out_slot[s].p) cudaFree(L->out_slot[s].p);
         if (L->stage[s]) cudaFreeHost(L->stage[s]);
         if (L->in_ev[s]) cudaEventDestroy(L->in_ev[s]);
       }
@@ -380,6 +386,7 @@ static int lane_run(PoolRun &R, Lane *L, std::vector<ShardJob> jobs, std::vector
     u64 bits = 0;
     u32 fold = 0;
     if ((rc = pipe_run(c, 0, false, nullptr, 0, true, &olen, &bits, &fold))) return rc;
+    trace_report(c);
     {
       agg.n_blocks += c->st.n_blocks; agg.kernel_launches += c->st.kernel_launches; agg.rle1_bytes += c->st.rle1_bytes;
       agg.mtf_syms += c->st.mtf_syms; agg.sort_slots += c->st.sort_slots; agg.d1_triggered |= c->st.d1_triggered;
@@ -463,13 +470,42 @@ static int pool_run_shards(Pool *p, Exchange *ex, std::vector<ShardJob> &jobs, s
   return rc;
 }
 
-static size_t pool_auto_shard(const Pool *p, size_t n, int level) {
+// Shard sizes of one stream.  Small batches of blocks use the GPU less well than large ones (latency-bound per-block
+// kernels, partial waves), so the stream is NOT cut evenly: the first shard of every lane is small -- its upload is the
+// only one nobody hides -- and every following wave is `growth` times larger: copies run ~2.5x faster than the kernels,
+// so the upload of wave k+1 still fits under the kernels of wave k.  `fixed` > 0: equal shards of that size.
+static std::vector<size_t> pool_plan(size_t n, int level, size_t lanes, size_t fixed, size_t first, double growth) {
+  std::vector<size_t> sizes;
+  if (n == 0) { sizes.push_back(0); return sizes; }
+  if (fixed) {
+    for (size_t o = 0; o < n; o += fixed) sizes.push_back(n - o < fixed ? n - o : fixed);
+    return sizes;
+  }
   const size_t B = (size_t)level * 100000;
-  size_t per = n / (p->lanes.size() * 4) + 1;             // four shards per lane: copies hide behind three of them
-  const size_t lo = 4 * B, hi = (size_t)48 << 20;         // at least four blocks a shard, at most 48 MiB
-  if (per < lo) per = lo;
-  if (per > hi) per = hi;
-  return (per + 4095) & ~(size_t)4095;
+  if (!first) first = 6 * B < ((size_t)6 << 20) ? (size_t)6 << 20 : 6 * B;   // six blocks or 6 MiB
+  if (growth < 1.0) growth = 2.5;
+  size_t left = n;
+  double w = (double)first;
+  while (left) {
+    if ((double)left <= w * (double)lanes * 1.3) {  // the last wave: what is left, split evenly over the lanes (no crumb shard)
+      const size_t parts = (double)left <= w * 0.65 ? 1 : (size_t)(((double)left + w * 1.3 - 1) / (w * 1.3));
+      for (size_t l = 0; l < parts; l++) {
+        size_t take = l + 1 == parts ? left : ((left / (parts - l)) + 4095) & ~(size_t)4095;
+        if (take > left) take = left;
+        sizes.push_back(take);
+        left -= take;
+      }
+      break;
+    }
+    for (size_t l = 0; l < lanes; l++) {              // a full wave: one shard per lane
+      const size_t take = ((size_t)w + 4095) & ~(size_t)4095;
+      sizes.push_back(take);
+      left -= take;
+    }
+    w *= growth;
+    if (w > (double)((size_t)128 << 20)) w = (double)((size_t)128 << 20);  // bounds the per-lane state (52 B per input byte)
+  }
+  return sizes;
 }
 static size_t pool_first_halo(const Pool *p, int level) {
   if (p->halo0) return p->halo0;
@@ -482,16 +518,18 @@ static int pool_compress_whole(Pool *p, const u8 *in, size_t n, int level, size_
   if (level < 1 || level > 9) return BZ2B200_E_LEVEL;
   p->err.clear();
   auto t0 = std::chrono::steady_clock::now();
-  if (!shard_bytes) shard_bytes = pool_auto_shard(p, n, level);
-  const size_t ns = n ? (n + shard_bytes - 1) / shard_bytes : 1;
+  const std::vector<size_t> plan = pool_plan(n, level, p->lanes.size(), shard_bytes, p->plan_first, p->plan_growth);
+  const size_t ns = plan.size();
   const size_t halo = pool_first_halo(p, level);
   std::vector<ShardJob> jobs(ns);
+  u64 at = 0;
   for (size_t j = 0; j < ns; j++) {
     ShardJob &J = jobs[j];
-    J.base = (u64)j * shard_bytes;
+    J.base = at;
+    at += plan[j];
     J.src = in + J.base;
     J.n_max = n - (size_t)J.base;
-    J.own_len = J.n_max < shard_bytes ? J.n_max : shard_bytes;
+    J.own_len = plan[j];
     J.n_avail = J.own_len + halo < J.n_max ? J.own_len + halo : J.n_max;
     J.index = (int)j;
     J.last = true;  // the buffer runs to the end of the input for every shard: a block that reaches n_max ends the stream
@@ -565,6 +603,250 @@ static int pool_compress_ranked(Pool *p, Group *grp, const bz2b200_shard_job *jo
     const ShardOut &o = outs[(size_t)i];
     results[i].seg = o.seg; results[i].seg_bytes = o.seg_bytes; results[i].info = o.info; results[i].bit_offset = o.bit_off;
     results[i].end_bit = o.tail.end_bit; results[i].blocks_through = o.tail.blocks; results[i].crc_fold_through = o.tail.fold;
+  }
+  p->st.ms_total = (float)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count() / 1000.f;
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------------------ decompress
+// Block-range decompression of ONE stream (last paragraph; BJ:1769-1796 walking blocks found by BJ:1434-1439):
+// the stream is cut into byte slices; a lane scans its slice for signatures and decodes every candidate at once, then
+// receives the state of the reference's walk from the slice before (where the next block starts, the running stream
+// CRC, the level), follows it through its own candidates and passes it on -- a chain of scalars like the cut offsets
+// of the compressor.  Output offsets are the running sum of decoded sizes (the `tail` chain).
+struct DecOut {
+  u8 *part = nullptr;     // ranks mode or overflow of the guessed output size: page-locked bytes of this range
+  u64 bytes = 0, out_off = 0;
+  int rc = 0;
+  std::string msg;
+  u32 blocks = 0;
+};
+static inline u64 walk_pack(const DecWalk &w) { return (u64)w.stream_crc | ((u64)w.level << 32) | ((u64)w.ended << 40); }
+static inline void walk_unpack(u64 a, u64 b, DecWalk &w) { w.cur = a; w.stream_crc = (u32)b; w.level = (u32)((b >> 32) & 0xff); w.ended = (u32)((b >> 40) & 1); }
+
+struct DecRun {
+  Pool *pool;
+  Exchange *ex;
+  u64 total_n;
+  int multistream, first_level;
+  bool pageable;
+  u8 *dst = nullptr;      // whole mode: the output buffer (capacity guessed from the hint); parts that do not fit stay apart
+  size_t dst_cap = 0;
+};
+
+static int lane_decode(DecRun &R, Lane *L, std::vector<ShardJob> jobs, std::vector<DecOut *> outs) {
+  Ctx *c = L->c;
+  CK(cudaSetDevice(c->device));
+  if (R.pool->dec_batch) c->dec_batch = R.pool->dec_batch;
+  const size_t nj = jobs.size();
+  const u8 *d_in[2] = {nullptr, nullptr};
+  std::future<int> up;
+  if (nj) {
+    const ShardJob j0 = jobs[0];
+    up = std::async(std::launch::async, [L, j0, &R, &d_in] { return lane_upload(L, j0, 0, R.pageable, &d_in[0]); });
+  }
+  bz2b200_stats agg{};
+  for (size_t k = 0; k < nj; k++) {
+    ShardJob &job = jobs[k];
+    DecOut &out = *outs[k];
+    const int slot = (int)(k & 1);
+    int rc = up.get();
+    if (rc) return rc;
+    if (k + 1 < nj) {
+      const ShardJob jn = jobs[k + 1];
+      const int ns = slot ^ 1;
+      up = std::async(std::launch::async, [L, jn, ns, &R, &d_in] { return lane_upload(L, jn, ns, R.pageable, &d_in[ns]); });
+    }
+    DecWalk Win, Wout;
+    bool have_in = false;
+    auto get_walk = [&](DecWalk &w) -> int {
+      if (!have_in) {
+        if (job.index == 0) { Win = DecWalk(); Win.level = (u32)R.first_level; }
+        else { u64 a = 0, b = 0; int r = R.ex->get_cut(job.index - 1, &a, &b); if (r) return r; walk_unpack(a, b, Win); }
+        have_in = true;
+      }
+      w = Win;
+      return 0;
+    };
+    bool cut_sent = false;
+    const std::function<int(const DecWalk &)> on_walk = [&](const DecWalk &w) -> int {
+      cut_sent = true;
+      return R.ex->put_cut(job.index, w.cur, walk_pack(w));
+    };
+    DecodeResult res;
+    const u64 lo_bit = job.base * 8, hi_bit = (job.base + job.own_len) * 8;
+    c->st = bz2b200_stats{};
+    c->err.clear();
+    for (;;) {
+      if (!job.on_device) CK(cudaStreamWaitEvent(c->stream, L->in_ev[slot], 0));
+      BufSink sink(&L->out_slot[slot]);
+      int need_more = 0;
+      rc = decode_range(c, d_in[slot], job.n_avail, job.base, R.total_n, lo_bit, hi_bit, R.multistream, DEC_STREAM, get_walk, sink, res, Wout, &need_more,
+                        &on_walk);
+      if (rc == BZ2B200_E_CUDA || rc == BZ2B200_E_PEER || rc == BZ2B200_E_ARG) return rc;  // infrastructure: everybody stops
+      if (!need_more) break;
+      if (job.n_avail >= job.n_max) { c->err = "internal: range needs input beyond the stream"; return BZ2B200_E_ARG; }
+      const size_t halo = job.n_avail - job.own_len;
+      const size_t grown = job.own_len + (halo < (4u << 20) ? (16u << 20) : halo * 4);
+      job.n_avail = grown < job.n_max ? grown : job.n_max;
+      if (!job.on_device && (rc = lane_upload(L, job, slot, R.pageable, &d_in[slot]))) return rc;
+    }
+    trace_report(c);
+    // a data error ends the walk here; the slices after it decode nothing, the slices before it still count: the
+    // caller reports the error of the lowest slice (the first in stream order, like the reference)
+    out.rc = rc;
+    out.msg = c->err;
+    if (rc) { Wout = Win; Wout.ended = 1; res.out_len = 0; }
+    if (!cut_sent && (rc = R.ex->put_cut(job.index, Wout.cur, walk_pack(Wout)))) return rc;
+    ExTail prev;
+    prev.end_bit = 0;
+    if (job.index > 0 && (rc = R.ex->get_tail(job.index - 1, &prev))) return rc;
+    ExTail mine;
+    mine.end_bit = prev.end_bit + res.out_len;   // `end_bit` carries the running OUTPUT offset here
+    mine.blocks = prev.blocks + c->st.n_blocks;
+    if ((rc = R.ex->put_tail(job.index, mine))) return rc;
+    out.bytes = res.out_len;
+    out.out_off = prev.end_bit;
+    out.blocks = c->st.n_blocks;
+    agg.n_blocks += c->st.n_blocks; agg.kernel_launches += c->st.kernel_launches; agg.rle1_bytes += c->st.rle1_bytes;
+    if (out.bytes) {
+      if (R.dst && out.out_off + out.bytes <= R.dst_cap) {
+        CK(cudaMemcpyAsync(R.dst + out.out_off, L->out_slot[slot].p, (size_t)out.bytes, cudaMemcpyDeviceToHost, c->stream));
+      } else {
+        out.part = (u8 *)result_pool().get((size_t)out.bytes);
+        if (!out.part) return BZ2B200_E_OUT_OF_MEMORY;
+        CK(cudaMemcpyAsync(out.part, L->out_slot[slot].p, (size_t)out.bytes, cudaMemcpyDeviceToHost, c->stream));
+      }
+    }
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaGetLastError());
+  c->st = agg;
+  return 0;
+}
+
+static int pool_run_decode(Pool *p, DecRun &R, std::vector<ShardJob> &jobs, std::vector<DecOut> &outs) {
+  const size_t nl = p->lanes.size();
+  outs.assign(jobs.size(), DecOut());
+  std::vector<std::vector<ShardJob>> lj(nl);
+  std::vector<std::vector<DecOut *>> lo(nl);
+  for (size_t i = 0; i < jobs.size(); i++) { lj[i % nl].push_back(jobs[i]); lo[i % nl].push_back(&outs[i]); }
+  std::vector<int> rcs(nl, 0);
+  std::vector<std::thread> th;
+  for (size_t l = 1; l < nl; l++)
+    if (!lj[l].empty()) th.emplace_back([&, l] { rcs[l] = lane_decode(R, p->lanes[l], lj[l], lo[l]); if (rcs[l]) R.ex->fail(rcs[l]); });
+  rcs[0] = lane_decode(R, p->lanes[0], lj[0], lo[0]);
+  if (rcs[0]) R.ex->fail(rcs[0]);
+  for (auto &t : th) t.join();
+  p->st = bz2b200_stats{};
+  int rc = 0;
+  for (size_t l = 0; l < nl; l++) {
+    if (rcs[l] && (!rc || rc == BZ2B200_E_PEER)) { rc = rcs[l]; p->err = p->lanes[l]->c->err; }
+    if (lj[l].empty()) continue;
+    const bz2b200_stats &s = p->lanes[l]->c->st;
+    p->st.n_blocks += s.n_blocks; p->st.kernel_launches += s.kernel_launches; p->st.rle1_bytes += s.rle1_bytes;
+  }
+  return rc;
+}
+
+static size_t pool_dec_slice(const Pool *p, size_t n) {
+  size_t per = n / p->lanes.size() + 1;
+  const size_t lo = (size_t)24 << 20, hi = (size_t)96 << 20;  // >= ~80 blocks of text per slice (the parse is latency-bound below), <= one batch
+  if (per < lo) per = lo;
+  if (per > hi) per = hi;
+  return per;
+}
+static const size_t kDecHalo0 = (size_t)1200000;  // a level-9 block of incompressible data is ~1.1 MB of stream; grown on demand
+
+// Bzip2.decompressFile of one stream over every lane of the pool (host input, host output in page-locked result memory)
+static int pool_decompress_whole(Pool *p, const u8 *in, size_t n, int multistream, size_t size_hint, size_t slice_bytes, uint8_t **out, size_t *out_len) {
+  p->err.clear();
+  auto t0 = std::chrono::steady_clock::now();
+  if (n < 4 || in[0] != 'B' || in[1] != 'Z' || in[2] != 'h' || in[3] < '1' || in[3] > '9') return BZ2B200_E_NOT_BZIP_DATA;  // BJ:1408-1427
+  if (!slice_bytes) slice_bytes = pool_dec_slice(p, n);
+  const size_t ns = (n + slice_bytes - 1) / slice_bytes;
+  std::vector<ShardJob> jobs(ns);
+  for (size_t j = 0; j < ns; j++) {
+    ShardJob &J = jobs[j];
+    J.base = (u64)j * slice_bytes;
+    J.src = in + J.base;
+    J.n_max = n - (size_t)J.base;
+    J.own_len = J.n_max < slice_bytes ? J.n_max : slice_bytes;
+    const size_t h0 = p->halo0 ? p->halo0 : kDecHalo0;
+    J.n_avail = J.own_len + h0 < J.n_max ? J.own_len + h0 : J.n_max;
+    J.index = (int)j;
+  }
+  const size_t cap = size_hint ? size_hint : (n * 6 > ((size_t)1 << 20) ? n * 6 : (size_t)1 << 20);
+  u8 *dst = (u8 *)result_pool().get(cap);
+  if (!dst) return BZ2B200_E_OUT_OF_MEMORY;
+  LocalExchange ex((int)ns);
+  DecRun R{p, &ex, (u64)n, multistream, in[3] - '0', p->force_staging || is_pageable(in), dst, cap};
+  std::vector<DecOut> outs;
+  int rc = pool_run_decode(p, R, jobs, outs);
+  u64 total = 0;
+  bool apart = false;
+  for (size_t j = 0; j < ns && !rc; j++) {
+    if (outs[j].rc) { rc = outs[j].rc; p->err = outs[j].msg; break; }  // the first error in stream order
+    total = outs[j].out_off + outs[j].bytes;
+    apart |= outs[j].part != nullptr;
+  }
+  if (!rc && apart) {  // the guess was too small: one exact buffer, everything copied once more (highly compressible data)
+    u8 *big = (u8 *)result_pool().get((size_t)total);
+    if (!big) rc = BZ2B200_E_OUT_OF_MEMORY;
+    for (size_t j = 0; j < ns && !rc; j++) {
+      if (!outs[j].bytes) continue;
+      memcpy(big + outs[j].out_off, outs[j].part ? outs[j].part : dst + outs[j].out_off, (size_t)outs[j].bytes);
+    }
+    if (!rc) { result_pool().put(dst); dst = big; }
+  }
+  for (size_t j = 0; j < outs.size(); j++) if (outs[j].part) result_pool().put(outs[j].part);
+  if (rc) { result_pool().put(dst); return rc; }
+  *out = dst;
+  *out_len = (size_t)total;
+  p->st.in_bytes = n;
+  p->st.out_bytes = total;
+  p->st.ms_total = (float)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count() / 1000.f;
+  return BZ2B200_OK;
+}
+
+// this process's slices of a stream that spans the ranks of a group: results[i] = the decoded bytes of jobs[i] and
+// their offset in the output; the status of the whole stream is the first non-zero results[].rc in slice order
+static int pool_decompress_ranked(Pool *p, Group *grp, const bz2b200_shard_job *jobs_in, int n_jobs, int total_shards, uint64_t total_n, int first_level,
+                                  int multistream, int keep_on_device, bz2b200_range_result *results) {
+  if (n_jobs < 0 || total_shards < 1 || total_shards > GRP_SLOTS || (n_jobs && (!jobs_in || !results)) || first_level < 1 || first_level > 9) return BZ2B200_E_ARG;
+  p->err.clear();
+  auto t0 = std::chrono::steady_clock::now();
+  std::vector<ShardJob> jobs((size_t)n_jobs);
+  bool pageable = false;
+  for (int i = 0; i < n_jobs; i++) {
+    const bz2b200_shard_job &a = jobs_in[i];
+    if (a.index < 0 || a.index >= total_shards || (i && a.index <= jobs_in[i - 1].index) || a.own_len > a.n_readable || (a.n_readable && !a.src) ||
+        (a.on_device && ((uintptr_t)a.src & 15)))
+      return BZ2B200_E_ARG;
+    ShardJob &J = jobs[(size_t)i];
+    J.src = (const u8 *)a.src; J.n_max = a.n_readable; J.own_len = a.own_len; J.base = a.base; J.index = a.index; J.on_device = a.on_device != 0;
+    const size_t h0 = p->halo0 ? p->halo0 : kDecHalo0;
+    J.n_avail = J.own_len + h0 < J.n_max ? J.own_len + h0 : J.n_max;
+    if (!J.on_device && J.n_max && !i) pageable = is_pageable(J.src);
+  }
+  std::vector<DecOut> outs;
+  int rc;
+  if (grp) {
+    grp->epoch++;
+    GroupExchange ex(grp);
+    DecRun R{p, &ex, total_n, multistream, first_level, pageable || p->force_staging, nullptr, 0};
+    rc = pool_run_decode(p, R, jobs, outs);
+    int rb = ex.barrier();
+    if (!rc) rc = rb;
+  } else {
+    LocalExchange ex(total_shards);
+    DecRun R{p, &ex, total_n, multistream, first_level, pageable || p->force_staging, nullptr, 0};
+    rc = pool_run_decode(p, R, jobs, outs);
+  }
+  for (int i = 0; i < n_jobs && i < (int)outs.size(); i++) {
+    DecOut &o = outs[(size_t)i];
+    if (rc || keep_on_device) { if (o.part) result_pool().put(o.part); o.part = nullptr; }
+    results[i].part = o.part; results[i].bytes = o.bytes; results[i].out_offset = o.out_off; results[i].rc = o.rc; results[i].n_blocks = o.blocks;
   }
   p->st.ms_total = (float)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count() / 1000.f;
   return rc;

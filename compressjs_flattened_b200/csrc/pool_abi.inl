@@ -55,3 +55,33 @@ int bz2b200_debug_set_pool(bz2b200_ctx *ctx, size_t min_bytes, size_t shard_byte
   c->pool_min_bytes = min_bytes; c->pool_shard_bytes = shard_bytes; c->pool_halo0 = first_halo; c->pool_force_staging = force_staging != 0;
   return BZ2B200_OK;
 }
+int bz2b200_pool_set_plan(bz2b200_pool *pool, size_t first_bytes, double growth) {
+  Pool *p = reinterpret_cast<Pool *>(pool);
+  if (!p || (growth != 0 && growth < 1.0)) return BZ2B200_E_ARG;
+  p->plan_first = first_bytes; p->plan_growth = growth;
+  return BZ2B200_OK;
+}
+int bz2b200_pool_plan(size_t n, int level, int lanes, size_t first_bytes, double growth, size_t *sizes, int cap) {
+  if (level < 1 || level > 9 || lanes < 1 || !sizes || cap < 1 || (growth != 0 && growth < 1.0)) return BZ2B200_E_ARG;
+  const std::vector<size_t> v = pool_plan(n, level, (size_t)lanes, 0, first_bytes, growth);
+  if ((int)v.size() > cap) return BZ2B200_E_ARG;
+  for (size_t i = 0; i < v.size(); i++) sizes[i] = v[i];
+  return (int)v.size();
+}
+int bz2b200_pool_decompress(bz2b200_pool *pool, const uint8_t *in, size_t n, int multistream, size_t size_hint, size_t slice_bytes, uint8_t **out,
+                            size_t *out_len) {
+  Pool *p = reinterpret_cast<Pool *>(pool);
+  if (!p || !out || !out_len || (n && !in)) return BZ2B200_E_ARG;
+  return pool_decompress_whole(p, in, n, multistream, size_hint, slice_bytes, out, out_len);
+}
+int bz2b200_pool_decompress_shards(bz2b200_pool *pool, bz2b200_group *grp, const bz2b200_shard_job *jobs, int n_jobs, int total_shards,
+                                   uint64_t total_n, int first_level, int multistream, int keep_on_device, bz2b200_range_result *results) {
+  Pool *p = reinterpret_cast<Pool *>(pool);
+  if (!p) return BZ2B200_E_ARG;
+  return pool_decompress_ranked(p, reinterpret_cast<Group *>(grp), jobs, n_jobs, total_shards, total_n, first_level, multistream, keep_on_device, results);
+}
+int bz2b200_debug_set_decode_batch(bz2b200_ctx *ctx, bz2b200_pool *pool, uint32_t candidates) {
+  if (ctx) reinterpret_cast<Ctx *>(ctx)->dec_batch = candidates;
+  if (pool) reinterpret_cast<Pool *>(pool)->dec_batch = candidates;
+  return BZ2B200_OK;
+}

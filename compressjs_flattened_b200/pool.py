@@ -15,6 +15,16 @@ from . import _native
 from .bzip2 import Bzip2Error, _coerce_input, _deliver
 
 
+def shard_plan(n, level=9, lanes=2, first_bytes=0, growth=0.0, library=None):
+    """Shard sizes the scheduler would use for n bytes over `lanes` lanes (small first wave, growing waves)."""
+    lib = library or _native.default_library()
+    arr = (C.c_size_t * 4096)()
+    k = lib.L.bz2b200_pool_plan(int(n), level, lanes, int(first_bytes), float(growth), arr, 4096)
+    if k < 0:
+        raise ValueError(f"bz2b200_pool_plan failed ({k})")
+    return [int(arr[i]) for i in range(k)]
+
+
 class ShardGroup:
     def __init__(self, name, rank, world, timeout_ms=120_000, library=None):
         self._lib = library or _native.default_library()
@@ -82,6 +92,11 @@ class Bzip2Pool:
         if rc:
             self._raise(rc)
 
+    def set_plan(self, first_bytes=0, growth=0.0):
+        rc = self._L.bz2b200_pool_set_plan(self._p, int(first_bytes), float(growth))
+        if rc:
+            self._raise(rc)
+
     def compressFile(self, input, output=None, props=None, shard_bytes=0):
         level = props if isinstance(props, (int, float)) and not isinstance(props, bool) else 9  # BJ:2204-2206
         if level < 1 or level > 9 or int(level) != level:
@@ -103,6 +118,60 @@ class Bzip2Pool:
 
     def free_raw(self, ptr):
         self._L.bz2b200_free(ptr)
+
+    def decompressFile(self, input, output=None, multistream=False, slice_bytes=0):
+        """Bzip2.decompressFile of ONE stream, block ranges over the lanes of the pool.  `output` given as a size (the
+        reference's expected-size form, NPM/test/bzip2-basic.js:16) or a buffer doubles as the size hint."""
+        a = _coerce_input(input)
+        hint = output if isinstance(output, int) and not isinstance(output, bool) else (len(memoryview(output)) if isinstance(output, (bytearray, memoryview)) else 0)
+        out, n = C.POINTER(C.c_uint8)(), C.c_size_t()
+        rc = self._L.bz2b200_pool_decompress(self._p, a.ctypes.data, a.size, int(bool(multistream)), int(hint), int(slice_bytes), C.byref(out), C.byref(n))
+        if rc:
+            self._raise(rc)
+        return _deliver(self._take(out, n.value), output)
+
+    def decompress_raw(self, ptr, nbytes, multistream=False, size_hint=0, slice_bytes=0):
+        out, n = C.POINTER(C.c_uint8)(), C.c_size_t()
+        rc = self._L.bz2b200_pool_decompress(self._p, ptr, nbytes, int(bool(multistream)), int(size_hint), int(slice_bytes), C.byref(out), C.byref(n))
+        if rc:
+            self._raise(rc)
+        return out, n.value
+
+    def debug_decode_batch(self, candidates):
+        self._L.bz2b200_debug_set_decode_batch(None, self._p, candidates)
+
+    def decompress_shards(self, group, jobs, total_shards, total_n, first_level, multistream=False, keep_on_device=False, to_bytes=True):
+        """This process's byte slices of a stream that spans the group.  jobs: dicts {src, n_readable, own_len, base, index,
+        on_device}.  Returns [(bytes | pointer | None, out_offset, n_bytes, rc, n_blocks)] per job; the stream's status is
+        the first non-zero rc in slice order over ALL ranks."""
+        n = len(jobs)
+        arr = (_native.ShardJob * max(n, 1))()
+        keep = []
+        for i, j in enumerate(jobs):
+            src = j["src"]
+            if j.get("on_device"):
+                ptr, nr = int(src), int(j["n_readable"])
+            else:
+                a = src if isinstance(src, np.ndarray) else _coerce_input(src)
+                keep.append(a)
+                ptr, nr = a.ctypes.data, int(j.get("n_readable", a.size))
+            arr[i] = _native.ShardJob(ptr, nr, int(j["own_len"]), int(j["base"]), int(j["index"]), int(bool(j.get("on_device"))))
+        res = (_native.RangeResult * max(n, 1))()
+        rc = self._L.bz2b200_pool_decompress_shards(self._p, group._g if group is not None else None, arr, n, total_shards, int(total_n),
+                                                    int(first_level), int(bool(multistream)), int(bool(keep_on_device)), res)
+        if rc:
+            self._raise(rc)
+        out = []
+        for i in range(n):
+            r = res[i]
+            if r.part and to_bytes:
+                part = self._take(r.part, r.bytes)
+            elif r.part:
+                part = r.part
+            else:
+                part = b"" if (to_bytes and not keep_on_device) else None
+            out.append((part, int(r.out_offset), int(r.bytes), int(r.rc), int(r.n_blocks)))
+        return out
 
     def compress_shards(self, group, jobs, total_shards, level, keep_on_device=False, to_bytes=True):
         """jobs: list of dicts {src: bytes-like or device pointer (int), n_readable, own_len, base, index, on_device}.

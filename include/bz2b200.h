@@ -134,6 +134,11 @@ typedef struct bz2b200_group bz2b200_group;
 int bz2b200_pool_create(const int *devices, int n_devices, int lanes_per_device, bz2b200_pool **pool);
 void bz2b200_pool_destroy(bz2b200_pool *pool);
 int bz2b200_pool_compress(bz2b200_pool *pool, const uint8_t *in, size_t n, int level, size_t shard_bytes, uint8_t **out, size_t *out_len);
+/* shard plan of pool_compress when shard_bytes == 0: the first shard of every lane has first_bytes (0 = six blocks), every
+ * following wave is `growth` times larger (0 = 2.5): only the first upload is exposed, large batches do most of the work */
+int bz2b200_pool_set_plan(bz2b200_pool *pool, size_t first_bytes, double growth);
+/* the plan itself (for callers that hand out shards to ranks): returns the number of shards, sizes[] filled */
+int bz2b200_pool_plan(size_t n, int level, int lanes, size_t first_bytes, double growth, size_t *sizes, int cap);
 int bz2b200_pool_last_stats(bz2b200_pool *pool, bz2b200_stats *st);
 const char *bz2b200_pool_last_error(bz2b200_pool *pool);
 int bz2b200_group_open(const char *name, int rank, int world, int timeout_ms, bz2b200_group **grp);
@@ -158,11 +163,31 @@ typedef struct {
   uint64_t end_bit, blocks_through;
   uint32_t crc_fold_through, pad;
 } bz2b200_shard_result;
+/* Decompression of ONE stream over the lanes: pool_decompress for a stream held by this process (size_hint = expected
+ * output size, 0 = unknown: 6 x the input is reserved and a larger result is assembled by one more copy; slice_bytes
+ * = 0 picks the slices); pool_decompress_shards for this process's byte slices of a stream that spans a group.
+ * jobs[]: slice `index` = bytes [base, base + own_len) of the stream, n_readable >= own_len bytes readable at src (the
+ * rest is the halo a block that starts in the slice may run into; the library takes what it needs).  results[i]:
+ * the decoded bytes of the blocks whose signature starts in slice i, their offset in the output, and rc = the
+ * slice's own status; the status of the stream is the first non-zero rc in slice order (what the reference's
+ * sequential walk would have hit first). */
+typedef struct {
+  uint8_t *part;              /* page-locked; release with bz2b200_free (NULL with keep_on_device or 0 bytes) */
+  uint64_t bytes, out_offset;
+  int32_t rc;
+  uint32_t n_blocks;
+} bz2b200_range_result;
+int bz2b200_pool_decompress(bz2b200_pool *pool, const uint8_t *in, size_t n, int multistream, size_t size_hint, size_t slice_bytes, uint8_t **out,
+                            size_t *out_len);
+int bz2b200_pool_decompress_shards(bz2b200_pool *pool, bz2b200_group *grp, const bz2b200_shard_job *jobs, int n_jobs, int total_shards,
+                                   uint64_t total_n, int first_level, int multistream, int keep_on_device, bz2b200_range_result *results);
 int bz2b200_pool_compress_shards(bz2b200_pool *pool, bz2b200_group *grp, const bz2b200_shard_job *jobs, int n_jobs, int total_shards, int level,
                                  int keep_on_device, bz2b200_shard_result *results);
 /* tests/ only: block capacity, blocks per batch, first halo (0 = defaults) and forced staging for every lane of a pool;
  * and for a context: inputs of min_bytes or more go through its own two-lane pool in shards of shard_bytes (0 = auto). */
 int bz2b200_pool_debug(bz2b200_pool *pool, uint32_t block_cap, uint32_t batch_blocks, size_t first_halo, int force_staging);
+/* tests/ only: candidates per decode batch (0 = 320) for a context / every lane of a pool */
+int bz2b200_debug_set_decode_batch(bz2b200_ctx *ctx, bz2b200_pool *pool, uint32_t candidates);
 int bz2b200_debug_set_pool(bz2b200_ctx *ctx, size_t min_bytes, size_t shard_bytes, size_t first_halo, int force_staging);
 
 const char *bz2b200_strerror(int rc);

@@ -88,7 +88,10 @@ def _as_u8(buf):
 
 
 def _take(ptr, n):
-    out = C.string_at(ptr, n) if n else b""
+    if n >= 1 << 31:   # ctypes.string_at takes an int-sized length
+        out = bytes(memoryview((C.c_ubyte * n).from_address(C.addressof(ptr.contents))))
+    else:
+        out = C.string_at(ptr, n) if n else b""
     lib().orc_free(ptr)
     return out
 

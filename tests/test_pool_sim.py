@@ -68,6 +68,8 @@ def test_pool_lanes_and_devices(sim_lib, oracle):
     try:
         for level, shard in ((1, 0), (1, 120_000), (9, 200_000)):
             assert pool.compressFile(data, None, level, shard_bytes=shard) == oracle.compress(data, level)
+        pool.set_plan(30_000, 2.0)    # growing waves: 30, 30, 30, 30, 60, ... KB over the four lanes
+        assert pool.compressFile(data, None, 1) == oracle.compress(data, 1)
         with pytest.raises(ValueError):
             pool.compressFile(data, None, 0)
     finally:
@@ -155,3 +157,125 @@ def test_dead_peer_is_an_error_not_a_hang(sim_lib):
     p.join(timeout=30)
     grp.close()
     assert "peer" in msg
+
+
+# ------------------------------------------------------------------------------------------------ decompress
+def _streams(oracle):
+    rng = np.random.default_rng(33)
+    from compressjs_flattened_b200.corpus import gen_text
+    text = gen_text(70_000, 9).tobytes()
+    oracle.set_block_cap(1201)
+    try:
+        many = oracle.compress(text, 9)                                   # ~58 small blocks
+        runny = oracle.compress(_runny(rng, 40_000, 3, 0.5), 9)
+        rand = oracle.compress(rng.integers(0, 256, 9_000, dtype=np.uint8).tobytes(), 9)   # blocks larger than a slice
+    finally:
+        oracle.set_block_cap(0)
+    return {"many": (many, False), "runny": (runny, False), "rand": (rand, False),
+            "multi": (many + rand + oracle.compress(b"tail stream"), True), "first_only": (many + rand, False),
+            "empty": (oracle.compress(b""), False), "tiny": (oracle.compress(b"xyz"), False)}
+
+
+@pytest.mark.parametrize("name", ["many", "runny", "rand", "multi", "first_only", "empty", "tiny"])
+def test_pool_decompress_slices_equal_oracle(sim_lib, oracle, name):
+    """ONE stream decoded as byte slices over the lanes (walk state chained from slice to slice): slices smaller than a
+    block, halos that must grow, several batches per slice, multistream hops across slices, size hint and no hint."""
+    from compressjs_flattened_b200.pool import Bzip2Pool
+    blob, ms = _streams(oracle)[name]
+    exp = oracle.decompress(blob, ms)
+    pool = Bzip2Pool([0, 0], 2, library=sim_lib)
+    try:
+        for slice_bytes, halo, batch, hint in ((0, 0, 0, 0), (997, 64, 0, len(exp)), (4000, 16, 3, 0), (300, 8, 2, 0)):
+            pool.debug(first_halo=halo)
+            pool.debug_decode_batch(batch)
+            got = pool.decompressFile(blob, hint if hint else None, ms, slice_bytes=slice_bytes)
+            assert got == exp, (name, slice_bytes, halo, batch)
+    finally:
+        pool.close()
+
+
+def test_single_context_decode_in_batches(sim_lib, oracle):
+    """the candidates of a stream are decoded in batches, so device memory is bounded"""
+    from compressjs_flattened_b200.bzip2 import Bzip2Engine
+    blob, _ = _streams(oracle)["many"]
+    eng = Bzip2Engine(0, sim_lib)
+    eng._L.bz2b200_debug_set_decode_batch(eng._ctx, None, 5)
+    try:
+        assert eng.decompressFile(blob) == oracle.decompress(blob)
+        rows = []
+        eng.table(blob, lambda p, s: rows.append((p, s)))
+        assert rows == oracle.table(blob)
+    finally:
+        eng.close()
+
+
+def test_pool_decompress_errors_first_in_stream_order(sim_lib, oracle):
+    from compressjs_flattened_b200.bzip2 import Bzip2Error
+    from compressjs_flattened_b200.pool import Bzip2Pool
+    blob, _ = _streams(oracle)["many"]
+    pool = Bzip2Pool([0], 3, library=sim_lib)
+    cases = [blob[:len(blob) // 2], blob[:-3]]
+    for at in (len(blob) // 5, len(blob) // 2, len(blob) - 30):
+        b = bytearray(blob)
+        b[at] ^= 0x5A
+        cases.append(bytes(b))
+    two = bytearray(blob)     # two damaged places: the earlier one decides
+    two[len(blob) // 4] ^= 1
+    two[3 * len(blob) // 4] ^= 0xFF
+    cases.append(bytes(two))
+    cases += [b"", b"BZ", b"BZh0" + blob[4:], b"XXXX" + blob[4:]]
+    try:
+        for i, bad in enumerate(cases):
+            try:
+                exp = ("ok", oracle.decompress(bad))
+            except oracle.OracleError as e:
+                exp = ("err", e.errorCode)
+            try:
+                got = ("ok", pool.decompressFile(bad, None, False, slice_bytes=1500))
+            except Bzip2Error as e:
+                got = ("err", e.errorCode)
+            assert got == exp, i
+    finally:
+        pool.close()
+
+
+def _dec_rank_main(rank, world, name, blob, slice_bytes, q):
+    try:
+        from compressjs_flattened_b200 import _native
+        from compressjs_flattened_b200.pool import Bzip2Pool, ShardGroup
+        lib = _native.Library(SIM_SO)
+        grp = ShardGroup(name, rank, world, timeout_ms=60_000, library=lib)
+        pool = Bzip2Pool([0], 2, library=lib)
+        pool.debug(first_halo=100)
+        total = (len(blob) + slice_bytes - 1) // slice_bytes
+        jobs = [dict(src=np.frombuffer(blob[j * slice_bytes:], dtype=np.uint8), own_len=min(slice_bytes, len(blob) - j * slice_bytes), base=j * slice_bytes, index=j)
+                for j in range(total) if j % world == rank]
+        res = pool.decompress_shards(grp, jobs, total, len(blob), blob[3] - 0x30)
+        q.put((rank, [(j["index"],) + r for j, r in zip(jobs, res)]))
+        pool.close()
+        grp.close()
+    except Exception as e:  # pragma: no cover
+        q.put((rank, repr(e)))
+
+
+def test_group_of_processes_decodes_one_stream(sim_lib, oracle):
+    blob, _ = _streams(oracle)["many"]
+    exp = oracle.decompress(blob)
+    world, slice_bytes = 2, 2500
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    name = f"dec_{os.getpid()}"
+    procs = [ctx.Process(target=_dec_rank_main, args=(r, world, name, blob, slice_bytes, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=300) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    for r, v in got.items():
+        assert not isinstance(v, str), f"rank {r}: {v}"
+    parts = sorted(x for r in range(world) for x in got[r])
+    out = bytearray(len(exp))
+    for idx, part, off, nbytes, rc, nblk in parts:
+        assert rc == 0
+        out[off:off + nbytes] = part
+    assert bytes(out) == exp and sum(p[3] for p in parts) == len(exp)
