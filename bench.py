@@ -200,6 +200,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-big-check", action="store_true")
     ap.add_argument("--profile-only", action="store_true", help="device-resident compress steps only (for ncu runs)")
+    ap.add_argument("--e2e-only", action="store_true", help="development: only the host-call leg, printed per rank 0 as a short line")
+    ap.add_argument("--lanes", type=int, default=2)
+    ap.add_argument("--plan-first-mb", type=float, default=0.0)
+    ap.add_argument("--plan-growth", type=float, default=0.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     if args.impl == "reference":
@@ -302,9 +306,9 @@ def main():
     if world > 1:
         # ONE stream of world*mb MB as interleaved shards: wave k holds one shard of size plan[k] per rank, rank r takes shard
         # k*world + r.  Small first wave (its upload is the only exposed one), growing waves (copies hide under kernels).
-        pool = Bzip2Pool([local], 2)
+        pool = Bzip2Pool([local], args.lanes)
         grp = ShardGroup(f"bench_{os.environ.get('MASTER_PORT', '0')}_{os.getppid()}", rank, world)
-        plan = shard_plan(nbytes, level, 2)
+        plan = shard_plan(nbytes, level, args.lanes, int(args.plan_first_mb * 1e6), args.plan_growth)
         halo = 2_000_000
         total_bytes = world * nbytes
         e2e_jobs, keep, at = [], [], 0
@@ -347,6 +351,16 @@ def main():
         return (time.time() - e0) * 1e3, n
 
     e2e_ms, e2e_out = timed_host()
+    if args.e2e_only:
+        tt = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            print(json.dumps({"e2e_only": True, "n_gpus": world, "lanes": args.lanes, "plan_mb": [round(x / 1e6, 1) for x in (plan if world > 1 else [])],
+                              "ms_per_step": round(float(tt.item()) / args.steps, 3), "MBps": round(world * args.mb * args.steps / (float(tt.item()) / 1e3), 1)}), flush=True)
+        if world > 1:
+            pool.close(); grp.close(); dist.destroy_process_group()
+        return
     e2e_pageable_ms = None
     if world == 1:
         e2e_pageable_ms, _ = timed_host([h.ctypes.data for h in host])

@@ -36,7 +36,7 @@ namespace {
 struct ResultPool {
   std::mutex mu;
   std::vector<std::pair<void *, size_t>> live, idle;  // (pointer, capacity)
-  static const size_t kMinPinned = 1 << 20, kMaxIdle = 4;
+  static const size_t kMinPinned = 1 << 20, kMaxIdle = 48;  // a sharded call hands out one segment per shard
   void *get(size_t bytes) {
     if (bytes < kMinPinned) return malloc(bytes ? bytes : 1);
     std::lock_guard<std::mutex> g(mu);

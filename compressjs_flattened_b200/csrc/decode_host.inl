@@ -29,16 +29,17 @@ struct DecWalk {
   u32 level = 9;       // of the current stream: dbufSize = 100000 * level (BJ:1422)
   u32 ended = 0;       // nothing follows: end of stream, silent stop (BJ:1777), or an error upstream
 };
-// where decoded bytes go: `reserve` hands out device memory for the next `bytes` of the range, in order
+// where decoded bytes go: `reserve` hands out device memory for the next `bytes` of the range, in order, as (aligned start
+// of the buffer, offset in it) -- the kernels take absolute offsets, so a batch need not start on an aligned address
 struct DecSink {
   virtual ~DecSink() {}
-  virtual int reserve(Ctx *c, u64 bytes, u8 **d_dst) = 0;
+  virtual int reserve(Ctx *c, u64 bytes, u8 **d_base, u64 *off) = 0;
 };
 struct BufSink : DecSink {      // a growing device buffer, one batch after the other appended (grows by copy: rare)
   DevBuf *buf;
   u64 used = 0;
   explicit BufSink(DevBuf *b) : buf(b) {}
-  int reserve(Ctx *c, u64 bytes, u8 **d_dst) override {
+  int reserve(Ctx *c, u64 bytes, u8 **d_base, u64 *off) override {
     if (used + bytes + 64 > buf->cap) {
       DevBuf nb;
       size_t want = (size_t)(used + bytes) + (size_t)(used + bytes) / 4 + 4096;
@@ -49,7 +50,8 @@ struct BufSink : DecSink {      // a growing device buffer, one batch after the 
       if (buf->p) CK(cudaFree(buf->p));
       *buf = nb;
     }
-    *d_dst = reinterpret_cast<u8 *>(buf->p) + used;
+    *d_base = reinterpret_cast<u8 *>(buf->p);
+    *off = used;
     used += bytes;
     return 0;
   }
@@ -57,9 +59,10 @@ struct BufSink : DecSink {      // a growing device buffer, one batch after the 
 struct UserSink : DecSink {     // a caller-provided device buffer
   u8 *base; size_t cap; u64 used = 0;
   UserSink(u8 *b, size_t cp) : base(b), cap(cp) {}
-  int reserve(Ctx *c, u64 bytes, u8 **d_dst) override {
+  int reserve(Ctx *c, u64 bytes, u8 **d_base, u64 *off) override {
     if (used + bytes > cap) { c->err = "output buffer too small"; return BZ2B200_E_UNEXPECTED_OUTPUT_EOF; }
-    *d_dst = base + used;
+    *d_base = base;
+    *off = used;
     used += bytes;
     return 0;
   }
@@ -208,7 +211,9 @@ static int dec_invert(Ctx *c, const std::vector<DecBlk> &blks, const std::vector
   *bytes_out = total;
   if (!want_bytes) return 0;  // Bunzip.table: sizes only
   u8 *d_out = nullptr;
-  RC(sink.reserve(c, total, &d_out));
+  u64 out0 = 0;
+  RC(sink.reserve(c, total, &d_out, &out0));
+  for (auto &o : offs) o += out0;
   CK(cudaMemcpyAsync(d_off, offs.data(), 8 * ((size_t)nb + 1), cudaMemcpyHostToDevice, c->stream));
   LAUNCH(k_rle1_inv, (unsigned)nb, rli_threads, 0, P<u8>(c->dblk), BS, P<DecBlk>(c->dmeta), d_order, 1, d_len, d_off, d_out);
   // ---- block CRCs over the output (BJ:1756-1761) ----

@@ -632,6 +632,7 @@ struct DecRun {
   bool pageable;
   u8 *dst = nullptr;      // whole mode: the output buffer (capacity guessed from the hint); parts that do not fit stay apart
   size_t dst_cap = 0;
+  bool keep_on_device = false;  // ranks mode: the decoded bytes stay in the lane's output slot
 };
 
 static int lane_decode(DecRun &R, Lane *L, std::vector<ShardJob> jobs, std::vector<DecOut *> outs) {
@@ -709,7 +710,7 @@ static int lane_decode(DecRun &R, Lane *L, std::vector<ShardJob> jobs, std::vect
     out.out_off = prev.end_bit;
     out.blocks = c->st.n_blocks;
     agg.n_blocks += c->st.n_blocks; agg.kernel_launches += c->st.kernel_launches; agg.rle1_bytes += c->st.rle1_bytes;
-    if (out.bytes) {
+    if (out.bytes && !R.keep_on_device) {
       if (R.dst && out.out_off + out.bytes <= R.dst_cap) {
         CK(cudaMemcpyAsync(R.dst + out.out_off, L->out_slot[slot].p, (size_t)out.bytes, cudaMemcpyDeviceToHost, c->stream));
       } else {
@@ -780,7 +781,7 @@ static int pool_decompress_whole(Pool *p, const u8 *in, size_t n, int multistrea
   u8 *dst = (u8 *)result_pool().get(cap);
   if (!dst) return BZ2B200_E_OUT_OF_MEMORY;
   LocalExchange ex((int)ns);
-  DecRun R{p, &ex, (u64)n, multistream, in[3] - '0', p->force_staging || is_pageable(in), dst, cap};
+  DecRun R{p, &ex, (u64)n, multistream, in[3] - '0', p->force_staging || is_pageable(in), dst, cap, false};
   std::vector<DecOut> outs;
   int rc = pool_run_decode(p, R, jobs, outs);
   u64 total = 0;
@@ -834,13 +835,13 @@ static int pool_decompress_ranked(Pool *p, Group *grp, const bz2b200_shard_job *
   if (grp) {
     grp->epoch++;
     GroupExchange ex(grp);
-    DecRun R{p, &ex, total_n, multistream, first_level, pageable || p->force_staging, nullptr, 0};
+    DecRun R{p, &ex, total_n, multistream, first_level, pageable || p->force_staging, nullptr, 0, keep_on_device != 0};
     rc = pool_run_decode(p, R, jobs, outs);
     int rb = ex.barrier();
     if (!rc) rc = rb;
   } else {
     LocalExchange ex(total_shards);
-    DecRun R{p, &ex, total_n, multistream, first_level, pageable || p->force_staging, nullptr, 0};
+    DecRun R{p, &ex, total_n, multistream, first_level, pageable || p->force_staging, nullptr, 0, keep_on_device != 0};
     rc = pool_run_decode(p, R, jobs, outs);
   }
   for (int i = 0; i < n_jobs && i < (int)outs.size(); i++) {

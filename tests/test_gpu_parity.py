@@ -269,7 +269,7 @@ def test_decode_damaged_streams_match_oracle(oracle, parse_mode, monkeypatch):
 def test_decode_run_length_sum_cannot_wrap(gpu_engine, oracle):
     """run lengths that sum past 2^32 are a Data error (BJ:1647), never an out-of-bounds write."""
     from compressjs_flattened_b200.bzip2 import Bzip2Error
-    from test_sim_kernels import crafted_run_overflow_stream
+    from test_sim_kernels import _decode_outcome, crafted_run_overflow_stream
     for deep, tail in ((1023, 1000), (1024, 5000), (2047, 10)):
         blob, _ = crafted_run_overflow_stream(deep, tail)
         assert _decode_outcome(gpu_engine, blob, Bzip2Error) == ("err", -5) == _decode_outcome(oracle, blob, oracle.OracleError)
