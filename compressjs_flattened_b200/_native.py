@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-DEFAULT_SO = os.path.join(_HERE, "libbz2b200.so")
+DEFAULT_SO = os.environ.get("BZ2B200_LIB") or os.path.join(_HERE, "libbz2b200.so")   # BZ2B200_LIB: development builds of the same CUDA library
 
 E_LEVEL, E_CUDA, E_ARG, E_PEER = -100, -101, -102, -103
 

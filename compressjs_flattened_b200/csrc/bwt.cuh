@@ -110,11 +110,12 @@ __global__ void __launch_bounds__(256) k_sym_tab(BlkSort *__restrict__ bs) {
 // digit (bits 20..28) is counted on the way, so pass 0 needs no k_rs_hist.
 __global__ void __launch_bounds__(SEG_THREADS) k_keys_init(const u8 *__restrict__ blk, i64 blk_stride, const BlockRec *__restrict__ recs,
                                                            const u32 *__restrict__ seg_tile0, const u32 *__restrict__ tile_blk,
-                                                           const BlkSort *__restrict__ bs, u64 *__restrict__ keys, u32 *__restrict__ hist0) {
+                                                           const BlkSort *__restrict__ bs, u64 *__restrict__ keys, u32 *__restrict__ hist0,
+                                                           u32 tile_base) {
   __shared__ u8 code[256];
   __shared__ u8 sc[SORT_TILE + 48];
   __shared__ u32 h[512];
-  u32 tile = blockIdx.x, p = tile_blk[tile];
+  u32 tile = blockIdx.x + tile_base, p = tile_blk[tile];
   u32 n = recs[p].n;
   code[threadIdx.x] = bs[p].code[threadIdx.x];
   for (int i = threadIdx.x; i < 512; i += SEG_THREADS) h[i] = 0;
@@ -122,7 +123,7 @@ __global__ void __launch_bounds__(SEG_THREADS) k_keys_init(const u8 *__restrict_
   __syncthreads();
   const u8 *T = blk + (i64)p * blk_stride;
   u32 l0 = (tile - seg_tile0[p]) * SORT_TILE;
-  u64 g0 = (u64)tile * SORT_TILE;
+  u64 g0 = (u64)(tile - tile_base) * SORT_TILE;  // keys and per-tile histograms are local to the group of blocks being sorted
   const u32 m = n - l0 < SORT_TILE ? n - l0 : SORT_TILE;
   for (u32 j = threadIdx.x; j < m + L - 1; j += SEG_THREADS) {
     u32 x = l0 + j;
@@ -141,19 +142,19 @@ __global__ void __launch_bounds__(SEG_THREADS) k_keys_init(const u8 *__restrict_
     atomicAdd(&h[(u32)(key >> 20) & 511u], 1u);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 512; i += SEG_THREADS) hist0[(u64)tile * 512 + i] = h[i];
+  for (int i = threadIdx.x; i < 512; i += SEG_THREADS) hist0[(u64)(tile - tile_base) * 512 + i] = h[i];
 }
 // ---- one LSD radix pass (BITS-bit digit, 8 or 9), batched over blocks ---------------------------
 // seg_base (optional): slot at which segment p starts; default = seg_tile0[p] * SORT_TILE (block layout)
 template <int BITS>
 __global__ void __launch_bounds__(SORT_THREADS) k_rs_hist(const u64 *__restrict__ keys, const u32 *__restrict__ seg_cnt,
                                                           const u32 *__restrict__ seg_tile0, const u32 *__restrict__ tile_blk, int shift,
-                                                          u32 *__restrict__ hist, const u32 *__restrict__ seg_base) {
+                                                          u32 *__restrict__ hist, const u32 *__restrict__ seg_base, u32 tile_base = 0) {
   constexpr int NB = 1 << BITS;
   __shared__ u32 h[NB];
-  u32 tile = blockIdx.x, p = tile_blk[tile];
+  u32 tile = blockIdx.x + tile_base, p = tile_blk[tile];
   u32 cnt = seg_cnt[p], l0 = (tile - seg_tile0[p]) * SORT_TILE;
-  u64 g0 = seg_base ? (u64)seg_base[p] + l0 : (u64)tile * SORT_TILE;
+  u64 g0 = seg_base ? (u64)seg_base[p] + l0 : (u64)(tile - tile_base) * SORT_TILE;
   for (int i = threadIdx.x; i < NB; i += SORT_THREADS) h[i] = 0;
   __syncthreads();
   u64 k[SORT_E];
@@ -168,19 +169,20 @@ __global__ void __launch_bounds__(SORT_THREADS) k_rs_hist(const u64 *__restrict_
     if (l0 + o < cnt) atomicAdd(&h[(u32)(k[e] >> shift) & (NB - 1)], 1u);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < NB; i += SORT_THREADS) hist[(u64)tile * NB + i] = h[i];
+  for (int i = threadIdx.x; i < NB; i += SORT_THREADS) hist[(u64)(tile - tile_base) * NB + i] = h[i];
 }
 // per block: column-wise exclusive prefix over its tiles (in place) and the digit totals.  grid (nb, NB / 32), 512
 // threads: a CTA owns 32 digits (lane = digit), its 16 warps split the block's tiles into contiguous ranges: sum of
 // the own range, exclusive scan over the warps in shared memory, then the prefixes of the own range.
 #define RSS_WARPS 16
 template <int BITS>
-__global__ void __launch_bounds__(RSS_WARPS * 32) k_rs_scan(u32 *__restrict__ hist, const u32 *__restrict__ seg_tile0, u32 *__restrict__ digit_tot) {
+__global__ void __launch_bounds__(RSS_WARPS * 32) k_rs_scan(u32 *__restrict__ hist, const u32 *__restrict__ seg_tile0, u32 *__restrict__ digit_tot,
+                                                            u32 p_base = 0, u32 tile_base = 0) {
   constexpr int NB = 1 << BITS;
   __shared__ u32 part[RSS_WARPS][32];
-  const u32 p = blockIdx.x, d = blockIdx.y * 32 + lane_id();
+  const u32 p = blockIdx.x + p_base, d = blockIdx.y * 32 + lane_id();
   const int w = warp_id();
-  const u32 t0 = seg_tile0[p], t1 = seg_tile0[p + 1], nt = t1 - t0;
+  const u32 t0 = seg_tile0[p] - tile_base, t1 = seg_tile0[p + 1] - tile_base, nt = t1 - t0;
   const u32 per = (nt + RSS_WARPS - 1) / RSS_WARPS;
   const u32 a = t0 + (u32)w * per < t1 ? t0 + (u32)w * per : t1, b = a + per < t1 ? a + per : t1;
   u32 sum = 0;
@@ -200,13 +202,13 @@ template <int BITS>
 __global__ void __launch_bounds__(SORT_THREADS, 3) k_rs_scatter(const u64 *__restrict__ keys_in, u64 *__restrict__ keys_out,
                                                              const u32 *__restrict__ seg_cnt, const u32 *__restrict__ seg_tile0,
                                                              const u32 *__restrict__ tile_blk, int shift, const u32 *__restrict__ hist,
-                                                             const u32 *__restrict__ digit_tot, const u32 *__restrict__ seg_base) {
+                                                             const u32 *__restrict__ digit_tot, const u32 *__restrict__ seg_base, u32 tile_base = 0) {
   constexpr int NB = 1 << BITS;
   __shared__ u16 wcnt[SORT_THREADS / 32][NB];  // a warp ranks 256 keys: counts fit 16 bits
   __shared__ u32 base[NB];
-  u32 tile = blockIdx.x, p = tile_blk[tile];
+  u32 tile = blockIdx.x + tile_base, p = tile_blk[tile];
   u32 cnt = seg_cnt[p], l0 = (tile - seg_tile0[p]) * SORT_TILE;
-  u64 gp = seg_base ? (u64)seg_base[p] : (u64)seg_tile0[p] * SORT_TILE, g0 = gp + l0;
+  u64 gp = seg_base ? (u64)seg_base[p] : (u64)(seg_tile0[p] - tile_base) * SORT_TILE, g0 = gp + l0;
   int lane = lane_id(), w = warp_id();
   for (int i = threadIdx.x; i < (SORT_THREADS / 32) * NB / 2; i += SORT_THREADS) reinterpret_cast<u32 *>(&wcnt[0][0])[i] = 0;
   {  // base of digit d = keys of the block with a smaller digit (scan of the totals) + keys with digit d in earlier tiles
@@ -214,7 +216,7 @@ __global__ void __launch_bounds__(SORT_THREADS, 3) k_rs_scatter(const u64 *__res
     __shared__ u32 ws[33];
     u32 tot_d = threadIdx.x < NB ? digit_tot[(u64)p * NB + threadIdx.x] : 0u, tot;
     u32 ex = block_excl_sum<u32>(tot_d, tot, ws);
-    if (threadIdx.x < NB) base[threadIdx.x] = ex + hist[(u64)tile * NB + threadIdx.x];
+    if (threadIdx.x < NB) base[threadIdx.x] = ex + hist[(u64)(tile - tile_base) * NB + threadIdx.x];
   }
   __syncthreads();
   u64 key[SORT_E];
@@ -327,7 +329,7 @@ __global__ void __launch_bounds__(R0_THREADS) k_rank0(const u64 *__restrict__ ke
                                                       const u32 *__restrict__ seg_tile0, const u32 *__restrict__ tile_blk,
                                                       u32 *__restrict__ isa, i64 stride, u32 *__restrict__ act_idx, u32 *__restrict__ act_rank,
                                                       u64 *__restrict__ status, u32 *__restrict__ ticket, u32 *__restrict__ n_act_out, u32 ntiles,
-                                                      const u8 *__restrict__ T, u8 *__restrict__ L, BlockRec *__restrict__ recs) {
+                                                      const u8 *__restrict__ T, u8 *__restrict__ L, BlockRec *__restrict__ recs, u32 tile_base) {
   __shared__ u64 sk[SORT_TILE + 2];  // sk[1 + i] = key of tile slot i; sk[0] / sk[m + 1] = the neighbours
   __shared__ int wlast[R0_THREADS / 32];
   __shared__ u32 wkeep[R0_THREADS / 32];
@@ -338,7 +340,7 @@ __global__ void __launch_bounds__(R0_THREADS) k_rank0(const u64 *__restrict__ ke
   __syncthreads();
   const u32 tile = sh_tile, p = tile_blk[tile];
   const u32 cnt = seg_cnt[p], l0 = (tile - seg_tile0[p]) * SORT_TILE;
-  const u64 gp = (u64)seg_tile0[p] * SORT_TILE;
+  const u64 gp = (u64)(seg_tile0[p] - tile_base) * SORT_TILE;  // the ticket runs over all tiles of the batch, the keys are the group's
   const u32 m = cnt - l0 < SORT_TILE ? cnt - l0 : SORT_TILE;
   for (u32 i = threadIdx.x; i < m + 2; i += R0_THREADS) {
     i64 j = (i64)l0 - 1 + i;
