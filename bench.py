@@ -201,7 +201,7 @@ def main():
     ap.add_argument("--no-big-check", action="store_true")
     ap.add_argument("--profile-only", action="store_true", help="device-resident compress steps only (for ncu runs)")
     ap.add_argument("--e2e-only", action="store_true", help="development: only the host-call leg, printed per rank 0 as a short line")
-    ap.add_argument("--lanes", type=int, default=2)
+    ap.add_argument("--lanes", type=int, default=1, help="lanes per rank of the N>1 host-call leg (measured best at 8 ranks: 1, plan [25, 75] MB)")
     ap.add_argument("--plan-first-mb", type=float, default=0.0)
     ap.add_argument("--plan-growth", type=float, default=0.0)
     args = ap.parse_args()

@@ -85,6 +85,7 @@ class Library:
         L.bz2b200_debug_set_block_cap.argtypes = [vp, C.c_uint32]
         L.bz2b200_debug_set_batch_blocks.argtypes = [vp, C.c_uint32]
         L.bz2b200_debug_set_ignore_block_crc.argtypes = [vp, C.c_int]
+        L.bz2b200_debug_huffman_lengths.argtypes = [vp, vp, C.c_int, C.c_int]
         L.bz2b200_shard_begin.argtypes = [vp, vp, C.c_size_t, C.c_int, C.c_int]
         L.bz2b200_shard_cut.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(ShardInfo)]
         L.bz2b200_shard_compress.argtypes = [vp, C.POINTER(ShardInfo)]

@@ -361,6 +361,14 @@ class Bzip2Engine:
         if rc:
             self._raise(rc)
 
+    def debug_huffman_lengths(self, sorted_freqs, maxlen):
+        """tests only: HuffmanAllocator.allocateHuffmanCodeLengths (BJ:1275-1298) run by the device copy of the allocator"""
+        a = np.asarray(sorted_freqs, dtype=np.int32).copy()
+        rc = self._L.bz2b200_debug_huffman_lengths(self._ctx, a.ctypes.data, a.size, int(maxlen))
+        if rc:
+            self._raise(rc)
+        return [int(x) for x in a]
+
     def debug_set_pool(self, min_bytes=32_000_000, shard_bytes=0, first_halo=0, force_staging=False):
         """tests only: which inputs compressFile sends through the context's two-lane pool, and how they are cut"""
         rc = self._L.bz2b200_debug_set_pool(self._ctx, min_bytes, shard_bytes, first_halo, int(bool(force_staging)))

@@ -123,10 +123,13 @@ struct Ctx {
   int parse_mode = 0;      // BZ2B200_PARSE: 0 = by block count, 1 = k_huff_parse, 2 = k_huff_parse_win (development aid)
   std::vector<cudaEvent_t> trace_ev, trace_pool;
   std::vector<const char *> trace_names;
-  void *rb_pin = nullptr;  // page-locked scratch of rb_add / rb_sync
-  void *rb_dst[8];
-  size_t rb_off[8], rb_len[8], rb_used = 0;
+  void *rb_pin = nullptr;  // mapped page-locked scratch of rb_add / rb_sync (host address) and its device address
+  void *rb_dev = nullptr;
+  const void *rb_src[4];
+  void *rb_dst[4];
+  size_t rb_off[4], rb_len[4], rb_used = 0;
   int rb_n = 0;
+  u32 rb_seq = 0;
   bool ignore_block_crc = false;  // tests only (bz2b200_debug_set_ignore_block_crc)
   u32 cap_override = 0;    // tests only
   u32 batch_override = 0;  // tests only: blocks per batch
@@ -162,19 +165,55 @@ struct Ctx {
     }                                                                                    \
   } while (0)
 
-// Small device -> host read-backs (block / slot counts) land in page-locked scratch: a copy to pageable memory goes
-// through the driver's staging path and costs several microseconds more per round trip.
+// Small device -> host read-backs (block / slot counts): a one-warp kernel copies the pending words into a page of MAPPED
+// host memory and writes a sequence number last; the host spins on that word.  Against cudaMemcpyAsync + cudaStreamSynchronize
+// this saves the copy-engine command and the driver's wake-up per round trip (~20 round trips per compress call).
+struct RbItem { const void *src; u32 off, bytes; };
+__global__ void k_readback(RbItem i0, RbItem i1, RbItem i2, RbItem i3, int n, volatile u8 *host_page, u32 seq) {
+  const RbItem it[4] = {i0, i1, i2, i3};
+  for (int k = 0; k < n; k++)
+    for (u32 b = threadIdx.x; b < it[k].bytes; b += blockDim.x) host_page[it[k].off + b] = reinterpret_cast<const u8 *>(it[k].src)[b];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) { *reinterpret_cast<volatile u32 *>(host_page + 1020) = seq; __threadfence_system(); }
+}
 int rb_add(Ctx *c, void *dst, const void *dev_src, size_t bytes) {
-  if (!c->rb_pin) CK(cudaMallocHost(&c->rb_pin, 1024));
-  if (c->rb_n >= 8 || c->rb_used + bytes > 1024) { c->err = "internal: read-back scratch full"; return BZ2B200_E_CUDA; }
-  CK(cudaMemcpyAsync((char *)c->rb_pin + c->rb_used, dev_src, bytes, cudaMemcpyDeviceToHost, c->stream));
+  if (!c->rb_pin) {
+#ifndef BZ_SIM
+    CK(cudaHostAlloc(&c->rb_pin, 1024, cudaHostAllocMapped));
+    CK(cudaHostGetDevicePointer(&c->rb_dev, c->rb_pin, 0));
+#else
+    CK(cudaMallocHost(&c->rb_pin, 1024));
+    c->rb_dev = c->rb_pin;
+#endif
+    memset(c->rb_pin, 0, 1024);
+  }
+  if (c->rb_n >= 4 || c->rb_used + bytes > 1000) { c->err = "internal: read-back scratch full"; return BZ2B200_E_CUDA; }
+  c->rb_src[c->rb_n] = dev_src;
   c->rb_dst[c->rb_n] = dst; c->rb_off[c->rb_n] = c->rb_used; c->rb_len[c->rb_n] = bytes;
   c->rb_n++;
   c->rb_used += (bytes + 15) & ~(size_t)15;
   return 0;
 }
 int rb_sync(Ctx *c) {
-  CK(cudaStreamSynchronize(c->stream));
+  if (!c->rb_n) { CK(cudaStreamSynchronize(c->stream)); return 0; }
+  RbItem it[4] = {};
+  for (int i = 0; i < c->rb_n; i++) { it[i].src = c->rb_src[i]; it[i].off = (u32)c->rb_off[i]; it[i].bytes = (u32)c->rb_len[i]; }
+  const u32 seq = ++c->rb_seq;
+  KLAUNCH(k_readback, 1, 32, 0, c->stream, it[0], it[1], it[2], it[3], c->rb_n, (volatile u8 *)c->rb_dev, seq);
+#ifndef BZ_SIM
+  volatile u32 *flag = reinterpret_cast<volatile u32 *>((u8 *)c->rb_pin + 1020);
+  for (unsigned spin = 0; *flag != seq; spin++) {
+    if ((spin & 0xfffff) == 0xfffff && cudaStreamQuery(c->stream) != cudaErrorNotReady) {  // the kernel is gone: done, or a fault upstream
+      if (*flag == seq) break;
+      CK(cudaStreamSynchronize(c->stream));
+      CK(cudaGetLastError());
+      c->err = "internal: read-back kernel did not publish";
+      return BZ2B200_E_CUDA;
+    }
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
+#endif
   for (int i = 0; i < c->rb_n; i++) memcpy(c->rb_dst[i], (char *)c->rb_pin + c->rb_off[i], c->rb_len[i]);
   c->rb_n = 0;
   c->rb_used = 0;
@@ -473,7 +512,11 @@ int pipe_stages(Ctx *c) {
         for (int pass = 0; pass < 5; pass++) {  // bits 20..63, 9 bits a pass
           if (pass) LAUNCH(k_rs_hist<9>, gt, SORT_THREADS, 0, ki, seg_cnt, tile0, tblk, 20 + pass * 9, P<u32>(c->hist), (const u32 *)nullptr, tb);  // pass 0: k_keys_init
           if (c->rs2 && tb == 0 && gt == Ta) {  // whole batch at once: table of absolute positions + pipelined scatter (rsort2.cuh)
+#if RS2_SCAN1
+            LAUNCH(k_rs_scan<9>, dim3((unsigned)nb, 512 / 32), RSS_WARPS * 32, 0, P<u32>(c->hist), tile0, P<u32>(c->digit_base), 0u, 0u);
+#else
             LAUNCH(k_rs_bases, (unsigned)nb, 512, 0, P<u32>(c->hist), tile0);
+#endif
             if (c->ev_ok) {
               if (c->dom_used + 2 > c->dom_ev.size()) {
                 cudaEvent_t a, b2;
@@ -483,7 +526,7 @@ int pipe_stages(Ctx *c) {
               CK(cudaEventRecord(c->dom_ev[c->dom_used], c->stream));
             }
             const unsigned g2 = gt < (unsigned)(2 * c->sms) ? gt : (unsigned)(2 * c->sms);
-            LAUNCH(k_rs_scatter2, g2, RS2_THREADS, sizeof(Rs2Smem), ki, ko, P<u32>(c->hist), P<RsTile>(c->rs_tiles), gt, 20 + pass * 9);
+            LAUNCH(k_rs_scatter2, g2, RS2_THREADS, sizeof(Rs2Smem), ki, ko, P<u32>(c->hist), P<RsTile>(c->rs_tiles), gt, 20 + pass * 9, P<u32>(c->digit_base));
             if (c->ev_ok) { CK(cudaEventRecord(c->dom_ev[c->dom_used + 1], c->stream)); c->dom_used += 2; }
             c->st.dom_launches++;
             c->st.dom_bytes += 16ull * gn;
@@ -877,6 +920,7 @@ int bz2b200_compress(bz2b200_ctx *ctx, const uint8_t *in, size_t n, int level, u
     Pool *p = c->own_pool;
     p->cap_override = c->cap_override; p->batch_override = c->batch_override;
     p->halo0 = c->pool_halo0; p->force_staging = c->pool_force_staging;
+    p->plan_first = n / 2 + 1;  // one device, two lanes: two halves measured best (profiles/r02_pool_plans.md)
     int prc = pool_compress_whole(p, in, n, level, c->pool_shard_bytes, out, out_len);
     c->st = p->st;
     c->err = p->err;
@@ -1107,6 +1151,19 @@ long long bz2b200_debug_fetch(bz2b200_ctx *ctx, int what, int blk, void *dst, si
   if (bytes > cap) bytes = cap;
   if (bytes && cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) return BZ2B200_E_CUDA;
   return (long long)bytes;
+}
+
+int bz2b200_debug_huffman_lengths(bz2b200_ctx *ctx, int32_t *a, int n, int maxlen) {
+  Ctx *c = reinterpret_cast<Ctx *>(ctx);
+  if (!c || !a || n < 0 || n > 1 << 20 || maxlen < 1 || maxlen > 32) return BZ2B200_E_ARG;
+  CK(cudaSetDevice(c->device));
+  if (!n) return BZ2B200_OK;
+  ENS(c->dmisc, 4 * (size_t)n + 64);
+  CK(cudaMemcpyAsync(c->dmisc.p, a, 4 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  LAUNCH(k_debug_ha_allocate, 1, 32, 0, P<int>(c->dmisc), n, maxlen);
+  CK(cudaMemcpyAsync(a, c->dmisc.p, 4 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return BZ2B200_OK;
 }
 
 int bz2b200_debug_set_batch_blocks(bz2b200_ctx *ctx, uint32_t blocks) {

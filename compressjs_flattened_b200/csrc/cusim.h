@@ -189,6 +189,7 @@ static inline void __syncthreads() { cusim::syncthreads(); }
 static inline void __syncwarp(unsigned mask = 0xffffffffu) { (void)mask; uint64_t o[32]; cusim::exchange(0, o); }
 static inline void __threadfence() {}
 static inline void __threadfence_block() {}
+static inline void __threadfence_system() {}
 
 template <typename T> static inline T __shfl_sync(unsigned mask, T v, int src, int width = 32) {
   (void)mask; uint64_t o[32], x = 0; memcpy(&x, &v, sizeof(T)); cusim::exchange(x, o);

@@ -109,6 +109,11 @@ __device__ inline void ha_allocate(int *a, int N, int maxlen) {
   }
 }
 
+// tests/ only (bz2b200_debug_huffman_lengths): the allocator on the device over one array of ascending frequencies
+__global__ void k_debug_ha_allocate(int *a, int N, int maxlen) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) ha_allocate(a, N, maxlen);
+}
+
 // rebuild tables [0, ng) from freq (StaticHuffman ctor, BJ:1866-1894); blockDim.x == HUF_BT
 struct HufBuildSmem {
   u32 freq[BZ_MAX_GROUPS][BZ_MAX_SYMS];

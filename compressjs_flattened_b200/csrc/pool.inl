@@ -472,8 +472,8 @@ static int pool_run_shards(Pool *p, Exchange *ex, std::vector<ShardJob> &jobs, s
 
 // Shard sizes of one stream.  Small batches of blocks use the GPU less well than large ones (latency-bound per-block
 // kernels, partial waves), so the stream is NOT cut evenly: the first shard of every lane is small -- its upload is the
-// only one nobody hides -- and every following wave is `growth` times larger: copies run ~2.5x faster than the kernels,
-// so the upload of wave k+1 still fits under the kernels of wave k.  `fixed` > 0: equal shards of that size.
+// only one nobody hides -- and every following wave is `growth` times larger (copies run ~2.5x faster than the kernels,
+// so the upload of wave k+1 still fits under the kernels of wave k).  `fixed` > 0: equal shards of that size.
 static std::vector<size_t> pool_plan(size_t n, int level, size_t lanes, size_t fixed, size_t first, double growth) {
   std::vector<size_t> sizes;
   if (n == 0) { sizes.push_back(0); return sizes; }
@@ -482,8 +482,14 @@ static std::vector<size_t> pool_plan(size_t n, int level, size_t lanes, size_t f
     return sizes;
   }
   const size_t B = (size_t)level * 100000;
-  if (!first) first = 6 * B < ((size_t)6 << 20) ? (size_t)6 << 20 : 6 * B;   // six blocks or 6 MiB
-  if (growth < 1.0) growth = 2.5;
+  // Measured on B200 (profiles/r02_pool_plans.md): a batch of few blocks costs ~1 ms more than its share of a large one
+  // (per-block CTAs, host round trips), so few shards win: a quarter of a lane's share first (its upload is the exposed
+  // one, the rest travels under its kernels), then everything else.
+  if (!first) {
+    first = n / (4 * lanes) + 1;
+    if (first < 6 * B) first = 6 * B;
+  }
+  if (growth < 1.0) growth = 3.0;
   size_t left = n;
   double w = (double)first;
   while (left) {

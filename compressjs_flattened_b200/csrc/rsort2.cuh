@@ -53,6 +53,9 @@ __global__ void __launch_bounds__(512) k_rs_bases(u32 *__restrict__ hist, const 
 #ifndef RS2_PACK
 #define RS2_PACK 1
 #endif
+#ifndef RS2_SCAN1
+#define RS2_SCAN1 1   // 1: table rows from k_rs_scan (bwt.cuh) + the block's digit totals, scanned here per tile
+#endif
 #ifndef RS2_DIRECT
 #define RS2_DIRECT 0
 #endif
@@ -60,7 +63,10 @@ __global__ void __launch_bounds__(512) k_rs_bases(u32 *__restrict__ hist, const 
 #define RS2_WARPS (RS2_THREADS / 32)
 struct Rs2Smem {
   u64 keys[2][SORT_TILE];          // tile k / tile k+1; the consumed one doubles as the digit-ordered staging buffer
-  u32 gbase[2][512];               // table row of the tile (k_rs_bases)
+  u32 gbase[2][512];               // table row of the tile (k_rs_bases; RS2_SCAN1: k_rs_scan's prefix over the earlier tiles)
+#if RS2_SCAN1
+  u32 dtot[2][512];                // digit totals of the tile's block
+#endif
 #if RS2_PACK
   u32 wcnt[RS2_WARPS / 2][512];    // per-warp digit counts (two warps per word, 16 bits each), then first staging slot of (warp, digit)
 #else
@@ -69,6 +75,7 @@ struct Rs2Smem {
   u32 lpos[512];                   // first staging slot of every digit of the tile
   u32 delta[512];                  // position in the block minus staging slot, per digit
   u32 ws[34];
+  u64 ws64[34];
   RsTile info[2];
   u64 mbar[2];
 };
@@ -101,23 +108,31 @@ __device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) {
 
 // one elected thread: the keys of `tile` and its table row travel to shared memory buffer b
 __device__ __forceinline__ void rs2_fetch(Rs2Smem &sm, int b, u32 tile, const u64 *__restrict__ keys_in, const u32 *__restrict__ hist,
-                                          const RsTile *__restrict__ tinfo) {
+                                          const RsTile *__restrict__ tinfo, const u32 *__restrict__ digit_tot) {
   const RsTile ti = tinfo[tile];
   sm.info[b] = ti;
   const u32 kbytes = ((ti.m * 8u) + 15u) & ~15u;  // slots are padded to whole tiles: the 8 extra bytes exist
 #ifndef BZ_SIM
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the buffer was written by ordinary stores (staging) before
-  mbar_expect_tx(&sm.mbar[b], kbytes + 2048u);
+  mbar_expect_tx(&sm.mbar[b], kbytes + 2048u * (1 + RS2_SCAN1));
   tma_load_1d(sm.keys[b], keys_in + ti.g0, kbytes, &sm.mbar[b]);
   tma_load_1d(sm.gbase[b], hist + (u64)tile * 512, 2048u, &sm.mbar[b]);
+#if RS2_SCAN1
+  tma_load_1d(sm.dtot[b], digit_tot + (u64)ti.p * 512, 2048u, &sm.mbar[b]);
+#endif
 #else
   for (u32 i = 0; i < kbytes / 8; i++) sm.keys[b][i] = keys_in[ti.g0 + i];
   for (u32 i = 0; i < 512; i++) sm.gbase[b][i] = hist[(u64)tile * 512 + i];
+#if RS2_SCAN1
+  for (u32 i = 0; i < 512; i++) sm.dtot[b][i] = digit_tot[(u64)ti.p * 512 + i];
 #endif
+#endif
+  (void)digit_tot;
 }
 
 __global__ void __launch_bounds__(RS2_THREADS, 2) k_rs_scatter2(const u64 *__restrict__ keys_in, u64 *__restrict__ keys_out, const u32 *__restrict__ hist,
-                                                                const RsTile *__restrict__ tinfo, u32 ntiles, int shift) {
+                                                                const RsTile *__restrict__ tinfo, u32 ntiles, int shift,
+                                                                const u32 *__restrict__ digit_tot) {
   DYN_SMEM(Rs2Smem, smp);
   Rs2Smem &sm = *smp;
   const int lane = lane_id(), w = warp_id();
@@ -131,11 +146,11 @@ __global__ void __launch_bounds__(RS2_THREADS, 2) k_rs_scatter2(const u64 *__res
   }
   __syncthreads();
   u32 tile = blockIdx.x;
-  if (threadIdx.x == 0 && tile < ntiles) rs2_fetch(sm, 0, tile, keys_in, hist, tinfo);
+  if (threadIdx.x == 0 && tile < ntiles) rs2_fetch(sm, 0, tile, keys_in, hist, tinfo, digit_tot);
   for (u32 it = 0; tile < ntiles; it++, tile += gridDim.x) {
     const int b = (int)(it & 1);
     // tile k+1 starts travelling now; buffer b^1 was released by the barrier that ended the previous iteration
-    if (threadIdx.x == 0 && tile + gridDim.x < ntiles) rs2_fetch(sm, b ^ 1, tile + gridDim.x, keys_in, hist, tinfo);
+    if (threadIdx.x == 0 && tile + gridDim.x < ntiles) rs2_fetch(sm, b ^ 1, tile + gridDim.x, keys_in, hist, tinfo, digit_tot);
 #ifndef BZ_SIM
     mbar_wait(&sm.mbar[b], (it >> 1) & 1u);
 #else
@@ -200,8 +215,15 @@ __global__ void __launch_bounds__(RS2_THREADS, 2) k_rs_scatter2(const u64 *__res
         cw[q] = acc | ((acc + lo) << 16);
         acc += lo + hi;
       }
+#if RS2_SCAN1
+      u64 tot64;
+      const u64 ex = block_excl_sum<u64>(((u64)sm.dtot[b][d] << 32) | acc, tot64, reinterpret_cast<u64 *>(sm.ws64));
+      const u32 lp = (u32)ex, dbase = (u32)(ex >> 32);
+#else
       u32 tot;
       const u32 lp = block_excl_sum<u32>(acc, tot, sm.ws);
+      const u32 dbase = 0;
+#endif
 #pragma unroll
       for (int q = 0; q < RS2_WARPS / 2; q++) sm.wcnt[q][d] = cw[q] + lp * 0x10001u;  // every prefix < 4096: no carry between the halves
 #else
@@ -210,11 +232,12 @@ __global__ void __launch_bounds__(RS2_THREADS, 2) k_rs_scatter2(const u64 *__res
       for (int ww = 0; ww < RS2_WARPS; ww++) { cw[ww] = acc; acc += sm.wcnt[ww][d]; }
       u32 tot;
       const u32 lp = block_excl_sum<u32>(acc, tot, sm.ws);
+      const u32 dbase = 0;
 #pragma unroll
       for (int ww = 0; ww < RS2_WARPS; ww++) sm.wcnt[ww][d] = lp + cw[ww];
 #endif
       sm.lpos[d] = lp;
-      sm.delta[d] = sm.gbase[b][d] - lp;
+      sm.delta[d] = dbase + sm.gbase[b][d] - lp;
     }
     __syncthreads();
 #if RS2_DIRECT

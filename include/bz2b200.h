@@ -207,6 +207,9 @@ int bz2b200_debug_set_batch_blocks(bz2b200_ctx *ctx, uint32_t blocks);
 /* tests/ only: skip the block-CRC comparison of the decoder (BJ:1756-1761), so that what a damaged stream decodes TO
  * can be compared with the oracle.  Not reachable from the environment. */
 int bz2b200_debug_set_ignore_block_crc(bz2b200_ctx *ctx, int on);
+/* tests/ only: the device copy of HuffmanAllocator.allocateHuffmanCodeLengths (BJ:1275-1298) on a[0..n): frequencies in
+ * ascending order in, code lengths out (in place) -- pinned by the reference's own vectors, NPM/test/huffman.js:16-76 */
+int bz2b200_debug_huffman_lengths(bz2b200_ctx *ctx, int32_t *a, int n, int maxlen);
 
 #ifdef __cplusplus
 }

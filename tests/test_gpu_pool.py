@@ -1,0 +1,136 @@
+"""GPU tests of the shard scheduler (csrc/pool.inl) through the C-ABI: lanes of one device, several devices in one
+process (skipped below 2 visible GPUs), adversarial inputs at full size against the oracle's golden
+SHA-256, block-range decompression of one stream, and the device copy of the code-length allocator against the
+reference's own vectors."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import HERE
+
+pytestmark = pytest.mark.gpu
+GOLD = json.load(open(os.path.join(HERE, "golden", "corpus_goldens.json")))
+
+
+def _ngpu():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.fixture(scope="module")
+def pool2():
+    from compressjs_flattened_b200.pool import Bzip2Pool
+    p = Bzip2Pool([0], 2)
+    yield p
+    p.close()
+
+
+@pytest.mark.parametrize("name", ["zeros1e8", "ab5e7", "rand1e8", "line97x1e6"])
+@pytest.mark.parametrize("level", [9, 1])
+def test_adversarial_full_size_equals_oracle_golden(gpu_engine, name, level):
+    """SURVEY 8d C5b at full size: zeros(1e8) (one block eats ~46 MB of input: the cut walk, i64 offsets and -- through the
+    context's pool -- halos that must grow 40-fold), ('ab') x 5e7 (periodic: ceil(log2 n) doubling rounds, tie rule),
+    100 MB of random bytes, 1e6 copies of a 97-byte line.  SHA-256 of the stream == the oracle's golden; round trip."""
+    from compressjs_flattened_b200.corpus import gen_adversarial
+    data = gen_adversarial(name)
+    g = GOLD[f"adv:{name}:L{level}"]
+    assert hashlib.sha256(memoryview(data)).hexdigest() == g["input_sha256"]
+    comp = gpu_engine.compressFile(data, None, level)          # >= 32 MB: through the context's two-lane pool
+    assert (len(comp), hashlib.sha256(comp).hexdigest()) == (g["out_bytes"], g["out_sha256"])
+    assert gpu_engine.stats().n_blocks == g["n_blocks"]
+    gpu_engine.debug_set_pool(1 << 62)                         # and through the single-launch path
+    try:
+        comp1 = gpu_engine.compressFile(data, None, level)
+    finally:
+        gpu_engine.debug_set_pool()
+    assert comp1 == comp
+    back = gpu_engine.decompressFile(comp)
+    assert hashlib.sha256(back).hexdigest() == g["input_sha256"]
+
+
+def test_pool_plans_and_staging_same_stream(pool2):
+    from compressjs_flattened_b200.corpus import gen_text
+    data = gen_text(40_000_000, 8)
+    g = None
+    for first, growth, shard, staging in ((0, 0, 0, False), (3_000_000, 2.0, 0, True), (0, 0, 7_000_000, False)):
+        pool2.set_plan(first, growth)
+        pool2.debug(force_staging=staging)
+        comp = pool2.compressFile(data, None, 9, shard_bytes=shard)
+        h = hashlib.sha256(comp).hexdigest()
+        g = g or h
+        assert h == g
+    pool2.set_plan()
+    pool2.debug()
+    single = __import__("compressjs_flattened_b200").Bzip2Engine(0)
+    single.debug_set_pool(1 << 62)
+    assert hashlib.sha256(single.compressFile(data, None, 9)).hexdigest() == g
+    assert pool2.decompressFile(comp) == data.tobytes()
+    single.close()
+
+
+def test_pool_decompress_one_stream_in_slices(pool2, gpu_engine):
+    """block-range decompression: slices of the stream over the lanes, several slice sizes incl. slices smaller
+    than a block; multistream; errors are the first in stream order"""
+    from compressjs_flattened_b200.bzip2 import Bzip2Error
+    from compressjs_flattened_b200.corpus import gen_text
+    data = gen_text(30_000_000, 8).tobytes()
+    comp = gpu_engine.compressFile(data, None, 9)
+    for sl in (0, 3_000_000, 500_000):
+        assert pool2.decompressFile(comp, len(data), False, slice_bytes=sl) == data
+    ms = comp + gpu_engine.compressFile(data[:1_000_000], None, 1)
+    assert pool2.decompressFile(ms, None, True, slice_bytes=2_000_000) == data + data[:1_000_000]
+    assert pool2.decompressFile(ms, None, False, slice_bytes=2_000_000) == data
+    bad = bytearray(comp)
+    bad[len(comp) // 3] ^= 0x40
+    bad[2 * len(comp) // 3] ^= 0x40
+    with pytest.raises(Bzip2Error) as e1:
+        pool2.decompressFile(bytes(bad), None, False, slice_bytes=1_000_000)
+    with pytest.raises(Bzip2Error) as e2:
+        gpu_engine.decompressFile(bytes(bad))
+    assert e1.value.errorCode == e2.value.errorCode
+
+
+def test_single_context_decode_batches(gpu_engine):
+    """1000 level-1 blocks decode in batches of 320 candidates; a forced batch of 7 gives the same bytes"""
+    from compressjs_flattened_b200.corpus import gen_text
+    data = gen_text(20_000_000, 8).tobytes()
+    comp = gpu_engine.compressFile(data, None, 1)
+    gpu_engine._L.bz2b200_debug_set_decode_batch(gpu_engine._ctx, None, 7)
+    try:
+        assert gpu_engine.decompressFile(comp) == data
+    finally:
+        gpu_engine._L.bz2b200_debug_set_decode_batch(gpu_engine._ctx, None, 0)
+    rows = []
+    gpu_engine.table(comp, lambda p, s: rows.append(s))
+    assert sum(rows) == len(data) and len(rows) >= 200
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs 2 visible GPUs")
+def test_two_devices_in_one_process(gpu_engine):
+    """the multi-GPU form of the reference-facing call: one process, one pool over every visible device"""
+    from compressjs_flattened_b200.corpus import gen_text
+    from compressjs_flattened_b200.pool import Bzip2Pool
+    n = _ngpu()
+    data = gen_text(200_000_000, 8)
+    g = GOLD["text:200000000:8:L9"]
+    pool = Bzip2Pool(list(range(n)), 1)
+    try:
+        comp = pool.compressFile(data, None, 9)
+        assert (len(comp), hashlib.sha256(comp).hexdigest()) == (g["out_bytes"], g["out_sha256"])
+        back = pool.decompressFile(comp, len(data))
+        assert hashlib.sha256(back).hexdigest() == g["input_sha256"]
+    finally:
+        pool.close()
+
+
+def test_device_allocator_matches_reference_vectors(gpu_engine, oracle):
+    """VERDICT r1 parity gap: ha_allocate on the DEVICE against the reference's own allocator vectors (the oracle's copy is
+    pinned by the same vectors in test_oracle_golden.py)"""
+    from test_oracle_golden import HUFF_VECTORS
+    for freqs, limit, expect in HUFF_VECTORS:
+        got = gpu_engine.debug_huffman_lengths(freqs, limit)
+        assert got == list(expect), (freqs, limit)
+        assert got == oracle.huff_alloc(freqs, limit)

@@ -50,15 +50,21 @@ def test_bwt_matches_bruteforce(oracle):
             assert oracle.bwt(t) == (exp, rots.index(0))
 
 
+HUFF_VECTORS = [  # NPM/test/huffman.js:16-76: (frequencies ascending, length limit, expected code lengths)
+    ([1], 32, [1]),
+    ([1, 1], 32, [1, 1]),
+    ([1] * 5, 32, [3, 3, 2, 2, 2]),
+    ([0, 0, 1, 1, 1, 1], 3, [3, 3, 3, 3, 2, 2]),
+    (FIB[:36], 20, [20] * 16 + [19, 19, 18, 17, 16, 16, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1]),
+    (FIB[:22], 20, [20, 20, 19, 19, 19, 17, 16, 15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1]),
+    (FIB[:21], 20, [20, 20, 19, 18, 17, 16, 15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1]),
+    (FIB[:36], 6, [6] * 30 + [5, 5, 5, 4, 3, 2]),
+]
+
+
 def test_huffman_allocator_known_answers(oracle):  # NPM/test/huffman.js:16-76
-    assert oracle.huff_alloc([1], 32) == [1]
-    assert oracle.huff_alloc([1, 1], 32) == [1, 1]
-    assert oracle.huff_alloc([1] * 5, 32) == [3, 3, 2, 2, 2]
-    assert oracle.huff_alloc([0, 0, 1, 1, 1, 1], 3) == [3, 3, 3, 3, 2, 2]
-    assert oracle.huff_alloc(FIB[:36], 20) == [20] * 16 + [19, 19, 18, 17, 16, 16, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1]
-    assert oracle.huff_alloc(FIB[:22], 20) == [20, 20, 19, 19, 19, 17, 16, 15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1]
-    assert oracle.huff_alloc(FIB[:21], 20) == [20, 20, 19, 18, 17, 16, 15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1]
-    assert oracle.huff_alloc(FIB[:36], 6) == [6] * 30 + [5, 5, 5, 4, 3, 2]
+    for freqs, limit, expect in HUFF_VECTORS:
+        assert oracle.huff_alloc(freqs, limit) == expect
 
 
 def test_fls(oracle):  # NPM/test/test-fls.js:14-47

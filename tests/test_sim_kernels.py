@@ -409,3 +409,16 @@ def test_decode_run_length_sum_cannot_wrap(sim_engine, oracle):
     assert wrapped <= 900_000   # the old u32 sum would have passed the dbuf check
     assert _decode_outcome(oracle, blob, oracle.OracleError) == ("err", -5)
     assert _decode_outcome(sim_engine, blob, Bzip2Error) == ("err", -5)
+
+
+def test_device_allocator_matches_reference_vectors(sim_engine, oracle):
+    """the product's copy of the code-length allocator (huff.cuh ha_allocate) against NPM/test/huffman.js:16-76 directly,
+    not only through whole-stream parity"""
+    from test_oracle_golden import HUFF_VECTORS
+    rng = np.random.default_rng(3)
+    for freqs, limit, expect in HUFF_VECTORS:
+        assert sim_engine.debug_huffman_lengths(freqs, limit) == list(expect)
+    for _ in range(40):   # and against the oracle's copy on random histograms (limit 20 as in BJ:1342)
+        n = int(rng.integers(3, 259))
+        f = sorted(int(x) for x in rng.integers(0, 1 << int(rng.integers(1, 20)), n))
+        assert sim_engine.debug_huffman_lengths(f, 20) == oracle.huff_alloc(f, 20)
