@@ -50,6 +50,15 @@ class RangeResult(C.Structure):
     _fields_ = [("part", C.POINTER(C.c_uint8)), ("bytes", C.c_uint64), ("out_offset", C.c_uint64), ("rc", C.c_int32), ("n_blocks", C.c_uint32)]
 
 
+def take_bytes(ptr, n):
+    """n bytes at a ctypes pointer as a bytes object (ctypes.string_at takes an int-sized length: streams above 2 GiB)"""
+    if not n:
+        return b""
+    if n < (1 << 31):
+        return C.string_at(ptr, n)
+    return bytes(memoryview((C.c_ubyte * n).from_address(C.addressof(ptr.contents))))
+
+
 class Library:
     """Thin typed view of the C ABI."""
 

@@ -342,18 +342,25 @@ static int lane_run(PoolRun &R, Lane *L, std::vector<ShardJob> jobs, std::vector
     up = std::async(std::launch::async, [L, j0, &R, &d_in] { return lane_upload(L, j0, 0, R.pageable, &d_in[0]); });
   }
   bz2b200_stats agg{};
+  static const bool ptrace = getenv("BZ2B200_POOL_TRACE") != nullptr;  // development aid: host timeline of every shard
+  auto now_ms = [] { return (double)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now().time_since_epoch()).count() / 1000.0; };
+  const double t_origin = now_ms();
   for (size_t k = 0; k < nj; k++) {
     ShardJob &job = jobs[k];
     ShardOut &out = *outs[k];
     const int slot = (int)(k & 1);
+    double tp[8] = {now_ms() - t_origin, 0, 0, 0, 0, 0, 0, 0};
     int rc = up.get();
     if (rc) return rc;
+    tp[1] = now_ms() - t_origin;
     u64 start = 0;
     bool have_start = job.index == 0;
     for (;;) {  // (again with a longer halo when the last owned block runs out of input)
       if (!job.on_device) CK(cudaStreamWaitEvent(c->stream, L->in_ev[slot], 0));
       if ((rc = pipe_begin(c, d_in[slot], job.n_avail, R.level))) return rc;
+      tp[2] = now_ms() - t_origin;
       if (!have_start) { if ((rc = R.ex->get_cut(job.index - 1, &start))) return rc; have_start = true; }
+      tp[3] = now_ms() - t_origin;
       const u64 s_local = start > job.base ? start - job.base : 0;
       const i64 own = (i64)(job.own_len < job.n_avail ? job.own_len : job.n_avail);
       if ((rc = pipe_cut(c, (i64)s_local, own))) return rc;
@@ -376,6 +383,7 @@ static int lane_run(PoolRun &R, Lane *L, std::vector<ShardJob> jobs, std::vector
       out.info.next_start = nxt > start ? nxt : start;
       out.info.complete = 1;
       if ((rc = R.ex->put_cut(job.index, out.info.next_start))) return rc;
+      tp[4] = now_ms() - t_origin;
     }
     if (k + 1 < nj) {  // the next shard of this lane travels while this one is compressed
       const ShardJob jn = jobs[k + 1];
@@ -386,6 +394,7 @@ static int lane_run(PoolRun &R, Lane *L, std::vector<ShardJob> jobs, std::vector
     u64 bits = 0;
     u32 fold = 0;
     if ((rc = pipe_run(c, 0, false, nullptr, 0, true, &olen, &bits, &fold))) return rc;
+    tp[5] = now_ms() - t_origin;
     trace_report(c);
     {
       agg.n_blocks += c->st.n_blocks; agg.kernel_launches += c->st.kernel_launches; agg.rle1_bytes += c->st.rle1_bytes;
@@ -399,6 +408,7 @@ static int lane_run(PoolRun &R, Lane *L, std::vector<ShardJob> jobs, std::vector
     out.info.crc_fold = fold;
     ExTail prev;
     if (job.index > 0 && (rc = R.ex->get_tail(job.index - 1, &prev))) return rc;
+    tp[6] = now_ms() - t_origin;
     ExTail mine;
     const u32 m = out.info.n_blocks & 31u;
     mine.end_bit = prev.end_bit + bits;
@@ -432,6 +442,10 @@ static int lane_run(PoolRun &R, Lane *L, std::vector<ShardJob> jobs, std::vector
         CK(cudaMemcpyAsync(out.seg, d_seg, seg_len, cudaMemcpyDeviceToHost, c->stream));
       }
     }
+    tp[7] = now_ms() - t_origin;
+    if (ptrace)
+      fprintf(stderr, "[bz2b200 pool] dev %d shard %d (%zu MB): start %.2f | upload ready %.2f | begin issued %.2f | cut arrived %.2f | cut done %.2f | stages done %.2f | tail arrived %.2f | emit issued %.2f ms\n",
+              c->device, job.index, job.own_len / 1000000, tp[0], tp[1], tp[2], tp[3], tp[4], tp[5], tp[6], tp[7]);
   }
   CK(cudaStreamSynchronize(c->stream));
   CK(cudaGetLastError());
@@ -491,7 +505,8 @@ static std::vector<size_t> pool_plan(size_t n, int level, size_t lanes, size_t f
   }
   if (growth < 1.0) growth = 3.0;
   size_t left = n;
-  double w = (double)first;
+  const double wmax = (double)((size_t)128 << 20);  // bounds the per-lane state (52 B per input byte)
+  double w = (double)first < wmax ? (double)first : wmax;
   while (left) {
     if ((double)left <= w * (double)lanes * 1.3) {  // the last wave: what is left, split evenly over the lanes (no crumb shard)
       const size_t parts = (double)left <= w * 0.65 ? 1 : (size_t)(((double)left + w * 1.3 - 1) / (w * 1.3));
@@ -509,7 +524,7 @@ static std::vector<size_t> pool_plan(size_t n, int level, size_t lanes, size_t f
       left -= take;
     }
     w *= growth;
-    if (w > (double)((size_t)128 << 20)) w = (double)((size_t)128 << 20);  // bounds the per-lane state (52 B per input byte)
+    if (w > wmax) w = wmax;
   }
   return sizes;
 }
@@ -758,7 +773,7 @@ static int pool_run_decode(Pool *p, DecRun &R, std::vector<ShardJob> &jobs, std:
 
 static size_t pool_dec_slice(const Pool *p, size_t n) {
   size_t per = n / p->lanes.size() + 1;
-  const size_t lo = (size_t)24 << 20, hi = (size_t)96 << 20;  // >= ~80 blocks of text per slice (the parse is latency-bound below), <= one batch
+  const size_t lo = (size_t)24 << 20, hi = (size_t)352 << 20;  // >= ~80 blocks of text per slice (the parse is latency-bound below), <= one batch of DEC_BATCH
   if (per < lo) per = lo;
   if (per > hi) per = hi;
   return per;

@@ -78,7 +78,7 @@ class Bzip2Pool:
         raise Bzip2Error(rc, msg + (": " + detail if detail else ""))
 
     def _take(self, ptr, n):
-        data = C.string_at(ptr, n) if n else b""
+        data = _native.take_bytes(ptr, n)
         self._L.bz2b200_free(ptr)
         return data
 

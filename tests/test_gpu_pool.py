@@ -94,7 +94,7 @@ def test_pool_decompress_one_stream_in_slices(pool2, gpu_engine):
 
 
 def test_single_context_decode_batches(gpu_engine):
-    """1000 level-1 blocks decode in batches of 320 candidates; a forced batch of 7 gives the same bytes"""
+    """candidates decode in batches (1280 at most); a forced batch of 7 gives the same bytes"""
     from compressjs_flattened_b200.corpus import gen_text
     data = gen_text(20_000_000, 8).tobytes()
     comp = gpu_engine.compressFile(data, None, 1)
