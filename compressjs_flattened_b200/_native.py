@@ -120,6 +120,12 @@ class Library:
         L.bz2b200_pool_decompress_shards.argtypes = [vp, vp, C.POINTER(ShardJob), C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int,
                                                      C.POINTER(RangeResult)]
         L.bz2b200_debug_set_decode_batch.argtypes = [vp, vp, C.c_uint32]
+        for name in ("zstream", "dstream"):
+            getattr(L, f"bz2b200_{name}_open").argtypes = [vp, C.c_int, C.c_size_t, C.POINTER(vp)]
+            getattr(L, f"bz2b200_{name}_feed").argtypes = [vp, vp, C.c_size_t, u8pp, szp]
+            getattr(L, f"bz2b200_{name}_finish").argtypes = [vp, u8pp, szp]
+            getattr(L, f"bz2b200_{name}_close").argtypes = [vp]
+            getattr(L, f"bz2b200_{name}_close").restype = None
         L.bz2b200_pool_debug.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_size_t, C.c_int]
         L.bz2b200_debug_set_pool.argtypes = [vp, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int]
         self.L = L

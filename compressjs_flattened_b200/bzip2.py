@@ -133,19 +133,12 @@ class Bzip2Engine:
             self._raise(rc)
         return _deliver(self._take(out, n.value), output)
 
-    def compressStream(self, source, sink=None, props=None, chunk_bytes=64 << 20):
-        """Stream flavour of compressFile (SURVEY 8f N2; what NPM/bin/compressjs:163-180 does with {readByte}/{writeByte}
-        streams): the source is read chunk by chunk and whole blocks are compressed as soon as the bytes after them (their
-        halo) have arrived, so neither the input nor the output is ever held in full.  Byte-identical to compressFile on
-        the concatenated input.  source: .read(n) -> bytes, or {readByte}; sink: .write(bytes), {writeByte}, or None
-        (the stream is returned as bytes).  Built on the shard calls: every chunk is a shard of the stream."""
-        level = props if isinstance(props, (int, float)) and not isinstance(props, bool) else 9  # BJ:2204-2206
-        if level < 1 or level > 9 or int(level) != level:
-            raise ValueError("Invalid block size multiplier")                                    # BJ:2208-2210
-        level = int(level)
+    # -- the stream flavour (what NPM/bin/compressjs:163-180 does with {readByte}/{writeByte} streams) --
+    @staticmethod
+    def _reader(source, piece):
         if hasattr(source, "read"):
-            read = source.read
-        elif hasattr(source, "readByte"):
+            return source.read
+        if hasattr(source, "readByte"):
             def read(n):
                 out = bytearray()
                 while len(out) < n:
@@ -154,66 +147,81 @@ class Bzip2Engine:
                         break
                     out.append(ch)
                 return bytes(out)
-        else:
-            view, pos = memoryview(_coerce_input(source)), [0]
+            return read
+        view, pos = memoryview(_coerce_input(source)), [0]
 
-            def read(n):
-                b = view[pos[0]:pos[0] + n].tobytes()
-                pos[0] += len(b)
-                return b
+        def read(n):
+            b = view[pos[0]:pos[0] + n].tobytes()
+            pos[0] += len(b)
+            return b
+        return read
+
+    def _pump(self, kind, handle, source, sink, piece):
+        """read pieces, feed them, hand on what comes back; the C stream object does the work (csrc/stream_abi.inl)"""
+        L = self._L
+        feed, finish = getattr(L, f"bz2b200_{kind}_feed"), getattr(L, f"bz2b200_{kind}_finish")
+        read = self._reader(source, piece)
         collected = bytearray() if sink is None else None
 
-        def put(b):
-            if not b:
+        def put(ptr, n):
+            data = self._take(ptr, n) if n else b""
+            if not data:
                 return
             if collected is not None:
-                collected.extend(b)
+                collected.extend(data)
             elif hasattr(sink, "write"):
-                sink.write(bytes(b))
+                sink.write(data)
             else:
-                for x in b:
+                for x in data:
                     sink.writeByte(x)
 
-        put(b"BZh" + bytes([0x30 + level]))                                                     # BJ:2223-2226
-        bitpos, tail, crc, buf, eof = 32, 0, 0, bytearray(), False
-        while True:
-            if not eof:
-                data = read(chunk_bytes)
-                eof = len(data) < chunk_bytes
-                buf += data
-            own = len(buf) if eof else len(buf) // 2          # the second half is the halo of the blocks of the first
-            if own or eof:
-                self.shard_begin(bytes(buf), level)
-                info = self.shard_cut(0, own, eof)
-                if not info.complete:                         # a block needs input that is not here yet: read on
-                    if eof:
-                        raise RuntimeError("internal: incomplete block at end of input")
-                    continue
-                if info.n_blocks:
-                    self.shard_compress(info)
-                    seg = self.shard_emit(info, bitpos & 7)
-                    merged = bytearray(seg)
-                    merged[0] |= tail
-                    end = bitpos + int(info.bits)
-                    nfull = (end >> 3) - (bitpos >> 3)        # bytes that are complete now
-                    put(merged[:nfull])
-                    tail = merged[nfull] if end & 7 else 0
-                    bitpos = end
-                    m = info.n_blocks & 31
-                    crc = (((crc << m) | (crc >> (32 - m))) & 0xFFFFFFFF if m else crc) ^ info.crc_fold   # BJ:2237
-                    del buf[:int(info.next_start)]
-            if eof:
-                break
-        foot = (0x177245385090 << 32) | crc                                                     # BJ:2245-2247
-        nbits = (bitpos & 7) + 80                     # the pending bits of the last byte, then the footer
-        pad = -nbits % 8                              # zero bits up to the byte boundary (BitStream.flush, BJ:127-132)
-        val = (tail << (nbits + pad - 8)) | (foot << pad) if bitpos & 7 else foot
-        put(val.to_bytes((nbits + pad) // 8, "big"))
+        out, n = C.POINTER(C.c_uint8)(), C.c_size_t()
+        try:
+            while True:
+                data = read(piece)
+                if not data:
+                    break
+                a = np.frombuffer(data, dtype=np.uint8)
+                rc = feed(handle, a.ctypes.data, a.size, C.byref(out), C.byref(n))
+                if rc:
+                    self._raise(rc)
+                put(out, n.value)
+                if len(data) < piece:
+                    break
+            rc = finish(handle, C.byref(out), C.byref(n))
+            if rc:
+                self._raise(rc)
+            put(out, n.value)
+        finally:
+            getattr(L, f"bz2b200_{kind}_close")(handle)
         if sink is None:
             return bytes(collected)
         if hasattr(sink, "flush"):
             sink.flush()
         return sink
+
+    def compressStream(self, source, sink=None, props=None, chunk_bytes=64 << 20, piece_bytes=None):
+        """Stream flavour of compressFile: the source is read piece by piece and whole blocks are compressed as soon as the
+        bytes after them (their halo) have arrived, so neither the input nor the output is ever held in full.
+        Byte-identical to compressFile on the concatenated input.  source: .read(n) -> bytes, {readByte}, or bytes-like;
+        sink: .write(bytes), {writeByte}, or None (the stream is returned as bytes)."""
+        level = props if isinstance(props, (int, float)) and not isinstance(props, bool) else 9  # BJ:2204-2206
+        if level < 1 or level > 9 or int(level) != level:
+            raise ValueError("Invalid block size multiplier")                                    # BJ:2208-2210
+        h = C.c_void_p()
+        rc = self._L.bz2b200_zstream_open(self._ctx, int(level), int(chunk_bytes), C.byref(h))
+        if rc:
+            self._raise(rc)
+        return self._pump("zstream", h, source, sink, int(piece_bytes or max(1, chunk_bytes // 4)))
+
+    def decompressStream(self, source, sink=None, multistream=False, chunk_bytes=16 << 20, piece_bytes=None):
+        """Stream flavour of decompressFile: blocks are decoded as soon as they are complete; the bytes of the blocks before
+        an error have been delivered when it is raised (like the reference, which writes as it goes)."""
+        h = C.c_void_p()
+        rc = self._L.bz2b200_dstream_open(self._ctx, int(bool(multistream)), int(chunk_bytes), C.byref(h))
+        if rc:
+            self._raise(rc)
+        return self._pump("dstream", h, source, sink, int(piece_bytes or max(1, chunk_bytes // 4)))
 
     def decompressFile(self, input, output=None, multistream=False):
         a = _coerce_input(input)

@@ -1189,5 +1189,6 @@ int bz2b200_debug_set_block_cap(bz2b200_ctx *ctx, uint32_t cap) {
 
 #include "decode_abi.inl"
 #include "pool_abi.inl"
+#include "stream_abi.inl"
 
 }  // extern "C"

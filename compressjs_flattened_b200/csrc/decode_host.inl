@@ -249,10 +249,11 @@ static int dec_invert(Ctx *c, const std::vector<DecBlk> &blks, const std::vector
 // owns the signatures that start in [lo_bit, hi_bit) (global).  get_walk() is called once, after the first batch has
 // been handed to the GPU, and returns the state of the walk at the start of the range; walk_out is the state after it
 // (on_walk, if given, receives it as soon as the walk is through -- before the last batch is inverted).
-// *need_more = 1 (rc 0): a block of this range reads past n_avail although the stream goes on -- call again with more.
+// *need_more = 1 (rc 0): a block of this range reads past n_avail although the stream goes on -- call again with more
+// (partial_ok: the blocks before it are decoded all the same and walk_out.cur is where that block starts: streaming).
 static int decode_range(Ctx *c, const u8 *d_in, size_t n_avail, u64 g0, u64 total_n, u64 lo_bit, u64 hi_bit, int multistream, int mode,
                         const std::function<int(DecWalk &)> &get_walk, DecSink &sink, DecodeResult &R, DecWalk &walk_out, int *need_more,
-                        const std::function<int(const DecWalk &)> *on_walk = nullptr) {
+                        const std::function<int(const DecWalk &)> *on_walk = nullptr, bool partial_ok = false) {
   int rc;
   *need_more = 0;
   R.tbl_pos.clear(); R.tbl_size.clear(); R.out_len = 0;
@@ -299,8 +300,9 @@ static int decode_range(Ctx *c, const u8 *d_in, size_t n_avail, u64 g0, u64 tota
       }
       W.ended = 1;
     } else {
-      while (!W.ended && !struct_err && W.cur < hi_bit) {
+      while (!W.ended && !struct_err && !*need_more && W.cur < hi_bit) {
         if (((W.cur + 7) >> 3) >= total_n) { W.ended = 1; break; }  // BJ:1777: silent stop at end of input
+        if (W.cur + 48 > (g0 + n_avail) * 8 && more_input) { *need_more = 1; if (partial_ok) break; return 0; }  // the signature itself has not arrived
         auto it = std::lower_bound(cand.begin() + (long)b0i, cand.end(), (W.cur - gbit0) << 1);
         if (it == cand.end() || gbit0 + (*it >> 1) != W.cur) {  // BJ:1438
           struct_err = BZ2B200_E_NOT_BZIP_DATA;
@@ -313,14 +315,14 @@ static int decode_range(Ctx *c, const u8 *d_in, size_t n_avail, u64 g0, u64 tota
         if (b.kind == 0) {
           // an error of a block that may have run into the end of the halo says nothing yet (zero bits read past the end
           // look like bad tables as well as like EOF): decode again with more input.  A block is at most DEC_MAX_BLOCK_BYTES long.
-          if (b.err && more_input && (g0 + n_avail) - (W.cur >> 3) < DEC_MAX_BLOCK_BYTES) { *need_more = 1; return 0; }
+          if (b.err && more_input && (g0 + n_avail) - (W.cur >> 3) < DEC_MAX_BLOCK_BYTES) { *need_more = 1; if (partial_ok) break; return 0; }
           if (b.err) { struct_err = b.err; c->err = "block at bit " + std::to_string(W.cur) + ": decode error"; break; }
           if (b.count > 100000u * W.level || b.orig_ptr > 100000u * W.level) { struct_err = BZ2B200_E_DATA_ERROR; c->err = "block larger than the stream's block size"; break; }
           W.stream_crc = b.target_crc ^ ((W.stream_crc << 1) | (W.stream_crc >> 31));  // BJ:1441
           chain.push_back((u32)(idx - b0i));
           W.cur = gbit0 + b.endbit;
         } else {
-          if (W.cur + 80 > (g0 + n_avail) * 8 && more_input) { *need_more = 1; return 0; }  // the footer's CRC lies beyond the halo
+          if (W.cur + 80 > (g0 + n_avail) * 8 && more_input) { *need_more = 1; if (partial_ok) break; return 0; }  // the footer's CRC lies beyond the halo
           if (mode != DEC_TABLE && b.target_crc != W.stream_crc) {  // BJ:1781-1786
             struct_err = BZ2B200_E_DATA_ERROR;
             char msg[96];
@@ -331,7 +333,12 @@ static int decode_range(Ctx *c, const u8 *d_in, size_t n_avail, u64 g0, u64 tota
           W.cur += 80;
           if (multistream && ((W.cur + 7) >> 3) < total_n) {  // BJ:1787-1792
             const u64 bytepos = (W.cur + 7) >> 3;
-            if (bytepos + 4 > g0 + n_avail && more_input) { *need_more = 1; return 0; }
+            if (bytepos + 4 > g0 + n_avail && more_input) {  // the next stream's header has not arrived: come back to this footer
+              *need_more = 1;
+              if (!partial_ok) return 0;
+              W.cur -= 80;
+              break;
+            }
             u8 hdr[4];
             if ((rc = fetch_bytes(c, d_in, n_avail, bytepos - g0, hdr))) return rc;
             if (bytepos + 4 > total_n || hdr[0] != 'B' || hdr[1] != 'Z' || hdr[2] != 'h') { struct_err = BZ2B200_E_NOT_BZIP_DATA; break; }
@@ -345,6 +352,7 @@ static int decode_range(Ctx *c, const u8 *d_in, size_t n_avail, u64 g0, u64 tota
       }
     }
     // the walk has left the range (or ended): whoever decodes the next range can go on while this batch is inverted
+    if (*need_more) next_batch = false;
     if (!next_batch && !struct_err && on_walk && (rc = (*on_walk)(W))) return rc;
     // ---- K-U4 of the batch's blocks ----
     u64 bytes = 0;

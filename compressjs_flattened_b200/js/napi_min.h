@@ -28,6 +28,11 @@ napi_status napi_set_element(napi_env, napi_value arr, uint32_t i, napi_value v)
 napi_status napi_create_object(napi_env, napi_value *);
 napi_status napi_set_named_property(napi_env, napi_value obj, const char *name, napi_value v);
 napi_status napi_create_string_utf8(napi_env, const char *, size_t, napi_value *);
+napi_status napi_create_external(napi_env, void *data, napi_finalize, void *hint, napi_value *result);
+napi_status napi_get_value_external(napi_env, napi_value, void **result);
+napi_status napi_get_array_length(napi_env, napi_value, uint32_t *);
+napi_status napi_get_element(napi_env, napi_value arr, uint32_t i, napi_value *result);
+napi_status napi_get_undefined(napi_env, napi_value *result);
 napi_status napi_define_properties(napi_env, napi_value obj, size_t n, const napi_property_descriptor *);
 #define NAPI_AUTO_LENGTH ((size_t)-1)
 #define NAPI_MODULE_INIT() napi_value napi_register_module_v1(napi_env env, napi_value exports)

@@ -22,9 +22,9 @@ class HostMailbox:
     a millisecond for a TCP-backed process group -- the chain of first-block offsets is N-1 hops long."""
     FIELDS = 6  # (chain, bits, G) x 2 alternating slots
 
-    def __init__(self, rank, world, key):
+    def __init__(self, rank, world, key, timeout_s=120.0):
         import numpy as np
-        self.rank, self.world, self.seq = rank, world, 0
+        self.rank, self.world, self.seq, self.timeout_s = rank, world, 0, timeout_s
         self.path = f"/dev/shm/bz2b200_mailbox_{key}"
         shape = (world, self.FIELDS * 2)
         if rank == 0:
@@ -50,8 +50,12 @@ class HostMailbox:
     def get(self, src, field):
         f = 2 * field + (self.seq & 1)
         row = self.m[src]
+        t0, spins = time.time(), 0
         while int(row[2 * f]) != self.seq:
             time.sleep(0)   # let other threads of this process have the interpreter
+            spins += 1
+            if spins & 0xfff == 0 and time.time() - t0 > self.timeout_s:   # a peer that died or never joined: an error, not a hang
+                raise TimeoutError(f"shard mailbox: rank {src} did not publish field {field} of round {self.seq} within {self.timeout_s} s")
         return int(row[2 * f + 1])
 
     def close(self):

@@ -190,6 +190,25 @@ int bz2b200_pool_debug(bz2b200_pool *pool, uint32_t block_cap, uint32_t batch_bl
 int bz2b200_debug_set_decode_batch(bz2b200_ctx *ctx, bz2b200_pool *pool, uint32_t candidates);
 int bz2b200_debug_set_pool(bz2b200_ctx *ctx, size_t min_bytes, size_t shard_bytes, size_t first_halo, int force_staging);
 
+/* ---- the stream flavour (csrc/stream_abi.inl) ----
+ * What Bzip2.compressFile / decompressFile do with {readByte} sources and {writeByte} sinks (BJ:178-272,
+ * NPM/bin/compressjs:60-180), without holding input or output in full: feed pieces of any size; every call returns the
+ * bytes that are complete (library-allocated, release with bz2b200_free; *out may be NULL with *out_len == 0).
+ *   zstream  byte-identical to bz2b200_compress on the concatenated input; chunk_bytes (0 = 64 MiB) is how much input is
+ *            collected before its blocks are cut (the second half of a chunk is the halo of the blocks of the first)
+ *   dstream  decodes every block as soon as it is complete (chunk_bytes, 0 = 16 MiB of stream, between attempts); errors
+ *            come out of the call that meets them, after the bytes of the blocks before */
+typedef struct bz2b200_zstream bz2b200_zstream;
+typedef struct bz2b200_dstream bz2b200_dstream;
+int bz2b200_zstream_open(bz2b200_ctx *ctx, int level, size_t chunk_bytes, bz2b200_zstream **zs);
+int bz2b200_zstream_feed(bz2b200_zstream *zs, const uint8_t *in, size_t n, uint8_t **out, size_t *out_len);
+int bz2b200_zstream_finish(bz2b200_zstream *zs, uint8_t **out, size_t *out_len);
+void bz2b200_zstream_close(bz2b200_zstream *zs);
+int bz2b200_dstream_open(bz2b200_ctx *ctx, int multistream, size_t chunk_bytes, bz2b200_dstream **ds);
+int bz2b200_dstream_feed(bz2b200_dstream *ds, const uint8_t *in, size_t n, uint8_t **out, size_t *out_len);
+int bz2b200_dstream_finish(bz2b200_dstream *ds, uint8_t **out, size_t *out_len);
+void bz2b200_dstream_close(bz2b200_dstream *ds);
+
 const char *bz2b200_strerror(int rc);
 const char *bz2b200_last_error(bz2b200_ctx *ctx);
 int bz2b200_last_stats(bz2b200_ctx *ctx, bz2b200_stats *st);

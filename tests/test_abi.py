@@ -44,3 +44,26 @@ def test_no_gpu_means_loud_failure():
     from compressjs_flattened_b200.bzip2 import Bzip2Engine
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         Bzip2Engine(0)
+
+
+def test_addon_compiles_against_the_header_and_shim_is_loadable_by_construction():
+    """The N-API addon marshals exactly the C ABI (compile check against a hand-declared N-API subset; Node is absent here).
+    The shim must load under vm.runInThisContext, where `require` is not in scope: no require at script
+    scope, and all seven globals of the joined script (BJ:3-10) are defined."""
+    import re
+    import subprocess
+    js = os.path.join(ROOT, "compressjs_flattened_b200", "js")
+    subprocess.check_call(["gcc", "-DBZ2B200_NAPI_MIN", "-Wall", "-Werror", "-fsyntax-only", os.path.join(js, "bz2b200_napi.c")])
+    shim = open(os.path.join(js, "bzip2_shim.js")).read()
+    code = "\n".join(line.split("//")[0] for line in shim.splitlines())
+    for name in ("Stream", "BitStream", "Util", "BWT", "CRC32", "HuffmanAllocator", "Bzip2"):
+        assert re.search(rf"^var {name}\b", code, re.M), name
+    depth, bare = 0, []
+    for line in code.splitlines():   # a call of require at brace depth 0 or 1 (script / IIFE scope) would run at load time
+        if re.search(r"(?<![.\w])require\(", line) and depth <= 1:
+            bare.append(line)
+        depth += line.count("{") - line.count("}")
+    assert not bare, bare
+    addon = open(os.path.join(js, "bz2b200_napi.c")).read()
+    for fn in ("compress", "decompress", "decompressBlock", "table", "zstreamOpen", "dstreamOpen", "streamFeed", "streamFinish", "streamClose", "useDevices"):
+        assert f'"{fn}"' in addon and f"a.{fn}(" in shim.replace("native().", "a.") or fn in ("compress", "decompress"), fn

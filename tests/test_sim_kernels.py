@@ -422,3 +422,68 @@ def test_device_allocator_matches_reference_vectors(sim_engine, oracle):
         n = int(rng.integers(3, 259))
         f = sorted(int(x) for x in rng.integers(0, 1 << int(rng.integers(1, 20)), n))
         assert sim_engine.debug_huffman_lengths(f, 20) == oracle.huff_alloc(f, 20)
+
+
+def test_stream_objects_feed_and_finish(sim_engine, oracle):
+    """csrc/stream_abi.inl: zstream == compressFile on the concatenation for any piece / chunk size (incl. blocks that need
+    more than a chunk of input), dstream == decompressFile with the stream arriving in crumbs; multistream; errors"""
+    import io
+    from compressjs_flattened_b200.bzip2 import Bzip2Error
+    rng = np.random.default_rng(17)
+    from compressjs_flattened_b200.corpus import gen_text
+    text = gen_text(60_000, 2).tobytes()
+    runny = _runny(rng, 30_000, 3, 0.6)
+    sim_engine.debug_set_block_cap(901)
+    oracle.set_block_cap(901)
+    try:
+        for data in (text, runny, b"", b"q" * 7000):
+            exp = oracle.compress(data, 9)
+            for chunk, piece in ((4000, 1000), (1500, 7), (100_000, 100_000), (64, 50)):
+                assert sim_engine.compressStream(io.BytesIO(data), None, 9, chunk_bytes=chunk, piece_bytes=piece) == exp, (len(data), chunk, piece)
+            for chunk, piece in ((3000, 800), (200, 13), (1 << 20, 1 << 20)):
+                assert sim_engine.decompressStream(io.BytesIO(exp), None, False, chunk_bytes=chunk, piece_bytes=piece) == data
+        ms = oracle.compress(text, 9) + oracle.compress(runny, 9) + oracle.compress(b"end")
+        assert sim_engine.decompressStream(io.BytesIO(ms), None, True, chunk_bytes=2500, piece_bytes=999) == text + runny + b"end"
+        assert sim_engine.decompressStream(io.BytesIO(ms), None, False, chunk_bytes=2500, piece_bytes=999) == text
+        good = oracle.compress(text, 9)
+        bad = bytearray(good)
+        bad[len(good) * 2 // 3] ^= 0x22
+        sink = io.BytesIO()
+        with pytest.raises(Bzip2Error) as e:
+            sim_engine.decompressStream(io.BytesIO(bytes(bad)), sink, False, chunk_bytes=2000, piece_bytes=500)
+        assert e.value.errorCode == -5 and 0 < len(sink.getvalue()) < len(text) and text.startswith(sink.getvalue())
+        for blob in (good[:len(good) // 2], b"BZ", b"XYZW" + good[4:]):
+            assert _decode_outcome(oracle, blob, oracle.OracleError)[0] == "err"
+            with pytest.raises(Bzip2Error) as e:
+                sim_engine.decompressStream(io.BytesIO(blob), None, False, chunk_bytes=1000, piece_bytes=300)
+            assert ("err", e.value.errorCode) == _decode_outcome(oracle, blob, oracle.OracleError)
+    finally:
+        oracle.set_block_cap(0)
+        sim_engine.debug_set_block_cap(0)
+
+
+def test_command_line_like_the_reference(sim_engine, oracle, tmp_path, capsys):
+    """NPM/bin/compressjs:7-58,163-180: -z is the default, level 7 by default, -d decodes the first stream only, -b extracts
+    one block, the same complaints for contradictory flags"""
+    from compressjs_flattened_b200.__main__ import main
+    from compressjs_flattened_b200.corpus import gen_text
+    data = gen_text(250_000, 12).tobytes()
+    src, z7, z1, back, blk = (str(tmp_path / n) for n in ("in.txt", "z7.bz2", "z1.bz2", "back.txt", "blk.bin"))
+    open(src, "wb").write(data)
+    assert main([src, z7], engine=sim_engine) == 0 and open(z7, "rb").read() == oracle.compress(data, 7)
+    assert main(["-z", "-1", src, z1], engine=sim_engine) == 0 and open(z1, "rb").read() == oracle.compress(data, 1)
+    assert main(["-d", z1, back], engine=sim_engine) == 0 and open(back, "rb").read() == data
+    two = str(tmp_path / "two.bz2")
+    open(two, "wb").write(open(z1, "rb").read() + oracle.compress(b"second"))
+    assert main(["-d", two, back], engine=sim_engine) == 0 and open(back, "rb").read() == data            # first stream only
+    assert main(["-d", "--multistream", two, back], engine=sim_engine) == 0 and open(back, "rb").read() == data + b"second"
+    pos, size = oracle.table(open(z1, "rb").read())[1]
+    assert main(["-d", "-b", str(pos), z1, blk], engine=sim_engine) == 0
+    assert open(blk, "rb").read() == oracle.decompress_block(open(z1, "rb").read(), pos) and len(open(blk, "rb").read()) == size
+    assert main(["-d", "-z", src], engine=sim_engine) == 1
+    assert main(["-z", "-b", "32", src], engine=sim_engine) == 1
+    assert main(["-3", "-4", src], engine=sim_engine) == 1
+    assert main(["-d", "-5", z1], engine=sim_engine) == 1
+    assert main(["-t", "lzp3", src], engine=sim_engine) == 1
+    err = capsys.readouterr().err
+    assert "Must specify either -d or -z." in err and "--block can only be used with decompression" in err and "Can't specify both -3 and -4" in err
