@@ -453,6 +453,28 @@ def main():
                "timing": "host wall clock around the collective call, stream resident in HBM, decoded bytes stay in HBM"}
         dec_e2e_ms = None
 
+    # ---------------- BASELINE configs[0]: the 2 MB HTML-like buffer, compress + decompress round trip through the host API ----------------
+    small = None
+    if world == 1 and not args.no_cpu_baseline:
+        from compressjs_flattened_b200.corpus import gen_html
+        hd = gen_html(2_130_640, 5)
+        hz = eng.compressFile(hd, None, 9)
+        eng.decompressFile(hz)
+        reps = 10
+        s0 = time.time()
+        for _ in range(reps):
+            hz = eng.compressFile(hd, None, 9)
+        s1 = time.time()
+        for _ in range(reps):
+            hb = eng.decompressFile(hz)
+        s2 = time.time()
+        gk = "html:2130640:5:L9"
+        small = {"workload": "BASELINE.json configs[0]: 2 130 640 B synthetic HTML-like text (gen_html, seed 5), level 9, 3 blocks, host buffers in and out",
+                 "compress_ms": round((s1 - s0) / reps * 1e3, 3), "decompress_ms": round((s2 - s1) / reps * 1e3, 3),
+                 "compress_MBps": round(2.13064 / ((s1 - s0) / reps), 1), "decompress_MBps": round(2.13064 / ((s2 - s1) / reps), 1),
+                 "roundtrip_bit_exact": hb == hd.tobytes(),
+                 "sha256_equals_oracle_golden": (hashlib.sha256(hz).hexdigest() == GOLD[gk]["out_sha256"]) if gk in GOLD else None}
+
     # ---------------- reduce over ranks ----------------
     t = torch.tensor([dev_ms, wall_ms, e2e_ms, dec_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -490,6 +512,7 @@ def main():
             "clocks": clocks,
             "parity": parity,
             "stitched_stream": stitched,
+            "small_file": small,
             "out_bytes_per_step": int(out_len), "blocks_per_step": int(st_last.n_blocks), "sort_rounds": int(st_last.sort_rounds),
         }
         if args.mode == "compress":

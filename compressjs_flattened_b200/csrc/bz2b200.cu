@@ -119,7 +119,7 @@ struct Ctx {
   int sms = 148;           // multiprocessors of the device
   unsigned ibwt_s = 64;    // splitter spacing of the inverse-BWT list ranking (BZ2B200_IBWT_S overrides: 64..1024)
   u32 r0_tiles = 1u << 30; // tiles per group of the round-0 sort (BZ2B200_R0_TILES; default: all blocks at once -- L2-sized groups were slower)
-  bool rs2 = true;         // BZ2B200_RS2=0: the first-generation scatter passes (development aid)
+  bool rs2 = false;        // BZ2B200_RS2=1: the TMA-pipelined scatter passes of rsort2.cuh (measured 0.15-0.25 ms per step slower: profiles/r02_scatter_variants.md)
   int parse_mode = 0;      // BZ2B200_PARSE: 0 = by block count, 1 = k_huff_parse, 2 = k_huff_parse_win (development aid)
   std::vector<cudaEvent_t> trace_ev, trace_pool;
   std::vector<const char *> trace_names;
@@ -858,7 +858,7 @@ int ctx_new(int device, Ctx **out) {
   c->ev_ok = true;
   { const char *t = getenv("BZ2B200_TRACE"); c->trace = t && *t && *t != '0'; }
   { const char *t = getenv("BZ2B200_PARSE"); c->parse_mode = t ? atoi(t) : 0; }
-  { const char *t = getenv("BZ2B200_RS2"); if (t && *t == '0') c->rs2 = false; }
+  { const char *t = getenv("BZ2B200_RS2"); if (t && *t) c->rs2 = *t != '0'; }
   { const char *t = getenv("BZ2B200_R0_TILES"); int v = t ? atoi(t) : 0; if (v > 0) c->r0_tiles = (u32)v; }
   { const char *t = getenv("BZ2B200_IBWT_S"); int v = t ? atoi(t) : 0; if (v == 64 || v == 128 || v == 256 || v == 512 || v == 1024) c->ibwt_s = (unsigned)v; }
   { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) c->sms = v; }

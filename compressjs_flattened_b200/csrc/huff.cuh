@@ -247,25 +247,48 @@ __global__ void __launch_bounds__(HUF_BT) k_huf_split(HufArrays ha) {
     if (sel[g] == which) atomicAdd(&chist[cost[g]], 1u);
   __syncthreads();
   const u32 len = counts[which], half = len >> 1;
-  if (threadIdx.x == 0) {  // cost bin that straddles the median position
-    u32 cum = 0, c = 0;
-    for (; c < 1024; c++) {
-      if (cum + chist[c] > half) break;
-      cum += chist[c];
+  {  // cost bin that straddles the median position: the first bin whose inclusive prefix exceeds `half` (scan of the 1024 bins)
+    constexpr int PER = 1024 / HUF_BT;
+    u32 v[PER], mine = 0;
+#pragma unroll
+    for (int q = 0; q < PER; q++) { v[q] = chist[threadIdx.x * PER + q]; mine += v[q]; }
+    u32 tot;
+    u32 ex = block_excl_sum<u32>(mine, tot, ws);
+    if (threadIdx.x == 0) { bcast[0] = 1024; bcast[1] = tot; }  // 1024 when len == 0 (cannot happen: the most-used table has a group)
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < PER; q++) {
+      if (ex <= half && ex + v[q] > half) { bcast[0] = threadIdx.x * PER + q; bcast[1] = ex; }  // exactly one bin qualifies
+      ex += v[q];
     }
-    bcast[0] = c;    // 1024 when len == 0 (cannot happen: the most-used table has a group)
-    bcast[1] = cum;  // groups strictly cheaper than that bin
   }
   __syncthreads();
   const u32 cstar = bcast[0], below = bcast[1];
+  // stable split: among the groups of `which` with cost == cstar, those at position >= half (in group order) move up.
+  // Every thread owns HS_E consecutive groups per round, so a round costs one block scan for HS_E * HUF_BT groups.
+  constexpr int HS_E = 8;
   u32 carry = 0;
-  for (u32 base = 0; base < nsel; base += HUF_BT) {
-    u32 g = base + threadIdx.x;
-    bool mine = g < nsel && sel[g] == which;
-    u32 cg = mine ? cost[g] : 0;
-    u32 flag = (mine && cg == cstar) ? 1u : 0u, tot;
-    u32 occ = carry + block_excl_sum<u32>(flag, tot, ws);
-    if (mine && (cg > cstar || (cg == cstar && below + occ >= half))) sel[g] = (u8)ng;
+  for (u32 base = 0; base < nsel; base += HUF_BT * HS_E) {
+    const u32 g0 = base + threadIdx.x * HS_E;
+    u32 fl = 0, mn = 0, cnt = 0;
+    u32 cgv[HS_E];
+#pragma unroll
+    for (int e = 0; e < HS_E; e++) {
+      const u32 g = g0 + e;
+      const bool mine = g < nsel && sel[g] == which;
+      cgv[e] = mine ? cost[g] : 0;
+      if (mine) mn |= 1u << e;
+      if (mine && cgv[e] == cstar) { fl |= 1u << e; cnt++; }
+    }
+    u32 tot;
+    u32 occ = carry + block_excl_sum<u32>(cnt, tot, ws);
+#pragma unroll
+    for (int e = 0; e < HS_E; e++) {
+      if ((mn >> e) & 1u) {
+        if (cgv[e] > cstar || (cgv[e] == cstar && below + occ >= half)) sel[g0 + e] = (u8)ng;
+        occ += (fl >> e) & 1u;
+      }
+    }
     carry += tot;
   }
   u32 *fq = ha.freq + (i64)p * BZ_MAX_GROUPS * BZ_MAX_SYMS;

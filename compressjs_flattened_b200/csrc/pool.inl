@@ -495,6 +495,11 @@ static std::vector<size_t> pool_plan(size_t n, int level, size_t lanes, size_t f
     for (size_t o = 0; o < n; o += fixed) sizes.push_back(n - o < fixed ? n - o : fixed);
     return sizes;
   }
+  if (growth >= 1000.0 && first && first < n) {  // two shards: `first`, then everything else
+    sizes.push_back(first);
+    sizes.push_back(n - first);
+    return sizes;
+  }
   const size_t B = (size_t)level * 100000;
   // Measured on B200 (profiles/r02_pool_plans.md): a batch of few blocks costs ~1 ms more than its share of a large one
   // (per-block CTAs, host round trips), so few shards win: a quarter of a lane's share first (its upload is the exposed

@@ -1,4 +1,9 @@
-// rsort2.cuh -- the radix passes of the round-0 sort (K-S2), second generation.
+// rsort2.cuh -- the radix passes of the round-0 sort (K-S2), second generation.  NOT the default (BZ2B200_RS2=1 selects
+// it): on B200 it measures 0.60 ms per pass against 0.58 ms for k_rs_scatter and 14.60-14.70 ms per 100 MB step against
+// 14.45 ms (profiles/r02_scatter_variants.md) -- the pass is bound by shared-memory wavefronts and the MATCH pipe (ncu: LSU
+// wavefronts 42-57 %, ADU 42-64 %, DRAM 25-39 % of peak), not by load latency or DRAM, so hiding the loads behind TMA
+// buys nothing and the extra barriers of the staged write-out cost a little.  Kept because it is the right shape once the
+// ranking gets cheaper, and as the evidence for that statement.
 //
 // k_rs_scatter (bwt.cuh) is bound by the latency chain of ONE tile: dependent metadata loads, the block-wide digit scan,
 // the key loads, the ranking, the scattered stores -- a CTA spends ~10 us on 4096 keys and three resident CTAs per SM do

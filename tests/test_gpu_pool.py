@@ -134,3 +134,24 @@ def test_device_allocator_matches_reference_vectors(gpu_engine, oracle):
         got = gpu_engine.debug_huffman_lengths(freqs, limit)
         assert got == list(expect), (freqs, limit)
         assert got == oracle.huff_alloc(freqs, limit)
+
+
+def test_stream_objects_on_the_gpu(gpu_engine):
+    """zstream / dstream (csrc/stream_abi.inl) at real block sizes: 30 MB of text in 4 MiB chunks == compressFile; the
+    decoder fed in 1 MiB pieces gives the input back; level 1; a damaged stream raises after delivering the blocks before"""
+    import io
+    from compressjs_flattened_b200.bzip2 import Bzip2Error
+    from compressjs_flattened_b200.corpus import gen_text
+    data = gen_text(30_000_000, 8).tobytes()
+    whole = gpu_engine.compressFile(data, None, 9)
+    assert gpu_engine.compressStream(io.BytesIO(data), None, 9, chunk_bytes=4 << 20) == whole
+    assert gpu_engine.decompressStream(io.BytesIO(whole), None, False, chunk_bytes=2 << 20, piece_bytes=1 << 20) == data
+    z1 = gpu_engine.compressStream(io.BytesIO(data[:5_000_000]), None, 1, chunk_bytes=1 << 20, piece_bytes=333_333)
+    assert z1 == gpu_engine.compressFile(data[:5_000_000], None, 1)
+    assert gpu_engine.decompressStream(io.BytesIO(whole + z1), None, True, chunk_bytes=3 << 20) == data + data[:5_000_000]
+    bad = bytearray(whole)
+    bad[len(whole) // 2] ^= 0x08
+    sink = io.BytesIO()
+    with pytest.raises(Bzip2Error):
+        gpu_engine.decompressStream(io.BytesIO(bytes(bad)), sink, False, chunk_bytes=2 << 20)
+    assert 0 < len(sink.getvalue()) < len(data) and data.startswith(sink.getvalue())
