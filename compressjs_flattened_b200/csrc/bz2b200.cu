@@ -102,7 +102,7 @@ struct Ctx {
   DevBuf isa, keysA, keysB, valsB, actI0, actI1, actR0, actR1, lb_status, lbm, hist, digit_base;
   DevBuf seg_cnt, seg_tile0, tile_blk, tile_i0, tile_i1, totals;
   DevBuf Lcol, ranks, lastocc, A, freq, meta, W, bit_off, scrc, out, out_len, used_bits;
-  DevBuf rs_tiles;
+  DevBuf rs_tiles, gbounds;
   DevBuf key2, big_cnt, big_old, big_rank, big_tile0, big_tblk, totals2;
   DevBuf recs_cand, cand_first, out2, recs_all, blksort, r2_status, hfreq, hlens, hplen, hcodes, hsel, hcost, hgoff, hblk;
   // decode-side buffers
@@ -149,7 +149,7 @@ struct Ctx {
                      &isa, &keysA, &keysB, &valsB, &actI0, &actI1, &actR0, &actR1, &lb_status, &lbm, &hist, &digit_base,
                      &seg_cnt, &seg_tile0, &tile_blk, &tile_i0, &tile_i1, &totals,
                      &Lcol, &ranks, &lastocc, &A, &freq, &meta, &W, &bit_off, &scrc, &out, &out_len, &used_bits,
-                     &rs_tiles, &key2, &big_cnt, &big_old, &big_rank, &big_tile0, &big_tblk, &totals2,
+                     &rs_tiles, &gbounds, &key2, &big_cnt, &big_old, &big_rank, &big_tile0, &big_tblk, &totals2,
                      &recs_cand, &cand_first, &out2, &recs_all, &blksort, &r2_status, &hfreq, &hlens, &hplen, &hcodes, &hsel, &hcost, &hgoff, &hblk,
                      &d_in, &cand, &ncand, &dmeta, &dsyms, &dL, &dtt, &dwalk, &dblk, &dout, &dmisc, &dsel, &doff, &dperm, &dmap};
     for (DevBuf *b : all) pool.push_back(b);
@@ -553,8 +553,13 @@ int pipe_stages(Ctx *c) {
       const u32 ntiles = (n_act + RF_T0 - 1) / RF_T0, ctiles = (n_act + CK_TILE - 1) / CK_TILE;
       CK(cudaMemsetAsync(lbm, 0, 16, c->stream));
       CK(cudaMemsetAsync(status, 0, 8 * (size_t)ctiles, c->stream));
+      ENS(c->gbounds, 8 * ((size_t)ntiles + 2));
+      u32 *gb_lo = P<u32>(c->gbounds), *gb_lo2 = gb_lo + ntiles + 1;
+      LAUNCH(k_group_bounds, (ntiles + 1 + 7) / 8, 256, 0, actR[0], n_act, ntiles, gb_lo, gb_lo2, P<u32>(c->big_cnt), P<u32>(c->big_old), P<u32>(c->big_rank),
+             lbm + 2, big_cap);
       LAUNCH(k_sort_groups, ntiles, RF_THREADS, sizeof(RfSmem), P<u32>(c->key2), actI[0], actR[0], n_act, P<u32>(c->isa), (u32)BS, magic, actI[1],
-             actR[1], P<u32>(c->big_cnt), P<u32>(c->big_old), P<u32>(c->big_rank), lbm + 2, big_cap, P<u8>(c->blk), P<u8>(c->Lcol), P<BlockRec>(c->recs));
+             actR[1], P<u32>(c->big_cnt), P<u32>(c->big_old), P<u32>(c->big_rank), lbm + 2, big_cap, P<u8>(c->blk), P<u8>(c->Lcol), P<BlockRec>(c->recs),
+             gb_lo, gb_lo2);
       RC(rb_add(c, hv, lbm, sizeof hv));
       RC(rb_sync(c));
       const u32 n_big = hv[2];

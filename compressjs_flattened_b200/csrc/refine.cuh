@@ -200,11 +200,40 @@ __device__ __forceinline__ void cta_radix_group(RfSmem &sm, u32 a, u32 s) {
   }
 }
 
+// Tile bounds of k_sort_groups, one warp per nominal boundary j = tile * RF_T0: the start of the group that contains slot j
+// (bounds[tile]); a boundary that falls into a BIG group (> RF_T0 slots) registers the group once (the tile that holds
+// its first nominal boundary) and bounds_hi[tile] = the group's end, which is where the tile's own groups begin.
+// Was the prologue of k_sort_groups: two warps searching, then one thread, between two CTA-wide barriers (16 % of that
+// kernel's stall samples, profiles/r02_ncu_sort_groups_source.txt).
+__global__ void __launch_bounds__(256) k_group_bounds(const u32 *__restrict__ a_rank, u32 n_act, u32 ntiles, u32 *__restrict__ bounds,
+                                                     u32 *__restrict__ bounds_lo2, u32 *__restrict__ big_cnt, u32 *__restrict__ big_base,
+                                                     u32 *__restrict__ big_rank, u32 *__restrict__ n_big, u32 big_cap) {
+  const u32 tile = blockIdx.x * 8 + warp_id();
+  if (tile > ntiles) return;
+  const u32 *R = a_rank;
+  const u32 j = tile * RF_T0;
+  u32 lo = j < n_act ? group_start_warp(R, j) : n_act;
+  u32 lo2 = lo;  // first slot this tile sorts: past a big group that covers the boundary
+  if (lane_id() == 0) {
+    if (tile < ntiles && lo + RF_T0 < n_act && R[lo + RF_T0] == R[lo]) {  // the group that contains j is big: not sorted by k_sort_groups
+      const u32 e = lower_bound_u32(R, lo + RF_T0, n_act, R[lo] + 1);
+      if (j < lo + RF_T0) {  // first tile whose boundary falls into the group: register it
+        const u32 slot = atomicAdd(n_big, 1u);
+        if (slot < big_cap) { big_cnt[slot] = e - lo; big_base[slot] = lo; big_rank[slot] = R[lo]; }
+      }
+      lo2 = e;
+    }
+    bounds[tile] = lo;
+    bounds_lo2[tile] = lo2;
+  }
+}
+
 __global__ void __launch_bounds__(RF_THREADS, 6) k_sort_groups(const u32 *__restrict__ key2, const u32 *__restrict__ a_idx, const u32 *__restrict__ a_rank,
                                                             u32 n_act, u32 *__restrict__ isa, u32 stride, u64 magic, u32 *__restrict__ s_idx,
                                                             u32 *__restrict__ s_rank, u32 *__restrict__ big_cnt, u32 *__restrict__ big_base,
                                                             u32 *__restrict__ big_rank, u32 *__restrict__ n_big, u32 big_cap,
-                                                            const u8 *__restrict__ T, u8 *__restrict__ L, BlockRec *__restrict__ recs) {
+                                                            const u8 *__restrict__ T, u8 *__restrict__ L, BlockRec *__restrict__ recs,
+                                                            const u32 *__restrict__ bounds, const u32 *__restrict__ bounds_lo2) {
   DYN_SMEM(RfSmem, smp);
   RfSmem &sm = *smp;
   const int lane = lane_id(), w = warp_id();
@@ -219,28 +248,11 @@ __global__ void __launch_bounds__(RF_THREADS, 6) k_sort_groups(const u32 *__rest
     pk[e] = pi[e] = 0;
     if (j < j1) { pk[e] = key2[j]; pi[e] = a_idx[j]; }
   }
-  // ---- tile bounds [lo, hi): whole groups only ----
-  if (w < 2) {
-    const u32 j = w == 0 ? j0 : j1;
-    u32 res = j < n_act ? group_start_warp(R, j) : n_act;
-    if (lane == 0) sm.bc[w] = res;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    u32 lo = sm.bc[0], hi = sm.bc[1];
-    if (hi < lo) hi = lo;
-    if (lo + RF_T0 < n_act && R[lo + RF_T0] == R[lo]) {  // the group that contains j0 is big: not sorted here
-      u32 e = lower_bound_u32(R, lo + RF_T0, n_act, R[lo] + 1);
-      if (j0 < lo + RF_T0) {  // first tile whose boundary falls into the group: register it
-        u32 slot = atomicAdd(n_big, 1u);
-        if (slot < big_cap) { big_cnt[slot] = e - lo; big_base[slot] = lo; big_rank[slot] = R[lo]; }
-      }
-      lo = e < hi ? e : hi;
-    }
-    sm.bc[0] = lo; sm.bc[1] = hi; sm.bc[2] = 0; sm.bc[3] = 0; sm.bc[4] = 0;
-  }
-  __syncthreads();
-  const u32 lo = sm.bc[0], hi = sm.bc[1];
+  // ---- tile bounds [lo, hi): whole groups only (k_group_bounds) ----
+  u32 lo = bounds_lo2[tile], hi = bounds[tile + 1];
+  if (hi < lo) lo = hi;
+  if (threadIdx.x < 5) sm.bc[threadIdx.x] = 0;
+  (void)big_cnt; (void)big_base; (void)big_rank; (void)n_big; (void)big_cap;
   const u32 m = hi - lo;  // < 2 * RF_T0
   if (m == 0) return;
   // ---- into shared memory: the prefetched slots that fall into [lo, hi), then the slots before j0 ----
