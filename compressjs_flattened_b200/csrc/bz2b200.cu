@@ -925,7 +925,8 @@ int bz2b200_compress(bz2b200_ctx *ctx, const uint8_t *in, size_t n, int level, u
     Pool *p = c->own_pool;
     p->cap_override = c->cap_override; p->batch_override = c->batch_override;
     p->halo0 = c->pool_halo0; p->force_staging = c->pool_force_staging;
-    p->plan_first = n / 2 + 1;  // one device, two lanes: two halves measured best (profiles/r02_pool_plans.md)
+    p->plan_first = n / 5 * 2 + 1;  // one device, two lanes: two shards of 40 / 60 % measured best (profiles/r02_pool_two_shard_plans_n1.log)
+    p->plan_growth = 1000.0;
     int prc = pool_compress_whole(p, in, n, level, c->pool_shard_bytes, out, out_len);
     c->st = p->st;
     c->err = p->err;

@@ -392,10 +392,67 @@ __global__ void __launch_bounds__(RLE_THREADS) k_rle_emit(const u8 *__restrict__
                                                           u8 *__restrict__ blk, i64 blk_stride, i64 tile_first_owned) {
   __shared__ i64 ws64[33];
   __shared__ u32 ws32[33];
+  __shared__ u8 stage[RLE_TILE + RLE_TILE / 4 + 64];  // a tile emits at most 5 bytes per 4 of input (a count byte after every 4th of a run)
+  __shared__ int sh_simple, sh_k;
   RleView v;
   u32 tt;
   i64 tile = tile_first_owned + blockIdx.x;
   rle_view(in, N, tile, head_carry, v, tt, ws64, ws32);
+  // ---- fast path: the whole tile lies inside ONE block, past that block's fresh first run, and the block takes everything
+  // the tile emits (no cut inside): the tile's bytes are contiguous in the block, so they are staged in shared memory and
+  // written out with coalesced stores instead of one byte store per input byte (text: every tile but the ~2 per block
+  // that hold a cut or a first run) ----
+  {
+    const i64 t0 = tile * RLE_TILE, t1 = t0 + RLE_TILE < N ? t0 + RLE_TILE : N;
+    if (threadIdx.x == 0) {
+      int lo = 0, hi = nblocks - 1;
+      while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (recs[mid].s <= t0) lo = mid; else hi = mid - 1;
+      }
+      const BlockRec r0 = recs[lo];
+      // count bytes look ahead at most 251 input bytes (same tile or not, they read `in` directly): only the cut matters
+      sh_simple = (r0.s <= t0 && t1 <= r0.p && t0 >= r0.e_true && t1 < r0.p) ? 1 : 0;
+      sh_k = lo;
+    }
+    __syncthreads();
+    if (sh_simple) {
+      const BlockRec r = recs[sh_k];
+      const u64 gt = g_tile[tile];
+      const u64 base = r.outR + (gt - r.Ge);  // block offset of the tile's first emitted byte
+      if (base + tt <= (u64)r.n && base + tt < (u64)B - 1) {  // nothing of the tile is clipped by the block end or lands on the forced-zero count slot
+        u32 o = v.gpre;
+        for (int j = 0; j < v.nvalid; j++) {
+          const u32 e = (v.em >> (2 * j)) & 3u;
+          if (e) {
+            stage[o] = v.b[j];
+            if (e == 2) {
+              u32 cnt = 0;
+              i64 x = v.p0 + j + 1;
+              while (cnt < 251 && x < N && in[x] == v.b[j]) { cnt++; x++; }
+              stage[o + 1] = (u8)cnt;
+            }
+            o += e;
+          }
+        }
+        __syncthreads();
+        u8 *dst = blk + (i64)sh_k * blk_stride + base;
+        const u32 head = (u32)((16 - ((uintptr_t)dst & 15)) & 15);  // bytes up to the first 16-byte boundary
+        const u32 hb = head < tt ? head : tt;
+        if (threadIdx.x < hb) dst[threadIdx.x] = stage[threadIdx.x];
+        const u32 nvec = (tt - hb) / 16;
+        for (u32 q = threadIdx.x; q < nvec; q += RLE_THREADS) {
+          const u8 *sp = stage + hb + 16 * q;  // shared memory is read byte-wise: the staging offset is not aligned
+          u32 w[4];
+#pragma unroll
+          for (int a = 0; a < 4; a++) w[a] = (u32)sp[4 * a] | ((u32)sp[4 * a + 1] << 8) | ((u32)sp[4 * a + 2] << 16) | ((u32)sp[4 * a + 3] << 24);
+          *reinterpret_cast<uint4 *>(dst + hb + 16 * q) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        for (u32 q = hb + 16 * nvec + threadIdx.x; q < tt; q += RLE_THREADS) dst[q] = stage[q];
+        return;
+      }
+    }
+  }
   if (v.nvalid == 0) return;
   // block containing p0: last k with recs[k].s <= p0
   int lo = 0, hi = nblocks - 1;
