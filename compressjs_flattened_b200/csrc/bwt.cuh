@@ -61,87 +61,153 @@ __global__ void k_seg_init(const BlockRec *__restrict__ recs, int nb, u32 *__res
 }
 
 // ---- key construction ------------------------------------------------------------------------
-// The first sort covers as many symbols as fit 44 bits: the bytes of a block are first renumbered densely
-// (order-preserving), b = bits per symbol, L = 44 / b symbols (5 for binary data, 6 for text, 22 for DNA).
+// The first sort covers as many symbols as fit 44 bits.  Round 1 gave every symbol of a block the same number of bits
+// (dense codes, b = ceil(log2 alphabet): 6 symbols of text).  Now the bytes get an ORDER-PRESERVING PREFIX-FREE code
+// whose lengths follow the symbol frequencies (an alphabetic tree built by weight-balanced bisection, depth limited to
+// ceil(log2 alphabet) + 1), and a key is the first 44 bits of the code string of the rotation: comparing such bit
+// strings is comparing the rotations, frequent symbols take few bits, so a key of text covers ~8 symbols instead of 6
+// and every key value is about equally likely -- fewer and smaller tie groups for the doubling rounds.  Keys that are
+// equal agree on every symbol that lies wholly inside the 44 bits, at least L = 44 / (longest code) of them; L is the
+// first doubling distance.  Finer-than-L ranks are harmless: a rank never contradicts the final order, and equal ranks
+// still mean "equal on the first L symbols", which is all the doubling step needs.
 struct BlkSort {
-  u32 used[8];  // bitmap of the byte values of the block
-  u32 b, L;     // bits per symbol, symbols in the first key (= h of the first doubling round)
+  u32 cnt[256];   // occurrences of every byte value in the block
+  u32 L, maxlen;  // first doubling distance; longest code
   u32 pad[6];
-  u8 code[256]; // byte -> dense code
+  u8 clen[256];   // code length of a byte value (0: does not occur)
+  u16 cval[256];  // code, right-aligned
 };
-// grid (32, nb): used-byte bitmap of every block
+// grid (32, nb): byte histogram of every block (warp-private counters in shared memory)
 __global__ void __launch_bounds__(256) k_sym_used(const u8 *__restrict__ blk, i64 blk_stride, const BlockRec *__restrict__ recs,
                                                   BlkSort *__restrict__ bs) {
-  __shared__ u8 flag[256];  // flag[c] = 1: plain stores, every writer writes the same value
+  __shared__ u32 h[8][256];
   const u32 p = blockIdx.y, n = recs[p].n;
   const u8 *T = blk + (i64)p * blk_stride;
-  flag[threadIdx.x] = 0;
+  for (int i = threadIdx.x; i < 8 * 256; i += 256) (&h[0][0])[i] = 0;
   __syncthreads();
+  u32 *hw = h[warp_id()];
   const u32 nv = n / 16;  // whole 16-byte vectors, then the tail byte by byte
   for (u32 x = blockIdx.x * 256 + threadIdx.x; x < nv; x += gridDim.x * 256) {
     uint4 v4 = reinterpret_cast<const uint4 *>(T)[x];
     u32 wv4[4] = {v4.x, v4.y, v4.z, v4.w};
 #pragma unroll
-    for (int k = 0; k < 16; k++) flag[(wv4[k >> 2] >> (8 * (k & 3))) & 0xffu] = 1;
+    for (int k = 0; k < 16; k++) atomicAdd(&hw[(wv4[k >> 2] >> (8 * (k & 3))) & 0xffu], 1u);
   }
   if (blockIdx.x == 0)
-    for (u32 i = nv * 16 + threadIdx.x; i < n; i += 256) flag[T[i]] = 1;
+    for (u32 i = nv * 16 + threadIdx.x; i < n; i += 256) atomicAdd(&hw[T[i]], 1u);
   __syncthreads();
-  u32 b = __ballot_sync(FULL_MASK, flag[threadIdx.x] != 0);  // warp w covers bytes 32w .. 32w+31
-  if (lane_id() == 0 && b) atomicOr(&bs[p].used[warp_id()], b);
+  u32 tot = 0;
+#pragma unroll
+  for (int w = 0; w < 8; w++) tot += h[w][threadIdx.x];
+  if (tot) atomicAdd(&bs[p].cnt[threadIdx.x], tot);
 }
-// nb CTAs of 256 threads: dense codes, b and L
-__global__ void __launch_bounds__(256) k_sym_tab(BlkSort *__restrict__ bs) {
+// nb CTAs of 256 threads (thread = byte value): the code of every byte value, L
+__global__ void __launch_bounds__(256) k_sym_tab(BlkSort *__restrict__ bs, u32 key_bits) {
   __shared__ u32 ws[33];
+  __shared__ u32 P[257];     // P[r] = occurrences of the first r used symbols (by value)
+  __shared__ u32 wmax[8];
   BlkSort &B = bs[blockIdx.x];
   const u32 c = threadIdx.x;
-  u32 used = (B.used[c >> 5] >> (c & 31)) & 1u, alpha;
-  u32 idx = block_excl_sum<u32>(used, alpha, ws);
-  B.code[c] = (u8)idx;
+  const u32 f = B.cnt[c];
+  u32 used = f ? 1u : 0u, alpha;
+  const u32 r = block_excl_sum<u32>(used, alpha, ws);  // rank of this byte among the used ones
+  u32 tot;
+  const u32 pre = block_excl_sum<u32>(f, tot, ws);
+  if (used) P[r] = pre;
+  if (c == 0) P[alpha] = tot;
+  __syncthreads();
+  u32 len = 0, val = 0;
+  if (used) {
+    if (alpha == 1) { len = 1; val = 0; }
+    else {
+      u32 lb = 1;
+      while ((1u << lb) < alpha) lb++;
+      const u32 lmax = lb + (alpha > 2 ? 1u : 0u);  // depth limit of the tree
+      u32 lo = 0, hi = alpha;                       // the node: used symbols [lo, hi)
+      while (hi - lo > 1) {
+        const u32 cap = 1u << (lmax - len - 1);     // leaves a child may still hold
+        // split where the weights balance: first s with 2 * P[s] >= P[lo] + P[hi] ...
+        const u64 mid2 = (u64)P[lo] + P[hi];
+        u32 a = lo + 1, z = hi - 1;
+        while (a < z) {
+          const u32 m = (a + z) >> 1;
+          if (2ull * P[m] < mid2) a = m + 1; else z = m;
+        }
+        u32 s = a;
+        if (s > lo + 1 && 2ull * P[s] >= mid2 && mid2 - 2ull * P[s - 1] < 2ull * P[s] - mid2) s--;  // ... or the one before, whichever is closer
+        // ... inside what the depth limit allows on either side
+        const u32 smin = hi > cap + lo ? hi - cap : lo + 1, smax = lo + cap < hi - 1 ? lo + cap : hi - 1;
+        if (s < smin) s = smin;
+        if (s > smax) s = smax;
+        val <<= 1;
+        if (r >= s) { val |= 1u; lo = s; } else hi = s;
+        len++;
+      }
+    }
+  }
+  B.clen[c] = (u8)len;
+  B.cval[c] = (u16)val;
+  u32 mx = warp_max<u32>(len);
+  if (lane_id() == 0) wmax[warp_id()] = mx;
+  __syncthreads();
   if (c == 0) {
-    u32 b = 1;
-    while ((1u << b) < alpha) b++;
-    B.b = b;
-    B.L = 44 / b;
+    u32 m = 1;
+    for (int w = 0; w < 8; w++) if (wmax[w] > m) m = wmax[w];
+    B.maxlen = m;
+    B.L = key_bits / m;
   }
 }
-// dense codes of the first L symbols of each rotation, left-aligned in bits 20..63; rotation index in the low 20 bits.
-// The tile's bytes (+ L-1 more, cyclically) are staged in shared memory as codes; the histogram of the first radix
-// digit (bits 20..28) is counted on the way, so pass 0 needs no k_rs_hist.
+// the first key_bits (44, or 36: one radix pass less) bits of the code string of each rotation, from bit 20 up; rotation
+// index in the low 20 bits.  The tile's bytes (+ 43 more, cyclically: a key never needs more than 44 symbols) are staged
+// in shared memory.  A thread owns 16 CONSECUTIVE rotations and slides a bit window over their code string (drop the
+// first symbol's code, append codes at the end): ~2 table look-ups per rotation instead of one per covered symbol.  The
+// keys go through shared memory so that the global stores are coalesced; the histogram of the first radix digit (bits
+// 20..28) is counted on the way, so pass 0 needs no k_rs_hist.
 __global__ void __launch_bounds__(SEG_THREADS) k_keys_init(const u8 *__restrict__ blk, i64 blk_stride, const BlockRec *__restrict__ recs,
                                                            const u32 *__restrict__ seg_tile0, const u32 *__restrict__ tile_blk,
                                                            const BlkSort *__restrict__ bs, u64 *__restrict__ keys, u32 *__restrict__ hist0,
-                                                           u32 tile_base) {
-  __shared__ u8 code[256];
+                                                           u32 tile_base, u32 key_bits) {
+  __shared__ u32 cw[256];  // length << 16 | code
   __shared__ u8 sc[SORT_TILE + 48];
   __shared__ u32 h[512];
+  __shared__ u64 sk[SORT_TILE];
   u32 tile = blockIdx.x + tile_base, p = tile_blk[tile];
   u32 n = recs[p].n;
-  code[threadIdx.x] = bs[p].code[threadIdx.x];
+  cw[threadIdx.x] = ((u32)bs[p].clen[threadIdx.x] << 16) | bs[p].cval[threadIdx.x];
   for (int i = threadIdx.x; i < 512; i += SEG_THREADS) h[i] = 0;
-  const u32 b = bs[p].b, L = bs[p].L;
   __syncthreads();
   const u8 *T = blk + (i64)p * blk_stride;
   u32 l0 = (tile - seg_tile0[p]) * SORT_TILE;
   u64 g0 = (u64)(tile - tile_base) * SORT_TILE;  // keys and per-tile histograms are local to the group of blocks being sorted
   const u32 m = n - l0 < SORT_TILE ? n - l0 : SORT_TILE;
-  for (u32 j = threadIdx.x; j < m + L - 1; j += SEG_THREADS) {
+  for (u32 j = threadIdx.x; j < m + 43; j += SEG_THREADS) {
     u32 x = l0 + j;
-    while (x >= n) x -= n;
-    sc[j] = code[T[x]];
+    x %= n;
+    sc[j] = T[x];
   }
   __syncthreads();
-  const int shift = 64 - (int)(L * b);
-  for (int e = 0; e < SEG_E; e++) {
-    u32 j = e * SEG_THREADS + threadIdx.x;
-    if (j >= m) continue;
-    u64 key = 0;
-    for (u32 k = 0; k < L; k++) key = (key << b) | sc[j + k];
-    key = (key << shift) | (l0 + j);
-    keys[g0 + j] = key;
-    atomicAdd(&h[(u32)(key >> 20) & 511u], 1u);
+  {
+    const u32 j0 = threadIdx.x * SEG_E;
+    u64 buf = 0;       // code bits of symbols j .. kk-1, left-aligned
+    u32 bits = 0, kk = j0;
+    for (u32 e = 0; e < SEG_E; e++) {
+      const u32 j = j0 + e;
+      if (j >= m) break;
+      while (bits < key_bits) {  // at most 43 + 9 bits are ever held
+        const u32 w = cw[sc[kk++]], l = w >> 16;
+        buf |= (u64)(w & 0xffffu) << (64 - bits - l);
+        bits += l;
+      }
+      const u64 key = ((buf >> (64 - key_bits)) << 20) | (l0 + j);
+      sk[j] = key;
+      atomicAdd(&h[(u32)(key >> 20) & 511u], 1u);
+      const u32 lj = cw[sc[j]] >> 16;  // the window moves on by the first symbol's code
+      buf <<= lj;
+      bits -= lj;
+    }
   }
   __syncthreads();
+  for (u32 j = threadIdx.x; j < m; j += SEG_THREADS) keys[g0 + j] = sk[j];
   for (int i = threadIdx.x; i < 512; i += SEG_THREADS) hist0[(u64)(tile - tile_base) * 512 + i] = h[i];
 }
 // ---- one LSD radix pass (BITS-bit digit, 8 or 9), batched over blocks ---------------------------

@@ -119,6 +119,7 @@ struct Ctx {
   int sms = 148;           // multiprocessors of the device
   unsigned ibwt_s = 64;    // splitter spacing of the inverse-BWT list ranking (BZ2B200_IBWT_S overrides: 64..1024)
   u32 r0_tiles = 1u << 30; // tiles per group of the round-0 sort (BZ2B200_R0_TILES; default: all blocks at once -- L2-sized groups were slower)
+  u32 key_bits = 44;       // bits of the first sort key (BZ2B200_KEY_BITS=36: four radix passes instead of five, shallower keys)
   bool rs2 = false;        // BZ2B200_RS2=1: the TMA-pipelined scatter passes of rsort2.cuh (measured 0.15-0.25 ms per step slower: profiles/r02_scatter_variants.md)
   int parse_mode = 0;      // BZ2B200_PARSE: 0 = by block count, 1 = k_huff_parse, 2 = k_huff_parse_win (development aid)
   std::vector<cudaEvent_t> trace_ev, trace_pool;
@@ -467,7 +468,7 @@ int pipe_stages(Ctx *c) {
     ENS(c->blksort, sizeof(BlkSort) * (size_t)nb);
     CK(cudaMemsetAsync(c->blksort.p, 0, sizeof(BlkSort) * (size_t)nb, c->stream));
     LAUNCH(k_sym_used, dim3(32, (unsigned)nb), 256, 0, P<u8>(c->blk), BS, P<BlockRec>(c->recs), P<BlkSort>(c->blksort));
-    LAUNCH(k_sym_tab, (unsigned)nb, 256, 0, P<BlkSort>(c->blksort));
+    LAUNCH(k_sym_tab, (unsigned)nb, 256, 0, P<BlkSort>(c->blksort), c->key_bits);
     ENS(c->rs_tiles, sizeof(RsTile) * (size_t)(Ta + 1));
     if (Ta) LAUNCH(k_rs_tiles, (Ta + 255) / 256, 256, 0, seg_cnt, tile0, tblk, (u32)Ta, P<RsTile>(c->rs_tiles));
     u64 total_n = 0;
@@ -507,9 +508,10 @@ int pipe_stages(Ctx *c) {
         while (b1 < nb && (b1 == b0 || gt + tiles_of[b1] <= c->r0_tiles)) { gt += tiles_of[b1]; gn += hrecs[(size_t)b1].n; b1++; }
         const u32 tb = tile_first[b0];
         const unsigned gb = (unsigned)(b1 - b0);
-        LAUNCH(k_keys_init, gt, SEG_THREADS, 0, P<u8>(c->blk), BS, P<BlockRec>(c->recs), tile0, tblk, P<BlkSort>(c->blksort), kA, P<u32>(c->hist), tb);
+        LAUNCH(k_keys_init, gt, SEG_THREADS, 0, P<u8>(c->blk), BS, P<BlockRec>(c->recs), tile0, tblk, P<BlkSort>(c->blksort), kA, P<u32>(c->hist), tb, c->key_bits);
         u64 *ki = kA, *ko = kB;
-        for (int pass = 0; pass < 5; pass++) {  // bits 20..63, 9 bits a pass
+        const int npass = (int)(c->key_bits + 8) / 9;
+        for (int pass = 0; pass < npass; pass++) {  // bits 20 .. 20 + key_bits, 9 bits a pass
           if (pass) LAUNCH(k_rs_hist<9>, gt, SORT_THREADS, 0, ki, seg_cnt, tile0, tblk, 20 + pass * 9, P<u32>(c->hist), (const u32 *)nullptr, tb);  // pass 0: k_keys_init
           if (c->rs2 && tb == 0 && gt == Ta) {  // whole batch at once: table of absolute positions + pipelined scatter (rsort2.cuh)
 #if RS2_SCAN1
@@ -863,6 +865,7 @@ int ctx_new(int device, Ctx **out) {
   c->ev_ok = true;
   { const char *t = getenv("BZ2B200_TRACE"); c->trace = t && *t && *t != '0'; }
   { const char *t = getenv("BZ2B200_PARSE"); c->parse_mode = t ? atoi(t) : 0; }
+  { const char *t = getenv("BZ2B200_KEY_BITS"); int v = t ? atoi(t) : 0; if (v == 36 || v == 44 || v == 27) c->key_bits = (u32)v; }
   { const char *t = getenv("BZ2B200_RS2"); if (t && *t) c->rs2 = *t != '0'; }
   { const char *t = getenv("BZ2B200_R0_TILES"); int v = t ? atoi(t) : 0; if (v > 0) c->r0_tiles = (u32)v; }
   { const char *t = getenv("BZ2B200_IBWT_S"); int v = t ? atoi(t) : 0; if (v == 64 || v == 128 || v == 256 || v == 512 || v == 1024) c->ibwt_s = (unsigned)v; }
