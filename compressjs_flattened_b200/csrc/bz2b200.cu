@@ -119,6 +119,7 @@ struct Ctx {
   int sms = 148;           // multiprocessors of the device
   unsigned ibwt_s = 64;    // splitter spacing of the inverse-BWT list ranking (BZ2B200_IBWT_S overrides: 64..1024)
   u32 r0_tiles = 1u << 30; // tiles per group of the round-0 sort (BZ2B200_R0_TILES; default: all blocks at once -- L2-sized groups were slower)
+  u32 key_slack = 2;       // depth limit of the code tree above ceil(log2 alphabet) (BZ2B200_KEY_SLACK=0..3)
   u32 key_bits = 44;       // bits of the first sort key (BZ2B200_KEY_BITS=36: four radix passes instead of five, shallower keys)
   bool rs2 = false;        // BZ2B200_RS2=1: the TMA-pipelined scatter passes of rsort2.cuh (measured 0.15-0.25 ms per step slower: profiles/r02_scatter_variants.md)
   int parse_mode = 0;      // BZ2B200_PARSE: 0 = by block count, 1 = k_huff_parse, 2 = k_huff_parse_win (development aid)
@@ -468,7 +469,7 @@ int pipe_stages(Ctx *c) {
     ENS(c->blksort, sizeof(BlkSort) * (size_t)nb);
     CK(cudaMemsetAsync(c->blksort.p, 0, sizeof(BlkSort) * (size_t)nb, c->stream));
     LAUNCH(k_sym_used, dim3(32, (unsigned)nb), 256, 0, P<u8>(c->blk), BS, P<BlockRec>(c->recs), P<BlkSort>(c->blksort));
-    LAUNCH(k_sym_tab, (unsigned)nb, 256, 0, P<BlkSort>(c->blksort), c->key_bits);
+    LAUNCH(k_sym_tab, (unsigned)nb, 256, 0, P<BlkSort>(c->blksort), c->key_bits, c->key_slack);
     ENS(c->rs_tiles, sizeof(RsTile) * (size_t)(Ta + 1));
     if (Ta) LAUNCH(k_rs_tiles, (Ta + 255) / 256, 256, 0, seg_cnt, tile0, tblk, (u32)Ta, P<RsTile>(c->rs_tiles));
     u64 total_n = 0;
@@ -865,6 +866,7 @@ int ctx_new(int device, Ctx **out) {
   c->ev_ok = true;
   { const char *t = getenv("BZ2B200_TRACE"); c->trace = t && *t && *t != '0'; }
   { const char *t = getenv("BZ2B200_PARSE"); c->parse_mode = t ? atoi(t) : 0; }
+  { const char *t = getenv("BZ2B200_KEY_SLACK"); if (t && *t >= '0' && *t <= '3') c->key_slack = (u32)(*t - '0'); }
   { const char *t = getenv("BZ2B200_KEY_BITS"); int v = t ? atoi(t) : 0; if (v == 36 || v == 44 || v == 27) c->key_bits = (u32)v; }
   { const char *t = getenv("BZ2B200_RS2"); if (t && *t) c->rs2 = *t != '0'; }
   { const char *t = getenv("BZ2B200_R0_TILES"); int v = t ? atoi(t) : 0; if (v > 0) c->r0_tiles = (u32)v; }
