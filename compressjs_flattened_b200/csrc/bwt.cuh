@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(SEG_THREADS) k_keys_init(const u8 *__restrict_
   const u32 m = n - l0 < SORT_TILE ? n - l0 : SORT_TILE;
   for (u32 j = threadIdx.x; j < m + 43; j += SEG_THREADS) {
     u32 x = l0 + j;
-    x %= n;
+    if (x >= n) x %= n;
     sc[j] = T[x];
   }
   __syncthreads();
