@@ -37,7 +37,9 @@ namespace {
 struct ResultPool {
   std::mutex mu;
   std::vector<std::pair<void *, size_t>> live, idle;  // (pointer, capacity)
+  size_t idle_bytes = 0;
   static const size_t kMinPinned = 1 << 20, kMaxIdle = 48;  // a sharded call hands out one segment per shard
+  static const size_t kMaxIdleBytes = (size_t)12 << 30;     // page-locked memory kept for reuse
   void *get(size_t bytes) {
     if (bytes < kMinPinned) return malloc(bytes ? bytes : 1);
     std::lock_guard<std::mutex> g(mu);
@@ -47,6 +49,7 @@ struct ResultPool {
     if (best < idle.size()) {
       auto e = idle[best];
       idle.erase(idle.begin() + (long)best);
+      idle_bytes -= e.second;
       live.push_back(e);
       return e.first;
     }
@@ -67,7 +70,7 @@ struct ResultPool {
         if (live[i].first == p) {
           auto e = live[i];
           live.erase(live.begin() + (long)i);
-          if (idle.size() < kMaxIdle) { idle.push_back(e); return; }
+          if (idle.size() < kMaxIdle && idle_bytes + e.second <= kMaxIdleBytes) { idle.push_back(e); idle_bytes += e.second; return; }
 #ifndef BZ_SIM
           cudaFreeHost(p);
 #endif

@@ -14,13 +14,13 @@ void bz2b200_pool_destroy(bz2b200_pool *pool) { pool_delete(reinterpret_cast<Poo
 int bz2b200_pool_compress(bz2b200_pool *pool, const uint8_t *in, size_t n, int level, size_t shard_bytes, uint8_t **out, size_t *out_len) {
   Pool *p = reinterpret_cast<Pool *>(pool);
   if (!p || !out || !out_len || (n && !in)) return BZ2B200_E_ARG;
-  return pool_compress_whole(p, in, n, level, shard_bytes, out, out_len);
+  try { return pool_compress_whole(p, in, n, level, shard_bytes, out, out_len); } catch (...) { p->err = "host exception (thread or memory)"; return BZ2B200_E_OUT_OF_MEMORY; }
 }
 int bz2b200_pool_compress_shards(bz2b200_pool *pool, bz2b200_group *grp, const bz2b200_shard_job *jobs, int n_jobs, int total_shards, int level,
                                  int keep_on_device, bz2b200_shard_result *results) {
   Pool *p = reinterpret_cast<Pool *>(pool);
   if (!p) return BZ2B200_E_ARG;
-  return pool_compress_ranked(p, reinterpret_cast<Group *>(grp), jobs, n_jobs, total_shards, level, keep_on_device, results);
+  try { return pool_compress_ranked(p, reinterpret_cast<Group *>(grp), jobs, n_jobs, total_shards, level, keep_on_device, results); } catch (...) { p->err = "host exception (thread or memory)"; return BZ2B200_E_OUT_OF_MEMORY; }
 }
 int bz2b200_pool_last_stats(bz2b200_pool *pool, bz2b200_stats *st) {
   Pool *p = reinterpret_cast<Pool *>(pool);
@@ -72,13 +72,13 @@ int bz2b200_pool_decompress(bz2b200_pool *pool, const uint8_t *in, size_t n, int
                             size_t *out_len) {
   Pool *p = reinterpret_cast<Pool *>(pool);
   if (!p || !out || !out_len || (n && !in)) return BZ2B200_E_ARG;
-  return pool_decompress_whole(p, in, n, multistream, size_hint, slice_bytes, out, out_len);
+  try { return pool_decompress_whole(p, in, n, multistream, size_hint, slice_bytes, out, out_len); } catch (...) { p->err = "host exception (thread or memory)"; return BZ2B200_E_OUT_OF_MEMORY; }
 }
 int bz2b200_pool_decompress_shards(bz2b200_pool *pool, bz2b200_group *grp, const bz2b200_shard_job *jobs, int n_jobs, int total_shards,
                                    uint64_t total_n, int first_level, int multistream, int keep_on_device, bz2b200_range_result *results) {
   Pool *p = reinterpret_cast<Pool *>(pool);
   if (!p) return BZ2B200_E_ARG;
-  return pool_decompress_ranked(p, reinterpret_cast<Group *>(grp), jobs, n_jobs, total_shards, total_n, first_level, multistream, keep_on_device, results);
+  try { return pool_decompress_ranked(p, reinterpret_cast<Group *>(grp), jobs, n_jobs, total_shards, total_n, first_level, multistream, keep_on_device, results); } catch (...) { p->err = "host exception (thread or memory)"; return BZ2B200_E_OUT_OF_MEMORY; }
 }
 int bz2b200_debug_set_decode_batch(bz2b200_ctx *ctx, bz2b200_pool *pool, uint32_t candidates) {
   if (ctx) reinterpret_cast<Ctx *>(ctx)->dec_batch = candidates;

@@ -90,7 +90,7 @@ static int zstream_step(bz2b200_zstream *z, bool eof, std::vector<u8> &out, bool
   return BZ2B200_OK;
 }
 
-int bz2b200_zstream_feed(bz2b200_zstream *z, const uint8_t *in, size_t n, uint8_t **out, size_t *out_len) {
+static int zstream_feed_impl(bz2b200_zstream *z, const uint8_t *in, size_t n, uint8_t **out, size_t *out_len) {
   if (!z || !out || !out_len || (n && !in)) return BZ2B200_E_ARG;
   std::vector<u8> o;
   if (!z->header_sent) {  // BJ:2223-2226
@@ -110,7 +110,7 @@ int bz2b200_zstream_feed(bz2b200_zstream *z, const uint8_t *in, size_t n, uint8_
   return stream_out(o, out, out_len);
 }
 
-int bz2b200_zstream_finish(bz2b200_zstream *z, uint8_t **out, size_t *out_len) {
+static int zstream_finish_impl(bz2b200_zstream *z, uint8_t **out, size_t *out_len) {
   if (!z || !out || !out_len) return BZ2B200_E_ARG;
   std::vector<u8> o;
   if (!z->header_sent) {
@@ -187,7 +187,7 @@ static int dstream_drain(bz2b200_dstream *d, bool eof, std::vector<u8> &o) {
   return BZ2B200_OK;
 }
 
-int bz2b200_dstream_feed(bz2b200_dstream *d, const uint8_t *in, size_t n, uint8_t **out, size_t *out_len) {
+static int dstream_feed_impl(bz2b200_dstream *d, const uint8_t *in, size_t n, uint8_t **out, size_t *out_len) {
   if (!d || !out || !out_len || (n && !in)) return BZ2B200_E_ARG;
   std::vector<u8> o;
   d->buf.insert(d->buf.end(), in, in + n);
@@ -198,10 +198,24 @@ int bz2b200_dstream_feed(bz2b200_dstream *d, const uint8_t *in, size_t n, uint8_
   return stream_out(o, out, out_len);
 }
 
-int bz2b200_dstream_finish(bz2b200_dstream *d, uint8_t **out, size_t *out_len) {
+static int dstream_finish_impl(bz2b200_dstream *d, uint8_t **out, size_t *out_len) {
   if (!d || !out || !out_len) return BZ2B200_E_ARG;
   std::vector<u8> o;
   int rc = dstream_drain(d, true, o);
   if (rc) return rc;
   return stream_out(o, out, out_len);
+}
+
+// no exception crosses the ABI (std::vector growth is the one thing that can throw here)
+int bz2b200_zstream_feed(bz2b200_zstream *z, const uint8_t *in, size_t n, uint8_t **out, size_t *out_len) {
+  try { return zstream_feed_impl(z, in, n, out, out_len); } catch (...) { return BZ2B200_E_OUT_OF_MEMORY; }
+}
+int bz2b200_zstream_finish(bz2b200_zstream *z, uint8_t **out, size_t *out_len) {
+  try { return zstream_finish_impl(z, out, out_len); } catch (...) { return BZ2B200_E_OUT_OF_MEMORY; }
+}
+int bz2b200_dstream_feed(bz2b200_dstream *d, const uint8_t *in, size_t n, uint8_t **out, size_t *out_len) {
+  try { return dstream_feed_impl(d, in, n, out, out_len); } catch (...) { return BZ2B200_E_OUT_OF_MEMORY; }
+}
+int bz2b200_dstream_finish(bz2b200_dstream *d, uint8_t **out, size_t *out_len) {
+  try { return dstream_finish_impl(d, out, out_len); } catch (...) { return BZ2B200_E_OUT_OF_MEMORY; }
 }
