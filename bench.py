@@ -435,10 +435,10 @@ def main():
         per = (nw + world - 1) // world
         per = (per + 15) & ~15   # slices of a device-resident stream start 16-byte aligned
         lo, hi = min(rank * per, nw), min((rank + 1) * per, nw)
-        job = [dict(src=whole_dev.data_ptr() + lo, on_device=True, n_readable=nw - lo, own_len=hi - lo, base=lo, index=rank)]
+        job = [dict(src=whole_dev.data_ptr() + lo, on_device=True, n_readable=nw - lo, own_len=hi - lo, base=lo, index=rank)] if hi > lo else []
         first_level = level
         r0 = pool.decompress_shards(grp, job, world, nw, first_level, keep_on_device=False)   # verification pass: bytes come back
-        part, off, nb_, rc_, nblk = r0[0]
+        part, off, nb_, rc_, nblk = r0[0] if r0 else (b"", 0, 0, 0, 0)
         exp = gen_range(off, off + nb_) if nb_ else np.zeros(0, dtype=np.uint8)
         ok = torch.tensor([int(rc_ == 0 and bytes(part) == exp.tobytes()), nb_, nblk], dtype=torch.int64, device=dev)
         dist.all_reduce(ok, op=dist.ReduceOp.SUM)

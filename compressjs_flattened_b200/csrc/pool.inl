@@ -154,7 +154,8 @@ int group_open(const char *name, int rank, int world, int timeout_ms, Group **ou
   g->rank = rank; g->world = world;
   if (timeout_ms > 0) g->timeout_ms = timeout_ms;
   g->path = std::string("/dev/shm/bz2b200_grp_") + name;
-  for (char &ch : g->path) if (ch == ' ') ch = '_';
+  for (size_t i = strlen("/dev/shm/"); i < g->path.size(); i++)  // the name stays a file name inside /dev/shm
+    if (g->path[i] == ' ' || g->path[i] == '/' || g->path[i] == '.') g->path[i] = '_';
   const size_t bytes = sizeof(GrpHeader);
   // whoever creates the file (O_EXCL) sizes it; a new file is all zeros, which is a valid empty state; `magic` is set last
   int fd = open(g->path.c_str(), O_RDWR | O_CREAT | O_EXCL, 0600);
@@ -704,7 +705,16 @@ static int lane_decode(DecRun &R, Lane *L, std::vector<ShardJob> jobs, std::vect
     const u64 lo_bit = job.base * 8, hi_bit = (job.base + job.own_len) * 8;
     c->st = bz2b200_stats{};
     c->err.clear();
+    bool bad_header = false;
+    if (job.index == 0) {  // whoever holds the first slice checks the stream header (BJ:1408-1427); the level travels with the walk
+      u8 hdr[4] = {0, 0, 0, 0};
+      const size_t hb = job.n_avail < 4 ? job.n_avail : 4;
+      if (job.on_device) { if (hb) CK(cudaMemcpy(hdr, job.src, hb, cudaMemcpyDeviceToHost)); }
+      else memcpy(hdr, job.src, hb);
+      bad_header = hb < 4 || hdr[0] != 'B' || hdr[1] != 'Z' || hdr[2] != 'h' || hdr[3] != (u8)('0' + R.first_level);
+    }
     for (;;) {
+      if (bad_header) { rc = BZ2B200_E_NOT_BZIP_DATA; c->err = "no bzip2 stream header, or not the level the caller announced"; get_walk(Win); break; }
       if (!job.on_device) CK(cudaStreamWaitEvent(c->stream, L->in_ev[slot], 0));
       BufSink sink(&L->out_slot[slot]);
       int need_more = 0;

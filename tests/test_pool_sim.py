@@ -279,3 +279,19 @@ def test_group_of_processes_decodes_one_stream(sim_lib, oracle):
         assert rc == 0
         out[off:off + nbytes] = part
     assert bytes(out) == exp and sum(p[3] for p in parts) == len(exp)
+
+
+def test_ranked_decode_checks_the_stream_header(sim_lib, oracle):
+    """the rank that holds slice 0 checks 'BZh<level>' (BJ:1408-1427); a wrong header is the stream's error, not a crash"""
+    from compressjs_flattened_b200.pool import Bzip2Pool
+    blob = oracle.compress(b"header check " * 300, 9)
+    pool = Bzip2Pool([0], 1, library=sim_lib)
+    try:
+        job = lambda b: [dict(src=np.frombuffer(b, dtype=np.uint8), own_len=len(b), base=0, index=0)]
+        part, off, n, rc, nblk = pool.decompress_shards(None, job(blob), 1, len(blob), 9)[0]
+        assert rc == 0 and part == b"header check " * 300
+        for bad, lvl in ((b"BZx9" + blob[4:], 9), (blob, 5), (b"BZ", 9)):
+            res = pool.decompress_shards(None, job(bad), 1, len(bad), lvl)[0]
+            assert res[3] == -2 and res[2] == 0
+    finally:
+        pool.close()
