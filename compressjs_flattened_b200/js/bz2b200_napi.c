@@ -32,7 +32,13 @@ static napi_value result_obj(napi_env env, int rc, uint8_t *out, size_t n) {
   napi_set_named_property(env, obj, "rc", v);
   if (rc == 0) {
     napi_value ab, ta; /* zero-copy: the library's buffer becomes the ArrayBuffer; freed by the finalizer */
-    napi_create_external_arraybuffer(env, out, n, free_result, NULL, &ab);
+    if (n == 0 || !out) { /* nothing complete yet (stream feeds): an ordinary empty buffer */
+      void *unused;
+      if (out) bz2b200_free(out);
+      n = 0;
+      napi_create_arraybuffer(env, 0, &unused, &ab);
+    } else
+      napi_create_external_arraybuffer(env, out, n, free_result, NULL, &ab);
     napi_create_typedarray(env, napi_uint8_array, n, ab, 0, &ta);
     napi_set_named_property(env, obj, "data", ta);
   } else {

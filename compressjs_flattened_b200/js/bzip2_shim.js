@@ -44,6 +44,13 @@ var Bzip2 = (function (root) {
     }
     return got === n ? buf : buf.subarray(0, got);
   }
+  function drain(src) {                    // a whole {readByte} source (decompressBlock / table need random access)
+    var parts = [], total = 0, piece;
+    do { piece = readPiece(src, 1 << 20); parts.push(piece); total += piece.length; } while (piece.length === (1 << 20));
+    var out = new Uint8Array(total), o = 0;
+    parts.forEach(function (p) { out.set(p, o); o += p.length; });
+    return out;
+  }
   function check(r) {                      // _throw (BJ:1384-1391)
     if (r.rc === 0) return r;
     if (r.rc === -100) throw new Error('Invalid block size multiplier');
@@ -106,12 +113,12 @@ var Bzip2 = (function (root) {
     return col.result();
   };
   B.decompressBlock = function (input, pos, output) {
-    var col = new Collector(output), bytes = isSource(input) ? readPiece(input, input.size || (1 << 30)) : toBytes(input);
+    var col = new Collector(output), bytes = isSource(input) ? drain(input) : toBytes(input);
     col.put(check(native().decompressBlock(bytes, pos)).data);
     return col.result();
   };
   B.table = function (input, callback, multistream) {
-    var bytes = isSource(input) ? readPiece(input, input.size || (1 << 30)) : toBytes(input);
+    var bytes = isSource(input) ? drain(input) : toBytes(input);
     check(native().table(bytes, !!multistream)).table.forEach(function (row) { callback(row[0], row[1]); });
   };
   // every GPU of the box behind the same call (bz2b200_pool_*): Bzip2.useDevices([0,1,2,3]) then compressFile as before

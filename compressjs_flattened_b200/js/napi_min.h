@@ -19,6 +19,7 @@ napi_status napi_get_typedarray_info(napi_env, napi_value, napi_typedarray_type 
 napi_status napi_get_value_int32(napi_env, napi_value, int32_t *);
 napi_status napi_get_value_double(napi_env, napi_value, double *);
 napi_status napi_get_value_bool(napi_env, napi_value, bool *);
+napi_status napi_create_arraybuffer(napi_env, size_t len, void **data, napi_value *result);
 napi_status napi_create_external_arraybuffer(napi_env, void *data, size_t len, napi_finalize, void *hint, napi_value *result);
 napi_status napi_create_typedarray(napi_env, napi_typedarray_type, size_t length, napi_value arraybuffer, size_t byte_offset, napi_value *result);
 napi_status napi_create_int32(napi_env, int32_t, napi_value *);

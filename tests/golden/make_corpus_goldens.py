@@ -26,7 +26,7 @@ big = "--big" in sys.argv
 out = json.load(open(PATH)) if os.path.exists(PATH) else {}
 cases = [("text", 100_000_000, 8, 9), ("text", 100_000_000, 8, 1), ("text", 10_000_000, 8, 9),
          ("html", 2_130_640, 5, 9), ("html", 2_130_640, 5, 1),
-         ("text", 200_000_000, 8, 9), ("text", 400_000_000, 8, 9), ("text", 800_000_000, 8, 9)]
+         ("text", 200_000_000, 8, 9), ("text", 400_000_000, 8, 9), ("text", 800_000_000, 8, 9), ("text", 120_000_000, 8, 9)]
 cases += [("adv", name, None, lv) for name in ADVERSARIAL for lv in (9, 1)]
 if big:
     cases += [("text", 1_000_000_000, 64, 9), ("text", 8_000_000_000, 64, 9)]

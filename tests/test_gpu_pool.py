@@ -155,3 +155,84 @@ def test_stream_objects_on_the_gpu(gpu_engine):
     with pytest.raises(Bzip2Error):
         gpu_engine.decompressStream(io.BytesIO(bytes(bad)), sink, False, chunk_bytes=2 << 20)
     assert 0 < len(sink.getvalue()) < len(data) and data.startswith(sink.getvalue())
+
+
+def _gpu_rank_main(rank, world, name, q):
+    try:
+        import hashlib as H
+        import numpy as np
+        from compressjs_flattened_b200.corpus import gen_text
+        from compressjs_flattened_b200.pool import Bzip2Pool, ShardGroup, shard_plan
+        n_rank, level, halo = 60_000_000, 9, 2_000_000
+        total = world * n_rank
+        plan = shard_plan(n_rank, level, 1)
+        grp = ShardGroup(name, rank, world, timeout_ms=120_000)
+        pool = Bzip2Pool([rank], 1)
+        jobs, at = [], 0
+        data = gen_text(total, 8)   # every rank makes the corpus; it only hands in its own shards
+        for k, sz in enumerate(plan):
+            base = world * at + rank * sz
+            jobs.append(dict(src=np.ascontiguousarray(data[base:min(base + sz + halo, total)]), own_len=sz, base=base, index=k * world + rank))
+            at += sz
+        res = pool.compress_shards(grp, jobs, len(plan) * world, level)
+        q.put(("segs", rank, [(j["index"], seg, (int(i.next_start), int(i.bits), int(i.n_blocks), int(i.crc_fold), int(i.complete), int(i.bit_phase)))
+                              for j, (seg, i, _, _) in zip(jobs, res)]))
+        stream = q_in[rank].get(timeout=300)   # the stitched stream comes back from the parent
+        per = ((len(stream) + world - 1) // world + 15) & ~15
+        lo, hi = min(rank * per, len(stream)), min((rank + 1) * per, len(stream))
+        sl = [dict(src=np.frombuffer(stream[lo:], dtype=np.uint8), own_len=hi - lo, base=lo, index=rank)]
+        part, off, nb, rc, nblk = pool.decompress_shards(grp, sl, world, len(stream), level)[0]
+        q.put(("part", rank, (off, nb, rc, H.sha256(part).hexdigest(), H.sha256(data[off:off + nb].tobytes()).hexdigest())))
+        pool.close()
+        grp.close()
+    except Exception as e:  # pragma: no cover
+        q.put(("error", rank, repr(e)))
+
+
+q_in = None
+
+
+def _gpu_rank_entry(rank, world, name, q, qs):
+    global q_in
+    q_in = qs
+    _gpu_rank_main(rank, world, name, q)
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs 2 visible GPUs")
+def test_two_ranks_two_gpus_one_stream(gpu_engine):
+    """one process per GPU (the torchrun shape of bench.py at N > 1): the ranks exchange the per-shard scalars through the
+    shared-memory group, their segments stitch into the oracle's stream (SHA golden), and the two ranks decode that ONE
+    stream back, each its byte slice"""
+    import multiprocessing as mp
+    from compressjs_flattened_b200 import _native
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    qs = [ctx.Queue() for _ in range(world)]
+    name = f"gputest_{os.getpid()}"
+    procs = [ctx.Process(target=_gpu_rank_entry, args=(r, world, name, q, qs)) for r in range(world)]
+    for p in procs:
+        p.start()
+    segs = []
+    for _ in range(world):
+        kind, rank, payload = q.get(timeout=600)
+        assert kind == "segs", (kind, rank, payload)
+        segs += payload
+    segs.sort()
+    stream = gpu_engine.stitch_shards(9, [s[1] for s in segs], [_native.ShardInfo(*s[2]) for s in segs])
+    g = GOLD["text:120000000:8:L9"] if "text:120000000:8:L9" in GOLD else None
+    if g:
+        assert (len(stream), hashlib.sha256(stream).hexdigest()) == (g["out_bytes"], g["out_sha256"])
+    assert gpu_engine.decompressFile(stream)[:1000] == __import__("compressjs_flattened_b200").corpus.gen_text(1000, 8).tobytes()
+    for r in range(world):
+        qs[r].put(stream)
+    total = 0
+    for _ in range(world):
+        kind, rank, payload = q.get(timeout=600)
+        assert kind == "part", (kind, rank, payload)
+        off, nb, rc, got, exp = payload
+        assert rc == 0 and got == exp
+        total += nb
+    assert total == world * 60_000_000
+    for p in procs:
+        p.join(timeout=120)
