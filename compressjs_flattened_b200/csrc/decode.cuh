@@ -898,29 +898,29 @@ __global__ void __launch_bounds__(256) k_imtf_index(const DecBlk *__restrict__ b
     u32 nxoff = c0 + lane + 1 <= lim ? Ok[c0 + lane + 1] : myoff;
     u32 mylen = c0 + lane < lim ? nxoff - myoff : 0u;
     u32 cnt = lim - c0 < 32 ? lim - c0 : 32;
-    u32 out_byte = 0;
-    const u32 runs = __ballot_sync(FULL_MASK, mylen > 1);  // RUNA/RUNB digits that stand for several bytes
-#define IMTF_DECODE_STEP(t)                                                                              \
-    {                                                                                                    \
-      imtf_sym(hot, cold, __shfl_sync(FULL_MASK, mysym, (int)(t)), lane);                                \
-      const u32 byte = __shfl_sync(FULL_MASK, hot, 0); /* the decoded byte is the front of the list */   \
-      if ((runs >> (t)) & 1u) { /* many copies of the front byte, written by the whole warp */           \
-        const u32 len = __shfl_sync(FULL_MASK, mylen, (int)(t)), o = __shfl_sync(FULL_MASK, myoff, (int)(t)); \
-        for (u32 q = lane; q < len; q += 32) Lk[o + q] = (u8)byte;                                       \
-      }                                                                                                  \
-      if (lane == (int)(t)) out_byte = byte;                                                             \
+    // Only LITERALS (symbols 2..256) move the list; RUNA/RUNB digits and end-of-block leave it alone and only repeat the
+    // byte at its front.  So the serial chain steps over the literals of the chunk alone (the source profile of the
+    // step-every-symbol version had 80 % issue activity at 37 warp instructions per symbol), every lane remembers the
+    // front after the last literal at or before it, and the bytes of the run digits are written afterwards.
+    u32 front = __shfl_sync(FULL_MASK, hot, 0);  // the front the chunk starts with
+    u32 lits = __ballot_sync(FULL_MASK, mysym - 2u < 255u);
+    while (lits) {
+      const int t = __ffs((int)lits) - 1;
+      lits &= lits - 1;
+      const u32 j = __shfl_sync(FULL_MASK, mysym, t) - 1;  // rank 1..255
+      if (j < 32) imtf_hot(hot, j, lane); else imtf_cold(hot, cold, j, lane);
+      const u32 f = __shfl_sync(FULL_MASK, hot, 0);
+      if (lane >= t) front = f;
     }
-    // (fully unrolled, 32 copies of the step with its run branch ran 60 % slower -- instruction cache)
-    if (cnt == 32) {
-#pragma unroll 1
-      for (int t0 = 0; t0 < 32; t0 += 4) {
-#pragma unroll
-        for (int u = 0; u < 4; u++) IMTF_DECODE_STEP(t0 + u)
-      }
-    } else {
-      for (u32 t = 0; t < cnt; t++) IMTF_DECODE_STEP(t)
+    const u32 out_byte = front;
+    u32 runs = __ballot_sync(FULL_MASK, mylen > 1);  // RUNA/RUNB digits that stand for several bytes: written by the whole warp
+    while (runs) {
+      const int t = __ffs((int)runs) - 1;
+      runs &= runs - 1;
+      const u32 len = __shfl_sync(FULL_MASK, mylen, t), o = __shfl_sync(FULL_MASK, myoff, t), byte = __shfl_sync(FULL_MASK, front, t);
+      for (u32 q = lane; q < len; q += 32) Lk[o + q] = (u8)byte;
     }
-#undef IMTF_DECODE_STEP
+    (void)cnt;
     if (mylen == 1) Lk[myoff] = (u8)out_byte;
   }
   u8 *P = segperm + ((u64)k * (DEC_SYM_STRIDE / IMTF_SEG + 1) + seg) * 256;
