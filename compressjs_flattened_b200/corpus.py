@@ -3,8 +3,9 @@
 gen_text(n, seed)  "enwik8-like": Zipf(1.05) words from a 65 536-word synthetic vocabulary
                    (letters by English frequency), wiki markup, punctuation/newlines, digit
                    groups and a <page>...<text xml:space="preserve"> boilerplate every ~6 KB.
-gen_html(n, seed)  "sample5-like": nested tags from a small tag vocabulary with
-                   data-parsoid-like attributes, text words and runs of 4-8 spaces.
+gen_html(n, seed)  "sample5-like": Parsoid-style HTML: prose with wiki links (target spelled three times),
+                   bold spans, paragraphs and citation marks carrying growing tsr/dsr source offsets,
+                   runs of 4-8 spaces; ratio 0.147 at level 9 (the reference's sample5.ref: 0.129).
 
 Chunk c (1 000 000 bytes) depends only on splitmix64(seed, c), so chunks can be produced in any
 order / in parallel and an 8 GB corpus never needs a serial pass.  Pure numpy integer arithmetic:
@@ -51,8 +52,8 @@ def _table():
     rank = np.arange(V)
     length = 1 + (h % np.uint64(4)).astype(np.int64) + np.minimum(9, (np.log2(rank + 2) * 0.62).astype(np.int64))
     length = np.clip(length, 1, 14)
-    tab = np.zeros((V + 10000 + 64, _MAXLEN), dtype=np.uint8)
-    lens = np.zeros(V + 10000 + 64, dtype=np.int64)
+    tab = np.zeros((V + 10000 + 96, _MAXLEN), dtype=np.uint8)
+    lens = np.zeros(V + 10000 + 96, dtype=np.int64)
     for k in range(14):
         with np.errstate(over="ignore"):
             hk = _mix(h + np.uint64(k * 7919 + 1))
@@ -71,8 +72,13 @@ def _table():
               b"-0", b"T1", b":5", b"Z</timestamp>\n      <contributor>\n", b"        <username>", b"</username>\n        <id>",
               b"</id>\n      </contributor>\n      <text ", b"xml:space=\"preserve\">", b"    ", b"     ", b"      ", b"       ", b"        ",
               b"<div class=\"", b"<span", b"<p", b"</p>\n", b"</div>\n", b"</span>", b"<a href=\"./", b"\"", b"</a> ", b"<li", b"</li>\n",
-              b" data-parsoid='{\"dsr\":[", b",", b"]}'", b"<td", b"</td>", b"<tr", b"</tr>\n", b">"]
-    assert len(pieces) <= 64
+              b" data-parsoid='{\"dsr\":[", b",", b"]}'", b"<td", b"</td>", b"<tr", b"</tr>\n", b">",
+              # appended for gen_html (indices above are unchanged, so gen_text's bytes are too)
+              b"<a rel=\"mw:WikiLink\" href=\"./", b"\" data-parsoid='{\"tsr\":[", b"],\"a\":{\"href\":\"./", b"\"},\"sa\":{\"href\":\"",
+              b"\"},\"stx\":\"piped\",\"dsr\":[", b",2]}'>", b"</a>", b"<b data-parsoid='{\"tsr\":[", b"],\"dsr\":[", b",3,3]}'>", b"</b>",
+              b"</p>\n\n<p data-parsoid='{\"dsr\":[", b",0,0]}'>", b"<span class=\"reference\" data-parsoid='{\"dsr\":[",
+              b"<a href=\"#cite_note-", b"\">[", b"]</a></span>", b"_"]
+    assert len(pieces) <= 96 and max(len(x) for x in pieces) <= _MAXLEN
     for i, s in enumerate(pieces):
         tab[V + 10000 + i, :len(s)] = np.frombuffer(s, dtype=np.uint8)
         lens[V + 10000 + i] = len(s)
@@ -162,37 +168,62 @@ def _text_chunk(seed, c):
 
 
 def _html_chunk(seed, c):
+    """Parsoid-like HTML: running prose (phrase structure as in gen_text, a 2 048-word vocabulary) with wiki links whose
+    target is spelled three times (href, a.href, sa.href), bold spans, paragraphs and citation marks, each carrying
+    data-parsoid source offsets (tsr/dsr) that grow with the text like a real position counter, plus the odd run of
+    4-8 spaces.  Tuned to the ratio of the reference's sample5.ref (2 130 640 B -> 0.129 at level 9; SURVEY C1b band
+    0.12-0.16)."""
     T = _table()
     N = T["names"]
-    K = 120_000
-    w = _words(_stream(seed, c, 10, K), T)
-    w2 = _words(_stream(seed, c, 13, K), T)
+    K = 90_000
+    VH = 2048
+    w = _words(_stream(seed, c, 10, K), T) % VH
+    hs = _stream(seed, c, 13, K)
+    follow = (hs % np.uint64(100)) < np.uint64(78)
+    follow[0] = False
+    with np.errstate(over="ignore"):
+        succ = _words(_mix(np.roll(w, 1).astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15) + ((hs >> np.uint64(40)) % np.uint64(1))), T) % VH
+    w = np.where(follow, succ, w)
     r = (_stream(seed, c, 11, K) % np.uint64(1000)).astype(np.int64)
     h = _stream(seed, c, 12, K)
-    n1 = T["NUM"] + (h % np.uint64(10000)).astype(np.int64)
-    n2 = T["NUM"] + ((h >> np.uint64(20)) % np.uint64(10000)).astype(np.int64)
-    cols = [np.full(K, -1, dtype=np.int64) for _ in range(11)]
+    wl = T["lens"][w]
+    # source offsets: a counter over the wikitext this would have been rendered from
+    pos = 800 + np.cumsum(wl + 1 + np.where(r < 70, 4, 0))
+    end = pos + wl + np.where(r < 70, 4 + (h % np.uint64(3)).astype(np.int64) * wl, 0)
+
+    def digits(v):  # decimal digits of v (>= 100) as table ids: leading part, tens, units
+        return T["NUM"] + (v // 100) % 10000, T["NUM"] + (v // 10) % 10, T["NUM"] + v % 10
+
+    p0, p1, p2 = digits(pos)
+    e0, e1, e2 = digits(end)
+    NC = 26
+    cols = [np.full(K, -1, dtype=np.int64) for _ in range(NC)]
     cols[0][:] = w  # plain token: word + separator
     cols[1][:] = N[b" "]
-    cols[1][(r >= 960) & (r < 985)] = N[b"\n"]
-    sp = r >= 985  # runs of 4-8 spaces
+    cols[1][(r >= 900) & (r < 945)] = N[b", "]
+    cols[1][(r >= 945) & (r < 985)] = N[b". "]
+    sp = r >= 996  # runs of 4-8 spaces
     cols[1][sp] = N[b"    "] + (h[sp] % np.uint64(5)).astype(np.int64)
-    tagsets = [(0, 60, b"<span", None, b"</span>"), (60, 100, b"<a href=\"./", b"\"", b"</a> "), (100, 130, b"<li", None, b"</li>\n"),
-               (130, 150, b"<p", None, b"</p>\n"), (150, 165, b"<td", None, b"</td>"), (165, 172, b"<tr", None, b"</tr>\n"),
-               (172, 185, b"<div class=\"", b"\"", b"</div>\n")]
-    for lo, hi, opener, quote, closer in tagsets:
-        m = (r >= lo) & (r < hi)
-        cols[0][m] = N[opener]
-        cols[1][m] = w2[m] if quote else -1
-        cols[2][m] = N[quote] if quote else -1
-        cols[3][m] = N[b" data-parsoid='{\"dsr\":["]
-        cols[4][m] = n1[m]
-        cols[5][m] = N[b","]
-        cols[6][m] = n2[m]
-        cols[7][m] = N[b"]}'"]
-        cols[8][m] = N[b">"]
-        cols[9][m] = w[m]
-        cols[10][m] = N[closer]
+
+    def put(m, seq):
+        for k, v in enumerate(seq):
+            cols[k][m] = v[m] if isinstance(v, np.ndarray) else v
+        for k in range(len(seq), NC):
+            cols[k][m] = -1
+
+    m = r < 70  # wiki link
+    put(m, [N[b"<a rel=\"mw:WikiLink\" href=\"./"], w, N[b"\" data-parsoid='{\"tsr\":["], p0, p1, p2, N[b","], e0, e1, e2,
+            N[b"],\"a\":{\"href\":\"./"], w, N[b"\"},\"sa\":{\"href\":\""], w, N[b"\"},\"stx\":\"piped\",\"dsr\":["], p0, p1, p2, N[b","], e0, e1, e2,
+            N[b",2]}'>"], w, N[b"</a>"], N[b" "]])
+    m = (r >= 70) & (r < 82)  # bold
+    put(m, [N[b"<b data-parsoid='{\"tsr\":["], p0, p1, p2, N[b","], e0, e1, e2, N[b"],\"dsr\":["], p0, p1, p2, N[b","], e0, e1, e2,
+            N[b",3,3]}'>"], w, N[b"</b>"], N[b" "]])
+    m = (r >= 82) & (r < 92)  # paragraph break
+    put(m, [N[b". "], N[b"</p>\n\n<p data-parsoid='{\"dsr\":["], p0, p1, p2, N[b","], e0, e1, e2, N[b",0,0]}'>"], w, N[b" "]])
+    m = (r >= 92) & (r < 100)  # citation mark
+    cite = T["NUM"] + (pos // 700) % 10000
+    put(m, [N[b"<span class=\"reference\" data-parsoid='{\"dsr\":["], p0, p1, p2, N[b","], e0, e1, e2, N[b"]}'"], N[b">"],
+            N[b"<a href=\"#cite_note-"], cite, N[b"\">["], cite, N[b"]</a></span>"], N[b" "]])
     ids = np.stack(cols, axis=1).reshape(-1)
     ids = ids[ids >= 0]
     return _assemble(ids, T, CHUNK)
