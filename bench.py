@@ -223,10 +223,18 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # one process per GPU: run on the CPUs next to it before any page-locked buffer exists (-1: the platform hides the node)
+    from compressjs_flattened_b200.pool import bind_thread_to_device
+    cpus_before = os.sched_getaffinity(0)
+    host_node = bind_thread_to_device(local)
     ctl = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
         ctl = dist.new_group(backend="gloo")   # verification gathers travel host-side
+    host_nodes = [host_node]
+    if world > 1:
+        host_nodes = [None] * world
+        dist.all_gather_object(host_nodes, host_node, group=ctl)
     sampler = ClockSampler(local)
     if rank == 0 and not os.environ.get("BENCH_NO_SAMPLER"):
         sampler.start()   # started early (corpus generation takes seconds): it is streaming well before the timed region
@@ -525,7 +533,9 @@ def main():
                                              "note": "N>1: stream and result resident in HBM"}
             line["compress"] = dict(comp_line, e2e=e2e)
             line["decompress"] = dec
+        line["host_numa_node"] = host_nodes   # per rank: the node its feeding thread was bound to (-1: hidden by the platform)
         if world == 1 and not args.no_cpu_baseline:
+            os.sched_setaffinity(0, cpus_before)   # the CPU arm gets every core the process started with
             line["cpu_baseline"] = cpu_baseline(level, args.cpu_sample_mb or args.mb, os.cpu_count() or 1)
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -113,6 +113,8 @@ class Library:
         L.bz2b200_pool_last_error.argtypes = [vp]
         L.bz2b200_pool_last_error.restype = C.c_char_p
         L.bz2b200_group_open.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+        L.bz2b200_bind_thread_to_device.argtypes = [C.c_int]
+        L.bz2b200_bind_thread_to_device.restype = C.c_int
         L.bz2b200_group_close.argtypes = [vp]
         L.bz2b200_group_close.restype = None
         L.bz2b200_pool_compress_shards.argtypes = [vp, vp, C.POINTER(ShardJob), C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(ShardResult)]

@@ -20,7 +20,11 @@
 #include <future>
 #include <mutex>
 #include <thread>
+#include <cctype>
+#include <cstdio>
+#include <cstdlib>
 #include <fcntl.h>
+#include <sched.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>

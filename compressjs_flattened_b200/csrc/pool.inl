@@ -294,6 +294,73 @@ static bool is_pageable(const void *p) {
 #endif
 }
 
+// ---- host placement: threads that feed a device run on the CPUs of the NUMA node the device hangs off -------------
+// Page-locked memory is placed where the thread that first touches it runs, and a copy whose host side sits on the
+// other socket crosses the socket interconnect: with eight ranks on a two-socket box that is the difference between
+// every rank having its own PCIe root and all of them sharing one link.  The node comes from sysfs
+// (/sys/bus/pci/devices/<bus id>/numa_node); a virtual machine that hides it (-1) leaves the threads where they are.
+// Library-owned threads (lanes 1.., upload helpers) bind themselves; the CALLER's thread is only bound when the host
+// asks for it (bz2b200_bind_thread_to_device), since narrowing a thread the library does not own is the host's call.
+// BZ2B200_NUMA=0 switches all of it off.
+struct NodeCpus { int node = -2; cpu_set_t set; };  // node -2: not looked up yet
+static int numa_node_cpus(int device, cpu_set_t *out) {
+  static std::mutex mu;
+  static NodeCpus tab[64];
+  if (device < 0 || device >= 64) return -1;
+  std::lock_guard<std::mutex> g(mu);
+  NodeCpus &e = tab[device];
+  if (e.node == -2) {
+    e.node = -1;
+    CPU_ZERO(&e.set);
+    const char *sw = getenv("BZ2B200_NUMA");
+    const char *root = getenv("BZ2B200_SYSFS");  // tests point this at a made-up tree
+    if (!root || !root[0]) root = "/sys";
+    char bus[32] = {0};
+    bool have_bus = false;
+#ifndef BZ_SIM
+    have_bus = cudaDeviceGetPCIBusId(bus, sizeof bus, device) == cudaSuccess;
+    if (!have_bus) cudaGetLastError();
+#else
+    if (const char *b = getenv("BZ2B200_SIM_BUSID")) { snprintf(bus, sizeof bus, "%s", b); have_bus = true; }  // the simulator has no PCI address
+#endif
+    if (!(sw && sw[0] == '0') && have_bus) {
+      for (char *q = bus; *q; q++) *q = (char)tolower(*q);
+      char path[512];
+      snprintf(path, sizeof path, "%s/bus/pci/devices/%s/numa_node", root, bus);
+      int node = -1;
+      if (FILE *f = fopen(path, "r")) { if (fscanf(f, "%d", &node) != 1) node = -1; fclose(f); }
+      if (node >= 0) {
+        snprintf(path, sizeof path, "%s/devices/system/node/node%d/cpulist", root, node);
+        if (FILE *f = fopen(path, "r")) {
+          int a, b, got = 0;
+          while (fscanf(f, "%d", &a) == 1) {  // "0-15,32-47"
+            b = a;
+            int ch = fgetc(f);
+            if (ch == '-') { if (fscanf(f, "%d", &b) != 1) break; ch = fgetc(f); }
+            for (int k = a; k <= b && k < CPU_SETSIZE; k++) { CPU_SET(k, &e.set); got++; }
+            if (ch != ',') break;
+          }
+          fclose(f);
+          if (got) e.node = node;
+        }
+      }
+    }
+  }
+  if (e.node >= 0 && out) *out = e.set;
+  return e.node;
+}
+// binds the calling thread; returns the node, or -1 when nothing is known or the node has none of the thread's CPUs
+static int numa_bind_self(int device) {
+  cpu_set_t want, have, both;
+  const int node = numa_node_cpus(device, &want);
+  if (node < 0) return -1;
+  if (sched_getaffinity(0, sizeof have, &have) != 0) return -1;
+  CPU_AND(&both, &want, &have);
+  if (CPU_COUNT(&both) == 0) return -1;
+  if (!CPU_EQUAL(&both, &have) && sched_setaffinity(0, sizeof both, &both) != 0) return -1;
+  return node;
+}
+
 // host -> device copy of one shard into an input slot of the lane (asynchronous on the lane's copy stream; pageable
 // input is first copied into page-locked staging memory by the calling thread -- a helper thread, see lane_run)
 static int lane_upload(Lane *L, const ShardJob &job, int slot, bool pageable, const u8 **d_in) {
@@ -340,7 +407,7 @@ static int lane_run(PoolRun &R, Lane *L, std::vector<ShardJob> jobs, std::vector
   std::future<int> up;
   if (nj) {
     const ShardJob j0 = jobs[0];
-    up = std::async(std::launch::async, [L, j0, &R, &d_in] { return lane_upload(L, j0, 0, R.pageable, &d_in[0]); });
+    up = std::async(std::launch::async, [L, j0, &R, &d_in] { numa_bind_self(L->c->device); return lane_upload(L, j0, 0, R.pageable, &d_in[0]); });
   }
   bz2b200_stats agg{};
   static const bool ptrace = getenv("BZ2B200_POOL_TRACE") != nullptr;  // development aid: host timeline of every shard
@@ -389,7 +456,7 @@ static int lane_run(PoolRun &R, Lane *L, std::vector<ShardJob> jobs, std::vector
     if (k + 1 < nj) {  // the next shard of this lane travels while this one is compressed
       const ShardJob jn = jobs[k + 1];
       const int ns = slot ^ 1;
-      up = std::async(std::launch::async, [L, jn, ns, &R, &d_in] { return lane_upload(L, jn, ns, R.pageable, &d_in[ns]); });
+      up = std::async(std::launch::async, [L, jn, ns, &R, &d_in] { numa_bind_self(L->c->device); return lane_upload(L, jn, ns, R.pageable, &d_in[ns]); });
     }
     size_t olen = 0;
     u64 bits = 0;
@@ -466,7 +533,7 @@ static int pool_run_shards(Pool *p, Exchange *ex, std::vector<ShardJob> &jobs, s
   std::vector<int> rcs(nl, 0);
   std::vector<std::thread> th;
   for (size_t l = 1; l < nl; l++)
-    if (!lj[l].empty()) th.emplace_back([&, l] { rcs[l] = lane_run(R, p->lanes[l], lj[l], lo[l]); if (rcs[l]) ex->fail(rcs[l]); });
+    if (!lj[l].empty()) th.emplace_back([&, l] { numa_bind_self(p->lanes[l]->c->device); rcs[l] = lane_run(R, p->lanes[l], lj[l], lo[l]); if (rcs[l]) ex->fail(rcs[l]); });
   rcs[0] = lane_run(R, p->lanes[0], lj[0], lo[0]);
   if (rcs[0]) ex->fail(rcs[0]);
   for (auto &t : th) t.join();
@@ -671,7 +738,7 @@ static int lane_decode(DecRun &R, Lane *L, std::vector<ShardJob> jobs, std::vect
   std::future<int> up;
   if (nj) {
     const ShardJob j0 = jobs[0];
-    up = std::async(std::launch::async, [L, j0, &R, &d_in] { return lane_upload(L, j0, 0, R.pageable, &d_in[0]); });
+    up = std::async(std::launch::async, [L, j0, &R, &d_in] { numa_bind_self(L->c->device); return lane_upload(L, j0, 0, R.pageable, &d_in[0]); });
   }
   bz2b200_stats agg{};
   for (size_t k = 0; k < nj; k++) {
@@ -683,7 +750,7 @@ static int lane_decode(DecRun &R, Lane *L, std::vector<ShardJob> jobs, std::vect
     if (k + 1 < nj) {
       const ShardJob jn = jobs[k + 1];
       const int ns = slot ^ 1;
-      up = std::async(std::launch::async, [L, jn, ns, &R, &d_in] { return lane_upload(L, jn, ns, R.pageable, &d_in[ns]); });
+      up = std::async(std::launch::async, [L, jn, ns, &R, &d_in] { numa_bind_self(L->c->device); return lane_upload(L, jn, ns, R.pageable, &d_in[ns]); });
     }
     DecWalk Win, Wout;
     bool have_in = false;
@@ -771,7 +838,7 @@ static int pool_run_decode(Pool *p, DecRun &R, std::vector<ShardJob> &jobs, std:
   std::vector<int> rcs(nl, 0);
   std::vector<std::thread> th;
   for (size_t l = 1; l < nl; l++)
-    if (!lj[l].empty()) th.emplace_back([&, l] { rcs[l] = lane_decode(R, p->lanes[l], lj[l], lo[l]); if (rcs[l]) R.ex->fail(rcs[l]); });
+    if (!lj[l].empty()) th.emplace_back([&, l] { numa_bind_self(p->lanes[l]->c->device); rcs[l] = lane_decode(R, p->lanes[l], lj[l], lo[l]); if (rcs[l]) R.ex->fail(rcs[l]); });
   rcs[0] = lane_decode(R, p->lanes[0], lj[0], lo[0]);
   if (rcs[0]) R.ex->fail(rcs[0]);
   for (auto &t : th) t.join();

@@ -22,6 +22,9 @@ int bz2b200_pool_compress_shards(bz2b200_pool *pool, bz2b200_group *grp, const b
   if (!p) return BZ2B200_E_ARG;
   try { return pool_compress_ranked(p, reinterpret_cast<Group *>(grp), jobs, n_jobs, total_shards, level, keep_on_device, results); } catch (...) { p->err = "host exception (thread or memory)"; return BZ2B200_E_OUT_OF_MEMORY; }
 }
+int bz2b200_bind_thread_to_device(int device) {
+  try { return numa_bind_self(device); } catch (...) { return -1; }
+}
 int bz2b200_pool_last_stats(bz2b200_pool *pool, bz2b200_stats *st) {
   Pool *p = reinterpret_cast<Pool *>(pool);
   if (!p || !st) return BZ2B200_E_ARG;

@@ -25,6 +25,13 @@ def shard_plan(n, level=9, lanes=2, first_bytes=0, growth=0.0, library=None):
     return [int(arr[i]) for i in range(k)]
 
 
+def bind_thread_to_device(device, library=None):
+    """Run the calling thread on the CPUs next to `device` (bz2b200_bind_thread_to_device): call before allocating
+    page-locked buffers in a one-process-per-GPU job.  Returns the NUMA node, or -1 when the platform hides it."""
+    lib = library or _native.default_library()
+    return int(lib.L.bz2b200_bind_thread_to_device(int(device)))
+
+
 class ShardGroup:
     def __init__(self, name, rank, world, timeout_ms=120_000, library=None):
         self._lib = library or _native.default_library()

@@ -139,6 +139,12 @@ int bz2b200_pool_compress(bz2b200_pool *pool, const uint8_t *in, size_t n, int l
 int bz2b200_pool_set_plan(bz2b200_pool *pool, size_t first_bytes, double growth);
 /* the plan itself (for callers that hand out shards to ranks): returns the number of shards, sizes[] filled */
 int bz2b200_pool_plan(size_t n, int level, int lanes, size_t first_bytes, double growth, size_t *sizes, int cap);
+/* Host placement.  Runs the CALLING thread on the CPUs of the NUMA node `device` is attached to (sysfs numa_node of its PCI
+ * address), so that page-locked memory it allocates afterwards and the copies it issues stay on the device's socket; call it
+ * once per feeding thread before allocating buffers (what `numactl --cpunodebind` does for a whole process).  Returns the node,
+ * or -1 when the platform does not say (virtual machines often hide it), the node has none of the thread's CPUs, or
+ * BZ2B200_NUMA=0: the thread is then left alone.  The library's own lane and upload threads do this by themselves. */
+int bz2b200_bind_thread_to_device(int device);
 int bz2b200_pool_last_stats(bz2b200_pool *pool, bz2b200_stats *st);
 const char *bz2b200_pool_last_error(bz2b200_pool *pool);
 int bz2b200_group_open(const char *name, int rank, int world, int timeout_ms, bz2b200_group **grp);

@@ -295,3 +295,53 @@ def test_ranked_decode_checks_the_stream_header(sim_lib, oracle):
             assert res[3] == -2 and res[2] == 0
     finally:
         pool.close()
+
+
+_BIND_CHILD = r"""
+import ctypes, os, sys
+L = ctypes.CDLL(sys.argv[1])
+L.bz2b200_bind_thread_to_device.argtypes = [ctypes.c_int]
+before = sorted(os.sched_getaffinity(0))
+node = L.bz2b200_bind_thread_to_device(int(sys.argv[2]))
+print(node, ",".join(map(str, before)), ",".join(map(str, sorted(os.sched_getaffinity(0)))))
+"""
+
+
+def _fake_sysfs(tmp_path, bus, node, cpulist):
+    d = tmp_path / "bus" / "pci" / "devices" / bus
+    d.mkdir(parents=True)
+    (d / "numa_node").write_text(f"{node}\n")
+    if node >= 0:
+        nd = tmp_path / "devices" / "system" / "node" / f"node{node}"
+        nd.mkdir(parents=True)
+        (nd / "cpulist").write_text(cpulist + "\n")
+
+
+@pytest.mark.parametrize("case", ["bind", "hidden", "foreign_cpus", "switched_off"])
+def test_bind_thread_to_device(sim_engine, tmp_path, case):
+    """bz2b200_bind_thread_to_device: sysfs numa_node of the device's PCI address -> the node's cpulist, intersected with the
+    thread's own CPUs (made-up sysfs tree; the simulator takes the PCI address from the environment).  A hidden node (-1),
+    a node with none of our CPUs, or BZ2B200_NUMA=0 leave the thread alone and return -1."""
+    import subprocess
+    import sys
+    mine = sorted(os.sched_getaffinity(0))
+    if len(mine) < 3:
+        pytest.skip("needs three CPUs")
+    env = dict(os.environ, BZ2B200_SYSFS=str(tmp_path), BZ2B200_SIM_BUSID="0000:1B:00.0")
+    expect_node, expect_cpus = -1, mine
+    if case == "bind":   # "a,b-c" with a range, plus CPUs that do not exist here
+        _fake_sysfs(tmp_path, "0000:1b:00.0", 1, f"{mine[0]},{mine[1]}-{mine[2]},{mine[-1] + 900}-{mine[-1] + 910}")
+        expect_node, expect_cpus = 1, sorted(set([mine[0]] + list(range(mine[1], mine[2] + 1))) & set(mine))
+    elif case == "hidden":
+        _fake_sysfs(tmp_path, "0000:1b:00.0", -1, "")
+    elif case == "foreign_cpus":
+        _fake_sysfs(tmp_path, "0000:1b:00.0", 0, f"{mine[-1] + 900}-{mine[-1] + 910}")
+    else:
+        _fake_sysfs(tmp_path, "0000:1b:00.0", 1, f"{mine[0]}")
+        env["BZ2B200_NUMA"] = "0"
+    out = subprocess.run([sys.executable, "-c", _BIND_CHILD, SIM_SO, "0"], env=env, capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, out.stderr
+    node, before, after = out.stdout.split()
+    assert int(node) == expect_node
+    assert [int(x) for x in before.split(",")] == mine
+    assert [int(x) for x in after.split(",")] == expect_cpus
