@@ -642,6 +642,18 @@ __global__ void __launch_bounds__(DECW_PT) k_huff_parse_win(const u8 *__restrict
       for (u32 t = 0, c = 0; t < BZ_MAX_GROUPS; t++)
         if ((tmask >> t) & 1u) { tabs |= t << (4 * c); c++; }
       const u32 opl = W / DECW_PT, nitems = ntabs * opl;  // (table slot, offset) items of this thread, all in flight together
+      u64 slots = 0;  // warp 0: nibble q = table slot of the window's q-th group (for the walk below)
+      if (lane < 32) {
+        const u32 t = ((u32)lane < DECW_KMAX && selector + lane < nsel) ? sm.selbuf[selector - sel0 + lane] : 0u;
+        const u32 sl = (u32)__popc(tmask & ((1u << t) - 1u));
+        u32 lo = lane < 8 ? sl << (4 * lane) : 0u, hi = (lane >= 8 && lane < 16) ? sl << (4 * (lane - 8)) : 0u;
+#pragma unroll
+        for (int d = 16; d; d >>= 1) {
+          lo |= __shfl_xor_sync(FULL_MASK, lo, d);
+          hi |= __shfl_xor_sync(FULL_MASK, hi, d);
+        }
+        slots = ((u64)hi << 32) | lo;
+      }
       // level 0: the code that would start at every offset, under every table of the window
       u32 nx[DECW_ITEMS];
       u16 *jr[DECW_ITEMS], *jw[DECW_ITEMS];  // J[slot][level][0] (gathers) and J[slot][level][own offset] (stores)
@@ -694,19 +706,18 @@ __global__ void __launch_bounds__(DECW_PT) k_huff_parse_win(const u8 *__restrict
         u32 pos = 0, g = 0;
         u32 lim = (DEC_SYM_STRIDE - 1 - flushed) / BZ_GROUP;  // groups g with flushed + (g + 1) * 50 < DEC_SYM_STRIDE
         if (lim > kq) lim = kq;
-        const u16 *Jn = sm.J + (u32)__popc(tmask & ((1u << sm.selbuf[selector - sel0]) - 1u)) * DECW_LEVELS * W;
+        // Four dependent reads per group and nothing else on the chain: the table slot of every group was packed into
+        // `slots` before the levels (a selector read here would sit between two groups' reads), the indices are clamped
+        // into the window instead of tested (a clamped read returns some valid entry that is never used), and the tests
+        // come behind the last read.
         while (g < lim && pos < W) {
-          const u16 *Jb = Jn;
-          Jn = sm.J + (u32)__popc(tmask & ((1u << sm.selbuf[selector - sel0 + (int)(g + 1 < lim ? g + 1 : g)]) - 1u)) * DECW_LEVELS * W;  // next group's table, off the chain
+          const u16 *Jb = sm.J + ((u32)(slots >> (4 * g)) & 15u) * DECW_LEVELS * W;
           const u16 *J16 = Jb + 4 * W;
           const u32 a = J16[pos];
-          if (a >= W) break;
-          const u32 b2 = J16[a];
-          if (b2 >= W) break;
-          const u32 c2 = J16[b2];
-          if (c2 >= W) break;
-          const u32 d2 = Jb[W + c2];
-          if (d2 == 0xffffu) break;
+          const u32 b2 = J16[min(a, W - 1u)];
+          const u32 c2 = J16[min(b2, W - 1u)];
+          const u32 d2 = Jb[W + min(c2, W - 1u)];
+          if ((a >= W) | (b2 >= W) | (c2 >= W) | (d2 == 0xffffu)) break;
           sm.starts[g] = (u16)pos;
           pos = d2;
           g++;
@@ -897,7 +908,6 @@ __global__ void __launch_bounds__(256) k_imtf_index(const DecBlk *__restrict__ b
     u32 myoff = c0 + lane <= lim ? Ok[c0 + lane] : 0u;   // Ok[m] exists: one entry past the last symbol
     u32 nxoff = c0 + lane + 1 <= lim ? Ok[c0 + lane + 1] : myoff;
     u32 mylen = c0 + lane < lim ? nxoff - myoff : 0u;
-    u32 cnt = lim - c0 < 32 ? lim - c0 : 32;
     // Only LITERALS (symbols 2..256) move the list; RUNA/RUNB digits and end-of-block leave it alone and only repeat the
     // byte at its front.  So the serial chain steps over the literals of the chunk alone (the source profile of the
     // step-every-symbol version had 80 % issue activity at 37 warp instructions per symbol), every lane remembers the
@@ -920,7 +930,6 @@ __global__ void __launch_bounds__(256) k_imtf_index(const DecBlk *__restrict__ b
       const u32 len = __shfl_sync(FULL_MASK, mylen, t), o = __shfl_sync(FULL_MASK, myoff, t), byte = __shfl_sync(FULL_MASK, front, t);
       for (u32 q = lane; q < len; q += 32) Lk[o + q] = (u8)byte;
     }
-    (void)cnt;
     if (mylen == 1) Lk[myoff] = (u8)out_byte;
   }
   u8 *P = segperm + ((u64)k * (DEC_SYM_STRIDE / IMTF_SEG + 1) + seg) * 256;
