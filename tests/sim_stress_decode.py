@@ -19,7 +19,7 @@ from compressjs_flattened_b200.corpus import gen_text  # noqa: E402
 
 trials = int(sys.argv[1]) if len(sys.argv) > 1 else 60
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 7)
-lib = _native.Library(os.path.join(HERE, "sim", "libbz2b200_sim.so"))
+lib = _native.Library(os.environ.get("BZ2B200_SIM_LIB") or os.path.join(HERE, "sim", "libbz2b200_sim.so"))  # e.g. an -fsanitize=address build
 
 
 def outcome(fn):
