@@ -582,17 +582,21 @@ static std::vector<size_t> pool_plan(size_t n, int level, size_t lanes, size_t f
   double w = (double)first < wmax ? (double)first : wmax;
   while (left) {
     if ((double)left <= w * (double)lanes * 1.3) {  // the last wave: what is left, split evenly over the lanes (no crumb shard)
-      const size_t parts = (double)left <= w * 0.65 ? 1 : (size_t)(((double)left + w * 1.3 - 1) / (w * 1.3));
+      size_t parts = (double)left <= w * 0.65 ? 1 : (size_t)(((double)left + w * 1.3 - 1) / (w * 1.3));
+      if (parts < 1) parts = 1;  // a first shard of one or two bytes: the quotient above can round below 1
       for (size_t l = 0; l < parts; l++) {
         size_t take = l + 1 == parts ? left : ((left / (parts - l)) + 4095) & ~(size_t)4095;
         if (take > left) take = left;
+        if (!take) break;  // the rounding gave the earlier parts everything
         sizes.push_back(take);
         left -= take;
       }
       break;
     }
     for (size_t l = 0; l < lanes; l++) {              // a full wave: one shard per lane
-      const size_t take = ((size_t)w + 4095) & ~(size_t)4095;
+      size_t take = ((size_t)w + 4095) & ~(size_t)4095;
+      if (take > left) take = left;  // shards far below 4 KiB (tests): the rounding must not run past the input
+      if (!take) break;
       sizes.push_back(take);
       left -= take;
     }

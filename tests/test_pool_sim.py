@@ -345,3 +345,33 @@ def test_bind_thread_to_device(sim_engine, tmp_path, case):
     assert int(node) == expect_node
     assert [int(x) for x in before.split(",")] == mine
     assert [int(x) for x in after.split(",")] == expect_cpus
+
+
+def test_shard_plan_invariants(sim_lib):
+    """bz2b200_pool_plan: for every size, lane count, first-shard size and growth the shards are non-empty and add up to the
+    input (a first shard of one byte once rounded the part count of the last wave down to zero: an empty plan)."""
+    import ctypes as C
+    arr = (C.c_size_t * 4096)()
+    for n in list(range(0, 40)) + [100, 4095, 4096, 4097, 10_000, 123_457, (1 << 24) + 5, 10 ** 8, 8 * 10 ** 9]:
+        for lanes in (1, 2, 3, 8):
+            for first in (0, 1, 2, 7, 4096, n // 5 * 2 + 1, 25_000_000):
+                for growth in (0.0, 1.0, 3.0, 1000.0):
+                    k = sim_lib.L.bz2b200_pool_plan(n, 9, lanes, first, growth, arr, 4096)
+                    if k < 0:   # more than 4096 shards: refused, not truncated
+                        assert first and first * 4096 < n
+                        continue
+                    sizes = [int(arr[i]) for i in range(k)]
+                    assert k >= 1 and sum(sizes) == n and (n == 0 or min(sizes) > 0), (n, lanes, first, growth, sizes[:8])
+
+
+def test_context_pool_on_tiny_inputs(sim_lib, oracle):
+    """bz2b200_compress through the context's own lanes for inputs of 1..9 bytes (plan_first = n / 5 * 2 + 1 = 1)."""
+    from compressjs_flattened_b200.bzip2 import Bzip2Engine
+    eng = Bzip2Engine(0, sim_lib)
+    eng.debug_set_pool(1)
+    try:
+        for n in range(1, 10):
+            data = bytes(range(65, 65 + n))
+            assert eng.compressFile(data, None, 9) == oracle.compress(data, 9)
+    finally:
+        eng.debug_set_pool()
