@@ -375,3 +375,29 @@ def test_context_pool_on_tiny_inputs(sim_lib, oracle):
             assert eng.compressFile(data, None, 9) == oracle.compress(data, 9)
     finally:
         eng.debug_set_pool()
+
+
+def test_object_lifecycles_leave_nothing_behind(tmp_path):
+    """tests/sim/leak_check.cpp under AddressSanitizer + LeakSanitizer: three rounds of create / use / destroy of a context
+    (whole-buffer calls, table, one block, a damaged stream, its own lanes), stream objects (finished and abandoned) and a
+    pool.  In the simulator device memory is host memory, so a buffer the library forgets to free -- on either side -- is
+    reported; the simulator's own fiber stacks are suppressed (tests/sim/lsan.supp)."""
+    import shutil
+    import subprocess
+    if not os.environ.get("BZ2B200_SANITIZER_TESTS"):
+        pytest.skip("opt-in (BZ2B200_SANITIZER_TESTS=1): builds the simulator with -fsanitize=address, ~100 s")
+    if not shutil.which("g++"):
+        pytest.skip("no g++")
+    asan = subprocess.run(["gcc", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+    if not os.path.isabs(asan) or not os.path.exists(asan):
+        pytest.skip("no libasan")
+    sim = os.path.join(HERE, "sim")
+    root = os.path.dirname(HERE)
+    subprocess.check_call([os.path.join(sim, "build_sim.sh")], env=dict(os.environ, SIM_SANITIZE="address"))
+    exe = str(tmp_path / "leak_check")
+    subprocess.check_call(["g++", "-std=c++17", "-g", "-fsanitize=address", "-I" + os.path.join(root, "include"), os.path.join(sim, "leak_check.cpp"),
+                           os.path.join(sim, "libbz2b200_sim_address.so"), "-Wl,-rpath," + sim, "-o", exe])
+    env = dict(os.environ, ASAN_OPTIONS="detect_stack_use_after_return=0",
+               LSAN_OPTIONS="suppressions=" + os.path.join(sim, "lsan.supp") + ":print_suppressions=0")
+    out = subprocess.run([exe], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "3 rounds done" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
