@@ -487,3 +487,24 @@ def test_command_line_like_the_reference(sim_engine, oracle, tmp_path, capsys):
     assert main(["-t", "lzp3", src], engine=sim_engine) == 1
     err = capsys.readouterr().err
     assert "Must specify either -d or -z." in err and "--block can only be used with decompression" in err and "Can't specify both -3 and -4" in err
+
+
+@pytest.mark.parametrize("parse_mode", ["1", "2"])
+def test_decode_foreign_libbz2_streams(sim_engine, parse_mode, monkeypatch):
+    """Streams made by libbz2 (Python's bz2: other table choices, code lengths up to 17, several streams back to back) on both
+    parse kernels: what any encoder wrote must come back (the reference decodes foreign streams, BJ:1769-1796)."""
+    import bz2
+    from compressjs_flattened_b200 import _native
+    from compressjs_flattened_b200.bzip2 import Bzip2Engine
+    from compressjs_flattened_b200.corpus import gen_html, gen_text
+    monkeypatch.setenv("BZ2B200_PARSE", parse_mode)
+    eng = Bzip2Engine(0, _native.Library(os.path.join(os.path.dirname(__file__), "sim", "libbz2b200_sim.so")))
+    rng = np.random.default_rng(3)
+    skew = rng.choice(256, 50_000, p=np.arange(1, 257)[::-1] ** 3.0 / (np.arange(1, 257) ** 3.0).sum()).astype(np.uint8).tobytes()
+    cases = [gen_text(70_000, 2).tobytes(), gen_html(40_000, 3).tobytes(), skew, bytes(30_000), b"a", b""]
+    for data in cases:
+        for level in (1, 9):
+            assert eng.decompressFile(bz2.compress(data, level)) == data
+    two = bz2.compress(cases[0][:20_000], 5) + bz2.compress(cases[2][:9_000], 2)
+    assert eng.decompressFile(two, None, True) == cases[0][:20_000] + cases[2][:9_000]
+    assert eng.decompressFile(two) == cases[0][:20_000]          # the reference stops after the first stream (multistream off)
