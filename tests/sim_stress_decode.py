@@ -1,8 +1,9 @@
 """Development aid (CPU simulator): randomized decode stress of BOTH parse kernels -- streams of many shapes (alphabets of
 1..256 symbols, skews, runs, text; 2..6 tables; block caps from 300 to 5000 bytes so that a stream has many blocks and
-selector groups) made by the oracle, decoded by the simulated kernels with BZ2B200_PARSE=1 and =2, compared with the input.
+selector groups) made by the oracle (plus one libbz2-made stream of the same input per trial), decoded by the simulated kernels with BZ2B200_PARSE=1 and =2, compared with the input.
 Damaged copies (one flipped bit) must give the oracle's outcome.
     python tests/sim_stress_decode.py [trials] [seed]"""
+import bz2
 import os
 import sys
 import time
@@ -59,12 +60,13 @@ for t in range(trials):
         pos = int(rng.integers(32, len(flipped) * 8 - 1))
         flipped[pos >> 3] ^= 0x80 >> (pos & 7)
     want_bad = outcome(lambda: O.decompress(bytes(flipped)))
+    foreign = bz2.compress(d.tobytes(), int(rng.integers(1, 10)))   # libbz2's table choices and code lengths
     for mode in ("1", "2"):
         os.environ["BZ2B200_PARSE"] = mode
         eng = Bzip2Engine(0, lib)
         got = outcome(lambda: eng.decompressFile(comp))
         got_bad = outcome(lambda: eng.decompressFile(bytes(flipped)))
-        ok = got == ("ok", d.tobytes()) and got_bad == want_bad
+        ok = got == ("ok", d.tobytes()) and got_bad == want_bad and outcome(lambda: eng.decompressFile(foreign)) == ("ok", d.tobytes())
         if not ok:
             bad += 1
             print(f"MISMATCH trial {t} mode {mode}: kind={kind} n={n} A={A} skew={skew} cap={cap} good={got[0]} bad={got_bad[0]}/{want_bad[0]}", flush=True)
